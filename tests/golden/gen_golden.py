@@ -1,0 +1,124 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (`/root/reference/src/models`,
+imported through `oracle/ref_shims.py`) on seeded synthetic inputs.
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python tests/golden/gen_golden.py
+
+Writes `tests/golden/<variant>.pt`, each a dict:
+    config        the reference config dict the model was built from
+    state_dict    the reference model's weights (float32)
+    batch, x_seed, x_kind   how to regenerate the input with oracle.vit_oracle.synthetic_batch
+    labels        the labels used
+    eval          fp32, dropout off: loss, logits, hidden_states (sample 0 only), last_hidden[:, 0]
+    grads         fp32, dropout off: d loss / d param for every param that received a grad
+    bf16          the same under torch.autocast('cpu', bfloat16): loss, logits, grads
+    train3        3 steps of clip_grad_norm_(0.5) + torch.optim.AdamW(lr=1e-3) with dropout off:
+                  losses, grad norms and the final weights
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+from oracle.vit_oracle import synthetic_batch  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def base_cfg(**model_over):
+    m = dict(name="vit", task_type="reg", image_size=4096, patch_size=32, hidden_size=32,
+             num_hidden_layers=3, num_attention_heads=2, stride_size=32, proj_fn="SW")
+    m.update(model_over)
+    return {"model": m, "loss": {"name": "mae"}, "data": {"param": "log_g"}, "noise": {"noise_level": 0},
+            "opt": {"type": "AdamW", "lr": 0.001}, "train": {"batch_size": 64}}
+
+
+def variants():
+    v = {}
+    v["baseline"] = (base_cfg(), 4, "dummy")                       # configs/exp/att_clp/baseline.yaml
+    v["config2"] = (base_cfg(num_hidden_layers=2), 4, "rand")      # configs/config.yaml model
+    v["rope"] = (base_cfg(image_size=1024, pos_encoding_type="rope"), 3, "rand")
+    v["learned"] = (base_cfg(image_size=1024, pos_encoding_type="learned"), 3, "rand")
+    v["cnn"] = (base_cfg(image_size=1000, proj_fn="CNN", stride_size=24), 3, "rand")   # floor patch count
+    v["stride8"] = (base_cfg(image_size=1024, stride_size=8), 2, "rand")               # overlapping windows
+    v["pad48"] = (base_cfg(image_size=1000, patch_size=48, stride_size=48), 3, "rand")  # zero-pad tail window
+    c = base_cfg(image_size=1024, task_type="cls", num_labels=3)
+    v["cls"] = (c, 5, "rand")
+    c = base_cfg(image_size=1024)
+    c["loss"]["name"] = "l1"
+    v["l1"] = (c, 4, "rand")
+    c = base_cfg(image_size=2048, hidden_size=64, num_attention_heads=4, num_hidden_layers=2)
+    c["data"]["param"] = "t_eff,log_g"
+    v["h64multi"] = (c, 3, "rand")
+    c = base_cfg(image_size=2048, hidden_size=128, num_attention_heads=2, num_hidden_layers=1,
+                 pos_encoding_type="rope", stride_size=16)
+    v["h128d64rope"] = (c, 2, "rand")
+    return v
+
+
+def run_variant(name, cfg, batch, kind):
+    torch.manual_seed(42)
+    model = ref_shims.reference_get_model(cfg)
+    model.eval()  # dropout off; grads still flow
+    spec_len = cfg["model"]["image_size"]
+    x, y = synthetic_batch(batch, spec_len, seed=7, kind=kind)
+    if cfg["model"]["task_type"] == "cls":
+        y = torch.randint(0, cfg["model"]["num_labels"], (batch,), generator=torch.Generator().manual_seed(3))
+    elif model.config.num_labels > 1:
+        y = torch.rand(batch, model.config.num_labels, generator=torch.Generator().manual_seed(3))
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    out = model(x, labels=y, output_hidden_states=True)
+    model.zero_grad()
+    out.loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    ev = dict(loss=out.loss.detach().clone(), logits=out.logits.detach().clone(),
+              hidden_states=[h[0].detach().clone() for h in out.hidden_states])
+    with torch.no_grad():
+        last = model.vit(x).last_hidden_state
+    ev["last_hidden_cls"] = last[:, 0].clone()
+
+    model.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        outb = model(x, labels=y)
+    outb.loss.backward()
+    bf = dict(loss=outb.loss.detach().float().clone(), logits=outb.logits.detach().float().clone(),
+              grads={k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+
+    # 3 training steps, Lightning semantics restated (basemodule.py:244, optimizer.py:108)
+    model.zero_grad()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0)
+    losses, norms = [], []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = model(x, labels=y).loss
+        loss.backward()
+        norms.append(torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5).detach().clone())
+        opt.step()
+        losses.append(loss.detach().clone())
+    tr = dict(losses=torch.stack(losses), grad_norms=torch.stack(norms),
+              state_dict={k: v.detach().clone() for k, v in model.state_dict().items()})
+
+    fix = dict(config=copy.deepcopy(cfg), state_dict=sd0, batch=batch, x_seed=7, x_kind=kind, labels=y,
+               eval=ev, grads=grads, bf16=bf, train3=tr, model_name=model.name, loss_name=model.loss_name,
+               torch_version=torch.__version__)
+    path = os.path.join(OUT, f"{name}.pt")
+    torch.save(fix, path)
+    print(f"{name}: loss={float(ev['loss']):.6f} bf16={float(bf['loss']):.6f} name={model.name} "
+          f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for name, (cfg, batch, kind) in variants().items():
+        if only and name not in only:
+            continue
+        run_variant(name, cfg, batch, kind)
