@@ -65,7 +65,7 @@ def test_oracle_train_steps(golden, name):
         assert abs(loss - float(fix["train3"]["losses"][i])) < 1e-5 * max(1.0, abs(loss))
         assert rel_err(tr.last_grad_norm, fix["train3"]["grad_norms"][i]) < 1e-4
     for k, v in fix["train3"]["state_dict"].items():
-        assert rel_err(tr.params[k], v, 1e-4) < 1e-4, k   # floor: key.bias only moves by ~1e-8 (zero grad)
+        assert rel_err(tr.params[k], v, 3e-3) < 1e-4, k   # floor = 3 steps x lr (key.bias has a zero gradient)
 
 
 def test_spec_quirks():
