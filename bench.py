@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s of the ViT step (fwd + bwd + clip + AdamW) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json `metric`: "train samples/sec ... (baseline.yaml shape)"):
+configs/exp/att_clp/baseline.yaml -- spectrum 4096, patch/stride 32 -> T=129, H=32, 2 heads, 3 layers,
+per-GPU batch 64 (Lightning DDP semantics: weak scaling), precision bf16-mixed, dropout 0.1 (as configured),
+grad clip 0.5, AdamW lr 1e-3.  Synthetic data, random-init weights.
+
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BASELINE_CFG = {
+    "model": dict(name="vit", task_type="reg", image_size=4096, patch_size=32, hidden_size=32,
+                  num_hidden_layers=3, num_attention_heads=2, stride_size=32, proj_fn="SW"),
+    "train": {"batch_size": 64, "precision": "bf16-mixed"},
+    "loss": {"name": "mae"}, "opt": {"type": "AdamW", "lr": 0.001},
+    "data": {"param": "log_g"}, "noise": {"noise_level": 0},
+}
+WORKLOAD = "configs/exp/att_clp/baseline.yaml ViT (L=4096,P=S=32,T=129,H=32,heads=2,layers=3), per-GPU batch 64, bf16-mixed, dropout 0.1, clip 0.5 + AdamW"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference step) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, batch: int = 64):
+    import torch
+    from oracle import vit_oracle as vo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = vo.spec_from_config(BASELINE_CFG)
+    tr = vo.OracleTrainer(spec, vo.init_params(spec, seed=42))
+    x, y = vo.synthetic_batch(batch, 4096, seed=0, kind="dummy")
+    torch.manual_seed(0)
+    for _ in range(warmup):
+        tr.step(x, y, train=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(x, y, train=True)
+    dt = time.perf_counter() - t0
+    return dict(value=batch * steps / dt, ms_per_step=1e3 * dt / steps, cores=torch.get_num_threads(),
+                sample=f"{steps} steps (after {warmup} warm-up) of the same workload at batch {batch}: oracle port of the "
+                       f"reference step (fp32, dropout 0.1, clip 0.5, AdamW), torch CPU ops on {torch.get_num_threads()} threads")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 100))
+    r = cpu_reference_run(steps, max(3, min(args.warmup, 5)))
+    line = {
+        "impl": "reference", "metric": "train samples/sec (baseline.yaml shape)", "value": r["value"],
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(3, min(args.warmup, 5)),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD.replace("bf16-mixed", "fp32 (reference default)")},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel timing (CUDA events around a graph of R back-to-back launches of ONE call)
+# ------------------------------------------------------------------------------------------------
+def call_work(name: str, args: tuple, es: int):
+    """(algorithmic flops, algorithmic bytes) of one C-ABI call; dims are read from its argument list
+    (see include/vit_b200.h).  Bytes = compulsory reads + writes of its operands."""
+    if name == "vitb200_linear_fwd":
+        M, N, K, act = args[5], args[6], args[7], args[8]
+        return 2.0 * M * N * K, (M * K + N * K + M * N * (2 if act else 1)) * es + 4 * N
+    if name == "vitb200_linear_dgrad":
+        M, N, K = args[4], args[5], args[6]
+        return 2.0 * M * N * K, (M * N + N * K + M * K * (2 if args[2] else 1)) * es
+    if name == "vitb200_linear_wgrad":
+        M, N, K = args[4], args[5], args[6]
+        return 2.0 * M * N * K, (M * N + M * K) * es + 4 * (N * K + N)
+    if name == "vitb200_attn_fwd":
+        B, T, h, d = args[8], args[9], args[10], args[11]
+        return 4.0 * B * h * T * T * d, 4 * B * T * h * d * es + 4 * B * h * T
+    if name == "vitb200_attn_bwd":
+        B, T, h, d = args[14], args[15], args[16], args[17]
+        return 10.0 * B * h * T * T * d, 8 * B * T * h * d * es + 8 * B * h * T
+    if name == "vitb200_add_ln_fwd":
+        M, H, cls_T = args[8], args[9], args[10]
+        if args[1] is None:
+            return 8.0 * M * H, M * H * (4 + es)
+        rows_ln = M // cls_T if cls_T else M
+        return 10.0 * M * H, M * H * (4 + es + 4) + rows_ln * H * es
+    if name == "vitb200_add_ln_bwd":
+        M, H, cls_T = args[10], args[11], args[12]
+        rows_ln = M // cls_T if cls_T else M
+        b = rows_ln * H * (es + 4) + M * H * 4 + (M * H * 4 if args[5] else 0) + (M * H * es if args[7] else 0)
+        return 14.0 * rows_ln * H, b
+    if name == "vitb200_patch_embed_fwd":
+        B, L, P, S, Np, nv, H = args[6:13]
+        return 2.0 * B * Np * P * H, 4 * B * L + 4 * B * (Np + 1) * H + es * H * P
+    if name == "vitb200_patch_embed_bwd":
+        B, L, P, S, Np, nv, H = args[6:13]
+        return 2.0 * B * Np * P * H, 4 * B * L + 4 * B * (Np + 1) * H + 4 * H * P
+    if name == "vitb200_head_loss_fwd":
+        B, H, C = args[6], args[7], args[8]
+        return 2.0 * B * H * C, B * H * es + 8 * B * C
+    if name == "vitb200_head_loss_bwd":
+        B, H, C = args[8], args[9], args[10]
+        return 4.0 * B * H * C, 2 * B * H * es + 8 * B * C
+    return 0.0, 0.0
+
+
+def time_calls(eng, progs, repeats: int = 20, iters: int = 5):
+    """Average device time of every call of the step, each measured alone as a CUDA graph of `repeats`
+    back-to-back launches (CUDA events on the launching stream)."""
+    import torch
+    from vit_b200 import _lib
+
+    out = []
+    stream = torch.cuda.current_stream(eng.device)
+    for prog in progs:
+        for fn, args in prog:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st = torch.cuda.current_stream(eng.device).cuda_stream
+                for _ in range(repeats):
+                    rc = fn(*args, st)
+                    if rc != 0:
+                        _lib.check(rc, fn.__name__)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            out.append((fn.__name__, args, e0.elapsed_time(e1) * 1e-3 / (iters * repeats)))
+            del g
+    return out
+
+
+def kernel_table(eng, train: bool):
+    import torch
+
+    es = 2 if eng.act_dtype == torch.bfloat16 else 4
+    eng.forward(train=train, with_labels=True)
+    eng.backward(train=train)
+    torch.cuda.synchronize()
+    progs = [eng._progs[("fwd", train, True)], eng._progs[("bwd", train, None)]]
+    rows = []
+    for name, args, sec in time_calls(eng, progs):
+        fl, by = call_work(name, args, es)
+        rows.append(dict(call=name.replace("vitb200_", ""), us=sec * 1e6, flops=fl, bytes=by))
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (train.batch_size)")
+    ap.add_argument("--precision", default="bf16-mixed")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--kernels-json", default=None, help="write the per-kernel timing table here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import vit_oracle as vo  # only for the synthetic-input generator, the FLOP model and cpu_baseline
+    from vit_b200 import dp, get_model
+    from vit_b200.step import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local, world = dp.init_from_env("nccl") if world > 1 else (0, 0, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    B = args.batch
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=60, warmup=3)
+        cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    torch.manual_seed(42)
+    cfg = json.loads(json.dumps(BASELINE_CFG))
+    model = get_model(cfg, precision=args.precision, device=dev)
+    model.train()
+    if world > 1:
+        dp.broadcast_parameters(model._arena.data)
+    step = TrainStep(model, B, lr=1e-3, grad_clip=0.5, use_graph=not args.no_graph, world_size=world, train=True)
+    spec = vo.spec_from_config(BASELINE_CFG)
+    fwd_flops, step_flops = vo.flops_per_sample(spec)
+
+    # input pool larger than L2 (126 MB): every step's inputs come from HBM, not from a warm L2
+    pool_n = max(8, int(160e6 // (B * 4096 * 4)) + 1)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    pool_x = torch.rand(pool_n, B, 4096, generator=g).to(dev)
+    pool_y = torch.rand(pool_n, B, generator=g).to(dev)
+    host_x = torch.rand(8, B, 4096, generator=g).pin_memory()
+    host_y = torch.rand(8, B, generator=g).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    loss_last = float(step.eng.loss[0])
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t[0]) / args.steps
+    value = world * B * 1e3 / ms_step
+
+    # ---- end to end through the public API: pinned host -> H2D -> step -> D2H loss, every step ----
+    for i in range(max(3, args.warmup // 4)):
+        step.step_host(host_x[i % 8], host_y[i % 8])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step.step_host(host_x[i % 8], host_y[i % 8])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te[0])
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel table + roofline of the dominant kernel (rank 0, after the timed regions) ----
+    rows = kernel_table(step.eng, train=True)
+    ksum_us = sum(r["us"] for r in rows)
+    top = max(rows, key=lambda r: r["us"])
+    ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    if ai >= ridge:
+        bound, achieved, peak, unit = "tensor", top["flops"] / (top["us"] * 1e-6) / 1e12, peaks["tf_sustained"], "TFLOP/s"
+    else:
+        bound, achieved, peak, unit = "hbm", top["bytes"] / (top["us"] * 1e-6) / 1e9, peaks["hbm"], "GB/s"
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": None, "kernel": top["call"], "kernel_us": top["us"], "peak_source": peaks["source"],
+                "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+                "share_of_step": top["us"] / max(ksum_us, 1e-9),
+                "note": "algorithmic bytes (or flops) of the call / its mean device time, timed alone as a CUDA graph "
+                        "of 20 back-to-back launches with CUDA events"}
+    agg = {}
+    for r in rows:
+        a = agg.setdefault(r["call"], dict(us=0.0, n=0, flops=0.0, bytes=0.0))
+        a["us"] += r["us"]; a["n"] += 1; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]
+    kernels = sorted(({"call": k, "launches": v["n"], "us_total": round(v["us"], 2),
+                       "gbs": round(v["bytes"] / (v["us"] * 1e-6) / 1e9, 1),
+                       "tflops": round(v["flops"] / (v["us"] * 1e-6) / 1e12, 3)} for k, v in agg.items()),
+                     key=lambda d: -d["us_total"])
+    if args.kernels_json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.kernels_json)), exist_ok=True)
+        json.dump({"rows": rows, "aggregate": kernels, "kernel_time_sum_us": ksum_us, "step_us": ms_step * 1e3},
+                  open(args.kernels_json, "w"), indent=1)
+
+    sweep = None
+    if not args.no_sweep and world == 1:
+        sweep = {}
+        for b2 in (1024, 8192):
+            try:
+                m2 = get_model(json.loads(json.dumps(BASELINE_CFG)), precision=args.precision, device=dev).train()
+                s2 = TrainStep(m2, b2, use_graph=not args.no_graph, train=True)
+                x2 = torch.rand(b2, 4096, device=dev); y2 = torch.rand(b2, device=dev)
+                for _ in range(3):
+                    s2.step(x2, y2)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n2 = 20 if b2 == 1024 else 5
+                a0.record(stream)
+                for _ in range(n2):
+                    s2.step(x2, y2)
+                a1.record(stream)
+                torch.cuda.synchronize()
+                msb = a0.elapsed_time(a1) / n2
+                sweep[f"batch_{b2}"] = {"samples_per_s": b2 * 1e3 / msb, "ms_per_step": msb,
+                                        "tflops_algorithmic": b2 * step_flops / (msb * 1e-3) / 1e12}
+                del s2, m2, x2, y2
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                sweep[f"batch_{b2}"] = {"error": str(ex)[:200]}
+
+    line = {
+        "metric": "train samples/sec (baseline.yaml shape)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if "bf16" in args.precision else "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
+                   "cuda_graph": not args.no_graph,
+                   "l2": f"inputs rotate through a pool of {pool_n} device batches ({pool_n * B * 4096 * 4 / 1e6:.0f} MB > 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step.h2d_bytes_per_step,
+                "d2h_bytes_per_step": step.d2h_bytes_per_step, "ms_per_step": 1e3 * float(te[0]) / args.steps},
+        "gpu_launches": step.kernel_launches() * args.steps,
+        "launches_per_step": step.kernel_launches(),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "step_tflops_algorithmic": world * B * step_flops / (ms_step * 1e-3) / 1e12,
+        "frac_of_bf16_sustained_peak": world * B * step_flops / (ms_step * 1e-3) / 1e12 / (world * peaks["tf_sustained"]),
+        "kernel_time_sum_us": ksum_us,
+        "kernels": kernels[:8],
+        "sweep": sweep,
+        "final_loss": loss_last,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+/* vit_b200 -- C ABI of the B200 (sm_100a) kernels behind the ViT encoder step of ViskaWei/VIT.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ *   - takes DEVICE pointers that the caller (PyTorch) allocated and owns; the library never
+ *     allocates device memory and never synchronises the host,
+ *   - takes the CUDA stream explicitly (`stream` is a cudaStream_t passed as void*), so it can be
+ *     called from the Python main thread, from the autograd engine's worker thread and under CUDA
+ *     graph capture,
+ *   - returns 0 on success or a negative VITB200_ERR_* code (no exceptions cross the ABI);
+ *     vitb200_strerror() / vitb200_last_cuda_error() give the text.
+ *
+ * Layouts: row-major contiguous.  Activations are [rows = B*T, H]; weights are in nn.Linear layout
+ * [out, in]; q/k/v are addressed in place inside a [B*T, ld] matrix (ld = 3H for the fused QKV
+ * projection) with head h at columns [h*d, (h+1)*d).
+ *
+ * `dtype` selects the activation / GEMM-operand type: VITB200_F32 (reference default precision
+ * '32', src/basemodule.py:233) or VITB200_BF16 (Lightning 'bf16-mixed' == torch.autocast(bf16):
+ * bf16 operands, fp32 accumulation, fp32 residual stream / LayerNorm / softmax / loss).
+ * Buffers typed `void*` hold that type; buffers typed `float*` are always fp32.
+ *
+ * Dropout masks are never stored.  They are a pure function of (seed, step, site, element index)
+ * through Philox4x32-10; `rng` points at two DEVICE uint64 {seed, step} so that a captured CUDA graph
+ * sees a new step on every replay.  `site` distinguishes the dropout call sites of one step.
+ *
+ * Each entry point names the reference code it replaces (paths relative to the reference repo;
+ * HF = transformers/models/vit/modeling_vit.py, the third-party file the reference builds on).
+ */
+#ifndef VIT_B200_H
+#define VIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITB200_VERSION 100
+
+#define VITB200_F32 0
+#define VITB200_BF16 1
+
+#define VITB200_OK 0
+#define VITB200_ERR_CUDA (-1)
+#define VITB200_ERR_SHAPE (-2)  /* unsupported shape (e.g. H % 4 != 0, head_dim not in {8,16,32,64,128}) */
+#define VITB200_ERR_ARG (-3)    /* null / inconsistent argument */
+#define VITB200_ERR_ALIGN (-4)  /* pointer not 16-byte aligned */
+#define VITB200_ERR_DEVICE (-5) /* not an sm_100 device */
+
+#define VITB200_ACT_NONE 0
+#define VITB200_ACT_GELU 1 /* erf GELU, src/models/builder.py:246 hidden_act='gelu' */
+
+#define VITB200_LOSS_MSE 0 /* nn.MSELoss  (src/models/specvit.py:53; note 'mae' selects this) */
+#define VITB200_LOSS_L1 1  /* nn.L1Loss   (src/models/specvit.py:53, loss name contains 'l1') */
+#define VITB200_LOSS_CE 2  /* nn.CrossEntropyLoss (src/models/specvit.py:48) */
+#define VITB200_LOSS_GIVEN 3 /* backward only: `labels` holds d(objective)/d(logits) [B,C] f32 (caller-side loss) */
+
+/* dropout sites of one step */
+#define VITB200_SITE_EMB 0u
+#define VITB200_SITE_ATTN(l) (1u + 3u * (uint32_t)(l))
+#define VITB200_SITE_PROJ(l) (2u + 3u * (uint32_t)(l))
+#define VITB200_SITE_MLP(l) (3u + 3u * (uint32_t)(l))
+
+const char* vitb200_strerror(int rc);
+const char* vitb200_last_cuda_error(void);
+int vitb200_version(void);
+/* Checks that `device` is compute capability 10.x and sets kernel attributes once. */
+int vitb200_init(int device);
+
+/* ---- patch embedding ----------------------------------------------------------------------
+ * Replaces SlidingWindowTokenizer.forward / Conv1DPatchTokenizer.forward
+ * (src/models/tokenization.py:43-50, 66-69) + SpectraEmbeddings.forward (src/models/embedding.py:79-100):
+ *   z[b,0,:]   = drop(cls + pos[0])
+ *   z[b,1+p,:] = drop(x[b, p*S : p*S+P] . w^T + bias + pos[1+p])       p < n_valid
+ *   z[b,1+p,:] = drop(bias + pos[1+p])                                 n_valid <= p < Np (zero-padded windows)
+ * x [B,L] f32; w [H,P] (dtype); bias [H], cls [H], pos [Np+1,H] or NULL: f32; z [B,Np+1,H] f32.
+ * In BF16 mode x and w are rounded to bf16 and the projection output is rounded to bf16 before the
+ * fp32 adds, as autocast does. */
+int vitb200_patch_embed_fwd(const float* x, const void* w, const float* bias, const float* cls, const float* pos,
+                            float* z, int B, int L, int P, int S, int Np, int n_valid, int H, float p_drop,
+                            const uint64_t* rng, uint32_t site, int dtype, void* stream);
+/* Backward of the above.  dz [B,Np+1,H] f32 is the gradient w.r.t. z.  Writes (or accumulates when
+ * accumulate != 0) dw [H,P], dbias [H], dcls [H], dpos [Np+1,H] (NULL when no learned positions), all f32.
+ * ws: vitb200_patch_embed_bwd_ws_bytes() bytes of scratch whose first 4096 bytes were zeroed once. */
+size_t vitb200_patch_embed_bwd_ws_bytes(int B, int Np, int P, int H);
+int vitb200_patch_embed_bwd(const float* dz, const float* x, float* dw, float* dbias, float* dcls, float* dpos,
+                            int B, int L, int P, int S, int Np, int n_valid, int H, float p_drop,
+                            const uint64_t* rng, uint32_t site, int accumulate, int dtype, void* ws, void* stream);
+
+/* ---- residual add + LayerNorm ---------------------------------------------------------------
+ * Replaces nn.LayerNorm before/after/final (HF:333,340,455; eps = 1e-12, src/models/builder.py:250)
+ * fused with the preceding residual add and hidden dropout (HF:267-268,310-312,337):
+ *   z_out = z_in + drop(delta)          (delta NULL: z_out is not written, LN reads z_in)
+ *   u     = LN(z_out) * gamma + beta ;  mean/rstd saved for backward
+ * z_in, z_out [M,H] f32; delta, u [M,H] (dtype); mean, rstd [M] f32.
+ * cls_T > 0: LayerNorm only rows r with r % cls_T == 0 (the CLS rows consumed by the head,
+ * src/models/specvit.py:78); u/mean/rstd are then compact, indexed r / cls_T. */
+int vitb200_add_ln_fwd(const float* z_in, const void* delta, float* z_out, void* u, float* mean, float* rstd,
+                       const float* gamma, const float* beta, int M, int H, int cls_T, float eps, float p_drop,
+                       const uint64_t* rng, uint32_t site, int dtype, void* stream);
+/* Backward: dz = dres + LN'(du) ; ddelta = dropmask * dz (dtype) ; dgamma, dbeta reduced over rows in a
+ * fixed order (deterministic).  du (dtype) is compact when cls_T > 0.  dres, ddelta may be NULL.
+ * ws: vitb200_add_ln_bwd_ws_bytes() bytes, first 4096 zeroed once. */
+size_t vitb200_add_ln_bwd_ws_bytes(int M, int H);
+int vitb200_add_ln_bwd(const void* du, const float* z, const float* mean, const float* rstd, const float* gamma,
+                       const float* dres, float* dz, void* ddelta, float* dgamma, float* dbeta, int M, int H,
+                       int cls_T, float p_drop, const uint64_t* rng, uint32_t site, int accumulate, int dtype,
+                       void* ws, void* stream);
+
+/* ---- Linear ---------------------------------------------------------------------------------
+ * Replaces nn.Linear forward for query/key/value (HF:228-230, fused as one [3H,H] weight), attention
+ * output.dense (HF:266), intermediate.dense + GELU (HF:297-298), output.dense (HF:309), and
+ * LinearPreprocessor (src/models/layers.py:62-63):
+ *   y = x . w^T + bias ; act == GELU: y holds the pre-activation and y_act = gelu(y)
+ * x [M,K], w [N,K], y, y_act [M,N] (dtype); bias [N] f32 or NULL. */
+int vitb200_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_act, int M, int N, int K,
+                       int act, int dtype, void* stream);
+/* dx[M,K] = dy[M,N] . w[N,K], optionally multiplied by gelu'(pre_act[M,K]) (the GELU feeding this
+ * Linear's input). */
+int vitb200_linear_dgrad(const void* dy, const void* w, const void* pre_act, void* dx, int M, int N, int K,
+                         int dtype, void* stream);
+/* dw[N,K] (+)= dy^T . x ; dbias[N] (+)= column sums of dy.  Split over rows with a fixed-order second
+ * stage (deterministic).  ws: vitb200_linear_wgrad_ws_bytes() bytes, first 4096 zeroed once. */
+size_t vitb200_linear_wgrad_ws_bytes(int M, int N, int K);
+int vitb200_linear_wgrad(const void* dy, const void* x, float* dw, float* dbias, int M, int N, int K,
+                         int accumulate, int dtype, void* ws, void* stream);
+
+/* ---- multi-head self-attention ----------------------------------------------------------------
+ * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and
+ * ViTSelfAttentionWithRoPE.forward (src/models/vit_with_rope.py:43-84; RoPE = src/models/rope.py:60-98):
+ *   P = softmax(q' k'^T * scale) ; ctx = drop(P) v ; lse = logsumexp of the scaled scores
+ * q,k,v: rows b*T+t of [B*T, ld] (dtype); ctx [B*T, heads*d] (dtype); lse [B,heads,T] f32.
+ * rope_cos/rope_sin [T, d/2] f32 or NULL (q' = rope(q), k' = rope(k)).  d in {8,16,32,64,128}. */
+int vitb200_attn_fwd(const void* q, const void* k, const void* v, int ld, void* ctx, float* lse,
+                     const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d, float scale,
+                     float p_drop, const uint64_t* rng, uint32_t site, int dtype, void* stream);
+/* Backward (flash style: P is recomputed from q, k, lse).  dsum [B,heads,T] f32 scratch.
+ * dq, dk, dv: rows of [B*T, ld_d] (dtype). */
+int vitb200_attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ctx, const void* dctx,
+                     const float* lse, float* dsum, void* dq, void* dk, void* dv, int ld_d, const float* rope_cos,
+                     const float* rope_sin, int B, int T, int heads, int d, float scale, float p_drop,
+                     const uint64_t* rng, uint32_t site, int dtype, void* stream);
+/* probs[B,heads,T,T] f32 = softmax probabilities before dropout (what the eager / RoPE attention returns
+ * as `attention_probs`, src/models/vit_with_rope.py:84); for hooks / output_attentions only. */
+int vitb200_attn_probs(const void* q, const void* k, int ld, const float* lse, float* probs, const float* rope_cos,
+                       const float* rope_sin, int B, int T, int heads, int d, float scale, int dtype, void* stream);
+
+/* ---- head + loss ---------------------------------------------------------------------------------
+ * Replaces MyViT.forward's head and loss (src/models/specvit.py:78-89):
+ *   logits = s . w^T + bias ; loss = MSE | L1 (mean over B*C) | CrossEntropy (mean over B)
+ * s [B,H] (dtype) = final-LayerNorm'd CLS rows; w [C,H] (dtype); bias [C] f32; labels: f32 [B*C] for
+ * MSE/L1, int64 [B] for CE (NULL: logits only); logits [B,C] f32; loss [1] f32. */
+int vitb200_head_loss_fwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
+                          float* loss, int B, int H, int C, int loss_kind, int dtype, void* stream);
+/* gloss: DEVICE scalar d(objective)/d(loss) or NULL (=1).  ds [B,H] (dtype); dw [C,H], dbias [C] f32. */
+int vitb200_head_loss_bwd(const void* s, const void* w, const float* logits, const void* labels,
+                          const float* gloss, void* ds, float* dw, float* dbias, int B, int H, int C, int loss_kind,
+                          int accumulate, int dtype, void* stream);
+
+/* ---- gradient clipping + AdamW ---------------------------------------------------------------------
+ * Replaces Lightning's gradient_clip_val -> torch.nn.utils.clip_grad_norm_ (src/basemodule.py:244) and
+ * torch.optim.AdamW.step (src/opt/optimizer.py:108) over ONE flat parameter arena.
+ * hyper (DEVICE, 8 floats): {lr, beta1, beta2, eps, weight_decay, max_norm (<=0: no clipping), grad_scale, 0}
+ * state (DEVICE, 8 floats): {step, grad_norm, clip_coef, bias_corr1, bias_corr2, 0, 0, 0}
+ * vitb200_grad_norm: grad_norm = ||grad_scale * g||_2, clip_coef = min(1, max_norm/(norm+1e-6)), step += 1.
+ * vitb200_adamw: p, m, v updated in place with g * grad_scale * clip_coef; if shadow != NULL it receives
+ * the bf16 copy of the new parameters (the GEMM operands of BF16 mode).  rng != NULL: rng[1] += 1. */
+size_t vitb200_grad_norm_ws_bytes(size_t n);
+int vitb200_grad_norm(const float* g, size_t n, const float* hyper, float* state, void* ws, void* stream);
+int vitb200_adamw(float* p, const float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                  const float* state, uint64_t* rng, void* stream);
+/* shadow[i] = bf16(p[i]) (after load_state_dict / an external optimizer touched the fp32 arena) */
+int vitb200_cast_bf16(const float* p, void* shadow, size_t n, void* stream);
+
+/* ---- elementwise helpers of the modular (hook-friendly, eval-only) module path ------------------------
+ * y = gelu(x) (HF:298 intermediate_act_fn as a separate module call); out = z + delta (HF:337,311). */
+int vitb200_gelu_fwd(const void* x, void* y, size_t n, int dtype, void* stream);
+int vitb200_residual_add(const float* z, const void* delta, float* out, size_t n, int dtype, void* stream);
+
+/* ---- test support ----------------------------------------------------------------------------------
+ * mask[i] = 1 if element i of dropout site `site` is kept.  For the attention site the element index
+ * is ((b*heads+h)*T + i) * round_up(T,4) + j; for every other site it is the linear index. */
+int vitb200_dropout_mask(uint8_t* mask, size_t n, float p_drop, const uint64_t* rng, uint32_t site, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI declared in include/vit_b200.h (the drop-in boundary).
+
+There is no CPU or PyTorch fallback: if `libvitb200.so` is missing this module raises, and every
+wrapper raises `RuntimeError(vitb200_strerror(rc))` on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+LOSS_MSE, LOSS_L1, LOSS_CE, LOSS_GIVEN = 0, 1, 2, 3
+SITE_EMB = 0
+
+
+def site_attn(l: int) -> int:
+    return 1 + 3 * l
+
+
+def site_proj(l: int) -> int:
+    return 2 + 3 * l
+
+
+def site_mlp(l: int) -> int:
+    return 3 + 3 * l
+
+
+_p, _i, _f, _u32, _sz = C.c_void_p, C.c_int, C.c_float, C.c_uint32, C.c_size_t
+
+# name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
+SIGNATURES = {
+    "vitb200_strerror": (C.c_char_p, [_i]),
+    "vitb200_last_cuda_error": (C.c_char_p, []),
+    "vitb200_version": (_i, []),
+    "vitb200_init": (_i, [_i]),
+    "vitb200_patch_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _u32, _i, _p]),
+    "vitb200_patch_embed_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "vitb200_patch_embed_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _u32, _i, _i, _p, _p]),
+    "vitb200_add_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
+    "vitb200_add_ln_bwd_ws_bytes": (_sz, [_i, _i]),
+    "vitb200_add_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u32, _i, _i, _p, _p]),
+    "vitb200_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vitb200_linear_dgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vitb200_linear_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
+    "vitb200_linear_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
+    "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
+    "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "vitb200_head_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vitb200_head_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vitb200_grad_norm_ws_bytes": (_sz, [_sz]),
+    "vitb200_grad_norm": (_i, [_p, _sz, _p, _p, _p, _p]),
+    "vitb200_adamw": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p]),
+    "vitb200_cast_bf16": (_i, [_p, _p, _sz, _p]),
+    "vitb200_gelu_fwd": (_i, [_p, _p, _sz, _i, _p]),
+    "vitb200_residual_add": (_i, [_p, _p, _p, _sz, _i, _p]),
+    "vitb200_dropout_mask": (_i, [_p, _sz, _f, _p, _u32, _p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libvitb200.so (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m vit_b200.build` (nvcc, sm_100a). "
+                "vit_b200 has no CPU/PyTorch fallback for its kernels."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.vitb200_strerror(rc).decode()
+        if rc == -1:
+            msg += ": " + lib.vitb200_last_cuda_error().decode()
+        raise RuntimeError(f"vit_b200 {what} failed ({rc}): {msg}")

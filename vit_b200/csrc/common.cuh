@@ -1,0 +1,167 @@
+// Shared device helpers for the vit_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/vit_b200.h"
+
+#define VB_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaPeekAtLastError();                \
+    if (e__ != cudaSuccess) return vb_cuda_error(e__);      \
+  } while (0)
+
+int vb_cuda_error(cudaError_t e);  // records the message for vitb200_last_cuda_error(), returns VITB200_ERR_CUDA
+
+namespace vb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// 4-wide typed loads/stores (activations are float or bf16; accumulation is always fp32)
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// round-trip through the activation type (identity for float): mirrors autocast's bf16 op outputs
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f<T>(from_f<T>(v)); }
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+template <typename T> __device__ __forceinline__ bool aligned_vec4(const T* p) {
+  return sizeof(T) == 4 ? aligned16(p) : aligned8(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions (fixed order => deterministic)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int W> __device__ __forceinline__ float group_sum(float v) {  // sum over W consecutive lanes
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int W> __device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG for dropout.  Masks are never stored: forward and backward
+// regenerate them from (seed, step, site, element index).
+//   key     = seed (64 bit)
+//   counter = { idx4.lo, idx4.hi, site, step }   with idx4 = element_index / 4
+// Element e of a tensor uses word (e & 3) of the block at idx4 = e >> 2.
+// keep(e) <=> uniform(e) >= p  with uniform = word * 2^-32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+struct DropCtx {
+  uint32_t k0, k1, site, step;
+  uint32_t thresh;  // keep <=> word >= thresh ; thresh = p * 2^32
+  float scale;      // 1 / (1 - p)
+  bool on;
+};
+__device__ __forceinline__ DropCtx make_drop(float p, uint64_t seed, uint32_t step, uint32_t site) {
+  DropCtx d;
+  d.on = p > 0.f;
+  d.k0 = (uint32_t)seed; d.k1 = (uint32_t)(seed >> 32);
+  d.site = site; d.step = step;
+  double t = (double)p * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  d.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  return d;
+}
+// 4 keep-multipliers (0 or 1/(1-p)) for elements [4*idx4, 4*idx4+3]
+__device__ __forceinline__ float4 drop4(const DropCtx& d, uint64_t idx4) {
+  if (!d.on) return make_float4(1.f, 1.f, 1.f, 1.f);
+  uint4 r = philox4x32_10((uint32_t)idx4, (uint32_t)(idx4 >> 32), d.site, d.step, d.k0, d.k1);
+  return make_float4(r.x >= d.thresh ? d.scale : 0.f, r.y >= d.thresh ? d.scale : 0.f,
+                     r.z >= d.thresh ? d.scale : 0.f, r.w >= d.thresh ? d.scale : 0.f);
+}
+__device__ __forceinline__ float drop1(const DropCtx& d, uint64_t idx) {
+  if (!d.on) return 1.f;
+  uint4 r = philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), d.site, d.step, d.k0, d.k1);
+  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return w >= d.thresh ? d.scale : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// erf-GELU (HF hidden_act='gelu' => torch.nn.functional.gelu, exact form)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "last block done" ticket: returns true in exactly one block (the last to arrive), after all
+// other blocks' global writes are visible.  The counter resets itself to 0 for the next launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblocks - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace vb

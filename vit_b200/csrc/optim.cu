@@ -1,0 +1,154 @@
+// Gradient-norm clipping + AdamW over one flat fp32 parameter arena (HBM-bound streaming kernels),
+// bf16 shadow refresh for BF16-mode GEMM operands, and the dropout-mask test helper.
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int OP_THREADS = 256;
+constexpr int OP_MAX_BLOCKS = 592;
+
+static inline int op_grid(size_t n) {
+  size_t g = (n / 4 + OP_THREADS * 4 - 1) / (OP_THREADS * 4);
+  if (g > OP_MAX_BLOCKS) g = OP_MAX_BLOCKS;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// hyper: {lr, b1, b2, eps, wd, max_norm, grad_scale, -} ; state: {step, norm, coef, bc1, bc2, -, -, -}
+__global__ void __launch_bounds__(OP_THREADS)
+grad_norm_kernel(const float* __restrict__ g, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
+                 float* __restrict__ partial, unsigned int* counter) {
+  __shared__ float red[OP_THREADS / 32];
+  float acc = 0.f;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * OP_THREADS) {
+    float4 v = g4[i];
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < OP_THREADS / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+  if (!last_block_ticket(counter, gridDim.x)) return;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) tot += (double)__ldcg(&partial[b]);
+    const float gs = hyper[6];
+    const float norm = (float)sqrt(tot) * fabsf(gs);
+    const float max_norm = hyper[5];
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    const float step = state[0] + 1.f;
+    state[0] = step;
+    state[1] = norm;
+    state[2] = coef;
+    state[3] = (float)(1.0 - pow((double)hyper[1], (double)step));
+    state[4] = (float)(1.0 - pow((double)hyper[2], (double)step));
+  }
+}
+
+__global__ void __launch_bounds__(OP_THREADS)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, const float* __restrict__ state,
+             uint64_t* rng) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float gmul = hyper[6] * state[2];
+  const float bc1 = state[3], bc2 = state[4];
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  const float decay = 1.f - lr * wd;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * OP_THREADS) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = ga[k] * gmul;
+      pa[k] *= decay;
+      ma[k] = fmaf(1.f - b1, gr - ma[k], ma[k]);          // exp_avg.lerp_(grad, 1 - beta1)
+      va[k] = fmaf(1.f - b2, gr * gr, b2 * va[k]);         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+      pa[k] -= step_size * (ma[k] / denom);
+    }
+    p4[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    m4[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    v4[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (shadow) Vec4<bf16>::st(shadow + i * 4, make_float4(pa[0], pa[1], pa[2], pa[3]));
+  }
+  if (rng && blockIdx.x == 0 && threadIdx.x == 0) rng[1] += 1ull;
+}
+
+__global__ void __launch_bounds__(OP_THREADS)
+cast_bf16_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, size_t n4) {
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * OP_THREADS)
+    Vec4<bf16>::st(shadow + i * 4, p4[i]);
+}
+
+__global__ void __launch_bounds__(OP_THREADS)
+dropout_mask_kernel(uint8_t* __restrict__ mask, size_t n, float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+  const DropCtx dc = make_drop(p_drop, rng ? rng[0] : 0ull, rng ? (uint32_t)rng[1] : 0u, site);
+  for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * OP_THREADS)
+    mask[i] = drop1(dc, i) > 0.f ? 1 : 0;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" size_t vitb200_grad_norm_ws_bytes(size_t n) {
+  (void)n;
+  return 4096 + OP_MAX_BLOCKS * sizeof(float);
+}
+
+extern "C" int vitb200_grad_norm(const float* g, size_t n, const float* hyper, float* state, void* ws, void* stream) {
+  if (!g || !hyper || !state || !ws) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return VITB200_ERR_ALIGN;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  grad_norm_kernel<<<op_grid(n), OP_THREADS, 0, (cudaStream_t)stream>>>(g, n / 4, hyper, state, partial, counter);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_adamw(float* p, const float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                             const float* state, uint64_t* rng, void* stream) {
+  if (!p || !g || !m || !v || !hyper || !state) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) != 0 || (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
+    return VITB200_ERR_ALIGN;
+  adamw_kernel<<<op_grid(n), OP_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow, n / 4, hyper, state, rng);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_cast_bf16(const float* p, void* shadow, size_t n, void* stream) {
+  if (!p || !shadow) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (reinterpret_cast<uintptr_t>(shadow) & 7) != 0) return VITB200_ERR_ALIGN;
+  if (n == 0) return VITB200_OK;
+  cast_bf16_kernel<<<op_grid(n), OP_THREADS, 0, (cudaStream_t)stream>>>(p, (bf16*)shadow, n / 4);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_dropout_mask(uint8_t* mask, size_t n, float p_drop, const uint64_t* rng, uint32_t site,
+                                    void* stream) {
+  if (!mask) return VITB200_ERR_ARG;
+  if (n == 0) return VITB200_OK;
+  size_t g = (n + OP_THREADS - 1) / OP_THREADS;
+  if (g > 4096) g = 4096;
+  dropout_mask_kernel<<<(int)g, OP_THREADS, 0, (cudaStream_t)stream>>>(mask, n, p_drop, rng, site);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}

@@ -1,0 +1,70 @@
+"""Data parallelism for the ViT step: one process per GPU, parameters replicated, the batch sharded by
+rank, ONE exchange step -- the gradient all-reduce (mean) over the flat gradient arena
+(reference: Lightning DDP via strategy='ddp', src/hardware_utils.py:86-95, src/basemodule.py:226-241).
+
+The arena is laid out so each layer's gradients are contiguous; backward produces buckets in the
+order head -> layer L-1 -> ... -> layer 0 -> embeddings, and each bucket's all-reduce is issued as soon
+as its kernels are enqueued, so NCCL (NVLink/NVSwitch) overlaps the remaining backward kernels.
+`vit.pooler.dense.*` lies outside every bucket: it never has a gradient, which is
+exactly what makes stock DDP raise on the reference model; here it is simply not exchanged.
+
+These helpers are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def backward_bucket_order(buckets: Sequence[Tuple[str, int, int]]) -> List[Tuple[str, int, int]]:
+    """ParamLayout.buckets is in forward order (embeddings, layer0.., head); backward finishes them reversed."""
+    return list(reversed(list(buckets)))
+
+
+def allreduce_bucket(flat_grad: torch.Tensor, start: int, end: int, group=None, async_op: bool = True):
+    """SUM all-reduce of flat_grad[start:end] in place; the 1/world mean factor is folded into the
+    optimizer kernel's grad_scale, so no extra pass over the gradients is needed."""
+    if end <= start:
+        return None
+    return dist.all_reduce(flat_grad[start:end], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def allreduce_all(flat_grad: torch.Tensor, buckets: Sequence[Tuple[str, int, int]], group=None) -> None:
+    works = [allreduce_bucket(flat_grad, s, e, group=group, async_op=True) for _, s, e in backward_bucket_order(buckets)]
+    for w in works:
+        if w is not None:
+            w.wait()
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the default group if needed."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def broadcast_parameters(flat_data: torch.Tensor, group=None, src: int = 0) -> None:
+    """Replicate rank `src`'s parameter arena (DDP's constructor does the same)."""
+    dist.broadcast(flat_data, src=src, group=group)

@@ -1,0 +1,432 @@
+"""The step engine: pre-allocated activations + the fixed kernel sequence of one ViT
+forward / backward / clip+AdamW step, expressed as C-ABI calls on an explicit stream so that the whole
+step can be captured in one CUDA graph (the configured shape is launch-latency bound).
+
+Call sequence restated from the reference:
+  forward   src/models/embedding.py:79-100 -> HF ViTLayer :328-346 x L -> HF :454-455 -> specvit.py:78-89
+  backward  autograd of the above, written out explicitly per fused region
+  update    clip_grad_norm_(0.5) (src/basemodule.py:244) + AdamW (src/opt/optimizer.py:108)
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, BF16, F32, SITE_EMB, site_attn, site_mlp, site_proj
+from .arena import ParamArena
+
+
+def _normalize_precision(precision) -> str:
+    p = str(precision).lower()
+    if p in ("32", "32-true", "fp32", "float32"):
+        return "fp32"
+    if p in ("bf16", "bf16-mixed", "bfloat16", "bf16-true"):
+        return "bf16"
+    raise ValueError(f"vit_b200: unsupported precision '{precision}' (use '32' or 'bf16-mixed')")
+
+
+class ViTEngine:
+    """Owns every activation / scratch buffer for a fixed batch size and runs the kernel programs."""
+
+    def __init__(self, cfg, arena: ParamArena, batch: int, precision: str, loss_kind: int, seed: int = 0,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_norm: float = 0.5, grad_scale: float = 1.0):
+        if arena.data.device.type != "cuda":
+            raise RuntimeError("vit_b200 kernels are CUDA-only (sm_100a); move the model to a CUDA device")
+        self.lib = _lib.load()
+        self.cfg, self.arena, self.B = cfg, arena, int(batch)
+        self.precision = _normalize_precision(precision)
+        self.dt = BF16 if self.precision == "bf16" else F32
+        self.act_dtype = torch.bfloat16 if self.dt == BF16 else torch.float32
+        if self.dt == BF16 and arena.shadow is None:
+            raise RuntimeError("bf16 engine needs an arena with a bf16 shadow")
+        self.loss_kind = loss_kind
+        dev = arena.data.device
+        self.device = dev
+        _lib.check(self.lib.vitb200_init(dev.index if dev.index is not None else torch.cuda.current_device()), "init")
+        c = cfg
+        B, T, H, I, Lh = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers
+        M = B * T
+        self.M = M
+        f32 = dict(dtype=torch.float32, device=dev)
+        act = dict(dtype=self.act_dtype, device=dev)
+        # ---- inputs / outputs ----
+        self.x = torch.zeros(B, c.image_size, **f32)
+        if loss_kind == _lib.LOSS_CE:
+            self.labels = torch.zeros(B, dtype=torch.int64, device=dev)
+        else:
+            self.labels = torch.zeros(B * c.num_labels, **f32)
+        self.logits = torch.zeros(B, c.num_labels, **f32)
+        self.loss = torch.zeros(1, **f32)
+        # ---- saved activations ----
+        self.z = [torch.empty(M, H, **f32) for _ in range(Lh + 1)]
+        self.hmid = [torch.empty(M, H, **f32) for _ in range(Lh)]
+        self.u = [torch.empty(M, H, **act) for _ in range(max(Lh, 1))]
+        self.u2 = [torch.empty(M, H, **act) for _ in range(Lh)]
+        self.stats = torch.empty(4 * max(Lh, 1) + 2, M, **f32)  # mean1,rstd1,mean2,rstd2 per layer + final
+        self.qkv = [torch.empty(M, 3 * H, **act) for _ in range(Lh)]
+        self.ctx = [torch.empty(M, H, **act) for _ in range(Lh)]
+        self.lse = [torch.empty(B, c.num_attention_heads, T, **f32) for _ in range(Lh)]
+        self.a = [torch.empty(M, I, **act) for _ in range(Lh)]
+        self.m = [torch.empty(M, I, **act) for _ in range(Lh)]
+        self.delta = torch.empty(M, H, **act)
+        self.s_cls = torch.empty(B, H, **act)
+        # ---- backward scratch (allocated lazily) ----
+        self._bwd_ready = False
+        # ---- device scalars ----
+        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=dev)  # {seed, step}, read as uint64
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, max_norm, grad_scale, 0.0], **f32)
+        self.state = torch.zeros(8, **f32)
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        # ---- rope tables (rope.py:37-57), [T, d/2] ----
+        self.rope_cos = self.rope_sin = None
+        if c.pos_encoding_type == "rope":
+            d = c.head_dim
+            inv_freq = 1.0 / (c.rope_base ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+            fr = torch.outer(torch.arange(T, dtype=torch.float32), inv_freq)
+            self.rope_cos = fr.cos().to(dev).contiguous()
+            self.rope_sin = fr.sin().to(dev).contiguous()
+        ws_bytes = self._ws_bytes()
+        self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+        self._progs = {}
+        self.launches = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _ws_bytes(self) -> int:
+        c, lib, M = self.cfg, self.lib, self.M
+        H, I = c.hidden_size, c.intermediate_size
+        n = [
+            lib.vitb200_add_ln_bwd_ws_bytes(M, H),
+            lib.vitb200_linear_wgrad_ws_bytes(M, 3 * H, H),
+            lib.vitb200_linear_wgrad_ws_bytes(M, H, H),
+            lib.vitb200_linear_wgrad_ws_bytes(M, I, H),
+            lib.vitb200_linear_wgrad_ws_bytes(M, H, I),
+            lib.vitb200_patch_embed_bwd_ws_bytes(self.B, c.num_patches, c.patch_size, H),
+            lib.vitb200_grad_norm_ws_bytes(self.arena.layout.n_opt),
+        ]
+        return int(max(n)) + 4096
+
+    def _alloc_backward(self):
+        if self._bwd_ready:
+            return
+        c, dev = self.cfg, self.device
+        B, T, H, I = self.B, c.tokens, c.hidden_size, c.intermediate_size
+        M = self.M
+        f32 = dict(dtype=torch.float32, device=dev)
+        act = dict(dtype=self.act_dtype, device=dev)
+        self.ds_cls = torch.empty(B, H, **act)
+        self.dzA = torch.empty(M, H, **f32)
+        self.dzB = torch.empty(M, H, **f32)
+        self.ddelta = torch.empty(M, H, **act)
+        self.dbig = torch.empty(M, I, **act)
+        self.du = torch.empty(M, H, **act)
+        self.dqkv = torch.empty(M, 3 * H, **act)
+        self.dctx = torch.empty(M, H, **act)
+        self.dsum = torch.empty(B, c.num_attention_heads, T, **f32)
+        self._bwd_ready = True
+
+    # ---- pointer helpers ----------------------------------------------------------------------
+    def _p(self, name: str) -> int:  # fp32 master parameter
+        return self.arena.data.data_ptr() + 4 * self.arena.layout.off(name)
+
+    def _g(self, name: str) -> int:  # fp32 gradient
+        return self.arena.grad.data_ptr() + 4 * self.arena.layout.off(name)
+
+    def _w(self, name: str) -> int:  # GEMM operand copy of a weight (bf16 shadow in bf16 mode)
+        if self.dt == BF16:
+            return self.arena.shadow.data_ptr() + 2 * self.arena.layout.off(name)
+        return self._p(name)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+        return None if t is None else t.data_ptr()
+
+    def _stat(self, i: int) -> int:
+        return self.stats[i].data_ptr()
+
+    # ---- programs -----------------------------------------------------------------------------
+    def _build_forward(self, train: bool, with_labels: bool) -> List[Tuple[Callable, tuple]]:
+        c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
+        ph = float(c.hidden_dropout_prob) if train else 0.0
+        pa = float(c.attention_probs_dropout_prob) if train else 0.0
+        eps = float(c.layer_norm_eps)
+        rng = self.rng.data_ptr()
+        es = 2 if dt == BF16 else 4
+        scale = 1.0 / math.sqrt(c.head_dim)
+        emb = "vit.embeddings."
+        pos = self._p(emb + "position_embeddings") if c.pos_encoding_type == "learned" else None
+        prog = []
+        prog.append((lib.vitb200_patch_embed_fwd, (
+            P_(self.x), self._w(emb + "patch_embeddings.projection.weight"),
+            self._p(emb + "patch_embeddings.projection.bias"), self._p(emb + "cls_token"), pos, P_(self.z[0]),
+            B, c.image_size, c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, dt)))
+        fin = 4 * max(Lh, 1)
+        if Lh == 0:
+            prog.append((lib.vitb200_add_ln_fwd, (
+                P_(self.z[0]), None, None, P_(self.s_cls), self._stat(fin), self._stat(fin + 1),
+                self._p("vit.layernorm.weight"), self._p("vit.layernorm.bias"), M, H, T, eps, 0.0, rng, 0, dt)))
+        else:
+            pre = "vit.encoder.layer.0."
+            prog.append((lib.vitb200_add_ln_fwd, (
+                P_(self.z[0]), None, None, P_(self.u[0]), self._stat(0), self._stat(1),
+                self._p(pre + "layernorm_before.weight"), self._p(pre + "layernorm_before.bias"),
+                M, H, 0, eps, 0.0, rng, 0, dt)))
+        for l in range(Lh):
+            pre = f"vit.encoder.layer.{l}."
+            qkv = self.qkv[l].data_ptr()
+            prog.append((lib.vitb200_linear_fwd, (
+                P_(self.u[l]), self._w(pre + "attention.attention.query.weight"),
+                self._p(pre + "attention.attention.query.bias"), qkv, None, M, 3 * H, H, ACT_NONE, dt)))
+            prog.append((lib.vitb200_attn_fwd, (
+                qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
+                P_(self.rope_cos), P_(self.rope_sin), B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
+                site_attn(l), dt)))
+            prog.append((lib.vitb200_linear_fwd, (
+                P_(self.ctx[l]), self._w(pre + "attention.output.dense.weight"),
+                self._p(pre + "attention.output.dense.bias"), P_(self.delta), None, M, H, H, ACT_NONE, dt)))
+            prog.append((lib.vitb200_add_ln_fwd, (
+                P_(self.z[l]), P_(self.delta), P_(self.hmid[l]), P_(self.u2[l]), self._stat(4 * l + 2),
+                self._stat(4 * l + 3), self._p(pre + "layernorm_after.weight"), self._p(pre + "layernorm_after.bias"),
+                M, H, 0, eps, ph, rng, site_proj(l), dt)))
+            prog.append((lib.vitb200_linear_fwd, (
+                P_(self.u2[l]), self._w(pre + "intermediate.dense.weight"), self._p(pre + "intermediate.dense.bias"),
+                P_(self.a[l]), P_(self.m[l]), M, I, H, ACT_GELU, dt)))
+            prog.append((lib.vitb200_linear_fwd, (
+                P_(self.m[l]), self._w(pre + "output.dense.weight"), self._p(pre + "output.dense.bias"),
+                P_(self.delta), None, M, H, I, ACT_NONE, dt)))
+            if l < Lh - 1:
+                nxt = f"vit.encoder.layer.{l + 1}."
+                prog.append((lib.vitb200_add_ln_fwd, (
+                    P_(self.hmid[l]), P_(self.delta), P_(self.z[l + 1]), P_(self.u[l + 1]), self._stat(4 * (l + 1)),
+                    self._stat(4 * (l + 1) + 1), self._p(nxt + "layernorm_before.weight"),
+                    self._p(nxt + "layernorm_before.bias"), M, H, 0, eps, ph, rng, site_mlp(l), dt)))
+            else:
+                prog.append((lib.vitb200_add_ln_fwd, (
+                    P_(self.hmid[l]), P_(self.delta), P_(self.z[Lh]), P_(self.s_cls), self._stat(fin),
+                    self._stat(fin + 1), self._p("vit.layernorm.weight"), self._p("vit.layernorm.bias"),
+                    M, H, T, eps, ph, rng, site_mlp(l), dt)))
+        hd = self.arena.layout.head_name
+        prog.append((lib.vitb200_head_loss_fwd, (
+            P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"),
+            P_(self.labels) if with_labels else None, P_(self.logits), P_(self.loss), B, H, c.num_labels,
+            self.loss_kind, dt)))
+        return prog
+
+    def _build_backward(self, train: bool, gloss_ptr: Optional[int] = None,
+                        given: bool = False) -> List[Tuple[Callable, tuple]]:
+        self._alloc_backward()
+        c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
+        ph = float(c.hidden_dropout_prob) if train else 0.0
+        pa = float(c.attention_probs_dropout_prob) if train else 0.0
+        rng = self.rng.data_ptr()
+        es = 2 if dt == BF16 else 4
+        scale = 1.0 / math.sqrt(c.head_dim)
+        ws = self.ws.data_ptr()
+        acc = 0
+        hd = self.arena.layout.head_name
+        fin = 4 * max(Lh, 1)
+        prog = []
+        if given:
+            if not hasattr(self, "dlogits"):
+                self.dlogits = torch.zeros(B, c.num_labels, dtype=torch.float32, device=self.device)
+            prog.append((lib.vitb200_head_loss_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.dlogits), None, P_(self.ds_cls),
+                self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels, _lib.LOSS_GIVEN, acc, dt)))
+        else:
+            prog.append((lib.vitb200_head_loss_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.labels), gloss_ptr,
+                P_(self.ds_cls), self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels,
+                self.loss_kind, acc, dt)))
+        cur, other = self.dzA, self.dzB
+        if Lh == 0:
+            prog.append((lib.vitb200_add_ln_bwd, (
+                P_(self.ds_cls), P_(self.z[0]), self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"),
+                None, P_(cur), None, self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), M, H, T, 0.0,
+                rng, 0, acc, dt, ws)))
+        else:
+            prog.append((lib.vitb200_add_ln_bwd, (
+                P_(self.ds_cls), P_(self.z[Lh]), self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"),
+                None, P_(cur), P_(self.ddelta), self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"),
+                M, H, T, ph, rng, site_mlp(Lh - 1), acc, dt, ws)))
+        for l in range(Lh - 1, -1, -1):
+            pre = f"vit.encoder.layer.{l}."
+            qkv = self.qkv[l].data_ptr()
+            dqkv = self.dqkv.data_ptr()
+            # MLP down:  delta2 = m . W2^T + b2
+            prog.append((lib.vitb200_linear_wgrad, (
+                P_(self.ddelta), P_(self.m[l]), self._g(pre + "output.dense.weight"), self._g(pre + "output.dense.bias"),
+                M, H, I, acc, dt, ws)))
+            prog.append((lib.vitb200_linear_dgrad, (
+                P_(self.ddelta), self._w(pre + "output.dense.weight"), P_(self.a[l]), P_(self.dbig), M, H, I, dt)))
+            # MLP up:  a = u2 . W1^T + b1   (dbig now holds da = dm * gelu'(a))
+            prog.append((lib.vitb200_linear_wgrad, (
+                P_(self.dbig), P_(self.u2[l]), self._g(pre + "intermediate.dense.weight"),
+                self._g(pre + "intermediate.dense.bias"), M, I, H, acc, dt, ws)))
+            prog.append((lib.vitb200_linear_dgrad, (
+                P_(self.dbig), self._w(pre + "intermediate.dense.weight"), None, P_(self.du), M, I, H, dt)))
+            # LN2 + residual + proj dropout
+            prog.append((lib.vitb200_add_ln_bwd, (
+                P_(self.du), P_(self.hmid[l]), self._stat(4 * l + 2), self._stat(4 * l + 3),
+                self._p(pre + "layernorm_after.weight"), P_(cur), P_(other), P_(self.ddelta),
+                self._g(pre + "layernorm_after.weight"), self._g(pre + "layernorm_after.bias"), M, H, 0, ph, rng,
+                site_proj(l), acc, dt, ws)))
+            cur, other = other, cur
+            # attention output projection
+            prog.append((lib.vitb200_linear_wgrad, (
+                P_(self.ddelta), P_(self.ctx[l]), self._g(pre + "attention.output.dense.weight"),
+                self._g(pre + "attention.output.dense.bias"), M, H, H, acc, dt, ws)))
+            prog.append((lib.vitb200_linear_dgrad, (
+                P_(self.ddelta), self._w(pre + "attention.output.dense.weight"), None, P_(self.dctx), M, H, H, dt)))
+            prog.append((lib.vitb200_attn_bwd, (
+                qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
+                P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
+                B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), dt)))
+            # fused QKV projection
+            prog.append((lib.vitb200_linear_wgrad, (
+                dqkv, P_(self.u[l]), self._g(pre + "attention.attention.query.weight"),
+                self._g(pre + "attention.attention.query.bias"), M, 3 * H, H, acc, dt, ws)))
+            prog.append((lib.vitb200_linear_dgrad, (
+                dqkv, self._w(pre + "attention.attention.query.weight"), None, P_(self.du), M, 3 * H, H, dt)))
+            # LN1 + residual (+ the previous layer's MLP dropout)
+            if l > 0:
+                prog.append((lib.vitb200_add_ln_bwd, (
+                    P_(self.du), P_(self.z[l]), self._stat(4 * l), self._stat(4 * l + 1),
+                    self._p(pre + "layernorm_before.weight"), P_(cur), P_(other), P_(self.ddelta),
+                    self._g(pre + "layernorm_before.weight"), self._g(pre + "layernorm_before.bias"), M, H, 0, ph,
+                    rng, site_mlp(l - 1), acc, dt, ws)))
+            else:
+                prog.append((lib.vitb200_add_ln_bwd, (
+                    P_(self.du), P_(self.z[0]), self._stat(0), self._stat(1),
+                    self._p(pre + "layernorm_before.weight"), P_(cur), P_(other), None,
+                    self._g(pre + "layernorm_before.weight"), self._g(pre + "layernorm_before.bias"), M, H, 0, 0.0,
+                    rng, 0, acc, dt, ws)))
+            cur, other = other, cur
+        emb = "vit.embeddings."
+        dpos = self._g(emb + "position_embeddings") if c.pos_encoding_type == "learned" else None
+        prog.append((lib.vitb200_patch_embed_bwd, (
+            P_(cur), P_(self.x), self._g(emb + "patch_embeddings.projection.weight"),
+            self._g(emb + "patch_embeddings.projection.bias"), self._g(emb + "cls_token"), dpos, B, c.image_size,
+            c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, acc, dt, ws)))
+        return prog
+
+    def _run(self, key, builder) -> None:
+        prog = self._progs.get(key)
+        if prog is None:
+            prog = builder()
+            self._progs[key] = prog
+            self.launches[key] = len(prog)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for fn, args in prog:
+            rc = fn(*args, st)
+            if rc != 0:
+                _lib.check(rc, fn.__name__)
+
+    # ---- public steps -------------------------------------------------------------------------
+    def refresh_shadow(self, force: bool = False) -> None:
+        """bf16 GEMM operands <- fp32 master weights (after load_state_dict / an external optimizer)."""
+        ar = self.arena
+        if ar.shadow is None or not (force or ar.shadow_stale()):
+            return
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_cast_bf16(ar.data.data_ptr(), ar.shadow.data_ptr(), ar.layout.n_total, st), "cast")
+        ar.mark_shadow_fresh()
+
+    def forward(self, train: bool, with_labels: bool = True) -> None:
+        self.refresh_shadow()
+        self._run(("fwd", train, with_labels), lambda: self._build_forward(train, with_labels))
+
+    def backward(self, train: bool, gloss: Optional[torch.Tensor] = None) -> None:
+        gp = None if gloss is None else gloss.data_ptr()
+        self._run(("bwd", train, gp), lambda: self._build_backward(train, gp))
+
+    def backward_from_dlogits(self, train: bool, dlogits: torch.Tensor) -> None:
+        """Backward when the caller computed its own loss from `logits` (labels=None forward)."""
+        key = ("bwd_given", train)
+        if key not in self._progs:
+            self._progs[key] = self._build_backward(train, None, given=True)
+            self.launches[key] = len(self._progs[key])
+        self.dlogits.copy_(dlogits.reshape(self.dlogits.shape))
+        self._run(key, lambda: None)
+
+    def _ensure_opt_state(self):
+        if self.exp_avg is None:
+            n = self.arena.layout.n_total
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+
+    def grad_norm(self) -> None:
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_grad_norm(self.arena.grad.data_ptr(), self.arena.layout.n_opt,
+                                              self.hyper.data_ptr(), self.state.data_ptr(), self.ws.data_ptr(), st),
+                   "grad_norm")
+
+    def adamw(self, advance_rng: bool = True) -> None:
+        self._ensure_opt_state()
+        ar = self.arena
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_adamw(
+            ar.data.data_ptr(), ar.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            None if ar.shadow is None else ar.shadow.data_ptr(), ar.layout.n_opt, self.hyper.data_ptr(),
+            self.state.data_ptr(), self.rng.data_ptr() if advance_rng else None, st), "adamw")
+        if ar.shadow is not None:
+            ar.mark_shadow_fresh()
+
+    def optimizer_step(self) -> None:
+        self.grad_norm()
+        self.adamw()
+
+    def advance_rng(self) -> None:
+        self.rng[1] += 1
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0] = lr
+
+    def set_grad_scale(self, s: float) -> None:
+        self.hyper[6] = s
+
+    def last_hidden_state(self) -> torch.Tensor:
+        """Final LayerNorm over ALL rows (HF:455) -- only needed by callers that ask for it."""
+        c = self.cfg
+        M, H, Lh = self.M, c.hidden_size, c.num_hidden_layers
+        out = torch.empty(M, H, dtype=self.act_dtype, device=self.device)
+        tmp = torch.empty(2, M, dtype=torch.float32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_add_ln_fwd(
+            self.z[Lh].data_ptr(), None, None, out.data_ptr(), tmp[0].data_ptr(), tmp[1].data_ptr(),
+            self._p("vit.layernorm.weight"), self._p("vit.layernorm.bias"), M, H, 0, float(c.layer_norm_eps), 0.0,
+            self.rng.data_ptr(), 0, self.dt, st), "final ln")
+        return out.view(self.B, c.tokens, H)
+
+    def attention_probs(self, l: int) -> torch.Tensor:
+        c = self.cfg
+        B, T, H = self.B, c.tokens, c.hidden_size
+        es = 2 if self.dt == BF16 else 4
+        probs = torch.empty(B, c.num_attention_heads, T, T, dtype=torch.float32, device=self.device)
+        qkv = self.qkv[l].data_ptr()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_attn_probs(
+            qkv, qkv + H * es, 3 * H, self.lse[l].data_ptr(), probs.data_ptr(), self._ptr(self.rope_cos),
+            self._ptr(self.rope_sin), B, T, c.num_attention_heads, c.head_dim, 1.0 / math.sqrt(c.head_dim), self.dt,
+            st), "attn_probs")
+        return probs
+
+    def dropout_mask(self, site: int, n: int, p: float) -> torch.Tensor:
+        """Test support: the keep-mask the kernels use for `site` at the CURRENT rng step."""
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_dropout_mask(out.data_ptr(), n, p, self.rng.data_ptr(), site, st), "mask")
+        return out
+
+    def kernel_launches(self, train: bool = True) -> int:
+        """Kernel launches of one fwd+bwd+update step (for bench.py's gpu_launches)."""
+        c = self.cfg
+        L = c.num_hidden_layers
+        fwd = 2 + 7 * L + 2          # embed, LN, 7 per layer, logits + loss
+        bwd = 2 + 1 + L * (4 + 4 + 2 + 2) + 2  # head (2), final LN, per layer, embed (prep + wgrad)
+        return fwd + bwd + 2

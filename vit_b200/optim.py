@@ -1,0 +1,71 @@
+"""FusedClipAdamW -- clip_grad_norm_ + torch.optim.AdamW as two kernels over the flat arena.
+
+Replaces Lightning's `gradient_clip_val` (src/basemodule.py:244 -> torch.nn.utils.clip_grad_norm_) followed
+by `torch.optim.AdamW.step` (src/opt/optimizer.py:108).  It is a `torch.optim.Optimizer`, so LR schedulers
+(ReduceLROnPlateau etc., src/opt/optimizer.py:94-99) and Lightning drive it through `param_groups[0]['lr']`.
+Pass `max_norm=0` when the trainer already clips (Lightning's gradient_clip_val).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class FusedClipAdamW(torch.optim.Optimizer):
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_norm: float = 0.5):
+        self.model = model
+        params = [p for p in model.parameters()]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm))
+        self._state = None
+
+    def _buffers(self):
+        ar = self.model._arena
+        if self._state is None or self._state["arena"] is not ar:
+            dev = ar.data.device
+            n = ar.layout.n_total
+            self._state = dict(
+                arena=ar, m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+                hyper=torch.zeros(8, device=dev), st=torch.zeros(8, device=dev),
+                ws=torch.zeros(int(_lib.load().vitb200_grad_norm_ws_bytes(n)) + 4096, dtype=torch.uint8, device=dev))
+        return self._state
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        s = self._buffers()
+        ar = s["arena"]
+        if ar.data.device.type != "cuda":
+            raise RuntimeError("vit_b200 has no CPU path")
+        g = self.param_groups[0]
+        lay = ar.layout
+        # gather p.grad into the flat gradient arena (no-op copy when p.grad already aliases it)
+        for name, p in zip(self.model._param_names, self.model._param_list):
+            e = lay.entries[name]
+            if e.offset >= lay.n_opt:
+                continue
+            dst = ar.grad[e.offset:e.offset + e.numel]
+            if p.grad is None:
+                dst.zero_()
+            elif p.grad.data_ptr() != dst.data_ptr():
+                dst.copy_(p.grad.reshape(-1))
+        s["hyper"].copy_(torch.tensor([g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
+                                       g["max_norm"], 1.0, 0.0]), non_blocking=True)
+        st = torch.cuda.current_stream(ar.data.device).cuda_stream
+        _lib.check(lib.vitb200_grad_norm(ar.grad.data_ptr(), lay.n_opt, s["hyper"].data_ptr(), s["st"].data_ptr(),
+                                         s["ws"].data_ptr(), st), "grad_norm")
+        _lib.check(lib.vitb200_adamw(ar.data.data_ptr(), ar.grad.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(),
+                                     None if ar.shadow is None else ar.shadow.data_ptr(), lay.n_opt,
+                                     s["hyper"].data_ptr(), s["st"].data_ptr(), None, st), "adamw")
+        if ar.shadow is not None:
+            ar.mark_shadow_fresh()
+        return loss
+
+    @property
+    def last_grad_norm(self) -> torch.Tensor:
+        return self._buffers()["st"][1]

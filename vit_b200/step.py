@@ -1,0 +1,191 @@
+"""TrainStep -- the reference's training step without Lightning, on the B200 engine.
+
+Semantics restated from the reference:
+    zero_grad -> forward (src/vit.py:83-92 -> src/models/specvit.py:68-94) -> backward
+    -> [DDP mean all-reduce, src/hardware_utils.py:95] -> clip_grad_norm_(train.grad_clip = 0.5,
+    src/basemodule.py:244) -> AdamW.step (src/opt/optimizer.py:108)
+All kernels of a step are launched through the C ABI on one stream and, by default, captured into a single
+CUDA graph (the configured shape is launch-bound).  `step()` takes device tensors; `step_host()` is the
+end-to-end call: pinned-host inputs -> H2D -> step -> D2H of the loss.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import dp as _dp
+from .model import MyViT
+
+
+class TrainStep:
+    def __init__(self, model: MyViT, batch_size: int, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, grad_clip: float = 0.5, use_graph: bool = True, process_group=None,
+                 world_size: int = 1, noise_level: float = 0.0, train: bool = True):
+        self.model = model
+        model._opt_hyper = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=grad_clip)
+        model._engines.pop(batch_size, None)
+        self.eng = model._engine(batch_size)
+        self.B = batch_size
+        self.train = train  # dropout on (model.train()) or off
+        self.world = int(world_size)
+        self.group = process_group
+        if self.world > 1:
+            self.eng.set_grad_scale(1.0 / self.world)
+        self.noise_level = float(noise_level)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        c = model.config
+        self.h_x = torch.empty(batch_size, c.image_size, dtype=torch.float32, pin_memory=True)
+        self.h_y = torch.empty(self.eng.labels.shape, dtype=self.eng.labels.dtype, pin_memory=True)
+        self.h_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+        self._segments = None
+
+    # ---- one step's kernel sequence (also what gets captured) ---------------------------------
+    def _launch(self) -> None:
+        eng = self.eng
+        eng.forward(train=self.train, with_labels=True)
+        if self.world > 1:
+            self._backward_overlapped()
+        else:
+            eng.backward(train=self.train)
+        eng.optimizer_step()
+
+    def _backward_overlapped(self) -> None:
+        """Backward in bucket-sized segments; each bucket's all-reduce is issued as soon as its kernels are
+        enqueued so that NCCL runs under the remaining backward kernels."""
+        eng = self.eng
+        key = ("bwd", self.train, None)
+        if key not in eng._progs:
+            eng._progs[key] = eng._build_backward(self.train, None)
+            eng.launches[key] = len(eng._progs[key])
+        prog = eng._progs[key]
+        L = eng.cfg.num_hidden_layers
+        # program layout: [head_bwd, final_ln_bwd] + 11 calls per layer (L-1 .. 0) + [embed_bwd]
+        cuts = [2] + [2 + 11 * (i + 1) for i in range(L)] + [len(prog)]
+        buckets = _dp.backward_bucket_order(eng.arena.layout.buckets)
+        st = torch.cuda.current_stream(eng.device).cuda_stream
+        works, lo = [], 0
+        from . import _lib
+        for (name, s, e), hi in zip(buckets, cuts):
+            for fn, args in prog[lo:hi]:
+                rc = fn(*args, st)
+                if rc != 0:
+                    _lib.check(rc, fn.__name__)
+            lo = hi
+            works.append(_dp.allreduce_bucket(eng.arena.grad, s, e, group=self.group, async_op=True))
+        for w in works:
+            if w is not None:
+                w.wait()
+
+    def _snapshot(self):
+        e = self.eng
+        e._ensure_opt_state()
+        return [t.clone() for t in (e.arena.data, e.exp_avg, e.exp_avg_sq, e.state, e.rng)] + \
+               ([e.arena.shadow.clone()] if e.arena.shadow is not None else [])
+
+    def _restore(self, snap) -> None:
+        e = self.eng
+        dst = [e.arena.data, e.exp_avg, e.exp_avg_sq, e.state, e.rng] + \
+              ([e.arena.shadow] if e.arena.shadow is not None else [])
+        for d, s in zip(dst, snap):
+            d.copy_(s)
+        e.arena.mark_shadow_fresh()
+
+    def _capture(self) -> None:
+        eng = self.eng
+        eng.refresh_shadow()
+        snap = self._snapshot()
+        side = torch.cuda.Stream(device=eng.device)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(side):
+            self._launch()  # loads every kernel before capture; state is restored below
+        torch.cuda.current_stream(eng.device).wait_stream(side)
+        self._restore(snap)
+        torch.cuda.synchronize(eng.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch()
+        self.graph = g
+
+    # ---- public -----------------------------------------------------------------------------
+    def step(self, flux: torch.Tensor, labels: torch.Tensor, error: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """flux [B, L] and labels on the device (or pinned host): runs one full training step and returns the
+        loss as a 0-dim device tensor (no host sync)."""
+        eng = self.eng
+        if self.noise_level > 0 and error is not None:  # src/vit.py:86-88
+            flux = flux.to(eng.device, non_blocking=True)
+            flux = flux + torch.randn_like(flux) * error.to(eng.device, non_blocking=True) * self.noise_level
+        self.model._stage_inputs(eng, flux, labels)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            eng.refresh_shadow()
+            self._launch()
+        return eng.loss[0]
+
+    def step_host(self, flux_host: torch.Tensor, labels_host: torch.Tensor) -> float:
+        """End-to-end step: host inputs -> pinned staging -> H2D -> step -> D2H loss (blocking)."""
+        self.h_x.copy_(flux_host)
+        self.h_y.copy_(labels_host.reshape(self.h_y.shape))
+        loss = self.step(self.h_x, self.h_y)
+        self.h_loss.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        return float(self.h_loss[0])
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.h_x.numel() * 4 + self.h_y.numel() * self.h_y.element_size()
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return 4
+
+    def set_lr(self, lr: float) -> None:
+        self.eng.set_lr(lr)
+
+    def kernel_launches(self) -> int:
+        return self.eng.kernel_launches(self.train)
+
+
+class EvalStep:
+    """scripts/test.py semantics: model.eval(), no_grad, forward only (one forward per batch)."""
+
+    def __init__(self, model: MyViT, batch_size: int, use_graph: bool = True):
+        self.model = model
+        self.eng = model._engine(batch_size)
+        self.use_graph = use_graph
+        self.graph = None
+        c = model.config
+        self.h_x = torch.empty(batch_size, c.image_size, dtype=torch.float32, pin_memory=True)
+        self.h_logits = torch.empty(batch_size, c.num_labels, dtype=torch.float32, pin_memory=True)
+
+    def forward(self, flux: torch.Tensor) -> torch.Tensor:
+        eng = self.eng
+        self.model._stage_inputs(eng, flux, None)
+        if self.use_graph:
+            if self.graph is None:
+                eng.refresh_shadow()
+                side = torch.cuda.Stream(device=eng.device)
+                side.wait_stream(torch.cuda.current_stream(eng.device))
+                with torch.cuda.stream(side):
+                    eng.forward(train=False, with_labels=False)
+                torch.cuda.current_stream(eng.device).wait_stream(side)
+                torch.cuda.synchronize(eng.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eng.forward(train=False, with_labels=False)
+                self.graph = g
+            self.graph.replay()
+        else:
+            eng.forward(train=False, with_labels=False)
+        return eng.logits
+
+    def forward_host(self, flux_host: torch.Tensor) -> torch.Tensor:
+        self.h_x.copy_(flux_host)
+        logits = self.forward(self.h_x)
+        self.h_logits.copy_(logits, non_blocking=True)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        return self.h_logits
