@@ -133,7 +133,7 @@ static int patch_bwd_t(const float* dz, const float* x, float* dw, float* dbias,
   const size_t dtok_b = align256((size_t)B * Np * H * sizeof(float));
   float* partial = reinterpret_cast<float*>(base + 4096 + dtok_b);
   const size_t part_b = align256((size_t)chunks * (Np + 1) * H * sizeof(float));
-  void* gemm_ws = base + 4096 + dtok_b + part_b;
+  float* gemm_partial = reinterpret_cast<float*>(base + 4096 + dtok_b + part_b);
   const int M = B * Np;
   embed_bwd_prep_kernel<T><<<chunks, EB_THREADS, 0, st>>>(dz, dtok, partial, dcls, dpos, B, Np, H, pc, p_drop, rng,
                                                           site, accumulate, counter);
@@ -144,8 +144,9 @@ static int patch_bwd_t(const float* dz, const float* x, float* dw, float* dbias,
   EpiWgradPE epi{dw, dbias, P, accumulate};
   const int bn = pe_wgrad_bn(P);
   const int splits = gemm_splits(H, P + 1, M, bn);
-  if (bn == 32) return launch_gemm<32>(A, Bm, epi, H, P + 1, M, splits, gemm_ws, st);
-  return launch_gemm<64>(A, Bm, epi, H, P + 1, M, splits, gemm_ws, st);
+  // tickets live in the first 4096 bytes of ws for every kernel (they run back to back and reset themselves)
+  if (bn == 32) return launch_gemm<32>(A, Bm, epi, H, P + 1, M, splits, counter, gemm_partial, st);
+  return launch_gemm<64>(A, Bm, epi, H, P + 1, M, splits, counter, gemm_partial, st);
 }
 
 }  // namespace vb
@@ -167,13 +168,13 @@ extern "C" int vitb200_patch_embed_fwd(const float* x, const void* w, const floa
     AccUnfoldK<false> A{x, L, S, Np, n_valid, M, P};
     AccKMajor<float> Bm{(const float*)w, P, H, P};
     EpiPatchLazy<float> epi{z, bias, cls, pos, Np, H, p_drop, rng, site};
-    return launch_gemm<64>(A, Bm, epi, M, H, P, 1, nullptr, st);
+    return launch_gemm<64>(A, Bm, epi, M, H, P, 1, nullptr, nullptr, st);
   }
   if (dtype == VITB200_BF16) {
     AccUnfoldK<true> A{x, L, S, Np, n_valid, M, P};
     AccKMajor<bf16> Bm{(const bf16*)w, P, H, P};
     EpiPatchLazy<bf16> epi{z, bias, cls, pos, Np, H, p_drop, rng, site};
-    return launch_gemm<64>(A, Bm, epi, M, H, P, 1, nullptr, st);
+    return launch_gemm<64>(A, Bm, epi, M, H, P, 1, nullptr, nullptr, st);
   }
   return VITB200_ERR_ARG;
 }
@@ -184,7 +185,7 @@ extern "C" size_t vitb200_patch_embed_bwd_ws_bytes(int B, int Np, int P, int H) 
   size_t dtok = align256((size_t)B * Np * H * sizeof(float));
   size_t part = align256((size_t)chunks * (Np + 1) * H * sizeof(float));
   int splits = gemm_splits(H, P + 1, B * Np, pe_wgrad_bn(P));
-  size_t gemm = 4096 + (splits > 1 ? (size_t)splits * H * (P + 1) * sizeof(float) : 0);
+  size_t gemm = splits > 1 ? (size_t)splits * H * (P + 1) * sizeof(float) : 0;
   return 4096 + dtok + part + gemm;
 }
 

@@ -204,16 +204,16 @@ static inline int gemm_splits(int M, int N, int K, int BN) {
 
 template <int BN, class AAcc, class BAcc, class Epi>
 static inline int launch_gemm(const AAcc& A, const BAcc& B, const Epi& epi, int M, int N, int K, int splits,
-                              void* ws, cudaStream_t st) {
+                              unsigned int* counters, float* partial, cudaStream_t st) {
   if (M <= 0 || N <= 0) return VITB200_OK;
   int k_chunk = ceil_div(ceil_div(K, splits), GBK) * GBK;
   if (k_chunk <= 0) k_chunk = GBK;
   splits = ceil_div(K, k_chunk);
   if (splits < 1) splits = 1;
   dim3 grid(ceil_div(N, BN), ceil_div(M, GBM), splits);
-  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-  float* partial = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096) : nullptr;
-  if (splits > 1 && ws == nullptr) return VITB200_ERR_ARG;
+  // `counters`: >= 1024 zero-initialised uints (self-resetting tickets, shared by all kernels that run
+  // one after another on a stream); `partial`: splits * M * N floats of scratch.
+  if (splits > 1 && (counters == nullptr || partial == nullptr)) return VITB200_ERR_ARG;
   gemm_simt_kernel<BN, AAcc, BAcc, Epi><<<grid, GNT, 0, st>>>(A, B, epi, M, N, K, k_chunk, partial, counters);
   VB_CHECK_LAUNCH();
   return VITB200_OK;

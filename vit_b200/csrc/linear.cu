@@ -61,8 +61,8 @@ static int linear_fwd_t(const void* x, const void* w, const float* bias, void* y
   AccKMajor<T> A{(const T*)x, K, M, K};
   AccKMajor<T> B{(const T*)w, K, N, K};
   EpiBiasAct<T> epi{(T*)y, (T*)y_act, bias, N, act};
-  if (N <= 32) return launch_gemm<32>(A, B, epi, M, N, K, 1, nullptr, st);
-  return launch_gemm<64>(A, B, epi, M, N, K, 1, nullptr, st);
+  if (N <= 32) return launch_gemm<32>(A, B, epi, M, N, K, 1, nullptr, nullptr, st);
+  return launch_gemm<64>(A, B, epi, M, N, K, 1, nullptr, nullptr, st);
 }
 
 template <typename T>
@@ -72,8 +72,8 @@ static int linear_dgrad_t(const void* dy, const void* w, const void* pre, void* 
   AccKMajor<T> A{(const T*)dy, N, M, N};
   AccMNMajor<T, false> B{(const T*)w, K, K, N};
   EpiDgrad<T> epi{(T*)dx, (const T*)pre, K};
-  if (K <= 32) return launch_gemm<32>(A, B, epi, M, K, N, 1, nullptr, st);
-  return launch_gemm<64>(A, B, epi, M, K, N, 1, nullptr, st);
+  if (K <= 32) return launch_gemm<32>(A, B, epi, M, K, N, 1, nullptr, nullptr, st);
+  return launch_gemm<64>(A, B, epi, M, K, N, 1, nullptr, nullptr, st);
 }
 
 static inline int wgrad_bn(int K) { return (K + 1) <= 32 ? 32 : 64; }
@@ -87,8 +87,10 @@ static int linear_wgrad_t(const void* dy, const void* x, float* dw, float* db, i
   EpiWgrad epi{dw, db, K, accumulate};
   int bn = wgrad_bn(K);
   int splits = gemm_splits(N, K + 1, M, bn);
-  if (bn == 32) return launch_gemm<32>(A, B, epi, N, K + 1, M, splits, ws, st);
-  return launch_gemm<64>(A, B, epi, N, K + 1, M, splits, ws, st);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  if (bn == 32) return launch_gemm<32>(A, B, epi, N, K + 1, M, splits, counters, partial, st);
+  return launch_gemm<64>(A, B, epi, N, K + 1, M, splits, counters, partial, st);
 }
 
 }  // namespace vb
