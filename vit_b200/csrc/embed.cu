@@ -92,6 +92,7 @@ static inline int eb_chunks(int B, int* per_chunk) {
 // passed by value, so it carries the pointer and builds the context lazily.
 template <typename T>
 struct EpiPatchLazy {
+  static constexpr bool kSplit = false;
   float* z; const float* bias; const float* cls; const float* pos; int Np, H; float p_drop; const uint64_t* rng;
   uint32_t site;
   template <int TN>
@@ -103,19 +104,20 @@ struct EpiPatchLazy {
 };
 
 struct EpiWgradPE {  // output [H, P + 1]: column P is the bias gradient (ones-column trick)
+  static constexpr bool kSplit = true;
   float* dw; float* db; int Kw; int accumulate;
+  __device__ __forceinline__ void apply1(int m, int n, float v) const {
+    if (n < Kw) {
+      size_t o = (size_t)m * Kw + n;
+      dw[o] = accumulate ? dw[o] + v : v;
+    } else if (n == Kw) {
+      db[m] = accumulate ? db[m] + v : v;
+    }
+  }
   template <int TN>
   __device__ __forceinline__ void apply(int m, int n0, const float (&v)[TN]) const {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int n = n0 + j;
-      if (n < Kw) {
-        size_t o = (size_t)m * Kw + n;
-        dw[o] = accumulate ? dw[o] + v[j] : v[j];
-      } else if (n == Kw) {
-        db[m] = accumulate ? db[m] + v[j] : v[j];
-      }
-    }
+    for (int j = 0; j < TN; ++j) apply1(m, n0 + j, v[j]);
   }
 };
 

@@ -154,33 +154,41 @@ __global__ void __launch_bounds__(GNT) gemm_simt_kernel(AAcc A, BAcc B, Epi epi,
     __syncthreads();
   }
 
-  if (gridDim.z > 1) {
-    // stage 1: every split writes its partial tile; stage 2: the last CTA of this tile sums all
-    // splits in split order (fixed order => bitwise deterministic) and runs the epilogue.
-    const size_t MN = (size_t)M * N;
+  if constexpr (Epi::kSplit) {
+    if (gridDim.z > 1) {
+      // stage 1: every split writes its partial tile; stage 2: the last CTA of this tile sums all
+      // splits in split order (fixed order => bitwise deterministic) and runs the epilogue.  The tile's
+      // valid elements are spread over all 256 threads and the loads of 8 splits are issued together.
+      const size_t MN = (size_t)M * N;
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      int m = m0 + ty * TM + i;
-      if (m >= M) continue;
+      for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= M) continue;
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        int n = n0 + tx * TN + j;
-        if (n < N) partial[blockIdx.z * MN + (size_t)m * N + n] = acc[i][j];
+        for (int j = 0; j < TN; ++j) {
+          int n = n0 + tx * TN + j;
+          if (n < N) partial[blockIdx.z * MN + (size_t)m * N + n] = acc[i][j];
+        }
       }
-    }
-    if (!last_block_ticket(&counters[blockIdx.y * gridDim.x + blockIdx.x], gridDim.z)) return;
+      if (!last_block_ticket(&counters[blockIdx.y * gridDim.x + blockIdx.x], gridDim.z)) return;
+      const int tm = min(GBM, M - m0), tn = min(BN, N - n0);
+      const unsigned int Z = gridDim.z;
+      for (int e = tid; e < tm * tn; e += GNT) {
+        const int m = m0 + e / tn, n = n0 + e % tn;
+        const float* src = partial + (size_t)m * N + n;
+        float sum = 0.f;
+        unsigned int z = 0;
+        for (; z + 8 <= Z; z += 8) {
+          float v[8];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      int m = m0 + ty * TM + i;
-      if (m >= M) continue;
+          for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(z + q) * MN);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        int n = n0 + tx * TN + j;
-        float s = 0.f;
-        if (n < N)
-          for (unsigned int z = 0; z < gridDim.z; ++z) s += __ldcg(&partial[z * MN + (size_t)m * N + n]);
-        acc[i][j] = s;
+          for (int q = 0; q < 8; ++q) sum += v[q];
+        }
+        for (; z < Z; ++z) sum += __ldcg(src + (size_t)z * MN);
+        epi.apply1(m, n, sum);
       }
+      return;
     }
   }
 #pragma unroll
@@ -195,9 +203,9 @@ static inline int gemm_splits(int M, int N, int K, int BN) {
   long long tiles = (long long)ceil_div(M, GBM) * ceil_div(N, BN);
   if (tiles >= 296 || tiles > 1024) return 1;
   int want = (int)((296 + tiles - 1) / tiles);
-  int max_by_k = ceil_div(K, 4 * GBK);
+  int max_by_k = ceil_div(K, 8 * GBK);
   int s = want < max_by_k ? want : max_by_k;
-  if (s > 128) s = 128;
+  if (s > 64) s = 64;  // the second stage is one CTA per tile: keep its serial part short
   if (s < 1) s = 1;
   return s;
 }

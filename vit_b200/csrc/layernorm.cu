@@ -185,21 +185,29 @@ add_ln_bwd_kernel(const T* __restrict__ du, const float* __restrict__ z, const f
     partial[(size_t)blockIdx.x * 2 * H + H + i] = red[1][i];
   }
   if (!last_block_ticket(counter, gridDim.x)) return;
-  for (int i = threadIdx.x; i < H; i += LN_THREADS) {
-    float sg = 0.f, sb = 0.f;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-      sg += __ldcg(&partial[(size_t)b * 2 * H + i]);
-      sb += __ldcg(&partial[(size_t)b * 2 * H + H + i]);
+  // 2H output columns over all threads; 8 partial loads in flight per thread, summed in CTA order
+  for (int i = threadIdx.x; i < 2 * H; i += LN_THREADS) {
+    float sum = 0.f;
+    unsigned int b = 0;
+    const unsigned int nb = gridDim.x;
+    for (; b + 8 <= nb; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldcg(&partial[(size_t)(b + q) * 2 * H + i]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum += v[q];
     }
-    if (dgamma) dgamma[i] = accumulate ? dgamma[i] + sg : sg;
-    if (dbeta) dbeta[i] = accumulate ? dbeta[i] + sb : sb;
+    for (; b < nb; ++b) sum += __ldcg(&partial[(size_t)b * 2 * H + i]);
+    float* dst = i < H ? dgamma : dbeta;
+    const int c = i < H ? i : i - H;
+    if (dst) dst[c] = accumulate ? dst[c] + sum : sum;
   }
 }
 
-static inline int ln_grid(int M, int lpr) {
+static inline int ln_grid(int M, int lpr, int max_blocks = LN_MAX_BLOCKS) {
   long long rows_per_block = (LN_THREADS / 32) * (32 / lpr);
   long long g = (M + rows_per_block - 1) / rows_per_block;
-  if (g > LN_MAX_BLOCKS) g = LN_MAX_BLOCKS;
+  if (g > max_blocks) g = max_blocks;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -249,7 +257,7 @@ extern "C" int vitb200_add_ln_bwd(const void* du, const float* z, const float* m
   if (!du || !z || !mean || !rstd || !gamma || !dz || !ws) return VITB200_ERR_ARG;
   if (M == 0) return VITB200_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int lpr = ln_lpr(H), grid = ln_grid(M, lpr);
+  const int lpr = ln_lpr(H), grid = ln_grid(M, lpr, 148);  // one CTA per SM: the second stage reads `grid` partials
   const bool small = (H / 4) <= 32;
   unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);

@@ -6,6 +6,7 @@ namespace vb {
 
 template <typename T>
 struct EpiBiasAct {
+  static constexpr bool kSplit = false;
   T* y; T* y_act; const float* bias; int N; int act;
   template <int TN>
   __device__ __forceinline__ void apply(int m, int n0, const float (&v)[TN]) const {
@@ -23,6 +24,7 @@ struct EpiBiasAct {
 
 template <typename T>
 struct EpiDgrad {
+  static constexpr bool kSplit = false;
   T* dx; const T* pre; int K;
   template <int TN>
   __device__ __forceinline__ void apply(int m, int n0, const float (&v)[TN]) const {
@@ -39,19 +41,20 @@ struct EpiDgrad {
 };
 
 struct EpiWgrad {  // output [N_w, K_w + 1]: column K_w is the bias gradient (ones-column trick)
+  static constexpr bool kSplit = true;
   float* dw; float* db; int Kw; int accumulate;
+  __device__ __forceinline__ void apply1(int m, int n, float v) const {
+    if (n < Kw) {
+      size_t o = (size_t)m * Kw + n;
+      dw[o] = accumulate ? dw[o] + v : v;
+    } else if (n == Kw && db) {
+      db[m] = accumulate ? db[m] + v : v;
+    }
+  }
   template <int TN>
   __device__ __forceinline__ void apply(int m, int n0, const float (&v)[TN]) const {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int n = n0 + j;
-      if (n < Kw) {
-        size_t o = (size_t)m * Kw + n;
-        dw[o] = accumulate ? dw[o] + v[j] : v[j];
-      } else if (n == Kw && db) {
-        db[m] = accumulate ? db[m] + v[j] : v[j];
-      }
-    }
+    for (int j = 0; j < TN; ++j) apply1(m, n0 + j, v[j]);
   }
 };
 
