@@ -125,6 +125,20 @@ size_t vitb200_linear_wgrad_ws_bytes(int M, int N, int K);
 int vitb200_linear_wgrad(const void* dy, const void* x, float* dw, float* dbias, int M, int N, int K,
                          int accumulate, int dtype, void* ws, void* stream);
 
+/* The bf16 Linear entry points above run on the tcgen05 tensor cores (TMA-staged tiles, TMEM accumulator,
+ * fused epilogue; csrc/gemm_tc.cu) whenever N % 8 == 0, K % 8 == 0 and the pointers are 16-byte aligned; fp32 mode
+ * and odd shapes use the SIMT kernel.  The tensor-core kernels are also exported directly (bf16 only), and the
+ * automatic choice can be overridden for A/B tests: mode 0 = automatic, 1 = SIMT only; returns the old mode. */
+int vitb200_tc_supported(int M, int N, int K);
+int vitb200_tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_act, int M, int N, int K,
+                          int act, void* stream);
+int vitb200_tc_linear_dgrad(const void* dy, const void* w, const void* pre_act, void* dx, int M, int N, int K,
+                            void* stream);
+size_t vitb200_tc_linear_wgrad_ws_bytes(int M, int N, int K);
+int vitb200_tc_linear_wgrad(const void* dy, const void* x, float* dw, float* dbias, int M, int N, int K,
+                            int accumulate, void* ws, void* stream);
+int vitb200_set_gemm_mode(int mode);
+
 /* ---- multi-head self-attention ----------------------------------------------------------------
  * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and
  * ViTSelfAttentionWithRoPE.forward (src/models/vit_with_rope.py:43-84; RoPE = src/models/rope.py:60-98):

@@ -48,6 +48,12 @@ SIGNATURES = {
     "vitb200_linear_dgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vitb200_linear_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
     "vitb200_linear_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "vitb200_tc_supported": (_i, [_i, _i, _i]),
+    "vitb200_tc_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vitb200_tc_linear_dgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "vitb200_tc_linear_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
+    "vitb200_tc_linear_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "vitb200_set_gemm_mode": (_i, [_i]),
     "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

@@ -100,10 +100,32 @@ static int linear_wgrad_t(const void* dy, const void* x, float* dw, float* db, i
 
 using namespace vb;
 
+// tensor-core (tcgen05 / TMA) implementations, gemm_tc.cu
+extern "C" int vitb200_tc_supported(int M, int N, int K);
+extern "C" int vitb200_tc_linear_fwd(const void*, const void*, const float*, void*, void*, int, int, int, int, void*);
+extern "C" int vitb200_tc_linear_dgrad(const void*, const void*, const void*, void*, int, int, int, void*);
+extern "C" size_t vitb200_tc_linear_wgrad_ws_bytes(int, int, int);
+extern "C" int vitb200_tc_linear_wgrad(const void*, const void*, float*, float*, int, int, int, int, void*, void*);
+
+// 0 = automatic (bf16 GEMMs on tcgen05 whenever the shape allows), 1 = SIMT only (A/B tests, debugging)
+static int g_gemm_mode = 0;
+extern "C" int vitb200_set_gemm_mode(int mode) {
+  int old = g_gemm_mode;
+  if (mode == 0 || mode == 1) g_gemm_mode = mode;
+  return old;
+}
+static inline bool use_tc(int dtype, int M, int N, int K, const void* a, const void* b, const void* c) {
+  return dtype == VITB200_BF16 && g_gemm_mode == 0 && vitb200_tc_supported(M, N, K) &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
 extern "C" int vitb200_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_act, int M, int N,
                                   int K, int act, int dtype, void* stream) {
   if (!x || !w || !y || M < 0 || N <= 0 || K <= 0) return VITB200_ERR_ARG;
   if (act == VITB200_ACT_GELU && !y_act) return VITB200_ERR_ARG;
+  if (M == 0) return VITB200_OK;
+  if (use_tc(dtype, M, N, K, x, w, y) && (!y_act || (reinterpret_cast<uintptr_t>(y_act) & 15) == 0))
+    return vitb200_tc_linear_fwd(x, w, bias, y, y_act, M, N, K, act, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32) return linear_fwd_t<float>(x, w, bias, y, y_act, M, N, K, act, st);
   if (dtype == VITB200_BF16) return linear_fwd_t<bf16>(x, w, bias, y, y_act, M, N, K, act, st);
@@ -113,6 +135,9 @@ extern "C" int vitb200_linear_fwd(const void* x, const void* w, const float* bia
 extern "C" int vitb200_linear_dgrad(const void* dy, const void* w, const void* pre_act, void* dx, int M, int N, int K,
                                     int dtype, void* stream) {
   if (!dy || !w || !dx || M < 0 || N <= 0 || K <= 0) return VITB200_ERR_ARG;
+  if (M == 0) return VITB200_OK;
+  if (use_tc(dtype, M, N, K, dy, w, dx) && (!pre_act || (reinterpret_cast<uintptr_t>(pre_act) & 15) == 0))
+    return vitb200_tc_linear_dgrad(dy, w, pre_act, dx, M, N, K, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32) return linear_dgrad_t<float>(dy, w, pre_act, dx, M, N, K, st);
   if (dtype == VITB200_BF16) return linear_dgrad_t<bf16>(dy, w, pre_act, dx, M, N, K, st);
@@ -122,12 +147,16 @@ extern "C" int vitb200_linear_dgrad(const void* dy, const void* w, const void* p
 extern "C" size_t vitb200_linear_wgrad_ws_bytes(int M, int N, int K) {
   int splits = gemm_splits(N, K + 1, M, wgrad_bn(K));
   // launch_gemm may lower the split count, never raise it
-  return 4096 + (splits > 1 ? (size_t)splits * N * (K + 1) * sizeof(float) : 0);
+  size_t simt = 4096 + (splits > 1 ? (size_t)splits * N * (K + 1) * sizeof(float) : 0);
+  size_t tcb = (M > 0 && vitb200_tc_supported(M, N, K)) ? vitb200_tc_linear_wgrad_ws_bytes(M, N, K) : 0;
+  return simt > tcb ? simt : tcb;
 }
 
 extern "C" int vitb200_linear_wgrad(const void* dy, const void* x, float* dw, float* dbias, int M, int N, int K,
                                     int accumulate, int dtype, void* ws, void* stream) {
   if (!dy || !x || !dw || !ws || M < 0 || N <= 0 || K <= 0) return VITB200_ERR_ARG;
+  if (M > 0 && use_tc(dtype, M, N, K, dy, x, dw))
+    return vitb200_tc_linear_wgrad(dy, x, dw, dbias, M, N, K, accumulate, ws, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32) return linear_wgrad_t<float>(dy, x, dw, dbias, M, N, K, accumulate, ws, st);
   if (dtype == VITB200_BF16) return linear_wgrad_t<bf16>(dy, x, dw, dbias, M, N, K, accumulate, ws, st);
