@@ -139,6 +139,52 @@ int vitb200_tc_linear_wgrad(const void* dy, const void* x, float* dw, float* dbi
                             int accumulate, void* ws, void* stream);
 int vitb200_set_gemm_mode(int mode);
 
+/* ---- fused row-chain kernels (bf16, hidden_size 32 or 64) ------------------------------------------------------
+ * At the configured shape (H=32) a step is launch/latency bound, so every row-wise op between two attention
+ * calls runs in ONE kernel: a CTA owns 128 token rows, all weights of the layer are TMA-staged in shared memory,
+ * the four GEMMs run on tcgen05 with the accumulator in TMEM, and each epilogue (bias, dropout, residual,
+ * LayerNorm, GELU) writes the next GEMM's A operand straight back into (swizzled) shared memory:
+ *   embed : x -> patch GEMM -> +bias,+pos,CLS,dropout -> z0 -> LN1 -> QKV GEMM                 (embedding.py:79-100, HF:333)
+ *   layer : ctx -> out-proj -> dropout,+res -> LN2 -> MLP-up,GELU -> MLP-down -> dropout,+res
+ *           -> (LN1 + QKV of the next layer | final LN of the CLS rows)                         (HF:266-346,455)
+ * Same math, same dropout masks, same saved-for-backward tensors as the unfused entry points above. */
+typedef struct {
+  int B, L, P, S, Np, n_valid, H;   /* spectrum length L, patch P, stride S, Np patches, H hidden; T = Np+1 */
+  float eps, p_drop;
+  const uint64_t* rng;
+  const float* x;                   /* [B, L] f32 */
+  const void* w_p;                  /* [H, P] bf16 */
+  const float *b_p, *cls, *pos;     /* [H], [H], [T,H] or NULL */
+  const float *ln_g, *ln_b;         /* LN1 of layer 0 */
+  const void* w_qkv;                /* [3H, H] bf16 */
+  const float* b_qkv;               /* [3H] */
+  float* z0;                        /* [B*T, H] f32 */
+  void* u;                          /* [B*T, H] bf16 */
+  float *mean, *rstd;               /* [B*T] */
+  void* qkv;                        /* [B*T, 3H] bf16 */
+} vitb200_embed_fwd_args;
+
+typedef struct {
+  int B, T, H, last;                /* last != 0: final LayerNorm of the CLS rows instead of LN1 + QKV */
+  float eps, p_drop;
+  const uint64_t* rng;
+  uint32_t site_proj, site_mlp;
+  const void* ctx;                  /* [B*T, H] bf16 attention output */
+  const float* z_in;                /* [B*T, H] f32 residual stream entering the layer */
+  const void *w_o, *w_1, *w_2, *w_qkv;          /* bf16 [H,H], [4H,H], [H,4H], [3H,H] (next layer; unused if last) */
+  const float *b_o, *ln2_g, *ln2_b, *b_1, *b_2, *lnn_g, *lnn_b, *b_qkv;
+  float* hmid; void* u2; float *mean2, *rstd2;  /* saved for backward */
+  void *a, *m;                      /* [B*T, 4H] bf16 pre / post GELU */
+  float* z_out;                     /* [B*T, H] f32 */
+  void* u_next;                     /* [B*T, H] bf16, or [B, H] (CLS rows) if last */
+  float *mean_n, *rstd_n;           /* [B*T], or [B] if last */
+  void* qkv_next;                   /* [B*T, 3H] bf16 (unused if last) */
+} vitb200_layer_fwd_args;
+
+int vitb200_fused_supported(int H, int P);
+int vitb200_fused_embed_fwd(const vitb200_embed_fwd_args* args, void* stream);
+int vitb200_fused_layer_fwd(const vitb200_layer_fwd_args* args, void* stream);
+
 /* ---- multi-head self-attention ----------------------------------------------------------------
  * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and
  * ViTSelfAttentionWithRoPE.forward (src/models/vit_with_rope.py:43-84; RoPE = src/models/rope.py:60-98):

@@ -32,6 +32,20 @@ def site_mlp(l: int) -> int:
 
 _p, _i, _f, _u32, _sz = C.c_void_p, C.c_int, C.c_float, C.c_uint32, C.c_size_t
 
+
+class EmbedFwdArgs(C.Structure):  # vitb200_embed_fwd_args
+    _fields_ = [(n, _i) for n in ("B", "L", "P", "S", "Np", "n_valid", "H")] + [("eps", _f), ("p_drop", _f)] + \
+               [(n, _p) for n in ("rng", "x", "w_p", "b_p", "cls", "pos", "ln_g", "ln_b", "w_qkv", "b_qkv", "z0", "u",
+                                  "mean", "rstd", "qkv")]
+
+
+class LayerFwdArgs(C.Structure):  # vitb200_layer_fwd_args
+    _fields_ = [(n, _i) for n in ("B", "T", "H", "last")] + [("eps", _f), ("p_drop", _f), ("rng", _p),
+                                                              ("site_proj", _u32), ("site_mlp", _u32)] + \
+               [(n, _p) for n in ("ctx", "z_in", "w_o", "w_1", "w_2", "w_qkv", "b_o", "ln2_g", "ln2_b", "b_1", "b_2",
+                                  "lnn_g", "lnn_b", "b_qkv", "hmid", "u2", "mean2", "rstd2", "a", "m", "z_out", "u_next",
+                                  "mean_n", "rstd_n", "qkv_next")]
+
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
 SIGNATURES = {
     "vitb200_strerror": (C.c_char_p, [_i]),
@@ -54,6 +68,9 @@ SIGNATURES = {
     "vitb200_tc_linear_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
     "vitb200_tc_linear_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "vitb200_set_gemm_mode": (_i, [_i]),
+    "vitb200_fused_supported": (_i, [_i, _i]),
+    "vitb200_fused_embed_fwd": (_i, [_p, _p]),
+    "vitb200_fused_layer_fwd": (_i, [_p, _p]),
     "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

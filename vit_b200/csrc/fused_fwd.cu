@@ -1,0 +1,470 @@
+// Fused forward row-chain kernels (bf16 mode, H in {32, 64}).  See include/vit_b200.h.
+//
+// One CTA = 128 token rows = 128 threads; thread t owns row t of the tile and TMEM lane t.
+// Thread 0 issues TMA and tcgen05.mma; every GEMM's accumulator sits in TMEM columns [0, N);
+// after each GEMM all threads read their row back (tcgen05.ld), apply the epilogue in registers
+// (a whole row of H values lives in one thread, so LayerNorm needs no shuffles), store what backward
+// needs to HBM, and write the next GEMM's A operand into shared memory in the UMMA K-major / 128B-swizzle
+// layout (16-byte chunk c of row r goes to chunk c ^ (r & 7)).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace vb {
+using namespace vb::tc;
+
+constexpr int FF_ROWS = 128;
+constexpr int FF_THREADS = 128;
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+  pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+  return pk;
+}
+// A-operand tile: k-blocks of 64 columns, 16 KB each; row r = 128 bytes; chunk swizzle within the row
+__device__ __forceinline__ void swz_store(uint8_t* tile, int r, int chunk, uint4 v) {
+  uint8_t* p = tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+// values v[0..N) (already rounded to bf16 precision) -> global row (bf16) and the swizzled smem tile
+template <int N>
+__device__ __forceinline__ void emit_row_bf16(const float (&v)[N], bf16* gdst, bool store_g, uint8_t* tile, int r,
+                                              int chunk0) {
+#pragma unroll
+  for (int j = 0; j < N; j += 8) {
+    uint4 pk = pack8_bf16(&v[j]);
+    if (store_g) *reinterpret_cast<uint4*>(gdst + j) = pk;
+    if (tile) swz_store(tile, r, chunk0 + (j >> 3), pk);
+  }
+}
+template <int H>
+__device__ __forceinline__ void layer_norm_row(const float (&x)[H], const float* __restrict__ g,
+                                               const float* __restrict__ b, float eps, float (&y)[H], float& mu,
+                                               float& rs) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < H; ++j) s += x[j];
+  mu = s * (1.f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < H; ++j) { float d = x[j] - mu; q = fmaf(d, d, q); }
+  rs = rsqrtf(q * (1.f / H) + eps);
+#pragma unroll
+  for (int j = 0; j < H; ++j) y[j] = bf16_round((x[j] - mu) * rs * g[j] + b[j]);
+}
+// one thread issues a whole K-major x K-major GEMM: D[128, N] = A[128, K] * B[N, K]^T
+__device__ __forceinline__ void issue_gemm_kk(uint32_t tmem_d, uint32_t sA, uint32_t sB, uint32_t b_kblock_bytes, int N,
+                                              int K, uint64_t* done_bar) {
+  const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  const int ksteps = (K + 15) / 16;
+  for (int k = 0; k < ksteps; ++k) {
+    const int kb = k >> 2, kk = k & 3;
+    const uint64_t da = make_sdesc_sw128(sA + kb * 16384 + kk * 32, 16, 1024);
+    const uint64_t db = make_sdesc_sw128(sB + kb * b_kblock_bytes + kk * 32, 16, 1024);
+    umma_bf16(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+  }
+  umma_commit(done_bar);
+}
+
+// ================================================================================================
+// layer kernel
+// ================================================================================================
+template <int H>
+__global__ void __launch_bounds__(FF_THREADS, 1)
+fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmWo,
+                       const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                       const __grid_constant__ CUtensorMap tmWq, const vitb200_layer_fwd_args P) {
+  constexpr int I = 4 * H;
+  constexpr int KB_I = I / 64;                     // k-blocks of the MLP-down GEMM
+  constexpr uint32_t SZ_A = 16384, SZ_M = KB_I * 16384, SZ_WO = H * 128, SZ_W1 = I * 128, SZ_W2 = KB_I * H * 128,
+                     SZ_WQ = 3 * H * 128;
+  constexpr uint32_t TMEM_COLS = I < 32 ? 32 : I;  // 128 / 256
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = base;
+  uint8_t* sM = sA + SZ_A;
+  uint8_t* sWo = sM + SZ_M;
+  uint8_t* sW1 = sWo + SZ_WO;
+  uint8_t* sW2 = sW1 + SZ_W1;
+  uint8_t* sWq = sW2 + SZ_W2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWq + SZ_WQ);
+  uint64_t *b_in = bars, *b_w1 = bars + 1, *b_w2 = bars + 2, *b_wq = bars + 3, *b_mma = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = P.B * P.T;
+  const int r0 = blockIdx.x * FF_ROWS;
+  const int row = r0 + tid;
+  const bool valid = row < M;
+  const int rowc = valid ? row : M - 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmCtx); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    if (!P.last) tma_prefetch_desc(&tmWq);
+    mbar_init(b_in, 1); mbar_init(b_w1, 1); mbar_init(b_w2, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_expect_tx(b_in, SZ_A + SZ_WO);
+    tma_load_2d(sA, &tmCtx, b_in, 0, r0);
+    tma_load_2d(sWo, &tmWo, b_in, 0, 0);
+    mbar_expect_tx(b_w1, SZ_W1);
+    tma_load_2d(sW1, &tmW1, b_w1, 0, 0);
+    mbar_expect_tx(b_w2, SZ_W2);
+#pragma unroll
+    for (int kb = 0; kb < KB_I; ++kb) tma_load_2d(sW2 + kb * H * 128, &tmW2, b_w2, kb * 64, 0);
+    if (!P.last) {
+      mbar_expect_tx(b_wq, SZ_WQ);
+      tma_load_2d(sWq, &tmWq, b_wq, 0, 0);
+    }
+  }
+  // residual row (overlaps the TMA loads)
+  float h[H];
+  {
+    const float4* zp = reinterpret_cast<const float4*>(P.z_in + (size_t)rowc * H);
+#pragma unroll
+    for (int j = 0; j < H / 4; ++j) { float4 t = zp[j]; h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w; }
+  }
+  const uint64_t seed = P.rng ? P.rng[0] : 0ull;
+  const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
+  uint32_t mma_phase = 0;
+
+  // ---- 1. attention output projection + dropout + residual, LayerNorm-after ----
+  if (tid == 0) {
+    mbar_wait(b_in, 0);
+    tc_fence_after();
+    issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sWo), 0, H, H, b_mma);
+  }
+  mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+  tc_fence_after();
+  {
+    const DropCtx dc = make_drop(P.p_drop, seed, step, P.site_proj);
+#pragma unroll
+    for (int c0 = 0; c0 < H; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
+        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + P.b_o[c0 + j + 0]) * kp.x);
+        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + P.b_o[c0 + j + 1]) * kp.y);
+        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + P.b_o[c0 + j + 2]) * kp.z);
+        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + P.b_o[c0 + j + 3]) * kp.w);
+      }
+    }
+    float u2[H], mu, rs;
+    layer_norm_row<H>(h, P.ln2_g, P.ln2_b, P.eps, u2, mu, rs);
+    if (valid) {
+      float4* hp = reinterpret_cast<float4*>(P.hmid + (size_t)row * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) hp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      P.mean2[row] = mu; P.rstd2[row] = rs;
+    }
+    emit_row_bf16<H>(u2, reinterpret_cast<bf16*>(P.u2) + (size_t)rowc * H, valid, sA, tid, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---- 2. MLP up + GELU ----
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(b_w1, 0);
+    issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sW1), 0, I, H, b_mma);
+  }
+  mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < I; c0 += 32) {
+    float v[32], g[32];
+    tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = bf16_round(v[j] + P.b_1[c0 + j]);
+      g[j] = gelu_f(v[j]);
+    }
+    emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.a) + (size_t)rowc * I + c0, valid, nullptr, 0, 0);
+    emit_row_bf16<32>(g, reinterpret_cast<bf16*>(P.m) + (size_t)rowc * I + c0, valid, sM, tid, c0 >> 3);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---- 3. MLP down + dropout + residual, then LN1 of the next layer (or the final LN of CLS rows) ----
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(b_w2, 0);
+    issue_gemm_kk(tmem, smem_u32(sM), smem_u32(sW2), H * 128, H, I, b_mma);
+  }
+  mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+  tc_fence_after();
+  {
+    const DropCtx dc = make_drop(P.p_drop, seed, step, P.site_mlp);
+#pragma unroll
+    for (int c0 = 0; c0 < H; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
+        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + P.b_2[c0 + j + 0]) * kp.x);
+        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + P.b_2[c0 + j + 1]) * kp.y);
+        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + P.b_2[c0 + j + 2]) * kp.z);
+        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + P.b_2[c0 + j + 3]) * kp.w);
+      }
+    }
+    if (valid) {
+      float4* zp = reinterpret_cast<float4*>(P.z_out + (size_t)row * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) zp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    }
+    float un[H], mu, rs;
+    layer_norm_row<H>(h, P.lnn_g, P.lnn_b, P.eps, un, mu, rs);
+    if (!P.last) {
+      if (valid) { P.mean_n[row] = mu; P.rstd_n[row] = rs; }
+      emit_row_bf16<H>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)rowc * H, valid, sA, tid, 0);
+    } else if (valid && (row % P.T) == 0) {
+      const int b = row / P.T;
+      P.mean_n[b] = mu; P.rstd_n[b] = rs;
+      emit_row_bf16<H>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)b * H, true, nullptr, 0, 0);
+    }
+  }
+  if (!P.last) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- 4. fused Q/K/V projection of the next layer ----
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(b_wq, 0);
+      issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sWq), 0, 3 * H, H, b_mma);
+    }
+    mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < 3 * H; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += P.b_qkv[c0 + j];
+      emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.qkv_next) + (size_t)rowc * 3 * H + c0, valid, nullptr, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ================================================================================================
+// embedding kernel
+// ================================================================================================
+template <int H>
+__global__ void __launch_bounds__(FF_THREADS, 1)
+fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmWq,
+                       const vitb200_embed_fwd_args P) {
+  constexpr uint32_t SZ_A = 16384, SZ_WP = H * 128, SZ_WQ = 3 * H * 128;
+  constexpr uint32_t TMEM_COLS = 3 * H <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = base;
+  uint8_t* sWp = sA + SZ_A;
+  uint8_t* sWq = sWp + SZ_WP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWq + SZ_WQ);
+  uint64_t *b_wp = bars, *b_wq = bars + 1, *b_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int T = P.Np + 1, M = P.B * T;
+  const int r0 = blockIdx.x * FF_ROWS;
+  const int row = r0 + tid;
+  const bool valid = row < M;
+  const int rowc = valid ? row : M - 1;
+  const int b = rowc / T, t = rowc - b * T;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmWp); tma_prefetch_desc(&tmWq);
+    mbar_init(b_wp, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_expect_tx(b_wp, SZ_WP);
+    tma_load_2d(sWp, &tmWp, b_wp, 0, 0);
+    mbar_expect_tx(b_wq, SZ_WQ);
+    tma_load_2d(sWq, &tmWq, b_wq, 0, 0);
+  }
+  // A row = the patch window of this token (tokenization.py:45-48); CLS rows and padded windows are zero
+  {
+    const bool has = valid && t >= 1 && (t - 1) < P.n_valid;
+    const float* xp = P.x + (size_t)b * P.L + (size_t)(t >= 1 ? t - 1 : 0) * P.S;
+    const int nchunk = (P.P + 15) / 16 * 2;  // whole 16-element k-steps are read by the MMA
+    for (int c = 0; c < nchunk; ++c) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = c * 8 + q;
+        v[q] = (has && j < P.P) ? xp[j] : 0.f;
+      }
+      swz_store(sA, tid, c, pack8_bf16(v));
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  uint32_t mma_phase = 0;
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(b_wp, 0);
+    issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sWp), 0, H, P.P, b_mma);
+  }
+  mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+  tc_fence_after();
+  {
+    const uint64_t seed = P.rng ? P.rng[0] : 0ull;
+    const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
+    const DropCtx dc = make_drop(P.p_drop, seed, step, VITB200_SITE_EMB);
+    float z[H];
+#pragma unroll
+    for (int c0 = 0; c0 < H; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
+        const float kpa[4] = {kp.x, kp.y, kp.z, kp.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = c0 + j + q;
+          float e = t == 0 ? P.cls[c] : bf16_round(v[j + q] + P.b_p[c]);
+          if (P.pos) e += P.pos[(size_t)t * H + c];
+          z[c] = e * kpa[q];
+        }
+      }
+    }
+    float u[H], mu, rs;
+    layer_norm_row<H>(z, P.ln_g, P.ln_b, P.eps, u, mu, rs);
+    if (valid) {
+      float4* zp = reinterpret_cast<float4*>(P.z0 + (size_t)row * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) zp[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+      P.mean[row] = mu; P.rstd[row] = rs;
+    }
+    emit_row_bf16<H>(u, reinterpret_cast<bf16*>(P.u) + (size_t)rowc * H, valid, sA, tid, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(b_wq, 0);
+    issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sWq), 0, 3 * H, H, b_mma);
+  }
+  mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < 3 * H; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32(my_tmem + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += P.b_qkv[c0 + j];
+    emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.qkv) + (size_t)rowc * 3 * H + c0, valid, nullptr, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int H> static constexpr int layer_smem() {
+  return 16384 + (4 * H / 64) * 16384 + H * 128 + 4 * H * 128 + (4 * H / 64) * H * 128 + 3 * H * 128 + 1024 + 128;
+}
+template <int H> static constexpr int embed_smem() { return 16384 + H * 128 + 3 * H * 128 + 1024 + 128; }
+
+template <int H>
+static int launch_layer(const vitb200_layer_fwd_args* a, cudaStream_t st) {
+  const int M = a->B * a->T, I = 4 * H;
+  CUtensorMap tCtx, tWo, tW1, tW2, tWq;
+  int rc;
+  if ((rc = get_tmap(a->ctx, H, M, 64, 128, &tCtx))) return rc;
+  if ((rc = get_tmap(a->w_o, H, H, 64, H, &tWo))) return rc;
+  if ((rc = get_tmap(a->w_1, H, I, 64, I, &tW1))) return rc;
+  if ((rc = get_tmap(a->w_2, I, H, 64, H, &tW2))) return rc;
+  if (a->last) tWq = tWo;
+  else if ((rc = get_tmap(a->w_qkv, H, 3 * H, 64, 3 * H, &tWq))) return rc;
+  auto kern = fused_layer_fwd_kernel<H>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, layer_smem<H>());
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  kern<<<(M + FF_ROWS - 1) / FF_ROWS, FF_THREADS, layer_smem<H>(), st>>>(tCtx, tWo, tW1, tW2, tWq, *a);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+template <int H>
+static int launch_embed(const vitb200_embed_fwd_args* a, cudaStream_t st) {
+  const int M = a->B * (a->Np + 1);
+  CUtensorMap tWp, tWq;
+  int rc;
+  if ((rc = get_tmap(a->w_p, a->P, H, 64, H, &tWp))) return rc;
+  if ((rc = get_tmap(a->w_qkv, H, 3 * H, 64, 3 * H, &tWq))) return rc;
+  auto kern = fused_embed_fwd_kernel<H>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, embed_smem<H>());
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  kern<<<(M + FF_ROWS - 1) / FF_ROWS, FF_THREADS, embed_smem<H>(), st>>>(tWp, tWq, *a);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vitb200_fused_supported(int H, int P) {
+  return ((H == 32 || H == 64) && P % 8 == 0 && P >= 8 && P <= 64) ? 1 : 0;
+}
+
+extern "C" int vitb200_fused_layer_fwd(const vitb200_layer_fwd_args* a, void* stream) {
+  if (!a || !a->ctx || !a->z_in || !a->w_o || !a->w_1 || !a->w_2 || !a->hmid || !a->u2 || !a->a || !a->m || !a->z_out ||
+      !a->u_next || !a->mean2 || !a->rstd2 || !a->mean_n || !a->rstd_n)
+    return VITB200_ERR_ARG;
+  if (!a->last && (!a->w_qkv || !a->qkv_next || !a->b_qkv)) return VITB200_ERR_ARG;
+  if (a->B <= 0 || a->T <= 0) return VITB200_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->H == 32) return launch_layer<32>(a, st);
+  if (a->H == 64) return launch_layer<64>(a, st);
+  return VITB200_ERR_SHAPE;
+}
+
+extern "C" int vitb200_fused_embed_fwd(const vitb200_embed_fwd_args* a, void* stream) {
+  if (!a || !a->x || !a->w_p || !a->b_p || !a->cls || !a->ln_g || !a->ln_b || !a->w_qkv || !a->b_qkv || !a->z0 || !a->u ||
+      !a->mean || !a->rstd || !a->qkv)
+    return VITB200_ERR_ARG;
+  if (a->B <= 0 || !vitb200_fused_supported(a->H, a->P)) return VITB200_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->H == 32) return launch_embed<32>(a, st);
+  return launch_embed<64>(a, st);
+}

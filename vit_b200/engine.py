@@ -9,7 +9,9 @@ Call sequence restated from the reference:
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
 from typing import Callable, List, Optional, Tuple
 
 import torch
@@ -90,6 +92,11 @@ class ViTEngine:
             fr = torch.outer(torch.arange(T, dtype=torch.float32), inv_freq)
             self.rope_cos = fr.cos().to(dev).contiguous()
             self.rope_sin = fr.sin().to(dev).contiguous()
+        # fused row-chain kernels (tcgen05 GEMM chains per 128-row tile): bf16, H in {32, 64}
+        self.fused = bool(self.dt == BF16 and Lh >= 1 and I == 4 * H
+                          and self.lib.vitb200_fused_supported(H, c.patch_size)
+                          and os.environ.get("VITB200_FUSED", "1") != "0")
+        self._keep = []  # ctypes argument structs referenced by the cached programs
         ws_bytes = self._ws_bytes()
         self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
         self._progs = {}
@@ -149,7 +156,67 @@ class ViTEngine:
         return self.stats[i].data_ptr()
 
     # ---- programs -----------------------------------------------------------------------------
+    def _build_forward_fused(self, train: bool, with_labels: bool) -> List[Tuple[Callable, tuple]]:
+        """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L."""
+        c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        B, T, H, Lh, M = self.B, c.tokens, c.hidden_size, c.num_hidden_layers, self.M
+        ph = float(c.hidden_dropout_prob) if train else 0.0
+        pa = float(c.attention_probs_dropout_prob) if train else 0.0
+        eps = float(c.layer_norm_eps)
+        rng = self.rng.data_ptr()
+        scale = 1.0 / math.sqrt(c.head_dim)
+        emb = "vit.embeddings."
+        L0 = "vit.encoder.layer.0."
+        ea = _lib.EmbedFwdArgs(
+            B=B, L=c.image_size, P=c.patch_size, S=c.stride, Np=c.num_patches, n_valid=c.n_valid, H=H, eps=eps,
+            p_drop=ph, rng=rng, x=P_(self.x), w_p=self._w(emb + "patch_embeddings.projection.weight"),
+            b_p=self._p(emb + "patch_embeddings.projection.bias"), cls=self._p(emb + "cls_token"),
+            pos=self._p(emb + "position_embeddings") if c.pos_encoding_type == "learned" else None,
+            ln_g=self._p(L0 + "layernorm_before.weight"), ln_b=self._p(L0 + "layernorm_before.bias"),
+            w_qkv=self._w(L0 + "attention.attention.query.weight"), b_qkv=self._p(L0 + "attention.attention.query.bias"),
+            z0=P_(self.z[0]), u=P_(self.u[0]), mean=self._stat(0), rstd=self._stat(1), qkv=P_(self.qkv[0]))
+        self._keep.append(ea)
+        prog = [(lib.vitb200_fused_embed_fwd, (ctypes.addressof(ea),))]
+        fin = 4 * max(Lh, 1)
+        for l in range(Lh):
+            pre = f"vit.encoder.layer.{l}."
+            last = l == Lh - 1
+            nxt = "" if last else f"vit.encoder.layer.{l + 1}."
+            qkv = self.qkv[l].data_ptr()
+            prog.append((lib.vitb200_attn_fwd, (
+                qkv, qkv + H * 2, qkv + 2 * H * 2, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
+                P_(self.rope_cos), P_(self.rope_sin), B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
+                site_attn(l), dt)))
+            la = _lib.LayerFwdArgs(
+                B=B, T=T, H=H, last=1 if last else 0, eps=eps, p_drop=ph, rng=rng, site_proj=site_proj(l),
+                site_mlp=site_mlp(l), ctx=P_(self.ctx[l]), z_in=P_(self.z[l]),
+                w_o=self._w(pre + "attention.output.dense.weight"), w_1=self._w(pre + "intermediate.dense.weight"),
+                w_2=self._w(pre + "output.dense.weight"),
+                w_qkv=None if last else self._w(nxt + "attention.attention.query.weight"),
+                b_o=self._p(pre + "attention.output.dense.bias"), ln2_g=self._p(pre + "layernorm_after.weight"),
+                ln2_b=self._p(pre + "layernorm_after.bias"), b_1=self._p(pre + "intermediate.dense.bias"),
+                b_2=self._p(pre + "output.dense.bias"),
+                lnn_g=self._p("vit.layernorm.weight" if last else nxt + "layernorm_before.weight"),
+                lnn_b=self._p("vit.layernorm.bias" if last else nxt + "layernorm_before.bias"),
+                b_qkv=None if last else self._p(nxt + "attention.attention.query.bias"),
+                hmid=P_(self.hmid[l]), u2=P_(self.u2[l]), mean2=self._stat(4 * l + 2), rstd2=self._stat(4 * l + 3),
+                a=P_(self.a[l]), m=P_(self.m[l]), z_out=P_(self.z[l + 1]),
+                u_next=P_(self.s_cls) if last else P_(self.u[l + 1]),
+                mean_n=self._stat(fin) if last else self._stat(4 * (l + 1)),
+                rstd_n=self._stat(fin + 1) if last else self._stat(4 * (l + 1) + 1),
+                qkv_next=None if last else P_(self.qkv[l + 1]))
+            self._keep.append(la)
+            prog.append((lib.vitb200_fused_layer_fwd, (ctypes.addressof(la),)))
+        hd = self.arena.layout.head_name
+        prog.append((lib.vitb200_head_loss_fwd, (
+            P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"),
+            P_(self.labels) if with_labels else None, P_(self.logits), P_(self.loss), B, H, c.num_labels,
+            self.loss_kind, dt)))
+        return prog
+
     def _build_forward(self, train: bool, with_labels: bool) -> List[Tuple[Callable, tuple]]:
+        if self.fused:
+            return self._build_forward_fused(train, with_labels)
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
         ph = float(c.hidden_dropout_prob) if train else 0.0
@@ -424,9 +491,19 @@ class ViTEngine:
         return out
 
     def kernel_launches(self, train: bool = True) -> int:
-        """Kernel launches of one fwd+bwd+update step (for bench.py's gpu_launches)."""
-        c = self.cfg
-        L = c.num_hidden_layers
-        fwd = 2 + 7 * L + 2          # embed, LN, 7 per layer, logits + loss
-        bwd = 2 + 1 + L * (4 + 4 + 2 + 2) + 2  # head (2), final LN, per layer, embed (prep + wgrad)
-        return fwd + bwd + 2
+        """Kernel launches of one fwd+bwd+update step (for bench.py's gpu_launches), counted from the programs."""
+        if ("fwd", train, True) not in self._progs:
+            self._progs[("fwd", train, True)] = self._build_forward(train, True)
+        if ("bwd", train, None) not in self._progs:
+            self._progs[("bwd", train, None)] = self._build_backward(train, None)
+        per_call = {"vitb200_head_loss_fwd": 2, "vitb200_head_loss_bwd": 2, "vitb200_attn_bwd": 2,
+                    "vitb200_patch_embed_bwd": 2}
+        n = 2  # grad_norm + adamw
+        for key in (("fwd", train, True), ("bwd", train, None)):
+            for fn, args in self._progs[key]:
+                k = per_call.get(fn.__name__, 1)
+                if fn.__name__ == "vitb200_linear_wgrad" and self.dt == BF16 and \
+                        self.lib.vitb200_tc_supported(args[4], args[5], args[6]):
+                    k = 2  # column-sum (bias gradient) kernel + tensor-core wgrad
+                n += k
+        return n
