@@ -185,6 +185,48 @@ int vitb200_fused_supported(int H, int P);
 int vitb200_fused_embed_fwd(const vitb200_embed_fwd_args* args, void* stream);
 int vitb200_fused_layer_fwd(const vitb200_layer_fwd_args* args, void* stream);
 
+/* Fused backward (bf16, H = 32): autograd of the layer kernel above, split around attention backward.
+ *   upper : dz (grad of the layer output) -> MLP-down dgrad/wgrad -> gelu' -> MLP-up dgrad/wgrad -> LN2 backward
+ *           (+ residual) -> dh ; out-proj dgrad/wgrad -> dctx
+ *   lower : dqkv (from attention backward) -> QKV dgrad/wgrad -> LN1 backward (+ dh) -> dz of the layer input
+ * Persistent CTAs (grid = vitb200_fused_bwd_grid(M)) loop over 128-row tiles; dgrad and wgrad both run on tcgen05
+ * from the SAME shared-memory tiles (K-major view for dgrad, MN-major view for wgrad), weight gradients accumulate
+ * in TMEM across tiles, bias / LayerNorm gradients in registers.  Each CTA writes ONE partial gradient set to
+ * gpart[cta][n_opt] (same offsets as the gradient arena); vitb200_grad_reduce sums the CTA partials in CTA order
+ * (deterministic) into the gradient arena. */
+typedef struct {
+  int B, T, H;
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site_proj, site_mlp;
+  const float* dz;                   /* [B*T, H] f32 */
+  const void *m, *a, *u2, *ctx;      /* saved activations (bf16) */
+  const float *hmid, *mean2, *rstd2, *ln2_g;
+  const void *w_2, *w_1, *w_o;       /* bf16 [H,4H], [4H,H], [H,H] */
+  float* dh;                         /* [B*T, H] f32 out */
+  void* dctx;                        /* [B*T, H] bf16 out */
+  float* gpart;
+  int n_opt, off_w2, off_b2, off_w1, off_b1, off_ln2g, off_ln2b, off_wo, off_bo;
+} vitb200_layer_bwd_upper_args;
+
+typedef struct {
+  int B, T, H;
+  const void *dqkv, *u;              /* [B*T, 3H], [B*T, H] bf16 */
+  const float *z, *mean1, *rstd1, *ln1_g, *dh;
+  const void* w_qkv;                 /* bf16 [3H, H] */
+  float* dz;                         /* [B*T, H] f32 out: grad of the layer input */
+  float* gpart;
+  int n_opt, off_wqkv, off_bqkv, off_ln1g, off_ln1b;
+} vitb200_layer_bwd_lower_args;
+
+int vitb200_fused_bwd_supported(int H);
+int vitb200_fused_bwd_grid(int M);
+int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args* args, void* stream);
+int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args* args, void* stream);
+/* grad[i] = sum_{s < slots} gpart[s*stride + i] for i in [start, end), slots summed in order. */
+int vitb200_grad_reduce(const float* gpart, int slots, size_t stride, size_t start, size_t end, float* grad,
+                        void* stream);
+
 /* ---- multi-head self-attention ----------------------------------------------------------------
  * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and
  * ViTSelfAttentionWithRoPE.forward (src/models/vit_with_rope.py:43-84; RoPE = src/models/rope.py:60-98):

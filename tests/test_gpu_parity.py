@@ -309,3 +309,20 @@ def test_loss_curve_1000_steps(precision):
     worst = float(((a - b).abs() / b.abs()).max())
     assert worst < 0.01, f"loss curve deviates {worst:.4f} (> 1%)"
     assert float(b[-1]) < float(b[0]), "the oracle run itself must be learning"
+
+
+def test_fused_paths_are_the_ones_tested(golden):
+    """bf16 + H=32 must run the fused tcgen05 row-chain kernels (forward and backward); fp32 must not."""
+    dev = _cuda()
+    fix = golden("baseline")
+    eng = _build(fix, "bf16-mixed", dev)._engine(fix["batch"])
+    assert eng.fused and eng.fused_bwd
+    names = [fn.__name__ for fn, _ in eng._build_forward(True, True)]
+    assert names.count("vitb200_fused_layer_fwd") == 3 and names[0] == "vitb200_fused_embed_fwd"
+    names = [fn.__name__ for fn, _ in eng._build_backward(True, None)]
+    assert names.count("vitb200_fused_layer_bwd_upper") == 3 and names.count("vitb200_fused_layer_bwd_lower") == 3
+    assert names[-1] == "vitb200_grad_reduce"
+    eng64 = _build(golden("h64multi"), "bf16-mixed", dev)._engine(3)
+    assert eng64.fused and not eng64.fused_bwd       # H=64: fused forward, unfused (tcgen05 GEMM) backward
+    eng32 = _build(fix, "32", dev)._engine(fix["batch"])
+    assert not eng32.fused and not eng32.fused_bwd   # fp32 mode: SIMT fp32 kernels (1e-4 parity bar)

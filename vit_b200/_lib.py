@@ -46,6 +46,19 @@ class LayerFwdArgs(C.Structure):  # vitb200_layer_fwd_args
                                   "lnn_g", "lnn_b", "b_qkv", "hmid", "u2", "mean2", "rstd2", "a", "m", "z_out", "u_next",
                                   "mean_n", "rstd_n", "qkv_next")]
 
+class LayerBwdUpperArgs(C.Structure):  # vitb200_layer_bwd_upper_args
+    _fields_ = [(n, _i) for n in ("B", "T", "H")] + [("p_drop", _f), ("rng", _p), ("site_proj", _u32), ("site_mlp", _u32)] + \
+               [(n, _p) for n in ("dz", "m", "a", "u2", "ctx", "hmid", "mean2", "rstd2", "ln2_g", "w_2", "w_1", "w_o", "dh",
+                                  "dctx", "gpart")] + \
+               [(n, _i) for n in ("n_opt", "off_w2", "off_b2", "off_w1", "off_b1", "off_ln2g", "off_ln2b", "off_wo", "off_bo")]
+
+
+class LayerBwdLowerArgs(C.Structure):  # vitb200_layer_bwd_lower_args
+    _fields_ = [(n, _i) for n in ("B", "T", "H")] + \
+               [(n, _p) for n in ("dqkv", "u", "z", "mean1", "rstd1", "ln1_g", "dh", "w_qkv", "dz", "gpart")] + \
+               [(n, _i) for n in ("n_opt", "off_wqkv", "off_bqkv", "off_ln1g", "off_ln1b")]
+
+
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
 SIGNATURES = {
     "vitb200_strerror": (C.c_char_p, [_i]),
@@ -71,6 +84,11 @@ SIGNATURES = {
     "vitb200_fused_supported": (_i, [_i, _i]),
     "vitb200_fused_embed_fwd": (_i, [_p, _p]),
     "vitb200_fused_layer_fwd": (_i, [_p, _p]),
+    "vitb200_fused_bwd_supported": (_i, [_i]),
+    "vitb200_fused_bwd_grid": (_i, [_i]),
+    "vitb200_fused_layer_bwd_upper": (_i, [_p, _p]),
+    "vitb200_fused_layer_bwd_lower": (_i, [_p, _p]),
+    "vitb200_grad_reduce": (_i, [_p, _i, _sz, _sz, _sz, _p, _p]),
     "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

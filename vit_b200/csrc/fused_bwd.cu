@@ -1,0 +1,556 @@
+// Fused backward row-chain kernels (bf16 mode, H = 32).  See include/vit_b200.h.
+//
+// One CTA = 128 threads, thread t owns row t of the current 128-row tile and TMEM lane t.
+// Every activation-gradient tile (ddelta2, da, ddelta1, dqkv) is written/loaded ONCE into shared memory in
+// the 128B-swizzled row image and then consumed twice by tcgen05.mma:
+//   dgrad  dX = dY . W      : the tile is operand A, K-major view   (contraction over its columns)
+//   wgrad  dW = dY^T . X    : the tile is operand A, MN-major view  (contraction over its 128 rows)
+// wgrad accumulators stay in TMEM across the tiles of a persistent CTA and are written out once.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace vb {
+using namespace vb::tc;
+
+constexpr int FB_THREADS = 128;
+constexpr int FB_H = 32;
+constexpr int FB_I = 128;
+
+__device__ __forceinline__ uint4 fb_pack8(const float* v) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+  pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+  return pk;
+}
+__device__ __forceinline__ void fb_swz_store(uint8_t* tile, int r, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = v;
+}
+// sum over the 128 rows of column `col` of a swizzled bf16 tile (rows in order => deterministic)
+__device__ __forceinline__ float fb_colsum(const uint8_t* tile, int col) {
+  const uint8_t* blk = tile + (col >> 6) * 16384;
+  const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
+  float s = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 128; ++r) {
+    const bf16 v = *reinterpret_cast<const bf16*>(blk + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+    s += __bfloat162float(v);
+  }
+  return s;
+}
+
+// operand view for one tcgen05 GEMM
+struct Opnd {
+  uint32_t addr;   // shared address of the tile
+  uint32_t lbo;    // MN-major: byte stride between 64-wide MN groups; K-major: ignored (16)
+  uint32_t kblk;   // K-major: byte stride between 64-wide k-blocks
+  int mn;          // 1 = MN-major view (k = tile rows), 0 = K-major view (k = tile columns)
+};
+__device__ __forceinline__ uint64_t opnd_desc(const Opnd& o, int k) {
+  if (o.mn) return make_sdesc_sw128(o.addr + k * 2048, o.lbo, 1024);
+  return make_sdesc_sw128(o.addr + (k >> 2) * o.kblk + (k & 3) * 32, 16, 1024);
+}
+// D[128, N] (+)= A * B over `ksteps` k-steps of 16
+__device__ __forceinline__ void fb_issue(uint32_t tmem_d, const Opnd& A, const Opnd& B, int N, int ksteps, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(128, N, A.mn, B.mn);
+  for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, opnd_desc(A, k), opnd_desc(B, k), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+
+// ================================================================================================
+// upper: dz -> [W2 dgrad/wgrad] -> gelu' -> [W1 dgrad/wgrad] -> LN2 bwd -> dh ; [Wo dgrad/wgrad] -> dctx
+// ================================================================================================
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmU2,
+                       const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmW2,
+                       const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWo,
+                       const vitb200_layer_bwd_upper_args P) {
+  constexpr int H = FB_H, I = FB_I;
+  // shared memory map (all tile bases 1024-aligned); sD must be directly followed by sDA (see wgrad A views)
+  constexpr uint32_t O_D = 0, O_DA = 16384, O_M = O_DA + 32768, O_U2 = O_M + 32768, O_CTX = O_U2 + 16384,
+                     O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_BAR = O_WO + 4096;
+  // TMEM columns
+  constexpr uint32_t C_W2 = 0, C_W1 = 128, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t *sD = base + O_D, *sDA = base + O_DA, *sM = base + O_M, *sU2 = base + O_U2, *sCtx = base + O_CTX;
+  uint8_t *sW2 = base + O_W2, *sW1 = base + O_W1, *sWo = base + O_WO;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
+  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = P.B * P.T;
+  const int ntiles = (M + 127) / 128;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmU2); tma_prefetch_desc(&tmCtx);
+    tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWo);
+    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  // columns 32..63 of the sD tile are never written by the epilogues: zero them once (MN-major wgrad view reads them)
+#pragma unroll
+  for (int c = 4; c < 8; ++c) fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_expect_tx(b_w, 8192 + 16384 + 4096);
+    tma_load_2d(sW2, &tmW2, b_w, 0, 0);          // W2 [H rows, I cols]: two {64 cols, H rows} boxes
+    tma_load_2d(sW2 + 4096, &tmW2, b_w, 64, 0);
+    tma_load_2d(sW1, &tmW1, b_w, 0, 0);          // W1 [I rows, H cols]: one {64 cols (32 valid), 128 rows} box
+    tma_load_2d(sWo, &tmWo, b_w, 0, 0);          // Wo [H rows, H cols]
+  }
+  const uint32_t aD = smem_u32(sD), aDA = smem_u32(sDA), aM = smem_u32(sM), aU2 = smem_u32(sU2), aCtx = smem_u32(sCtx);
+  const uint32_t aW2 = smem_u32(sW2), aW1 = smem_u32(sW1), aWo = smem_u32(sWo);
+  // operand views
+  const Opnd D_k{aD, 16, 16384, 0};            // ddelta tile, K-major (K = H)
+  const Opnd D_mn{aD, 16384, 0, 1};            // ddelta tile, MN-major; MN group 1 aliases sDA: rows 64..127 of the
+                                               // product are never read (only H = 32 weight rows exist)
+  const Opnd DA_k{aDA, 16, 16384, 0};          // da tile, K-major (K = I, two k-blocks)
+  const Opnd DA_mn{aDA, 16384, 0, 1};          // da tile, MN-major (MN = I = 2 groups)
+  const Opnd M_mn{aM, 16384, 0, 1}, U2_mn{aU2, 16384, 0, 1}, CTX_mn{aCtx, 16384, 0, 1};
+  const Opnd W2_mn{aW2, 4096, 0, 1};           // B(n = i, k = h): N = I (2 groups of 64), K = H rows
+  const Opnd W1_mn{aW1, 16384, 0, 1};          // B(n = h, k = i): N = H, K = I rows
+  const Opnd WO_mn{aWo, 4096, 0, 1};           // B(n = k_out, k = n_in)
+
+  const uint64_t seed = P.rng ? P.rng[0] : 0ull;
+  const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
+  const DropCtx dc_mlp = make_drop(P.p_drop, seed, step, P.site_mlp);
+  const DropCtx dc_proj = make_drop(P.p_drop, seed, step, P.site_proj);
+
+  float acc_g[H], acc_b[H];  // LN2 gamma / beta gradients of this thread's rows
+#pragma unroll
+  for (int j = 0; j < H; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
+  float acc_b2 = 0.f, acc_b1 = 0.f, acc_bo = 0.f;  // bias gradients: thread j owns column j
+  uint32_t ph_mma = 0, ph_tile = 0;
+  int iter = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const int r0 = tile * 128, row = r0 + tid;
+    const bool valid = row < M;
+    const int rowc = valid ? row : M - 1;
+    if (tid == 0) {
+      mbar_expect_tx(b_tile, 32768 + 16384 + 16384);
+      tma_load_2d(sM, &tmM, b_tile, 0, r0);
+      tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
+      tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
+      tma_load_2d(sCtx, &tmCtx, b_tile, 0, r0);
+    }
+    // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
+    float dz[H];
+    {
+      const float4* p = reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) { float4 t = p[j]; dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w; }
+      float d2[H];
+#pragma unroll
+      for (int j = 0; j < H; j += 4) {
+        const float4 kp = drop4(dc_mlp, ((size_t)rowc * H + j) >> 2);
+        d2[j] = valid ? bf16_round(dz[j]) * kp.x : 0.f;         d2[j + 1] = valid ? bf16_round(dz[j + 1]) * kp.y : 0.f;
+        d2[j + 2] = valid ? bf16_round(dz[j + 2]) * kp.z : 0.f; d2[j + 3] = valid ? bf16_round(dz[j + 3]) * kp.w : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&d2[c * 8]));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (iter == 0) mbar_wait(b_w, 0);
+      mbar_wait(b_tile, ph_tile);
+      tc_fence_after();
+      fb_issue(tmem + C_DM, D_k, W2_mn, I, H / 16, false);        // dm[row, i]  = sum_h ddelta2[row,h] W2[h,i]
+      fb_issue(tmem + C_W2, D_mn, M_mn, I, 8, iter > 0);          // dW2[h, i]  += sum_rows ddelta2[row,h] m[row,i]
+      umma_commit(b_mma);
+    }
+    ph_tile ^= 1;
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    if (tid < H) acc_b2 += fb_colsum(sD, tid);
+    // ---- da = dm * gelu'(a) -> sDA ----
+#pragma unroll 1
+    for (int c0 = 0; c0 < I; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + C_DM + c0, v);
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.a) + (size_t)rowc * I + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 av = ap[q];
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(a2[e]);
+          o[2 * e] = valid ? bf16_round(v[q * 8 + 2 * e]) * gelu_grad_f(f.x) : 0.f;
+          o[2 * e + 1] = valid ? bf16_round(v[q * 8 + 2 * e + 1]) * gelu_grad_f(f.y) : 0.f;
+        }
+        fb_swz_store(sDA, tid, (c0 >> 3) + q, fb_pack8(o));
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      fb_issue(tmem + C_DU2, DA_k, W1_mn, H, I / 16, false);      // du2[row, h] = sum_i da[row,i] W1[i,h]
+      fb_issue(tmem + C_W1, DA_mn, U2_mn, H, 8, iter > 0);        // dW1[i, h]  += sum_rows da[row,i] u2[row,h]
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    acc_b1 += fb_colsum(sDA, tid);  // I = 128 columns = 128 threads
+    // ---- LayerNorm-after backward + residual -> dh ; ddelta1 = dropout'(dh) -> sD ----
+    {
+      float du[32];
+      tmem_ld_32x32(my_tmem + C_DU2, du);
+      const float mu = P.mean2[rowc], rs = P.rstd2[rowc];
+      float xh[H], g[H];
+      float s1 = 0.f, s2 = 0.f;
+      const float4* hp = reinterpret_cast<const float4*>(P.hmid + (size_t)rowc * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) {
+        const float4 t = hp[j];
+        xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const float d = valid ? bf16_round(du[j]) : 0.f;
+        acc_g[j] = fmaf(d, xh[j], acc_g[j]);
+        acc_b[j] += d;
+        g[j] = d * P.ln2_g[j];
+        s1 += g[j];
+        s2 = fmaf(g[j], xh[j], s2);
+      }
+      const float c1 = s1 * (1.f / H), c2 = s2 * (1.f / H);
+      float d1[H];
+#pragma unroll
+      for (int j = 0; j < H; ++j) dz[j] += rs * (g[j] - c1 - xh[j] * c2);  // dz now holds dh
+      if (valid) {
+        float4* op = reinterpret_cast<float4*>(P.dh + (size_t)row * H);
+#pragma unroll
+        for (int j = 0; j < H / 4; ++j) op[j] = make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]);
+      }
+#pragma unroll
+      for (int j = 0; j < H; j += 4) {
+        const float4 kp = drop4(dc_proj, ((size_t)rowc * H + j) >> 2);
+        d1[j] = valid ? bf16_round(dz[j]) * kp.x : 0.f;         d1[j + 1] = valid ? bf16_round(dz[j + 1]) * kp.y : 0.f;
+        d1[j + 2] = valid ? bf16_round(dz[j + 2]) * kp.z : 0.f; d1[j + 3] = valid ? bf16_round(dz[j + 3]) * kp.w : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&d1[c * 8]));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      fb_issue(tmem + C_DCTX, D_k, WO_mn, H, H / 16, false);      // dctx[row, k] = sum_n ddelta1[row,n] Wo[n,k]
+      fb_issue(tmem + C_WO, D_mn, CTX_mn, H, 8, iter > 0);        // dWo[n, k]  += sum_rows ddelta1[row,n] ctx[row,k]
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    if (tid < H) acc_bo += fb_colsum(sD, tid);
+    {
+      float v[32];
+      tmem_ld_32x32(my_tmem + C_DCTX, v);
+      if (valid) {
+        bf16* op = reinterpret_cast<bf16*>(P.dctx) + (size_t)row * H;
+#pragma unroll
+        for (int j = 0; j < H; j += 8) *reinterpret_cast<uint4*>(op + j) = fb_pack8(&v[j]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // all reads of sD / TMEM done before the next tile overwrites them
+  }
+
+  // ---- write this CTA's partial parameter gradients ----
+  float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
+  tc_fence_after();
+  if (iter > 0) {
+    if (warp == 0) {  // dW2 rows h = lanes 0..31, I columns
+#pragma unroll 1
+      for (int c0 = 0; c0 < I; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(my_tmem + C_W2 + c0, v);
+        float4* op = reinterpret_cast<float4*>(gp + P.off_w2 + (size_t)tid * I + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      float v[32];
+      tmem_ld_32x32(my_tmem + C_WO, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_wo + (size_t)tid * H);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    {  // dW1 rows i = lanes 0..127, H columns
+      float v[32];
+      tmem_ld_32x32(my_tmem + C_W1, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_w1 + (size_t)tid * H);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {  // a CTA without tiles contributes zeros
+    for (int e = tid; e < H * I; e += FB_THREADS) { gp[P.off_w2 + e] = 0.f; gp[P.off_w1 + e] = 0.f; }
+    for (int e = tid; e < H * H; e += FB_THREADS) gp[P.off_wo + e] = 0.f;
+  }
+  gp[P.off_b1 + tid] = acc_b1;
+  if (tid < H) { gp[P.off_b2 + tid] = acc_b2; gp[P.off_bo + tid] = acc_bo; }
+  // LN gamma/beta: reduce the per-thread sums over the 128 threads in thread order (scratch = sDA, 32 KB)
+  tc_fence_before();
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sDA);  // [2][H][128]
+#pragma unroll
+  for (int j = 0; j < H; ++j) { red[j * 128 + tid] = acc_g[j]; red[(H + j) * 128 + tid] = acc_b[j]; }
+  __syncthreads();
+  if (tid < 2 * H) {
+    float s = 0.f;
+    for (int t = 0; t < 128; ++t) s += red[tid * 128 + t];
+    if (tid < H) gp[P.off_ln2g + tid] = s; else gp[P.off_ln2b + tid - H] = s;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ================================================================================================
+// lower: dqkv -> [Wqkv dgrad/wgrad] -> LN1 bwd (+ dh) -> dz_in
+// ================================================================================================
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmU,
+                       const __grid_constant__ CUtensorMap tmWq, const vitb200_layer_bwd_lower_args P) {
+  constexpr int H = FB_H, Q = 3 * FB_H;
+  constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_BAR = O_WQ + 12288, O_RED = O_BAR + 1024;
+  constexpr uint32_t C_WQ = 0, C_DU = 32, TMEM_COLS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t *sDQ = base + O_DQ, *sU = base + O_U, *sWq = base + O_WQ;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
+  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* red = reinterpret_cast<float*>(base + O_RED);  // [2][H][128] floats = 32 KB
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = P.B * P.T;
+  const int ntiles = (M + 127) / 128;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmWq);
+    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  if (tid == 0) {
+    mbar_expect_tx(b_w, 12288);
+    tma_load_2d(sWq, &tmWq, b_w, 0, 0);  // Wqkv [3H rows, H cols]: {64 cols (32 valid), 96 rows}
+  }
+  const Opnd DQ_k{smem_u32(sDQ), 16, 16384, 0};        // dqkv tile, K-major (K = 3H = 96: 6 k-steps over 2 k-blocks)
+  const Opnd DQ_mn{smem_u32(sDQ), 16384, 0, 1};        // MN-major (MN = 96 of 128)
+  const Opnd U_mn{smem_u32(sU), 16384, 0, 1};
+  const Opnd WQ_mn{smem_u32(sWq), 16384, 0, 1};        // B(n = h, k = qkv row): N = H, K = 96 rows
+
+  float acc_g[H], acc_b[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
+  float acc_bq = 0.f;
+  uint32_t ph_mma = 0, ph_tile = 0;
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const int r0 = tile * 128, row = r0 + tid;
+    const bool valid = row < M;
+    const int rowc = valid ? row : M - 1;
+    if (tid == 0) {
+      mbar_expect_tx(b_tile, 32768 + 16384);
+      tma_load_2d(sDQ, &tmDQ, b_tile, 0, r0);
+      tma_load_2d(sDQ + 16384, &tmDQ, b_tile, 64, r0);
+      tma_load_2d(sU, &tmU, b_tile, 0, r0);
+      if (iter == 0) mbar_wait(b_w, 0);
+      mbar_wait(b_tile, ph_tile);
+      tc_fence_after();
+      fb_issue(tmem + C_DU, DQ_k, WQ_mn, H, Q / 16, false);      // du[row, h]   = sum_n dqkv[row,n] Wqkv[n,h]
+      fb_issue(tmem + C_WQ, DQ_mn, U_mn, H, 8, iter > 0);         // dWqkv[n, h] += sum_rows dqkv[row,n] u[row,h]
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-written dqkv tile below
+    ph_tile ^= 1;
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    if (tid < Q) acc_bq += fb_colsum(sDQ, tid);
+    {
+      float du[32];
+      tmem_ld_32x32(my_tmem + C_DU, du);
+      const float mu = P.mean1[rowc], rs = P.rstd1[rowc];
+      float xh[H], g[H], dz[H];
+      float s1 = 0.f, s2 = 0.f;
+      const float4* zp = reinterpret_cast<const float4*>(P.z + (size_t)rowc * H);
+      const float4* dp = reinterpret_cast<const float4*>(P.dh + (size_t)rowc * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) {
+        const float4 t = zp[j];
+        xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
+        const float4 d = dp[j];
+        dz[4 * j] = d.x; dz[4 * j + 1] = d.y; dz[4 * j + 2] = d.z; dz[4 * j + 3] = d.w;
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const float d = valid ? bf16_round(du[j]) : 0.f;
+        acc_g[j] = fmaf(d, xh[j], acc_g[j]);
+        acc_b[j] += d;
+        g[j] = d * P.ln1_g[j];
+        s1 += g[j];
+        s2 = fmaf(g[j], xh[j], s2);
+      }
+      const float c1 = s1 * (1.f / H), c2 = s2 * (1.f / H);
+      if (valid) {
+        float4* op = reinterpret_cast<float4*>(P.dz + (size_t)row * H);
+#pragma unroll
+        for (int j = 0; j < H / 4; ++j) {
+          float4 o;
+          o.x = dz[4 * j] + rs * (g[4 * j] - c1 - xh[4 * j] * c2);
+          o.y = dz[4 * j + 1] + rs * (g[4 * j + 1] - c1 - xh[4 * j + 1] * c2);
+          o.z = dz[4 * j + 2] + rs * (g[4 * j + 2] - c1 - xh[4 * j + 2] * c2);
+          o.w = dz[4 * j + 3] + rs * (g[4 * j + 3] - c1 - xh[4 * j + 3] * c2);
+          op[j] = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
+  tc_fence_after();
+  if (iter > 0) {
+    if (warp < 3) {  // dWqkv rows n = lanes 0..95
+      float v[32];
+      tmem_ld_32x32(my_tmem + C_WQ, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_wqkv + (size_t)tid * H);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+    for (int e = tid; e < Q * H; e += FB_THREADS) gp[P.off_wqkv + e] = 0.f;
+  }
+  if (tid < Q) gp[P.off_bqkv + tid] = acc_bq;
+#pragma unroll
+  for (int j = 0; j < H; ++j) { red[j * 128 + tid] = acc_g[j]; red[(H + j) * 128 + tid] = acc_b[j]; }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 2 * H) {
+    float s = 0.f;
+    for (int t = 0; t < 128; ++t) s += red[tid * 128 + t];
+    if (tid < H) gp[P.off_ln1g + tid] = s; else gp[P.off_ln1b + tid - H] = s;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// grad[i] = sum over slots (in slot order) of gpart[s*stride + i]
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, size_t start, size_t n4,
+                   float* __restrict__ grad) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4* src = reinterpret_cast<const float4*>(gpart + start) + i;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 4 <= slots; z += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t[q] = __ldcg(src + (size_t)(z + q) * (stride / 4));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+    }
+    for (; z < slots; ++z) {
+      const float4 t = __ldcg(src + (size_t)z * (stride / 4));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    reinterpret_cast<float4*>(grad + start)[i] = s;
+  }
+}
+
+constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 1024 + 1024;
+constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 1024 + 32768 + 1024;
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vitb200_fused_bwd_supported(int H) { return H == FB_H ? 1 : 0; }
+extern "C" int vitb200_fused_bwd_grid(int M) {
+  int tiles = (M + 127) / 128;
+  return tiles < 148 ? (tiles < 1 ? 1 : tiles) : 148;
+}
+
+extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args* a, void* stream) {
+  if (!a || !a->dz || !a->m || !a->a || !a->u2 || !a->ctx || !a->hmid || !a->mean2 || !a->rstd2 || !a->ln2_g ||
+      !a->w_2 || !a->w_1 || !a->w_o || !a->dh || !a->dctx || !a->gpart)
+    return VITB200_ERR_ARG;
+  if (a->H != FB_H) return VITB200_ERR_SHAPE;
+  if (a->B <= 0 || a->T <= 0) return VITB200_ERR_ARG;
+  const int M = a->B * a->T, H = FB_H, I = FB_I;
+  CUtensorMap tM, tU2, tCtx, tW2, tW1, tWo;
+  int rc;
+  if ((rc = get_tmap(a->m, I, M, 64, 128, &tM))) return rc;
+  if ((rc = get_tmap(a->u2, H, M, 64, 128, &tU2))) return rc;
+  if ((rc = get_tmap(a->ctx, H, M, 64, 128, &tCtx))) return rc;
+  if ((rc = get_tmap(a->w_2, I, H, 64, H, &tW2))) return rc;
+  if ((rc = get_tmap(a->w_1, H, I, 64, I, &tW1))) return rc;
+  if ((rc = get_tmap(a->w_o, H, H, 64, H, &tWo))) return rc;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(fused_bwd_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPPER_SMEM);
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  fused_bwd_upper_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, UPPER_SMEM, (cudaStream_t)stream>>>(tM, tU2, tCtx, tW2,
+                                                                                                    tW1, tWo, *a);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args* a, void* stream) {
+  if (!a || !a->dqkv || !a->u || !a->z || !a->mean1 || !a->rstd1 || !a->ln1_g || !a->dh || !a->w_qkv || !a->dz || !a->gpart)
+    return VITB200_ERR_ARG;
+  if (a->H != FB_H) return VITB200_ERR_SHAPE;
+  if (a->B <= 0 || a->T <= 0) return VITB200_ERR_ARG;
+  const int M = a->B * a->T, H = FB_H;
+  CUtensorMap tDQ, tU, tWq;
+  int rc;
+  if ((rc = get_tmap(a->dqkv, 3 * H, M, 64, 128, &tDQ))) return rc;
+  if ((rc = get_tmap(a->u, H, M, 64, 128, &tU))) return rc;
+  if ((rc = get_tmap(a->w_qkv, H, 3 * H, 64, 3 * H, &tWq))) return rc;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(fused_bwd_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOWER_SMEM);
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  fused_bwd_lower_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, LOWER_SMEM, (cudaStream_t)stream>>>(tDQ, tU, tWq, *a);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_grad_reduce(const float* gpart, int slots, size_t stride, size_t start, size_t end, float* grad,
+                                   void* stream) {
+  if (!gpart || !grad || slots <= 0 || end < start) return VITB200_ERR_ARG;
+  if ((stride | start | end) % 4 != 0) return VITB200_ERR_SHAPE;
+  if (end == start) return VITB200_OK;
+  const size_t n4 = (end - start) / 4;
+  size_t g = (n4 + 255) / 256;
+  if (g > 592) g = 592;
+  grad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(gpart, slots, stride, start, n4, grad);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}

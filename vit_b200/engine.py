@@ -96,6 +96,8 @@ class ViTEngine:
         self.fused = bool(self.dt == BF16 and Lh >= 1 and I == 4 * H
                           and self.lib.vitb200_fused_supported(H, c.patch_size)
                           and os.environ.get("VITB200_FUSED", "1") != "0")
+        self.fused_bwd = bool(self.fused and self.lib.vitb200_fused_bwd_supported(H)
+                              and os.environ.get("VITB200_FUSED_BWD", "1") != "0")
         self._keep = []  # ctypes argument structs referenced by the cached programs
         ws_bytes = self._ws_bytes()
         self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
@@ -284,8 +286,84 @@ class ViTEngine:
             self.loss_kind, dt)))
         return prog
 
+    def _build_backward_fused(self, train: bool, gloss_ptr: Optional[int], given: bool):
+        """head -> final LN -> [upper, attention bwd, lower] x L -> embed -> reduce of the per-CTA partials."""
+        self._alloc_backward()
+        c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        B, T, H, Lh, M = self.B, c.tokens, c.hidden_size, c.num_hidden_layers, self.M
+        ph = float(c.hidden_dropout_prob) if train else 0.0
+        pa = float(c.attention_probs_dropout_prob) if train else 0.0
+        rng = self.rng.data_ptr()
+        scale = 1.0 / math.sqrt(c.head_dim)
+        ws = self.ws.data_ptr()
+        lay = self.arena.layout
+        hd = lay.head_name
+        fin = 4 * max(Lh, 1)
+        G = int(lib.vitb200_fused_bwd_grid(M))
+        if not hasattr(self, "gpart"):
+            self.gpart = torch.zeros(G, lay.n_opt, dtype=torch.float32, device=self.device)  # padding stays zero
+        gp = self.gpart.data_ptr()
+        prog = []
+        if given:
+            if not hasattr(self, "dlogits"):
+                self.dlogits = torch.zeros(B, c.num_labels, dtype=torch.float32, device=self.device)
+            prog.append((lib.vitb200_head_loss_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.dlogits), None, P_(self.ds_cls),
+                self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels, _lib.LOSS_GIVEN, 0, dt)))
+        else:
+            prog.append((lib.vitb200_head_loss_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.labels), gloss_ptr,
+                P_(self.ds_cls), self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels,
+                self.loss_kind, 0, dt)))
+        cur, other = self.dzA, self.dzB
+        prog.append((lib.vitb200_add_ln_bwd, (
+            P_(self.ds_cls), P_(self.z[Lh]), self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"),
+            None, P_(cur), None, self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), M, H, T, 0.0,
+            rng, 0, 0, dt, ws)))
+        for l in range(Lh - 1, -1, -1):
+            pre = f"vit.encoder.layer.{l}."
+            qkv = self.qkv[l].data_ptr()
+            dqkv = self.dqkv.data_ptr()
+            ua = _lib.LayerBwdUpperArgs(
+                B=B, T=T, H=H, p_drop=ph, rng=rng, site_proj=site_proj(l), site_mlp=site_mlp(l), dz=P_(cur),
+                m=P_(self.m[l]), a=P_(self.a[l]), u2=P_(self.u2[l]), ctx=P_(self.ctx[l]), hmid=P_(self.hmid[l]),
+                mean2=self._stat(4 * l + 2), rstd2=self._stat(4 * l + 3), ln2_g=self._p(pre + "layernorm_after.weight"),
+                w_2=self._w(pre + "output.dense.weight"), w_1=self._w(pre + "intermediate.dense.weight"),
+                w_o=self._w(pre + "attention.output.dense.weight"), dh=P_(other), dctx=P_(self.dctx), gpart=gp,
+                n_opt=lay.n_opt, off_w2=lay.off(pre + "output.dense.weight"), off_b2=lay.off(pre + "output.dense.bias"),
+                off_w1=lay.off(pre + "intermediate.dense.weight"), off_b1=lay.off(pre + "intermediate.dense.bias"),
+                off_ln2g=lay.off(pre + "layernorm_after.weight"), off_ln2b=lay.off(pre + "layernorm_after.bias"),
+                off_wo=lay.off(pre + "attention.output.dense.weight"), off_bo=lay.off(pre + "attention.output.dense.bias"))
+            self._keep.append(ua)
+            prog.append((lib.vitb200_fused_layer_bwd_upper, (ctypes.addressof(ua),)))
+            prog.append((lib.vitb200_attn_bwd, (
+                qkv, qkv + H * 2, qkv + 2 * H * 2, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
+                P_(self.dsum), dqkv, dqkv + H * 2, dqkv + 2 * H * 2, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
+                B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), dt)))
+            la = _lib.LayerBwdLowerArgs(
+                B=B, T=T, H=H, dqkv=dqkv, u=P_(self.u[l]), z=P_(self.z[l]), mean1=self._stat(4 * l),
+                rstd1=self._stat(4 * l + 1), ln1_g=self._p(pre + "layernorm_before.weight"), dh=P_(other),
+                w_qkv=self._w(pre + "attention.attention.query.weight"), dz=P_(cur), gpart=gp, n_opt=lay.n_opt,
+                off_wqkv=lay.off(pre + "attention.attention.query.weight"),
+                off_bqkv=lay.off(pre + "attention.attention.query.bias"),
+                off_ln1g=lay.off(pre + "layernorm_before.weight"), off_ln1b=lay.off(pre + "layernorm_before.bias"))
+            self._keep.append(la)
+            prog.append((lib.vitb200_fused_layer_bwd_lower, (ctypes.addressof(la),)))
+        emb = "vit.embeddings."
+        dpos = self._g(emb + "position_embeddings") if c.pos_encoding_type == "learned" else None
+        prog.append((lib.vitb200_patch_embed_bwd, (
+            P_(cur), P_(self.x), self._g(emb + "patch_embeddings.projection.weight"),
+            self._g(emb + "patch_embeddings.projection.bias"), self._g(emb + "cls_token"), dpos, B, c.image_size,
+            c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, 0, dt, ws)))
+        start = lay.buckets[1][1]          # first encoder layer
+        end = lay.buckets[Lh][2]           # end of the last encoder layer
+        prog.append((lib.vitb200_grad_reduce, (gp, G, lay.n_opt, start, end, self.arena.grad.data_ptr())))
+        return prog
+
     def _build_backward(self, train: bool, gloss_ptr: Optional[int] = None,
                         given: bool = False) -> List[Tuple[Callable, tuple]]:
+        if self.fused_bwd:
+            return self._build_backward_fused(train, gloss_ptr, given)
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
