@@ -242,6 +242,18 @@ int vitb200_attn_bwd(const void* q, const void* k, const void* v, int ld, const 
                      const float* lse, float* dsum, void* dq, void* dk, void* dv, int ld_d, const float* rope_cos,
                      const float* rope_sin, int B, int T, int heads, int d, float scale, float p_drop,
                      const uint64_t* rng, uint32_t site, int dtype, void* stream);
+/* tcgen05 versions (bf16, head_dim 16 or 32, T <= 176 so that all keys of a (sample, head) fit one TMEM tile):
+ * S = Q K^T and O = P V (and dP, dQ, dK, dV in backward) run on the tensor cores with TMEM accumulators, Q/K/V tiles
+ * are TMA-loaded in place from the fused [B*T, 3H] QKV buffer (`qkv` = q pointer; k, v at +H, +2H; ld = 3H), softmax
+ * is done in registers.  vitb200_attn_fwd / _bwd above choose them automatically when the layout allows. */
+int vitb200_set_attn_mode(int mode); /* 0 = automatic, 1 = SIMT only (A/B tests); returns the old mode */
+int vitb200_attn_tc_supported(int T, int d, int ld, int H);
+int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin, int B,
+                        int T, int heads, int d, float scale, float p_drop, const uint64_t* rng, uint32_t site,
+                        void* stream);
+int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                        const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d, float scale,
+                        float p_drop, const uint64_t* rng, uint32_t site, void* stream);
 /* probs[B,heads,T,T] f32 = softmax probabilities before dropout (what the eager / RoPE attention returns
  * as `attention_probs`, src/models/vit_with_rope.py:84); for hooks / output_attentions only. */
 int vitb200_attn_probs(const void* q, const void* k, int ld, const float* lse, float* probs, const float* rope_cos,

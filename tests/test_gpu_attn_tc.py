@@ -1,0 +1,91 @@
+"""GPU: tcgen05 attention kernels (csrc/attention_tc.cu) vs. the SIMT kernels (same C-ABI entry point, mode
+switched) and vs. a plain fp32 torch attention built from the same bf16 inputs and the same dropout mask."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, scale, mask, p):
+    s = torch.matmul(q, k.transpose(-1, -2)) * scale
+    pr = torch.softmax(s, dim=-1)
+    prd = pr * mask / (1 - p) if p > 0 else pr
+    return torch.matmul(prd, v)
+
+
+@pytest.mark.parametrize("rope", [False, True])
+@pytest.mark.parametrize("B,T,heads,d,p", [(3, 129, 2, 16, 0.1), (2, 33, 4, 16, 0.0), (2, 160, 2, 32, 0.1),
+                                            (5, 128, 2, 16, 0.1), (1, 130, 1, 32, 0.0)])
+def test_attn_tc_matches_simt_and_torch(B, T, heads, d, p, rope):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vit_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    H = heads * d
+    assert lib.vitb200_attn_tc_supported(T, d, 3 * H, H) == 1
+    g = torch.Generator(device="cpu").manual_seed(T * 7 + d)
+    qkv = torch.randn(B * T, 3 * H, generator=g).to(dev).bfloat16()
+    dctx = torch.randn(B * T, H, generator=g).to(dev).bfloat16()
+    rng = torch.tensor([1234, 5], dtype=torch.int64, device=dev)
+    cos = sin = None
+    if rope:
+        inv = 1.0 / (10000.0 ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+        fr = torch.outer(torch.arange(T, dtype=torch.float32), inv)
+        cos, sin = fr.cos().to(dev).contiguous(), fr.sin().to(dev).contiguous()
+    scale = 1.0 / math.sqrt(d)
+    st = torch.cuda.current_stream().cuda_stream
+    P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    es = 2
+
+    def run(mode):
+        old = lib.vitb200_set_attn_mode(mode)
+        try:
+            ctx = torch.full((B * T, H), float("nan"), device=dev, dtype=torch.bfloat16)
+            lse = torch.zeros(B, heads, T, device=dev)
+            dsum = torch.zeros(B, heads, T, device=dev)
+            dq = torch.full((B * T, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+            q = qkv.data_ptr()
+            _lib.check(lib.vitb200_attn_fwd(q, q + H * es, q + 2 * H * es, 3 * H, ctx.data_ptr(), lse.data_ptr(), P(cos),
+                                            P(sin), B, T, heads, d, scale, p, rng.data_ptr(), 4, _lib.BF16, st), "fwd")
+            dqp = dq.data_ptr()
+            _lib.check(lib.vitb200_attn_bwd(q, q + H * es, q + 2 * H * es, 3 * H, ctx.data_ptr(), dctx.data_ptr(),
+                                            lse.data_ptr(), dsum.data_ptr(), dqp, dqp + H * es, dqp + 2 * H * es, 3 * H,
+                                            P(cos), P(sin), B, T, heads, d, scale, p, rng.data_ptr(), 4, _lib.BF16, st), "bwd")
+            torch.cuda.synchronize()
+            return ctx.float(), lse, dq.float()
+        finally:
+            lib.vitb200_set_attn_mode(old)
+
+    ctx_tc, lse_tc, dq_tc = run(0)
+    ctx_tc2, _, dq_tc2 = run(0)
+    assert torch.equal(ctx_tc, ctx_tc2) and torch.equal(dq_tc, dq_tc2), "tcgen05 attention must be deterministic"
+    ctx_s, lse_s, dq_s = run(1)
+    assert rel_err(ctx_tc, ctx_s) < 2e-2 and rel_err(lse_tc, lse_s) < 1e-3 and rel_err(dq_tc, dq_s) < 3e-2
+    # fp32 torch reference with the kernels' own dropout mask
+    Tpad = (T + 3) // 4 * 4
+    mask = torch.ones(B, heads, T, T, device=dev)
+    if p > 0:
+        m = torch.empty(B * heads * T * Tpad, dtype=torch.uint8, device=dev)
+        _lib.check(lib.vitb200_dropout_mask(m.data_ptr(), m.numel(), p, rng.data_ptr(), 4, st), "mask")
+        mask = m.view(B, heads, T, Tpad)[..., :T].float()
+    x = qkv.float().view(B, T, 3, heads, d).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    q_, k_, v_ = x[0], x[1], x[2]
+    if rope:
+        def rot(t):
+            t1, t2 = t.chunk(2, dim=-1)
+            c = torch.cat([cos, cos], -1)[None, None]
+            s = torch.cat([sin, sin], -1)[None, None]
+            return t * c + torch.cat([-t2, t1], -1) * s
+        q_, k_ = rot(q_), rot(k_)
+    out = _ref(q_, k_, v_, scale, mask, p)                                  # [B, heads, T, d]
+    out.backward(dctx.float().view(B, T, heads, d).permute(0, 2, 1, 3))
+    ref_ctx = out.permute(0, 2, 1, 3).reshape(B * T, H)
+    ref_dqkv = x.grad.permute(1, 3, 0, 2, 4).reshape(B * T, 3 * H)
+    assert rel_err(ctx_tc, ref_ctx) < 2e-2
+    assert rel_err(dq_tc, ref_dqkv) < 3e-2

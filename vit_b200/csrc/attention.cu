@@ -410,6 +410,24 @@ static int attn_dispatch(int which, const void* q, const void* k, const void* v,
 
 using namespace vb;
 
+extern "C" int vitb200_attn_tc_supported(int T, int d, int ld, int H);
+extern "C" int vitb200_attn_tc_fwd(const void*, void*, float*, const float*, const float*, int, int, int, int, float, float,
+                                   const uint64_t*, uint32_t, void*);
+extern "C" int vitb200_attn_tc_bwd(const void*, const void*, const void*, const float*, void*, const float*, const float*,
+                                   int, int, int, int, float, float, const uint64_t*, uint32_t, void*);
+// 0 = automatic (tcgen05 kernels when q/k/v are the column blocks of one fused bf16 QKV buffer), 1 = SIMT only
+static int g_attn_mode = 0;
+extern "C" int vitb200_set_attn_mode(int mode) {
+  int old = g_attn_mode;
+  if (mode == 0 || mode == 1) g_attn_mode = mode;
+  return old;
+}
+static inline bool fused_qkv(const void* q, const void* k, const void* v, int ld, int heads, int d) {
+  const int H = heads * d;
+  return ld == 3 * H && (const char*)k == (const char*)q + (size_t)H * 2 && (const char*)v == (const char*)q + (size_t)H * 4 &&
+         (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+}
+
 static int attn_check(int ld, int B, int Tlen, int heads, int d) {
   if (B < 0 || Tlen <= 0 || heads <= 0 || d <= 0) return VITB200_ERR_ARG;
   if (!(d == 8 || d == 16 || d == 32 || d == 64 || d == 128)) return VITB200_ERR_SHAPE;
@@ -426,6 +444,9 @@ extern "C" int vitb200_attn_fwd(const void* q, const void* k, const void* v, int
   if (rc) return rc;
   if (!q || !k || !v || !ctx || !lse || ((rope_cos == nullptr) != (rope_sin == nullptr))) return VITB200_ERR_ARG;
   if (B == 0) return VITB200_OK;
+  if (dtype == VITB200_BF16 && g_attn_mode == 0 && fused_qkv(q, k, v, ld, heads, d) &&
+      vitb200_attn_tc_supported(T, d, ld, heads * d) && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0)
+    return vitb200_attn_tc_fwd(q, ctx, lse, rope_cos, rope_sin, B, T, heads, d, scale, p_drop, rng, site, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32)
     return attn_dispatch<float>(0, q, k, v, ld, nullptr, nullptr, ctx, lse, nullptr, nullptr, nullptr, nullptr, 0,
@@ -447,6 +468,10 @@ extern "C" int vitb200_attn_bwd(const void* q, const void* k, const void* v, int
   if (!q || !k || !v || !ctx || !dctx || !lse || !dsum || !dq || !dk || !dv) return VITB200_ERR_ARG;
   if ((rope_cos == nullptr) != (rope_sin == nullptr)) return VITB200_ERR_ARG;
   if (B == 0) return VITB200_OK;
+  if (dtype == VITB200_BF16 && g_attn_mode == 0 && fused_qkv(q, k, v, ld, heads, d) && ld_d == ld &&
+      fused_qkv(dq, dk, dv, ld_d, heads, d) && vitb200_attn_tc_supported(T, d, ld, heads * d) &&
+      ((reinterpret_cast<uintptr_t>(ctx) | reinterpret_cast<uintptr_t>(dctx)) & 15) == 0)
+    return vitb200_attn_tc_bwd(q, ctx, dctx, lse, dq, rope_cos, rope_sin, B, T, heads, d, scale, p_drop, rng, site, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32)
     return attn_dispatch<float>(1, q, k, v, ld, ctx, dctx, nullptr, const_cast<float*>(lse), dsum, dq, dk, dv, ld_d,

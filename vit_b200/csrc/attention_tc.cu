@@ -1,0 +1,515 @@
+// Multi-head self-attention on tcgen05 for sequences whose keys fit one TMEM tile (T <= 176..208), bf16.
+//
+// One CTA (128 threads) per (sample, head).  Q/K/V tiles are TMA-loaded straight out of the fused
+// [B*T, 3H] QKV buffer (box = 64 columns starting at the head's column, so no head-major copy exists);
+// only the first d columns of each 128-byte row take part in the MMAs.
+//   forward : S = Q K^T (UMMA, fp32 in TMEM) -> softmax in registers (thread = query row; exp2 with the
+//             scale folded in; Philox dropout) -> P (bf16) to swizzled smem -> O = P V (UMMA, V as MN-major B)
+//   backward: S and dP = dO V^T by UMMA; thread = query row computes P, dS; dS and dropped P go to smem ONCE and
+//             are used as K-major A (dQ = dS K) and as MN-major A (dK = dS^T Q, dV = P^T dO), the latter
+//             accumulating in TMEM over the query tiles.  No atomics: results are bitwise reproducible.
+// Query tiles of 128 rows are looped inside the CTA (T = 129 -> 2 tiles, K/V staged once).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace vb {
+using namespace vb::tc;
+
+constexpr int AT_TC_THREADS = 128;
+constexpr float AT_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint4 at_pack8(const float* v) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+  pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+  return pk;
+}
+__device__ __forceinline__ void at_unpack8(uint4 pk, float* v) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(p[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+__device__ __forceinline__ uint8_t* at_swz(uint8_t* tile, int r, int chunk) {
+  return tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+}
+// row r (of a tile whose rows are 128 B) holds d values in chunks 0..d/8-1: load / store them
+template <int D>
+__device__ __forceinline__ void at_load_row(uint8_t* tile, int r, float (&x)[D]) {
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) at_unpack8(*reinterpret_cast<const uint4*>(at_swz(tile, r, c)), &x[c * 8]);
+}
+template <int D>
+__device__ __forceinline__ void at_store_row(uint8_t* tile, int r, const float (&x)[D]) {
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) *reinterpret_cast<uint4*>(at_swz(tile, r, c)) = at_pack8(&x[c * 8]);
+}
+// RoPE on a full head row held by one thread (rope.py:60-98); INV = transpose (for gradients)
+template <int D, bool INV>
+__device__ __forceinline__ void at_rope(float (&x)[D], const float* __restrict__ cosT, const float* __restrict__ sinT, int t) {
+#pragma unroll
+  for (int c = 0; c < D / 2; ++c) {
+    const float cs = cosT[(size_t)t * (D / 2) + c];
+    float sn = sinT[(size_t)t * (D / 2) + c];
+    if (INV) sn = -sn;
+    const float lo = x[c], hi = x[c + D / 2];
+    x[c] = lo * cs - hi * sn;
+    x[c + D / 2] = hi * cs + lo * sn;
+  }
+}
+
+struct AOp { uint32_t addr, lbo, kblk; int mn; };
+__device__ __forceinline__ uint64_t aop_desc(const AOp& o, int k) {
+  if (o.mn) return make_sdesc_sw128(o.addr + k * 2048, o.lbo, 1024);
+  return make_sdesc_sw128(o.addr + (k >> 2) * o.kblk + (k & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ void at_issue(uint32_t tmem_d, const AOp& A, const AOp& B, int N, int ksteps, bool acc) {
+  const uint32_t idesc = make_idesc_bf16(128, N, A.mn, B.mn);
+  for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, aop_desc(A, k), aop_desc(B, k), idesc, (acc || k > 0) ? 1u : 0u);
+}
+
+struct AttnTcParams {
+  const bf16* qkv;       // q pointer (k = q + H, v = q + 2H inside the same rows)
+  bf16* ctx; float* lse;
+  const bf16* dctx; bf16* dqkv; int ld_d;
+  const float* cosT; const float* sinT;
+  int B, T, heads, H, ld, KP;   // KP = keys padded to a multiple of 16
+  float scale, p_drop; const uint64_t* rng; uint32_t site;
+};
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int D>
+__global__ void __launch_bounds__(AT_TC_THREADS, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int KP = P.KP, nblk = (KP + 63) / 64, KW = nblk * 64;
+  const uint32_t kv_bytes = (uint32_t)KP * 128;
+  uint8_t* sQ = base;                       // 16 KB
+  uint8_t* sK = sQ + 16384;                 // 32 KB reserved
+  uint8_t* sV = sK + 32768;                 // 32 KB reserved
+  uint8_t* sP = sV + 32768;                 // nblk x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * 16384);
+  uint64_t *b_kv = bars, *b_q = bars + 1, *b_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  constexpr uint32_t TMEM_COLS = 512;
+  const uint32_t cS = 0, cO = 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y, T = P.T;
+  const int row0 = b * T;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
+    mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  if (tid == 0) {
+    mbar_expect_tx(b_kv, 2 * kv_bytes);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+  }
+  const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Kk{smem_u32(sK), 16, 16384, 0};
+  const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV), 16384, 0, 1};
+  const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
+  const int Tpad = (T + 3) & ~3;
+  const float sl2 = P.scale * AT_LOG2E;
+  uint32_t ph_q = 0, ph_mma = 0;
+  const int nq = (T + 127) / 128;
+
+  for (int qt = 0; qt < nq; ++qt) {
+    const int q0 = qt * 128, i = q0 + tid;
+    const bool valid = i < T;
+    if (tid == 0) {
+      mbar_expect_tx(b_q, 16384);
+      tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
+    }
+    if (qt == 0) mbar_wait(b_kv, 0);
+    mbar_wait(b_q, ph_q); ph_q ^= 1;
+    if (P.cosT) {  // rotate this thread's query row (and, once, its key rows) in place
+      float x[D];
+      at_load_row<D>(sQ, tid, x);
+      at_rope<D, false>(x, P.cosT, P.sinT, valid ? i : 0);
+      at_store_row<D>(sQ, tid, x);
+      if (qt == 0) {
+        for (int r = tid; r < KP; r += AT_TC_THREADS) {
+          at_load_row<D>(sK, r, x);
+          at_rope<D, false>(x, P.cosT, P.sinT, r < T ? r : 0);
+          at_store_row<D>(sK, r, x);
+        }
+      }
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      at_issue(tmem + cS, Qk, Kk, KP, D / 16, false);   // S[i, j] = q_i . k_j
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    // ---- softmax over the keys of this thread's row ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < KW; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + cS + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (c0 + j < T) mx = fmaxf(mx, v[j]);
+    }
+    const float mxs = mx * sl2;
+    float sum = 0.f;
+    const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + (valid ? i : 0)) * (uint64_t)Tpad;
+#pragma unroll 1
+    for (int c0 = 0; c0 < KW; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(my_tmem + cS + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float p4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          p4[q] = (c0 + j + q < T) ? exp2f(v[j + q] * sl2 - mxs) : 0.f;
+          sum += p4[q];
+        }
+        if (dc.on && c0 + j < T) {
+          const float4 kp = drop4(dc, (drow + (uint64_t)(c0 + j)) >> 2);
+          p4[0] *= kp.x; p4[1] *= kp.y; p4[2] *= kp.z; p4[3] *= kp.w;
+        }
+        v[j] = p4[0]; v[j + 1] = p4[1]; v[j + 2] = p4[2]; v[j + 3] = p4[3];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(at_swz(sP, tid, (c0 >> 3) + c)) = at_pack8(&v[c * 8]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      at_issue(tmem + cO, Pk, Vmn, D, KP / 16, false);  // O[i, c] = sum_j P[i, j] v[j, c]
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    {
+      float o[32];
+      tmem_ld_32x32(my_tmem + cO, o);  // D <= 32 columns are meaningful
+      if (valid) {
+        const float inv = 1.f / sum;
+        float r[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[c] = o[c] * inv;
+        bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&r[c]);
+        P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+template <int D>
+__global__ void __launch_bounds__(AT_TC_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmDO, const AttnTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int KP = P.KP, nblk = (KP + 63) / 64, KW = nblk * 64;
+  const uint32_t kv_bytes = (uint32_t)KP * 128;
+  uint8_t* sQ = base;                        // 16 KB
+  uint8_t* sDO = sQ + 16384;                 // 16 KB
+  uint8_t* sK = sDO + 16384;                 // 32 KB reserved
+  uint8_t* sV = sK + 32768;                  // 32 KB reserved
+  uint8_t* sDS = sV + 32768;                 // 4 x 16 KB reserved (nblk used; the MN view of key tile 1 may touch block 3)
+  uint8_t* sPT = sDS + 65536;                // 4 x 16 KB reserved
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPT + 65536);
+  uint64_t *b_kv = bars, *b_q = bars + 1, *b_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  constexpr uint32_t TMEM_COLS = 512;
+  // TMEM columns: S and dP take round_up(KP, 32) columns each (the 32-wide reads below may run past KP into the
+  // neighbouring region; those entries are masked), then dQ and the dK / dV accumulators of up to two key tiles
+  const uint32_t KPa = (uint32_t)((KP + 31) / 32 * 32);
+  const uint32_t cS = 0, cDP = KPa, cDQ = 2 * KPa, cDK0 = cDQ + 32, cDK1 = cDK0 + 32, cDV0 = cDK1 + 32, cDV1 = cDV0 + 32;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y, T = P.T;
+  const int row0 = b * T;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
+    mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  if (tid == 0) {
+    mbar_expect_tx(b_kv, 2 * kv_bytes);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+  }
+  const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Qmn{smem_u32(sQ), 16384, 0, 1};
+  const AOp DOk{smem_u32(sDO), 16, 16384, 0}, DOmn{smem_u32(sDO), 16384, 0, 1};
+  const AOp Kk{smem_u32(sK), 16, 16384, 0}, Kmn{smem_u32(sK), 16384, 0, 1}, Vk{smem_u32(sV), 16, 16384, 0};
+  const AOp DSk{smem_u32(sDS), 16, 16384, 0};
+  const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
+  const int Tpad = (T + 3) & ~3;
+  const float sl2 = P.scale * AT_LOG2E;
+  uint32_t ph_q = 0, ph_mma = 0;
+  const int nq = (T + 127) / 128;
+  const int nkt = (KP + 127) / 128;  // key tiles of the dK / dV accumulators (1 or 2)
+
+  for (int qt = 0; qt < nq; ++qt) {
+    const int q0 = qt * 128, i = q0 + tid;
+    const bool valid = i < T;
+    const int ic = valid ? i : T - 1;
+    if (tid == 0) {
+      mbar_expect_tx(b_q, 32768);
+      tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
+      tma_load_2d(sDO, &tmDO, b_q, h * D, row0 + q0);
+    }
+    if (qt == 0) mbar_wait(b_kv, 0);
+    mbar_wait(b_q, ph_q); ph_q ^= 1;
+    // rows of Q / dO beyond this sample must not leak into the dK / dV contractions: zero them
+    float dof[D];
+    if (!valid) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        *reinterpret_cast<uint4*>(at_swz(sQ, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(at_swz(sDO, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) dof[c] = 0.f;
+    } else {
+      at_load_row<D>(sDO, tid, dof);
+    }
+    if (P.cosT) {
+      float x[D];
+      if (valid) {
+        at_load_row<D>(sQ, tid, x);
+        at_rope<D, false>(x, P.cosT, P.sinT, i);
+        at_store_row<D>(sQ, tid, x);
+      }
+      if (qt == 0) {
+        for (int r = tid; r < KP; r += AT_TC_THREADS) {
+          at_load_row<D>(sK, r, x);
+          at_rope<D, false>(x, P.cosT, P.sinT, r < T ? r : 0);
+          at_store_row<D>(sK, r, x);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      at_issue(tmem + cS, Qk, Kk, KP, D / 16, false);    // S  = Q K^T
+      at_issue(tmem + cDP, DOk, Vk, KP, D / 16, false);  // dP = dO V^T
+      umma_commit(b_mma);
+    }
+    // D_i = dO_i . O_i (flash-attention backward's row statistic), lse_i
+    float Di = 0.f;
+    {
+      const bf16* op = P.ctx + (size_t)(row0 + ic) * P.H + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        float o8[8];
+        at_unpack8(*reinterpret_cast<const uint4*>(op + c), o8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Di = fmaf(dof[c + q], o8[q], Di);
+      }
+    }
+    const float lse2 = P.lse[(size_t)(b * P.heads + h) * T + ic] * AT_LOG2E;
+    const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + ic) * (uint64_t)Tpad;
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < KW; c0 += 32) {
+      float s[32], dp[32];
+      tmem_ld_32x32(my_tmem + cS + c0, s);
+      tmem_ld_32x32(my_tmem + cDP + c0, dp);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 kp = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (dc.on && c0 + j < T) kp = drop4(dc, (drow + (uint64_t)(c0 + j)) >> 2);
+        const float kpa[4] = {kp.x, kp.y, kp.z, kp.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool on = valid && (c0 + j + q < T);
+          const float p = on ? exp2f(s[j + q] * sl2 - lse2) : 0.f;
+          const float ds = p * (dp[j + q] * kpa[q] - Di) * P.scale;
+          s[j + q] = ds;               // dS (scale folded in)
+          dp[j + q] = p * kpa[q];      // dropped probabilities
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(at_swz(sDS, tid, (c0 >> 3) + c)) = at_pack8(&s[c * 8]);
+        *reinterpret_cast<uint4*>(at_swz(sPT, tid, (c0 >> 3) + c)) = at_pack8(&dp[c * 8]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      at_issue(tmem + cDQ, DSk, Kmn, D, KP / 16, false);                       // dQ[i,:]  = sum_j dS[i,j] k_j
+      for (int kt = 0; kt < nkt; ++kt) {
+        const AOp DSmn{smem_u32(sDS) + kt * 32768, 16384, 0, 1}, PTmn{smem_u32(sPT) + kt * 32768, 16384, 0, 1};
+        at_issue(tmem + (kt ? cDK1 : cDK0), DSmn, Qmn, D, 8, qt > 0);          // dK[j,:] += sum_i dS[i,j] q_i
+        at_issue(tmem + (kt ? cDV1 : cDV0), PTmn, DOmn, D, 8, qt > 0);         // dV[j,:] += sum_i P~[i,j] dO_i
+      }
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    {
+      float o[32];
+      tmem_ld_32x32(my_tmem + cDQ, o);
+      if (valid) {
+        float r[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[c] = o[c];
+        if (P.cosT) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) r[c] = bf16_round(r[c]);
+          at_rope<D, true>(r, P.cosT, P.sinT, i);
+        }
+        bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&r[c]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  // ---- dK, dV: thread = key row of key tile kt ----
+  tc_fence_after();
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int j = kt * 128 + tid;
+    float dk[32], dv[32];
+    tmem_ld_32x32(my_tmem + (kt ? cDK1 : cDK0), dk);
+    tmem_ld_32x32(my_tmem + (kt ? cDV1 : cDV0), dv);
+    if (j < T) {
+      float r[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) r[c] = dk[c];
+      if (P.cosT) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[c] = bf16_round(r[c]);
+        at_rope<D, true>(r, P.cosT, P.sinT, j);
+      }
+      bf16* dkp = P.dqkv + (size_t)(row0 + j) * P.ld_d + P.H + h * D;
+      bf16* dvp = P.dqkv + (size_t)(row0 + j) * P.ld_d + 2 * P.H + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        *reinterpret_cast<uint4*>(dkp + c) = at_pack8(&r[c]);
+        *reinterpret_cast<uint4*>(dvp + c) = at_pack8(&dv[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 1024;
+constexpr int AT_BWD_SMEM = 16384 + 16384 + 32768 + 32768 + 65536 + 65536 + 1024 + 1024;
+
+static inline int at_kp(int T) { return (T + 15) / 16 * 16; }
+
+}  // namespace vb
+
+using namespace vb;
+
+// q, k, v must be the three column blocks of one fused [B*T, 3H] bf16 buffer (k = q + H, v = q + 2H, ld = 3H)
+extern "C" int vitb200_attn_tc_supported(int T, int d, int ld, int H) {
+  if (!(d == 16 || d == 32)) return 0;
+  if (ld != 3 * H || (ld % 8) != 0) return 0;
+  const int KP = at_kp(T), KPa = (KP + 31) / 32 * 32;
+  if (KP > 256 || 2 * KPa + 32 * 5 > 512) return 0;  // TMEM columns of the backward kernel (T <= 176)
+  return 1;
+}
+
+extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin,
+                                   int B, int T, int heads, int d, float scale, float p_drop, const uint64_t* rng,
+                                   uint32_t site, void* stream) {
+  if (!qkv || !ctx || !lse || B <= 0 || T <= 0 || heads <= 0) return VITB200_ERR_ARG;
+  const int H = heads * d, ld = 3 * H;
+  if (!vitb200_attn_tc_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
+  const int M = B * T, KP = at_kp(T);
+  CUtensorMap tQ, tKV;
+  int rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
+  AttnTcParams P{(const bf16*)qkv, (bf16*)ctx, lse, nullptr, nullptr, 0, rope_cos, rope_sin, B, T, heads, H, ld, KP,
+                 scale, p_drop, rng, site};
+  dim3 grid(heads, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_F(DD)                                                                                             \
+  {                                                                                                              \
+    static bool done = false;                                                                                    \
+    if (!done) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM); \
+      if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
+      done = true;                                                                                               \
+    }                                                                                                            \
+    attn_tc_fwd_kernel<DD><<<grid, AT_TC_THREADS, AT_FWD_SMEM, st>>>(tQ, tKV, P);                                \
+  }
+  if (d == 16) LAUNCH_F(16) else LAUNCH_F(32)
+#undef LAUNCH_F
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                                   const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d,
+                                   float scale, float p_drop, const uint64_t* rng, uint32_t site, void* stream) {
+  if (!qkv || !ctx || !dctx || !lse || !dqkv || B <= 0 || T <= 0 || heads <= 0) return VITB200_ERR_ARG;
+  const int H = heads * d, ld = 3 * H;
+  if (!vitb200_attn_tc_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
+  const int M = B * T, KP = at_kp(T);
+  CUtensorMap tQ, tKV, tDO;
+  int rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
+  if ((rc = get_tmap(dctx, H, M, 64, 128, &tDO))) return rc;
+  AttnTcParams P{(const bf16*)qkv, (bf16*)const_cast<void*>(ctx), const_cast<float*>(lse), (const bf16*)dctx, (bf16*)dqkv,
+                 ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site};
+  dim3 grid(heads, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_B(DD)                                                                                             \
+  {                                                                                                              \
+    static bool done = false;                                                                                    \
+    if (!done) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BWD_SMEM); \
+      if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
+      done = true;                                                                                               \
+    }                                                                                                            \
+    attn_tc_bwd_kernel<DD><<<grid, AT_TC_THREADS, AT_BWD_SMEM, st>>>(tQ, tKV, tDO, P);                           \
+  }
+  if (d == 16) LAUNCH_B(16) else LAUNCH_B(32)
+#undef LAUNCH_B
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
