@@ -52,26 +52,41 @@ class TrainStep:
         eng.optimizer_step()
 
     def _backward_overlapped(self) -> None:
-        """Backward in bucket-sized segments; each bucket's all-reduce is issued as soon as its kernels are
-        enqueued so that NCCL runs under the remaining backward kernels."""
+        """Backward + gradient all-reduce (SUM; the 1/world mean is folded into the optimizer's grad_scale).
+
+        Unfused programs: backward runs in bucket-sized segments (head -> layer L-1 -> ... -> embeddings) and each
+        bucket's all-reduce is issued as soon as its kernels are enqueued, so NCCL overlaps the remaining kernels.
+        Fused programs: layer gradients only exist after the final partial-sum reduction kernel, and the last bucket is
+        on the critical path either way, so the whole optimised range goes out as ONE all-reduce (161 KB at the
+        configured shape: latency-bound, ~one NCCL launch)."""
         eng = self.eng
         key = ("bwd", self.train, None)
         if key not in eng._progs:
             eng._progs[key] = eng._build_backward(self.train, None)
             eng.launches[key] = len(eng._progs[key])
         prog = eng._progs[key]
+        st = torch.cuda.current_stream(eng.device).cuda_stream
+        from . import _lib
+
+        def run(seg):
+            for fn, args in seg:
+                rc = fn(*args, st)
+                if rc != 0:
+                    _lib.check(rc, fn.__name__)
+
+        if eng.fused_bwd:
+            run(prog)
+            w = _dp.allreduce_bucket(eng.arena.grad, 0, eng.arena.layout.n_opt, group=self.group, async_op=True)
+            if w is not None:
+                w.wait()
+            return
         L = eng.cfg.num_hidden_layers
         # program layout: [head_bwd, final_ln_bwd] + 11 calls per layer (L-1 .. 0) + [embed_bwd]
         cuts = [2] + [2 + 11 * (i + 1) for i in range(L)] + [len(prog)]
         buckets = _dp.backward_bucket_order(eng.arena.layout.buckets)
-        st = torch.cuda.current_stream(eng.device).cuda_stream
         works, lo = [], 0
-        from . import _lib
         for (name, s, e), hi in zip(buckets, cuts):
-            for fn, args in prog[lo:hi]:
-                rc = fn(*args, st)
-                if rc != 0:
-                    _lib.check(rc, fn.__name__)
+            run(prog[lo:hi])
             lo = hi
             works.append(_dp.allreduce_bucket(eng.arena.grad, s, e, group=self.group, async_op=True))
         for w in works:
@@ -104,7 +119,8 @@ class TrainStep:
         self._restore(snap)
         torch.cuda.synchronize(eng.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads (NCCL watchdog, data loaders) may touch CUDA while this thread captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._launch()
         self.graph = g
 
@@ -175,7 +191,7 @@ class EvalStep:
                 torch.cuda.current_stream(eng.device).wait_stream(side)
                 torch.cuda.synchronize(eng.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     eng.forward(train=False, with_labels=False)
                 self.graph = g
             self.graph.replay()
