@@ -70,6 +70,20 @@ __device__ __forceinline__ void at_issue(uint32_t tmem_d, const AOp& A, const AO
   for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, aop_desc(A, k), aop_desc(B, k), idesc, (acc || k > 0) ? 1u : 0u);
 }
 
+__device__ __forceinline__ void bar_main() { asm volatile("bar.sync 1, 128;" ::: "memory"); }     // the 4 MMA-path warps
+__device__ __forceinline__ void bar_all160() { asm volatile("bar.sync 2, 160;" ::: "memory"); }  // + the side-row warp
+__device__ __forceinline__ float warp_allsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_allmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+constexpr int AT_SIDE_KEYS = 6;  // keys per lane of the side-row warp: covers T <= 192
+
 struct AttnTcParams {
   const bf16* qkv;       // q pointer (k = q + H, v = q + 2H inside the same rows)
   bf16* ctx; float* lse;
@@ -83,7 +97,7 @@ struct AttnTcParams {
 // forward
 // ================================================================================================
 template <int D>
-__global__ void __launch_bounds__(AT_TC_THREADS, 1)
+__global__ void __launch_bounds__(160, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -125,8 +139,70 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int Tpad = (T + 3) & ~3;
   const float sl2 = P.scale * AT_LOG2E;
   uint32_t ph_q = 0, ph_mma = 0;
-  const int nq = (T + 127) / 128;
+  // T = 128 n + 1 (the CLS token makes every configured sequence one row longer than a tile): the last query row
+  // is handled by a 5th warp with plain FMAs, concurrently with the tensor-core tiles, instead of a whole extra tile.
+  const bool side = (T % 128 == 1) && T > 1 && P.cosT == nullptr;
+  const int nq = side ? T / 128 : (T + 127) / 128;
 
+  if (warp == 4) {
+    if (side) {
+      const int lane = tid & 31, i = T - 1;
+      mbar_wait(b_kv, 0);
+      float qf[D];
+      {
+        const bf16* qp = P.qkv + (size_t)(row0 + i) * P.ld + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) at_unpack8(*reinterpret_cast<const uint4*>(qp + c), &qf[c]);
+      }
+      float sc[AT_SIDE_KEYS];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
+        const int j = lane + 32 * jj;
+        float acc = -INFINITY;
+        if (j < T) {
+          float kr[D];
+          at_load_row<D>(sK, j, kr);
+          acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc = fmaf(qf[c], kr[c], acc);
+        }
+        sc[jj] = acc;
+        mx = fmaxf(mx, acc);
+      }
+      mx = warp_allmax(mx);
+      const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + i) * (uint64_t)Tpad;
+      float sum = 0.f, o[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < T) {
+          float p = exp2f((sc[jj] - mx) * sl2);
+          sum += p;
+          p *= drop1(dc, drow + (uint64_t)j);
+          p = bf16_round(p);
+          float vr[D];
+          at_load_row<D>(sV, j, vr);
+#pragma unroll
+          for (int c = 0; c < D; ++c) o[c] = fmaf(p, vr[c], o[c]);
+        }
+      }
+      sum = warp_allsum(sum);
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = warp_allsum(o[c]);
+      if (lane == 0) {
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int c = 0; c < D; ++c) o[c] *= inv;
+        bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&o[c]);
+        P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+      }
+    }
+  } else {
   for (int qt = 0; qt < nq; ++qt) {
     const int q0 = qt * 128, i = q0 + tid;
     const bool valid = i < T;
@@ -151,7 +227,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();
+    bar_main();
     if (tid == 0) {
       tc_fence_after();
       at_issue(tmem + cS, Qk, Kk, KP, D / 16, false);   // S[i, j] = q_i . k_j
@@ -194,7 +270,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    bar_main();
     if (tid == 0) {
       tc_fence_after();
       at_issue(tmem + cO, Pk, Vmn, D, KP / 16, false);  // O[i, c] = sum_j P[i, j] v[j, c]
@@ -217,8 +293,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     tc_fence_before();
-    __syncthreads();
+    bar_main();
   }
+  }
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -226,7 +304,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // backward
 // ================================================================================================
 template <int D>
-__global__ void __launch_bounds__(AT_TC_THREADS, 1)
+__global__ void __launch_bounds__(160, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const AttnTcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -243,6 +321,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPT + 65536);
   uint64_t *b_kv = bars, *b_q = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* xds = reinterpret_cast<float*>(bars + 8);  // side row: dS[j] (scale folded), dropped P[j], q row, dO row
+  float* xpt = xds + 256;
+  float* xq = xpt + 256;
+  float* xdo = xq + 32;
   constexpr uint32_t TMEM_COLS = 512;
   // TMEM columns: S and dP take round_up(KP, 32) columns each (the 32-wide reads below may run past KP into the
   // neighbouring region; those entries are masked), then dQ and the dK / dV accumulators of up to two key tiles
@@ -276,9 +358,68 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int Tpad = (T + 3) & ~3;
   const float sl2 = P.scale * AT_LOG2E;
   uint32_t ph_q = 0, ph_mma = 0;
-  const int nq = (T + 127) / 128;
+  const bool side = (T % 128 == 1) && T > 1 && P.cosT == nullptr;  // see the forward kernel
+  const int nq = side ? T / 128 : (T + 127) / 128;
   const int nkt = (KP + 127) / 128;  // key tiles of the dK / dV accumulators (1 or 2)
 
+  if (warp == 4) {
+    if (side) {
+      // last query row with plain FMAs: dq directly; its rank-1 contributions to dK / dV are handed to the key-row
+      // epilogue through shared memory (xds, xpt, xq, xdo)
+      const int lane = tid & 31, i = T - 1;
+      mbar_wait(b_kv, 0);
+      float qf[D], dof[D];
+      float Di = 0.f;
+      {
+        const bf16* qp = P.qkv + (size_t)(row0 + i) * P.ld + h * D;
+        const bf16* dp_ = P.dctx + (size_t)(row0 + i) * P.H + h * D;
+        const bf16* op = P.ctx + (size_t)(row0 + i) * P.H + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+          float o8[8];
+          at_unpack8(*reinterpret_cast<const uint4*>(qp + c), &qf[c]);
+          at_unpack8(*reinterpret_cast<const uint4*>(dp_ + c), &dof[c]);
+          at_unpack8(*reinterpret_cast<const uint4*>(op + c), o8);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) Di = fmaf(dof[c + q], o8[q], Di);
+        }
+      }
+      const float lse2 = P.lse[(size_t)(b * P.heads + h) * T + i] * AT_LOG2E;
+      const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + i) * (uint64_t)Tpad;
+      float dq[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) dq[c] = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < T) {
+          float kr[D], vr[D];
+          at_load_row<D>(sK, j, kr);
+          at_load_row<D>(sV, j, vr);
+          float sdot = 0.f, dp = 0.f;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { sdot = fmaf(qf[c], kr[c], sdot); dp = fmaf(dof[c], vr[c], dp); }
+          const float p = exp2f(sdot * sl2 - lse2);
+          const float keep = drop1(dc, drow + (uint64_t)j);
+          const float ds = bf16_round(p * (dp * keep - Di) * P.scale);
+          xds[j] = ds;
+          xpt[j] = bf16_round(p * keep);
+#pragma unroll
+          for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, kr[c], dq[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) dq[c] = warp_allsum(dq[c]);
+      if (lane == 0) {
+        bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&dq[c]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) { xq[c] = qf[c]; xdo[c] = dof[c]; }
+      }
+    }
+    bar_all160();  // side-row results visible to the key-row epilogue
+  } else {
   for (int qt = 0; qt < nq; ++qt) {
     const int q0 = qt * 128, i = q0 + tid;
     const bool valid = i < T;
@@ -320,7 +461,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    bar_main();
     if (tid == 0) {
       tc_fence_after();
       at_issue(tmem + cS, Qk, Kk, KP, D / 16, false);    // S  = Q K^T
@@ -370,7 +511,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    bar_main();
     if (tid == 0) {
       tc_fence_after();
       at_issue(tmem + cDQ, DSk, Kmn, D, KP / 16, false);                       // dQ[i,:]  = sum_j dS[i,j] k_j
@@ -401,9 +542,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     tc_fence_before();
-    __syncthreads();
+    bar_main();
   }
   // ---- dK, dV: thread = key row of key tile kt ----
+  bar_all160();
   tc_fence_after();
   for (int kt = 0; kt < nkt; ++kt) {
     const int j = kt * 128 + tid;
@@ -414,6 +556,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float r[D];
 #pragma unroll
       for (int c = 0; c < D; ++c) r[c] = dk[c];
+      if (side) {
+        const float a = xds[j], pt = xpt[j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) { r[c] = fmaf(a, xq[c], r[c]); dv[c] = fmaf(pt, xdo[c], dv[c]); }
+      }
       if (P.cosT) {
 #pragma unroll
         for (int c = 0; c < D; ++c) r[c] = bf16_round(r[c]);
@@ -429,12 +576,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
   tc_fence_before();
+  }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 1024;
-constexpr int AT_BWD_SMEM = 16384 + 16384 + 32768 + 32768 + 65536 + 65536 + 1024 + 1024;
+constexpr int AT_BWD_SMEM = 16384 + 16384 + 32768 + 32768 + 65536 + 65536 + 1024 + 4096;
 
 static inline int at_kp(int T) { return (T + 15) / 16 * 16; }
 
@@ -474,7 +622,7 @@ extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    attn_tc_fwd_kernel<DD><<<grid, AT_TC_THREADS, AT_FWD_SMEM, st>>>(tQ, tKV, P);                                \
+    attn_tc_fwd_kernel<DD><<<grid, 160, AT_FWD_SMEM, st>>>(tQ, tKV, P);                                \
   }
   if (d == 16) LAUNCH_F(16) else LAUNCH_F(32)
 #undef LAUNCH_F
@@ -506,7 +654,7 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    attn_tc_bwd_kernel<DD><<<grid, AT_TC_THREADS, AT_BWD_SMEM, st>>>(tQ, tKV, tDO, P);                           \
+    attn_tc_bwd_kernel<DD><<<grid, 160, AT_BWD_SMEM, st>>>(tQ, tKV, tDO, P);                           \
   }
   if (d == 16) LAUNCH_B(16) else LAUNCH_B(32)
 #undef LAUNCH_B
