@@ -312,13 +312,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const int KP = P.KP, nblk = (KP + 63) / 64, KW = nblk * 64;
   const uint32_t kv_bytes = (uint32_t)KP * 128;
+  // nblk <= 3 blocks of dS / P~ are written.  The MN-major view of key tile 1 spans blocks 2 and 3; block 3 then aliases
+  // the NEXT buffer (sPT block 0, resp. the first 16 KB of sK): finite bf16 data whose product rows (keys >= 192)
+  // are never read.
   uint8_t* sQ = base;                        // 16 KB
   uint8_t* sDO = sQ + 16384;                 // 16 KB
-  uint8_t* sK = sDO + 16384;                 // 32 KB reserved
+  uint8_t* sDS = sDO + 16384;                // 3 x 16 KB
+  uint8_t* sPT = sDS + 49152;                // 3 x 16 KB
+  uint8_t* sK = sPT + 49152;                 // 32 KB reserved
   uint8_t* sV = sK + 32768;                  // 32 KB reserved
-  uint8_t* sDS = sV + 32768;                 // 4 x 16 KB reserved (nblk used; the MN view of key tile 1 may touch block 3)
-  uint8_t* sPT = sDS + 65536;                // 4 x 16 KB reserved
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPT + 65536);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 32768);
   uint64_t *b_kv = bars, *b_q = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* xds = reinterpret_cast<float*>(bars + 8);  // side row: dS[j] (scale folded), dropped P[j], q row, dO row
@@ -582,7 +585,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 1024;
-constexpr int AT_BWD_SMEM = 16384 + 16384 + 32768 + 32768 + 65536 + 65536 + 1024 + 4096;
+constexpr int AT_BWD_SMEM = 16384 + 16384 + 49152 + 49152 + 32768 + 32768 + 1024 + 4096;
 
 static inline int at_kp(int T) { return (T + 15) / 16 * 16; }
 

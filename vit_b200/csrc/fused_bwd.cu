@@ -41,6 +41,11 @@ __device__ __forceinline__ float fb_colsum(const uint8_t* tile, int col) {
   return s;
 }
 
+// a 128-byte row of a TMA-loaded (128B-swizzled) tile: 16-byte chunk c of row r
+__device__ __forceinline__ const uint8_t* fb_swz_ptr(const uint8_t* tile, int r, int chunk) {
+  return tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+}
+
 // operand view for one tcgen05 GEMM
 struct Opnd {
   uint32_t addr;   // shared address of the tile
@@ -65,11 +70,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmU2,
                        const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWo,
+                       const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmHm,
                        const vitb200_layer_bwd_upper_args P) {
   constexpr int H = FB_H, I = FB_I;
   // shared memory map (all tile bases 1024-aligned); sD must be directly followed by sDA (see wgrad A views)
   constexpr uint32_t O_D = 0, O_DA = 16384, O_M = O_DA + 32768, O_U2 = O_M + 32768, O_CTX = O_U2 + 16384,
-                     O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_BAR = O_WO + 4096;
+                     O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_ACT = O_WO + 4096,
+                     O_HM = O_ACT + 32768, O_BAR = O_HM + 16384;
   // TMEM columns
   constexpr uint32_t C_W2 = 0, C_W1 = 128, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -77,17 +84,21 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t *sD = base + O_D, *sDA = base + O_DA, *sM = base + O_M, *sU2 = base + O_U2, *sCtx = base + O_CTX;
   uint8_t *sW2 = base + O_W2, *sW1 = base + O_W1, *sWo = base + O_WO;
+  const uint8_t *sAct = base + O_ACT, *sHm = base + O_HM;  // pre-GELU activations (bf16) and hmid rows (fp32), TMA-staged
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
   uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* s_g2 = reinterpret_cast<float*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int M = P.B * P.T;
   const int ntiles = (M + 127) / 128;
 
+  if (tid < H) s_g2[tid] = P.ln2_g[tid];
   if (tid == 0) {
     tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmU2); tma_prefetch_desc(&tmCtx);
     tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmAct); tma_prefetch_desc(&tmHm);
     mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
@@ -138,12 +149,16 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
     if (tid == 0) {
-      mbar_expect_tx(b_tile, 32768 + 16384 + 16384);
+      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384);
       tma_load_2d(sM, &tmM, b_tile, 0, r0);
       tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
       tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
       tma_load_2d(sCtx, &tmCtx, b_tile, 0, r0);
+      tma_load_2d(base + O_ACT, &tmAct, b_tile, 0, r0);
+      tma_load_2d(base + O_ACT + 16384, &tmAct, b_tile, 64, r0);
+      tma_load_2d(base + O_HM, &tmHm, b_tile, 0, r0);
     }
+    const float mu = P.mean2[rowc], rs = P.rstd2[rowc];  // issued early, consumed by the LayerNorm stage
     // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
     float dz[H];
     {
@@ -172,6 +187,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       fb_issue(tmem + C_W2, D_mn, M_mn, I, 8, iter > 0);          // dW2[h, i]  += sum_rows ddelta2[row,h] m[row,i]
       umma_commit(b_mma);
     }
+    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged a / hmid rows below
     ph_tile ^= 1;
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
@@ -181,10 +197,9 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     for (int c0 = 0; c0 < I; c0 += 32) {
       float v[32];
       tmem_ld_32x32(my_tmem + C_DM + c0, v);
-      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.a) + (size_t)rowc * I + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 av = ap[q];
+        const uint4 av = *reinterpret_cast<const uint4*>(fb_swz_ptr(sAct, tid, (c0 >> 3) + q));
         const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
         float o[8];
 #pragma unroll
@@ -212,13 +227,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     {
       float du[32];
       tmem_ld_32x32(my_tmem + C_DU2, du);
-      const float mu = P.mean2[rowc], rs = P.rstd2[rowc];
       float xh[H], g[H];
       float s1 = 0.f, s2 = 0.f;
-      const float4* hp = reinterpret_cast<const float4*>(P.hmid + (size_t)rowc * H);
 #pragma unroll
       for (int j = 0; j < H / 4; ++j) {
-        const float4 t = hp[j];
+        const float4 t = *reinterpret_cast<const float4*>(fb_swz_ptr(sHm, tid, j));
         xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
       }
 #pragma unroll
@@ -226,7 +239,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
         const float d = valid ? bf16_round(du[j]) : 0.f;
         acc_g[j] = fmaf(d, xh[j], acc_g[j]);
         acc_b[j] += d;
-        g[j] = d * P.ln2_g[j];
+        g[j] = d * s_g2[j];
         s1 += g[j];
         s2 = fmaf(g[j], xh[j], s2);
       }
@@ -326,9 +339,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
 // ================================================================================================
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmU,
-                       const __grid_constant__ CUtensorMap tmWq, const vitb200_layer_bwd_lower_args P) {
+                       const __grid_constant__ CUtensorMap tmWq, const __grid_constant__ CUtensorMap tmZ,
+                       const __grid_constant__ CUtensorMap tmDh, const vitb200_layer_bwd_lower_args P) {
   constexpr int H = FB_H, Q = 3 * FB_H;
-  constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_BAR = O_WQ + 12288, O_RED = O_BAR + 1024;
+  constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_Z = O_WQ + 12288, O_DH = O_Z + 16384,
+                     O_BAR = O_DH + 16384, O_RED = O_BAR + 1024;
   constexpr uint32_t C_WQ = 0, C_DU = 32, TMEM_COLS = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -338,12 +353,16 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* red = reinterpret_cast<float*>(base + O_RED);  // [2][H][128] floats = 32 KB
+  const uint8_t *sZ = base + O_Z, *sDh = base + O_DH;   // fp32 rows of z and dh, TMA-staged
+  float* s_g1 = reinterpret_cast<float*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int M = P.B * P.T;
   const int ntiles = (M + 127) / 128;
+  if (tid < H) s_g1[tid] = P.ln1_g[tid];
   if (tid == 0) {
     tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmWq);
+    tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmDh);
     mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
@@ -372,11 +391,14 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     const int r0 = tile * 128, row = r0 + tid;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
+    const float mu = P.mean1[rowc], rs = P.rstd1[rowc];  // issued early
     if (tid == 0) {
-      mbar_expect_tx(b_tile, 32768 + 16384);
+      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 16384);
       tma_load_2d(sDQ, &tmDQ, b_tile, 0, r0);
       tma_load_2d(sDQ + 16384, &tmDQ, b_tile, 64, r0);
       tma_load_2d(sU, &tmU, b_tile, 0, r0);
+      tma_load_2d(base + O_Z, &tmZ, b_tile, 0, r0);
+      tma_load_2d(base + O_DH, &tmDh, b_tile, 0, r0);
       if (iter == 0) mbar_wait(b_w, 0);
       mbar_wait(b_tile, ph_tile);
       tc_fence_after();
@@ -392,16 +414,13 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     {
       float du[32];
       tmem_ld_32x32(my_tmem + C_DU, du);
-      const float mu = P.mean1[rowc], rs = P.rstd1[rowc];
       float xh[H], g[H], dz[H];
       float s1 = 0.f, s2 = 0.f;
-      const float4* zp = reinterpret_cast<const float4*>(P.z + (size_t)rowc * H);
-      const float4* dp = reinterpret_cast<const float4*>(P.dh + (size_t)rowc * H);
 #pragma unroll
       for (int j = 0; j < H / 4; ++j) {
-        const float4 t = zp[j];
+        const float4 t = *reinterpret_cast<const float4*>(fb_swz_ptr(sZ, tid, j));
         xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
-        const float4 d = dp[j];
+        const float4 d = *reinterpret_cast<const float4*>(fb_swz_ptr(sDh, tid, j));
         dz[4 * j] = d.x; dz[4 * j + 1] = d.y; dz[4 * j + 2] = d.z; dz[4 * j + 3] = d.w;
       }
 #pragma unroll
@@ -409,7 +428,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
         const float d = valid ? bf16_round(du[j]) : 0.f;
         acc_g[j] = fmaf(d, xh[j], acc_g[j]);
         acc_b[j] += d;
-        g[j] = d * P.ln1_g[j];
+        g[j] = d * s_g1[j];
         s1 += g[j];
         s2 = fmaf(g[j], xh[j], s2);
       }
@@ -480,8 +499,8 @@ grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, si
   }
 }
 
-constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 1024 + 1024;
-constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 1024 + 32768 + 1024;
+constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 32768 + 16384 + 1024 + 1024;
+constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 16384 + 16384 + 1024 + 32768 + 1024;
 
 }  // namespace vb
 
@@ -500,8 +519,10 @@ extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args*
   if (a->H != FB_H) return VITB200_ERR_SHAPE;
   if (a->B <= 0 || a->T <= 0) return VITB200_ERR_ARG;
   const int M = a->B * a->T, H = FB_H, I = FB_I;
-  CUtensorMap tM, tU2, tCtx, tW2, tW1, tWo;
+  CUtensorMap tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm;
   int rc;
+  if ((rc = get_tmap(a->a, I, M, 64, 128, &tAct))) return rc;
+  if ((rc = get_tmap(a->hmid, 2 * H, M, 64, 128, &tHm))) return rc;  // fp32 [M, H] rows viewed as 2H bf16 (128 B)
   if ((rc = get_tmap(a->m, I, M, 64, 128, &tM))) return rc;
   if ((rc = get_tmap(a->u2, H, M, 64, 128, &tU2))) return rc;
   if ((rc = get_tmap(a->ctx, H, M, 64, 128, &tCtx))) return rc;
@@ -514,8 +535,8 @@ extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args*
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  fused_bwd_upper_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, UPPER_SMEM, (cudaStream_t)stream>>>(tM, tU2, tCtx, tW2,
-                                                                                                    tW1, tWo, *a);
+  fused_bwd_upper_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, UPPER_SMEM, (cudaStream_t)stream>>>(
+      tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -526,8 +547,10 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
   if (a->H != FB_H) return VITB200_ERR_SHAPE;
   if (a->B <= 0 || a->T <= 0) return VITB200_ERR_ARG;
   const int M = a->B * a->T, H = FB_H;
-  CUtensorMap tDQ, tU, tWq;
+  CUtensorMap tDQ, tU, tWq, tZ, tDh;
   int rc;
+  if ((rc = get_tmap(a->z, 2 * H, M, 64, 128, &tZ))) return rc;    // fp32 rows viewed as 2H bf16
+  if ((rc = get_tmap(a->dh, 2 * H, M, 64, 128, &tDh))) return rc;
   if ((rc = get_tmap(a->dqkv, 3 * H, M, 64, 128, &tDQ))) return rc;
   if ((rc = get_tmap(a->u, H, M, 64, 128, &tU))) return rc;
   if ((rc = get_tmap(a->w_qkv, H, 3 * H, 64, 3 * H, &tWq))) return rc;
@@ -537,7 +560,8 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  fused_bwd_lower_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, LOWER_SMEM, (cudaStream_t)stream>>>(tDQ, tU, tWq, *a);
+  fused_bwd_lower_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, LOWER_SMEM, (cudaStream_t)stream>>>(tDQ, tU, tWq, tZ,
+                                                                                                    tDh, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

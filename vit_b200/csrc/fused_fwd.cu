@@ -94,6 +94,10 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(sWq + SZ_WQ);
   uint64_t *b_in = bars, *b_w1 = bars + 1, *b_w2 = bars + 2, *b_wq = bars + 3, *b_mma = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  // bias / LayerNorm vectors: staged once in shared memory (a dependent global load per use stalls every epilogue)
+  float* prm = reinterpret_cast<float*>(bars + 8);
+  float *s_bo = prm, *s_g2 = prm + H, *s_b2ln = prm + 2 * H, *s_b2 = prm + 3 * H, *s_gn = prm + 4 * H, *s_bn = prm + 5 * H,
+        *s_b1 = prm + 6 * H, *s_bq = prm + 6 * H + I;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int M = P.B * P.T;
@@ -109,6 +113,12 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int j = threadIdx.x; j < H; j += FF_THREADS) {
+    s_bo[j] = P.b_o[j]; s_g2[j] = P.ln2_g[j]; s_b2ln[j] = P.ln2_b[j]; s_b2[j] = P.b_2[j];
+    s_gn[j] = P.lnn_g[j]; s_bn[j] = P.lnn_b[j];
+  }
+  for (int j = threadIdx.x; j < I; j += FF_THREADS) s_b1[j] = P.b_1[j];
+  if (!P.last) for (int j = threadIdx.x; j < 3 * H; j += FF_THREADS) s_bq[j] = P.b_qkv[j];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,14 +167,14 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
-        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + P.b_o[c0 + j + 0]) * kp.x);
-        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + P.b_o[c0 + j + 1]) * kp.y);
-        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + P.b_o[c0 + j + 2]) * kp.z);
-        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + P.b_o[c0 + j + 3]) * kp.w);
+        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + s_bo[c0 + j + 0]) * kp.x);
+        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + s_bo[c0 + j + 1]) * kp.y);
+        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + s_bo[c0 + j + 2]) * kp.z);
+        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + s_bo[c0 + j + 3]) * kp.w);
       }
     }
     float u2[H], mu, rs;
-    layer_norm_row<H>(h, P.ln2_g, P.ln2_b, P.eps, u2, mu, rs);
+    layer_norm_row<H>(h, s_g2, s_b2ln, P.eps, u2, mu, rs);
     if (valid) {
       float4* hp = reinterpret_cast<float4*>(P.hmid + (size_t)row * H);
 #pragma unroll
@@ -191,7 +201,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
     tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      v[j] = bf16_round(v[j] + P.b_1[c0 + j]);
+      v[j] = bf16_round(v[j] + s_b1[c0 + j]);
       g[j] = gelu_f(v[j]);
     }
     emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.a) + (size_t)rowc * I + c0, valid, nullptr, 0, 0);
@@ -218,10 +228,10 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
-        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + P.b_2[c0 + j + 0]) * kp.x);
-        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + P.b_2[c0 + j + 1]) * kp.y);
-        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + P.b_2[c0 + j + 2]) * kp.z);
-        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + P.b_2[c0 + j + 3]) * kp.w);
+        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + s_b2[c0 + j + 0]) * kp.x);
+        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + s_b2[c0 + j + 1]) * kp.y);
+        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + s_b2[c0 + j + 2]) * kp.z);
+        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + s_b2[c0 + j + 3]) * kp.w);
       }
     }
     if (valid) {
@@ -230,7 +240,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
       for (int j = 0; j < H / 4; ++j) zp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     }
     float un[H], mu, rs;
-    layer_norm_row<H>(h, P.lnn_g, P.lnn_b, P.eps, un, mu, rs);
+    layer_norm_row<H>(h, s_gn, s_bn, P.eps, un, mu, rs);
     if (!P.last) {
       if (valid) { P.mean_n[row] = mu; P.rstd_n[row] = rs; }
       emit_row_bf16<H>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)rowc * H, valid, sA, tid, 0);
@@ -257,7 +267,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
       float v[32];
       tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += P.b_qkv[c0 + j];
+      for (int j = 0; j < 32; ++j) v[j] += s_bq[c0 + j];
       emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.qkv_next) + (size_t)rowc * 3 * H + c0, valid, nullptr, 0, 0);
     }
   }
@@ -284,6 +294,8 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(sWq + SZ_WQ);
   uint64_t *b_wp = bars, *b_wq = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* prm = reinterpret_cast<float*>(bars + 8);
+  float *s_bp = prm, *s_cls = prm + H, *s_g = prm + 2 * H, *s_b = prm + 3 * H, *s_bq = prm + 4 * H;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int T = P.Np + 1, M = P.B * T;
@@ -299,6 +311,8 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int j = threadIdx.x; j < H; j += FF_THREADS) { s_bp[j] = P.b_p[j]; s_cls[j] = P.cls[j]; s_g[j] = P.ln_g[j]; s_b[j] = P.ln_b[j]; }
+  for (int j = threadIdx.x; j < 3 * H; j += FF_THREADS) s_bq[j] = P.b_qkv[j];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -353,14 +367,14 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = c0 + j + q;
-          float e = t == 0 ? P.cls[c] : bf16_round(v[j + q] + P.b_p[c]);
+          float e = t == 0 ? s_cls[c] : bf16_round(v[j + q] + s_bp[c]);
           if (P.pos) e += P.pos[(size_t)t * H + c];
           z[c] = e * kpa[q];
         }
       }
     }
     float u[H], mu, rs;
-    layer_norm_row<H>(z, P.ln_g, P.ln_b, P.eps, u, mu, rs);
+    layer_norm_row<H>(z, s_g, s_b, P.eps, u, mu, rs);
     if (valid) {
       float4* zp = reinterpret_cast<float4*>(P.z0 + (size_t)row * H);
 #pragma unroll
@@ -384,7 +398,7 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
     float v[32];
     tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += P.b_qkv[c0 + j];
+    for (int j = 0; j < 32; ++j) v[j] += s_bq[c0 + j];
     emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.qkv) + (size_t)rowc * 3 * H + c0, valid, nullptr, 0, 0);
   }
   tc_fence_before();
@@ -393,9 +407,9 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
 }
 
 template <int H> static constexpr int layer_smem() {
-  return 16384 + (4 * H / 64) * 16384 + H * 128 + 4 * H * 128 + (4 * H / 64) * H * 128 + 3 * H * 128 + 1024 + 128;
+  return 16384 + (4 * H / 64) * 16384 + H * 128 + 4 * H * 128 + (4 * H / 64) * H * 128 + 3 * H * 128 + 1024 + 64 + (13 * H) * 4 + 64;
 }
-template <int H> static constexpr int embed_smem() { return 16384 + H * 128 + 3 * H * 128 + 1024 + 128; }
+template <int H> static constexpr int embed_smem() { return 16384 + H * 128 + 3 * H * 128 + 1024 + 64 + (7 * H) * 4 + 64; }
 
 template <int H>
 static int launch_layer(const vitb200_layer_fwd_args* a, cudaStream_t st) {
