@@ -199,7 +199,8 @@ typedef struct {
   float p_drop;
   const uint64_t* rng;
   uint32_t site_proj, site_mlp;
-  const float* dz;                   /* [B*T, H] f32 */
+  const float* dz;                   /* [B*T, H] f32, or NULL when dz_cls is given */
+  const float* dz_cls;               /* [B, H] f32: gradient of the CLS rows only (all other rows are zero), or NULL */
   const void *m, *a, *u2, *ctx;      /* saved activations (bf16) */
   const float *hmid, *mean2, *rstd2, *ln2_g;
   const void *w_2, *w_1, *w_o;       /* bf16 [H,4H], [4H,H], [H,H] */
@@ -218,6 +219,20 @@ typedef struct {
   float* gpart;
   int n_opt, off_wqkv, off_bqkv, off_ln1g, off_ln1b;
 } vitb200_layer_bwd_lower_args;
+
+/* embedding backward (no learned positions, P % 16 == 0): dz0 -> dropout' -> dW_p (tcgen05, MN-major views of the
+ * gradient tile and of the re-built patch tile), db_p, dcls; partials go to gpart like the layer kernels. */
+typedef struct {
+  int B, L, P, S, Np, n_valid, H;
+  float p_drop;
+  const uint64_t* rng;
+  const float* dz0;                  /* [B*T, H] f32 */
+  const float* x;                    /* [B, L] f32 */
+  float* gpart;
+  int n_opt, off_wp, off_bp, off_cls;
+} vitb200_embed_bwd_args;
+int vitb200_fused_embed_bwd_supported(int H, int P, int learned_pos);
+int vitb200_fused_embed_bwd(const vitb200_embed_bwd_args* args, void* stream);
 
 int vitb200_fused_bwd_supported(int H);
 int vitb200_fused_bwd_grid(int M);
@@ -270,6 +285,18 @@ int vitb200_head_loss_fwd(const void* s, const void* w, const float* bias, const
 int vitb200_head_loss_bwd(const void* s, const void* w, const float* logits, const void* labels,
                           const float* gloss, void* ds, float* dw, float* dbias, int B, int H, int C, int loss_kind,
                           int accumulate, int dtype, void* stream);
+
+/* Single-launch variants for small heads (H <= 128, C <= 4): logits + loss in one kernel; head backward fused with the
+ * final-LayerNorm backward of the CLS rows (HF:455): z = residual stream after the last layer (row b at
+ * z + b*z_row_stride), mean/rstd [B] from the forward; outputs dz_cls [B,H] f32 (gradient of the CLS rows of the last
+ * layer's output; every other row's gradient is zero), dgamma/dbeta of vit.layernorm, dw/dbias of the head. */
+int vitb200_head_fused_supported(int H, int C);
+int vitb200_head_fused_fwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
+                           float* loss, int B, int H, int C, int loss_kind, int dtype, void* stream);
+int vitb200_head_fused_bwd(const void* s, const void* w, const float* logits, const void* labels, const float* gloss,
+                           const float* z, size_t z_row_stride, const float* mean, const float* rstd, const float* gamma,
+                           float* dz_cls, float* dgamma, float* dbeta, float* dw, float* dbias, int B, int H, int C,
+                           int loss_kind, int accumulate, int dtype, void* stream);
 
 /* ---- gradient clipping + AdamW ---------------------------------------------------------------------
  * Replaces Lightning's gradient_clip_val -> torch.nn.utils.clip_grad_norm_ (src/basemodule.py:244) and

@@ -48,7 +48,7 @@ class LayerFwdArgs(C.Structure):  # vitb200_layer_fwd_args
 
 class LayerBwdUpperArgs(C.Structure):  # vitb200_layer_bwd_upper_args
     _fields_ = [(n, _i) for n in ("B", "T", "H")] + [("p_drop", _f), ("rng", _p), ("site_proj", _u32), ("site_mlp", _u32)] + \
-               [(n, _p) for n in ("dz", "m", "a", "u2", "ctx", "hmid", "mean2", "rstd2", "ln2_g", "w_2", "w_1", "w_o", "dh",
+               [(n, _p) for n in ("dz", "dz_cls", "m", "a", "u2", "ctx", "hmid", "mean2", "rstd2", "ln2_g", "w_2", "w_1", "w_o", "dh",
                                   "dctx", "gpart")] + \
                [(n, _i) for n in ("n_opt", "off_w2", "off_b2", "off_w1", "off_b1", "off_ln2g", "off_ln2b", "off_wo", "off_bo")]
 
@@ -57,6 +57,11 @@ class LayerBwdLowerArgs(C.Structure):  # vitb200_layer_bwd_lower_args
     _fields_ = [(n, _i) for n in ("B", "T", "H")] + \
                [(n, _p) for n in ("dqkv", "u", "z", "mean1", "rstd1", "ln1_g", "dh", "w_qkv", "dz", "gpart")] + \
                [(n, _i) for n in ("n_opt", "off_wqkv", "off_bqkv", "off_ln1g", "off_ln1b")]
+
+
+class EmbedBwdArgs(C.Structure):  # vitb200_embed_bwd_args
+    _fields_ = [(n, _i) for n in ("B", "L", "P", "S", "Np", "n_valid", "H")] + [("p_drop", _f)] + \
+               [(n, _p) for n in ("rng", "dz0", "x", "gpart")] + [(n, _i) for n in ("n_opt", "off_wp", "off_bp", "off_cls")]
 
 
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
@@ -84,6 +89,8 @@ SIGNATURES = {
     "vitb200_fused_supported": (_i, [_i, _i]),
     "vitb200_fused_embed_fwd": (_i, [_p, _p]),
     "vitb200_fused_layer_fwd": (_i, [_p, _p]),
+    "vitb200_fused_embed_bwd_supported": (_i, [_i, _i, _i]),
+    "vitb200_fused_embed_bwd": (_i, [_p, _p]),
     "vitb200_fused_bwd_supported": (_i, [_i]),
     "vitb200_fused_bwd_grid": (_i, [_i]),
     "vitb200_fused_layer_bwd_upper": (_i, [_p, _p]),
@@ -98,6 +105,9 @@ SIGNATURES = {
     "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "vitb200_head_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vitb200_head_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vitb200_head_fused_supported": (_i, [_i, _i]),
+    "vitb200_head_fused_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vitb200_head_fused_bwd": (_i, [_p, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vitb200_grad_norm_ws_bytes": (_sz, [_sz]),
     "vitb200_grad_norm": (_i, [_p, _sz, _p, _p, _p, _p]),
     "vitb200_adamw": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p]),

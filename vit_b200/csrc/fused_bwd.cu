@@ -162,9 +162,16 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
     float dz[H];
     {
-      const float4* p = reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H);
+      // top layer: only the CLS rows carry a gradient (the head reads last_hidden_state[:, 0], specvit.py:78)
+      const bool from_cls = P.dz_cls != nullptr;
+      const bool nz = !from_cls || (rowc % P.T) == 0;
+      const float4* p = from_cls ? reinterpret_cast<const float4*>(P.dz_cls + (size_t)(rowc / P.T) * H)
+                                 : reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) { float4 t = p[j]; dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w; }
+      for (int j = 0; j < H / 4; ++j) {
+        float4 t = nz ? p[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w;
+      }
       float d2[H];
 #pragma unroll
       for (int j = 0; j < H; j += 4) {
@@ -476,6 +483,123 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ================================================================================================
+// embedding backward: dz0 -> dropout' -> dW_p = dtok^T . patches, db_p, dcls
+// ================================================================================================
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
+  constexpr int H = FB_H;
+  constexpr uint32_t O_D = 0, O_X = 16384, O_BAR = 32768, O_RED = O_BAR + 1024;
+  constexpr uint32_t TMEM_COLS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t *sD = base + O_D, *sX = base + O_X;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
+  uint64_t* b_mma = bars;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+  float* red = reinterpret_cast<float*>(base + O_RED);  // [H][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int T = P.Np + 1, M = P.B * T;
+  const int ntiles = (M + 127) / 128;
+  if (tid == 0) { mbar_init(b_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {  // zero both tiles once: unused columns must be finite for the MN-major views
+    fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
+    fb_swz_store(sX, tid, c, make_uint4(0u, 0u, 0u, 0u));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const Opnd D_mn{smem_u32(sD), 16384, 0, 1};   // MN group 1 aliases sX: product rows 64..127 are never read
+  const Opnd X_mn{smem_u32(sX), 16384, 0, 1};
+  const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, VITB200_SITE_EMB);
+  float acc_cls[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) acc_cls[j] = 0.f;
+  float acc_bp = 0.f;
+  uint32_t ph = 0;
+  int iter = 0;
+  const int nchunk = P.P / 8;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const int row = tile * 128 + tid;
+    const bool valid = row < M;
+    const int rowc = valid ? row : M - 1;
+    const int b = rowc / T, t = rowc - b * T;
+    float g[H];
+    {
+      const float4* p = reinterpret_cast<const float4*>(P.dz0 + (size_t)rowc * H);
+#pragma unroll
+      for (int j = 0; j < H / 4; ++j) {
+        const float4 v = p[j];
+        const float4 kp = drop4(dc, ((size_t)rowc * H + 4 * j) >> 2);
+        g[4 * j] = valid ? v.x * kp.x : 0.f;         g[4 * j + 1] = valid ? v.y * kp.y : 0.f;
+        g[4 * j + 2] = valid ? v.z * kp.z : 0.f;     g[4 * j + 3] = valid ? v.w * kp.w : 0.f;
+      }
+    }
+    if (t == 0) {  // CLS row: gradient of cls_token, no patch
+#pragma unroll
+      for (int j = 0; j < H; ++j) { acc_cls[j] += g[j]; g[j] = 0.f; }
+    }
+#pragma unroll
+    for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&g[c * 8]));
+    {
+      const bool has = valid && t >= 1 && (t - 1) < P.n_valid;
+      const float* xp = P.x + (size_t)b * P.L + (size_t)(t >= 1 ? t - 1 : 0) * P.S;
+      for (int c = 0; c < nchunk; ++c) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = has ? xp[c * 8 + q] : 0.f;
+        fb_swz_store(sX, tid, c, fb_pack8(v));
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      fb_issue(tmem, D_mn, X_mn, P.P, 8, iter > 0);   // dWp[h, j] += sum_rows dtok[row, h] x[row, j]
+      umma_commit(b_mma);
+    }
+    mbar_wait(b_mma, ph); ph ^= 1;
+    tc_fence_after();
+    if (tid < H) acc_bp += fb_colsum(sD, tid);
+    tc_fence_before();
+    __syncthreads();
+  }
+  float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
+  tc_fence_after();
+  if (warp == 0) {
+    if (iter > 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < P.P; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(my_tmem + c0, v);
+        for (int j = 0; j < 32 && c0 + j < P.P; ++j) gp[P.off_wp + (size_t)tid * P.P + c0 + j] = v[j];
+      }
+    } else {
+      for (int e = 0; e < P.P; ++e) gp[P.off_wp + (size_t)tid * P.P + e] = 0.f;
+    }
+    gp[P.off_bp + tid] = acc_bp;
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) red[j * 128 + tid] = acc_cls[j];
+  tc_fence_before();
+  __syncthreads();
+  if (tid < H) {
+    float s = 0.f;
+    for (int k = 0; k < 128; ++k) s += red[tid * 128 + k];
+    gp[P.off_cls + tid] = s;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+constexpr int EMBED_BWD_SMEM = 16384 + 16384 + 1024 + 16384 + 1024;
+
 // grad[i] = sum over slots (in slot order) of gpart[s*stride + i]
 __global__ void __launch_bounds__(256)
 grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, size_t start, size_t n4,
@@ -513,7 +637,7 @@ extern "C" int vitb200_fused_bwd_grid(int M) {
 }
 
 extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args* a, void* stream) {
-  if (!a || !a->dz || !a->m || !a->a || !a->u2 || !a->ctx || !a->hmid || !a->mean2 || !a->rstd2 || !a->ln2_g ||
+  if (!a || (!a->dz && !a->dz_cls) || !a->m || !a->a || !a->u2 || !a->ctx || !a->hmid || !a->mean2 || !a->rstd2 || !a->ln2_g ||
       !a->w_2 || !a->w_1 || !a->w_o || !a->dh || !a->dctx || !a->gpart)
     return VITB200_ERR_ARG;
   if (a->H != FB_H) return VITB200_ERR_SHAPE;
@@ -562,6 +686,26 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
   }
   fused_bwd_lower_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, LOWER_SMEM, (cudaStream_t)stream>>>(tDQ, tU, tWq, tZ,
                                                                                                     tDh, *a);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_fused_embed_bwd_supported(int H, int P, int learned_pos) {
+  return (H == FB_H && !learned_pos && P % 16 == 0 && P >= 16 && P <= 64) ? 1 : 0;
+}
+
+extern "C" int vitb200_fused_embed_bwd(const vitb200_embed_bwd_args* a, void* stream) {
+  if (!a || !a->dz0 || !a->x || !a->gpart) return VITB200_ERR_ARG;
+  if (!vitb200_fused_embed_bwd_supported(a->H, a->P, 0)) return VITB200_ERR_SHAPE;
+  if (a->B <= 0 || a->Np <= 0) return VITB200_ERR_ARG;
+  const int M = a->B * (a->Np + 1);
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(fused_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EMBED_BWD_SMEM);
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  fused_embed_bwd_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, EMBED_BWD_SMEM, (cudaStream_t)stream>>>(*a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

@@ -136,9 +136,172 @@ head_dw_kernel(const T* __restrict__ s, const float* __restrict__ logits, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-CTA fused variants (the head is a [B, H] x [H, C] problem: one launch instead of two / three)
+// ------------------------------------------------------------------------------------------------
+constexpr int HF_THREADS = 256;
+constexpr int HF_WARPS = HF_THREADS / 32;
+constexpr int HF_MAXC = 4;
+
+// logits + loss in one kernel: warp w handles samples w, w + 8, ... ; loss terms summed in sample order
+template <typename T>
+__global__ void __launch_bounds__(HF_THREADS)
+head_fused_fwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ bias,
+                      const void* __restrict__ labels, float* __restrict__ logits, float* __restrict__ loss, int B, int H,
+                      int C, int kind) {
+  __shared__ float wsum[HF_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc_loss = 0.f;
+  for (int b = warp; b < B; b += HF_WARPS) {
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
+      for (int h = lane; h < H; h += 32) a = fmaf(to_f<T>(s[(size_t)b * H + h]), to_f<T>(w[(size_t)c * H + h]), a);
+      a = warp_sum(a);
+      if (lane == 0) logits[(size_t)b * C + c] = round_to<T>(a + (bias ? bias[c] : 0.f));
+    }
+    __syncwarp();
+    if (labels && lane == 0) acc_loss += loss_term(logits, labels, b, C, kind);
+  }
+  if (!labels) return;
+  if (lane == 0) wsum[warp] = acc_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < HF_WARPS; ++k) t += wsum[k];
+    loss[0] = t / (kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+  }
+}
+
+// head backward + final-LayerNorm backward of the CLS rows in one kernel (C <= HF_MAXC):
+//   dl = dloss/dlogits ; ds = dl . W ; dz_cls = LN'(ds) ; dgamma, dbeta, dW, dbias reduced over samples in a
+//   fixed order (warp-strided sample order, then warps in order).
+template <typename T>
+__global__ void __launch_bounds__(HF_THREADS)
+head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ logits,
+                      const void* __restrict__ labels, const float* __restrict__ gloss, const float* __restrict__ z,
+                      size_t z_row_stride, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, float* __restrict__ dz_cls, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dbias, int B, int H, int C,
+                      int kind, int accumulate) {
+  extern __shared__ float red[];  // [HF_WARPS][(2 + C) * H + C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float g = gloss ? gloss[0] : 1.f;
+  constexpr int HPL = 4;   // columns per lane (H <= 128)
+  const int npl = (H + 31) / 32;
+  float ag[HPL], ab[HPL];      // dgamma / dbeta partials for columns lane, lane+32, ...
+  float aw[HF_MAXC][4];        // dW partials: only H <= 128 uses registers; larger H goes through the slow path below
+  float abias[HF_MAXC];
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < HF_MAXC; ++c) { abias[c] = 0.f; for (int i = 0; i < 4; ++i) aw[c][i] = 0.f; }
+  for (int b = warp; b < B; b += HF_WARPS) {
+    float dl[HF_MAXC];
+#pragma unroll
+    for (int c = 0; c < HF_MAXC; ++c) dl[c] = c < C ? dlogit<T>(logits, labels, b, c, B, C, kind, g) : 0.f;
+    const float mu = mean[b], rs = rstd[b];
+    float s1 = 0.f, s2 = 0.f;
+    float dsv[4], xh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int h = lane + 32 * i;
+      dsv[i] = 0.f; xh[i] = 0.f;
+      if (i < npl && h < H) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < HF_MAXC; ++c) if (c < C) a = fmaf(dl[c], to_f<T>(w[(size_t)c * H + h]), a);
+        a = round_to<T>(a);
+        dsv[i] = a;
+        xh[i] = (z[(size_t)b * z_row_stride + h] - mu) * rs;
+        const float gg = a * gamma[h];
+        s1 += gg;
+        s2 = fmaf(gg, xh[i], s2);
+        ag[i] = fmaf(a, xh[i], ag[i]);
+        ab[i] += a;
+        const float sv = to_f<T>(s[(size_t)b * H + h]);
+#pragma unroll
+        for (int c = 0; c < HF_MAXC; ++c) aw[c][i] = fmaf(dl[c], sv, aw[c][i]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < HF_MAXC; ++c) abias[c] += dl[c];
+    const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int h = lane + 32 * i;
+      if (i < npl && h < H) dz_cls[(size_t)b * H + h] = rs * (dsv[i] * gamma[h] - c1 - xh[i] * c2);
+    }
+  }
+  // cross-warp reduction in warp order
+  const int per = (2 + C) * H + C;
+  float* mine = red + (size_t)warp * per;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int h = lane + 32 * i;
+    if (i < npl && h < H) {
+      mine[h] = ag[i]; mine[H + h] = ab[i];
+      for (int c = 0; c < C; ++c) mine[(2 + c) * H + h] = aw[c][i];
+    }
+  }
+  if (lane == 0) for (int c = 0; c < C; ++c) mine[(2 + C) * H + c] = abias[c];
+  __syncthreads();
+  for (int e = threadIdx.x; e < per; e += HF_THREADS) {
+    float t = 0.f;
+    for (int k = 0; k < HF_WARPS; ++k) t += red[(size_t)k * per + e];
+    float* dst;
+    if (e < H) dst = dgamma + e;
+    else if (e < 2 * H) dst = dbeta + (e - H);
+    else if (e < (2 + C) * H) dst = dw + (e - 2 * H);
+    else dst = dbias ? dbias + (e - (2 + C) * H) : nullptr;
+    if (dst) *dst = accumulate ? *dst + t : t;
+  }
+}
+
 }  // namespace vb
 
 using namespace vb;
+
+extern "C" int vitb200_head_fused_supported(int H, int C) { return (H <= 128 && C <= HF_MAXC) ? 1 : 0; }
+
+extern "C" int vitb200_head_fused_fwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
+                                      float* loss, int B, int H, int C, int loss_kind, int dtype, void* stream) {
+  if (!s || !w || !logits || B <= 0 || H <= 0 || C <= 0 || (labels && !loss)) return VITB200_ERR_ARG;
+  if (loss_kind < 0 || loss_kind > 2) return VITB200_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VITB200_F32)
+    head_fused_fwd_kernel<float><<<1, HF_THREADS, 0, st>>>((const float*)s, (const float*)w, bias, labels, logits, loss, B, H, C, loss_kind);
+  else if (dtype == VITB200_BF16)
+    head_fused_fwd_kernel<bf16><<<1, HF_THREADS, 0, st>>>((const bf16*)s, (const bf16*)w, bias, labels, logits, loss, B, H, C, loss_kind);
+  else
+    return VITB200_ERR_ARG;
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_head_fused_bwd(const void* s, const void* w, const float* logits, const void* labels,
+                                      const float* gloss, const float* z, size_t z_row_stride, const float* mean,
+                                      const float* rstd, const float* gamma, float* dz_cls, float* dgamma, float* dbeta,
+                                      float* dw, float* dbias, int B, int H, int C, int loss_kind, int accumulate,
+                                      int dtype, void* stream) {
+  if (!s || !w || !logits || !labels || !z || !mean || !rstd || !gamma || !dz_cls || !dgamma || !dbeta || !dw)
+    return VITB200_ERR_ARG;
+  if (B <= 0 || !vitb200_head_fused_supported(H, C)) return VITB200_ERR_SHAPE;
+  if (loss_kind < 0 || loss_kind > 3) return VITB200_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)HF_WARPS * ((2 + C) * H + C) * sizeof(float);
+  if (dtype == VITB200_F32)
+    head_fused_bwd_kernel<float><<<1, HF_THREADS, smem, st>>>((const float*)s, (const float*)w, logits, labels, gloss, z,
+                                                              z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw,
+                                                              dbias, B, H, C, loss_kind, accumulate);
+  else if (dtype == VITB200_BF16)
+    head_fused_bwd_kernel<bf16><<<1, HF_THREADS, smem, st>>>((const bf16*)s, (const bf16*)w, logits, labels, gloss, z,
+                                                             z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw,
+                                                             dbias, B, H, C, loss_kind, accumulate);
+  else
+    return VITB200_ERR_ARG;
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
 
 extern "C" int vitb200_head_loss_fwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
                                      float* loss, int B, int H, int C, int loss_kind, int dtype, void* stream) {

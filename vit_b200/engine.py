@@ -210,7 +210,8 @@ class ViTEngine:
             self._keep.append(la)
             prog.append((lib.vitb200_fused_layer_fwd, (ctypes.addressof(la),)))
         hd = self.arena.layout.head_name
-        prog.append((lib.vitb200_head_loss_fwd, (
+        head_fn = lib.vitb200_head_fused_fwd if lib.vitb200_head_fused_supported(H, c.num_labels) else lib.vitb200_head_loss_fwd
+        prog.append((head_fn, (
             P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"),
             P_(self.labels) if with_labels else None, P_(self.logits), P_(self.loss), B, H, c.num_labels,
             self.loss_kind, dt)))
@@ -280,7 +281,8 @@ class ViTEngine:
                     self._stat(fin + 1), self._p("vit.layernorm.weight"), self._p("vit.layernorm.bias"),
                     M, H, T, eps, ph, rng, site_mlp(l), dt)))
         hd = self.arena.layout.head_name
-        prog.append((lib.vitb200_head_loss_fwd, (
+        head_fn = lib.vitb200_head_fused_fwd if lib.vitb200_head_fused_supported(H, c.num_labels) else lib.vitb200_head_loss_fwd
+        prog.append((head_fn, (
             P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"),
             P_(self.labels) if with_labels else None, P_(self.logits), P_(self.loss), B, H, c.num_labels,
             self.loss_kind, dt)))
@@ -304,28 +306,38 @@ class ViTEngine:
             self.gpart = torch.zeros(G, lay.n_opt, dtype=torch.float32, device=self.device)  # padding stays zero
         gp = self.gpart.data_ptr()
         prog = []
-        if given:
-            if not hasattr(self, "dlogits"):
-                self.dlogits = torch.zeros(B, c.num_labels, dtype=torch.float32, device=self.device)
-            prog.append((lib.vitb200_head_loss_bwd, (
-                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.dlogits), None, P_(self.ds_cls),
-                self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels, _lib.LOSS_GIVEN, 0, dt)))
+        if given and not hasattr(self, "dlogits"):
+            self.dlogits = torch.zeros(B, c.num_labels, dtype=torch.float32, device=self.device)
+        lab_ptr = P_(self.dlogits) if given else P_(self.labels)
+        kind = _lib.LOSS_GIVEN if given else self.loss_kind
+        gl = None if given else gloss_ptr
+        cur, other = self.dzA, self.dzB
+        top_cls = bool(lib.vitb200_head_fused_supported(H, c.num_labels))
+        if top_cls:
+            # head backward + final-LayerNorm backward of the CLS rows in one launch; only those rows carry a gradient
+            if not hasattr(self, "dz_cls"):
+                self.dz_cls = torch.zeros(B, H, dtype=torch.float32, device=self.device)
+            prog.append((lib.vitb200_head_fused_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), lab_ptr, gl, P_(self.z[Lh]), T * H,
+                self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"), P_(self.dz_cls),
+                self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), self._g(hd + ".weight"),
+                self._g(hd + ".bias"), B, H, c.num_labels, kind, 0, dt)))
         else:
             prog.append((lib.vitb200_head_loss_bwd, (
-                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.labels), gloss_ptr,
-                P_(self.ds_cls), self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels,
-                self.loss_kind, 0, dt)))
-        cur, other = self.dzA, self.dzB
-        prog.append((lib.vitb200_add_ln_bwd, (
-            P_(self.ds_cls), P_(self.z[Lh]), self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"),
-            None, P_(cur), None, self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), M, H, T, 0.0,
-            rng, 0, 0, dt, ws)))
+                P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), lab_ptr, gl, P_(self.ds_cls),
+                self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels, kind, 0, dt)))
+            prog.append((lib.vitb200_add_ln_bwd, (
+                P_(self.ds_cls), P_(self.z[Lh]), self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"),
+                None, P_(cur), None, self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), M, H, T, 0.0,
+                rng, 0, 0, dt, ws)))
         for l in range(Lh - 1, -1, -1):
             pre = f"vit.encoder.layer.{l}."
             qkv = self.qkv[l].data_ptr()
             dqkv = self.dqkv.data_ptr()
+            from_cls = top_cls and l == Lh - 1
             ua = _lib.LayerBwdUpperArgs(
-                B=B, T=T, H=H, p_drop=ph, rng=rng, site_proj=site_proj(l), site_mlp=site_mlp(l), dz=P_(cur),
+                B=B, T=T, H=H, p_drop=ph, rng=rng, site_proj=site_proj(l), site_mlp=site_mlp(l),
+                dz=None if from_cls else P_(cur), dz_cls=P_(self.dz_cls) if from_cls else None,
                 m=P_(self.m[l]), a=P_(self.a[l]), u2=P_(self.u2[l]), ctx=P_(self.ctx[l]), hmid=P_(self.hmid[l]),
                 mean2=self._stat(4 * l + 2), rstd2=self._stat(4 * l + 3), ln2_g=self._p(pre + "layernorm_after.weight"),
                 w_2=self._w(pre + "output.dense.weight"), w_1=self._w(pre + "intermediate.dense.weight"),
@@ -350,12 +362,23 @@ class ViTEngine:
             self._keep.append(la)
             prog.append((lib.vitb200_fused_layer_bwd_lower, (ctypes.addressof(la),)))
         emb = "vit.embeddings."
-        dpos = self._g(emb + "position_embeddings") if c.pos_encoding_type == "learned" else None
-        prog.append((lib.vitb200_patch_embed_bwd, (
-            P_(cur), P_(self.x), self._g(emb + "patch_embeddings.projection.weight"),
-            self._g(emb + "patch_embeddings.projection.bias"), self._g(emb + "cls_token"), dpos, B, c.image_size,
-            c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, 0, dt, ws)))
+        learned = c.pos_encoding_type == "learned"
         start = lay.buckets[1][1]          # first encoder layer
+        if lib.vitb200_fused_embed_bwd_supported(H, c.patch_size, 1 if learned else 0):
+            eb = _lib.EmbedBwdArgs(
+                B=B, L=c.image_size, P=c.patch_size, S=c.stride, Np=c.num_patches, n_valid=c.n_valid, H=H, p_drop=ph,
+                rng=rng, dz0=P_(cur), x=P_(self.x), gpart=gp, n_opt=lay.n_opt,
+                off_wp=lay.off(emb + "patch_embeddings.projection.weight"),
+                off_bp=lay.off(emb + "patch_embeddings.projection.bias"), off_cls=lay.off(emb + "cls_token"))
+            self._keep.append(eb)
+            prog.append((lib.vitb200_fused_embed_bwd, (ctypes.addressof(eb),)))
+            start = lay.buckets[0][1]      # the embeddings bucket is reduced from the CTA partials as well
+        else:
+            dpos = self._g(emb + "position_embeddings") if learned else None
+            prog.append((lib.vitb200_patch_embed_bwd, (
+                P_(cur), P_(self.x), self._g(emb + "patch_embeddings.projection.weight"),
+                self._g(emb + "patch_embeddings.projection.bias"), self._g(emb + "cls_token"), dpos, B, c.image_size,
+                c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, 0, dt, ws)))
         end = lay.buckets[Lh][2]           # end of the last encoder layer
         prog.append((lib.vitb200_grad_reduce, (gp, G, lay.n_opt, start, end, self.arena.grad.data_ptr())))
         return prog
@@ -574,8 +597,7 @@ class ViTEngine:
             self._progs[("fwd", train, True)] = self._build_forward(train, True)
         if ("bwd", train, None) not in self._progs:
             self._progs[("bwd", train, None)] = self._build_backward(train, None)
-        per_call = {"vitb200_head_loss_fwd": 2, "vitb200_head_loss_bwd": 2, "vitb200_attn_bwd": 2,
-                    "vitb200_patch_embed_bwd": 2}
+        per_call = {"vitb200_head_loss_fwd": 2, "vitb200_head_loss_bwd": 2, "vitb200_patch_embed_bwd": 2}
         n = 2  # grad_norm + adamw
         for key in (("fwd", train, True), ("bwd", train, None)):
             for fn, args in self._progs[key]:
@@ -583,5 +605,9 @@ class ViTEngine:
                 if fn.__name__ == "vitb200_linear_wgrad" and self.dt == BF16 and \
                         self.lib.vitb200_tc_supported(args[4], args[5], args[6]):
                     k = 2  # column-sum (bias gradient) kernel + tensor-core wgrad
+                if fn.__name__ == "vitb200_attn_bwd":
+                    tc = self.dt == BF16 and self.lib.vitb200_attn_tc_supported(
+                        self.cfg.tokens, self.cfg.head_dim, 3 * self.cfg.hidden_size, self.cfg.hidden_size)
+                    k = 1 if tc else 2  # tcgen05: one kernel; SIMT: dq pass + dk/dv pass
                 n += k
         return n
