@@ -173,6 +173,11 @@ def call_work(name: str, args: tuple, es: int):
     if name == "vitb200_patch_embed_bwd":
         B, L, P, S, Np, nv, H = args[6:13]
         return 2.0 * B * Np * P * H, 4 * B * L + 4 * B * (Np + 1) * H + 4 * H * P
+    if name.startswith("vitb200_fused_") or name.startswith("vitb200_head_fused"):
+        return fused_call_work(name, args)
+    if name == "vitb200_grad_reduce":
+        slots, start, end = args[1], args[3], args[4]
+        return float(slots * (end - start)), 4.0 * (slots + 1) * (end - start)
     if name == "vitb200_head_loss_fwd":
         B, H, C = args[6], args[7], args[8]
         return 2.0 * B * H * C, B * H * es + 8 * B * C
@@ -180,6 +185,77 @@ def call_work(name: str, args: tuple, es: int):
         B, H, C = args[8], args[9], args[10]
         return 4.0 * B * H * C, 2 * B * H * es + 8 * B * C
     return 0.0, 0.0
+
+
+def fused_call_work(name: str, args: tuple):
+    """Algorithmic (flops, bytes) of the fused row-chain kernels; dims come from their C argument structs."""
+    import ctypes
+    from vit_b200 import _lib
+
+    def st(tp):
+        return ctypes.cast(args[0], ctypes.POINTER(tp)).contents
+
+    if name == "vitb200_fused_layer_fwd":
+        a = st(_lib.LayerFwdArgs)
+        M, H = a.B * a.T, a.H
+        I = 4 * H
+        fl = 2.0 * M * (H * H + 2 * H * I + (0 if a.last else 3 * H * H))
+        by = M * (2 * H + 4 * H + 4 * H + 2 * H + 2 * I + 2 * I + 4 * H) + (0 if a.last else M * (2 * H + 6 * H)) + 2 * (H * H + 2 * H * I + 3 * H * H)
+        return fl, float(by)
+    if name == "vitb200_fused_embed_fwd":
+        a = st(_lib.EmbedFwdArgs)
+        M, H = a.B * (a.Np + 1), a.H
+        return 2.0 * M * (a.P * H + 3 * H * H), float(4 * a.B * a.L + M * (4 * H + 2 * H + 6 * H))
+    if name == "vitb200_fused_layer_bwd_upper":
+        a = st(_lib.LayerBwdUpperArgs)
+        M, H = a.B * a.T, a.H
+        I = 4 * H
+        fl = 2.0 * M * 2 * (2 * H * I + H * H)
+        by = M * ((0 if a.dz_cls else 4 * H) + 2 * I + 2 * I + 2 * H + 2 * H + 4 * H + 4 * H + 2 * H)
+        return fl, float(by)
+    if name == "vitb200_fused_layer_bwd_lower":
+        a = st(_lib.LayerBwdLowerArgs)
+        M, H = a.B * a.T, a.H
+        return 2.0 * M * 2 * 3 * H * H, float(M * (6 * H + 2 * H + 4 * H + 4 * H + 4 * H))
+    if name == "vitb200_fused_embed_bwd":
+        a = st(_lib.EmbedBwdArgs)
+        M, H = a.B * (a.Np + 1), a.H
+        return 2.0 * M * a.P * H, float(4 * a.B * a.L + 4 * M * H)
+    if name == "vitb200_head_fused_fwd":
+        B, H, C = args[6], args[7], args[8]
+        return 2.0 * B * H * C, float(B * H * 2 + 8 * B * C)
+    if name == "vitb200_head_fused_bwd":
+        B, H, C = args[15], args[16], args[17]
+        return 6.0 * B * H * C + 10.0 * B * H, float(B * H * (2 + 4 + 4) + 8 * B * C)
+    return 0.0, 0.0
+
+
+def tc_gemm_probe(dev, peaks):
+    """Tensor-pipe evidence at a scaled shape (hidden 768, the config's documented range): the tcgen05 Linear forward
+    alone, M = 128 x 129 rows, timed with CUDA events."""
+    import torch
+    from vit_b200 import _lib
+
+    lib = _lib.load()
+    out = {}
+    for (M, N, K) in ((16512, 3072, 768), (16512, 768, 3072)):
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = torch.randn(N, K, device=dev).bfloat16()
+        b = torch.zeros(N, device=dev)
+        y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        st = torch.cuda.current_stream(dev)
+        for _ in range(3):
+            _lib.check(lib.vitb200_tc_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, M, N, K, 0, st.cuda_stream), "probe")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10):
+            lib.vitb200_tc_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, M, N, K, 0, st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / 10
+        tf = 2.0 * M * N * K / sec / 1e12
+        out[f"linear_fwd_{M}x{N}x{K}"] = {"tflops": tf, "frac_of_bf16_burst_peak": tf / peaks["tf_burst"], "us": sec * 1e6}
+    return out
 
 
 def time_calls(eng, progs, repeats: int = 20, iters: int = 5):
@@ -358,6 +434,12 @@ def main():
         json.dump({"rows": rows, "aggregate": kernels, "kernel_time_sum_us": ksum_us, "step_us": ms_step * 1e3},
                   open(args.kernels_json, "w"), indent=1)
 
+    probe = None
+    if not args.no_sweep and world == 1:
+        try:
+            probe = tc_gemm_probe(dev, peaks)
+        except Exception as ex:  # noqa: BLE001
+            probe = {"error": str(ex)[:200]}
     sweep = None
     if not args.no_sweep and world == 1:
         sweep = {}
@@ -404,6 +486,7 @@ def main():
         "kernel_time_sum_us": ksum_us,
         "kernels": kernels[:8],
         "sweep": sweep,
+        "tc_gemm_probe": probe,
         "final_loss": loss_last,
     }
     print(json.dumps(line), flush=True)
