@@ -19,7 +19,7 @@
  * Buffers typed `void*` hold that type; buffers typed `float*` are always fp32.
  *
  * Dropout masks are never stored.  They are a pure function of (seed, step, site, element index)
- * through Philox4x32-10; `rng` points at two DEVICE uint64 {seed, step} so that a captured CUDA graph
+ * through Philox4x32-7; `rng` points at two DEVICE uint64 {seed, step} so that a captured CUDA graph
  * sees a new step on every replay.  `site` distinguishes the dropout call sites of one step.
  *
  * Each entry point names the reference code it replaces (paths relative to the reference repo;

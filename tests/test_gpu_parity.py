@@ -113,7 +113,7 @@ def test_dropout_on_vs_oracle_with_replayed_masks(pos, precision):
     out.loss.backward()
     eng = m._engine(B)
     T, H, a = spec.tokens, spec.hidden, spec.heads
-    Tpad = (T + 3) // 4 * 4
+    Tpad = (T + 7) // 8 * 8
     masks = {"emb": eng.dropout_mask(_lib.SITE_EMB, B * T * H, spec.p_hidden).view(B, T, H).cpu()}
     for l in range(spec.layers):
         masks[f"proj{l}"] = eng.dropout_mask(_lib.site_proj(l), B * T * H, spec.p_hidden).view(B, T, H).cpu()

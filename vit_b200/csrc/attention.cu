@@ -115,7 +115,7 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
   const int ic = valid ? i : Tlen - 1;
   const size_t row0 = (size_t)b * Tlen;
   const int Hd = heads * D;
-  const int Tpad = (Tlen + 3) & ~3;
+  const int Tpad = attn_drop_tpad(Tlen);
   const DropCtx dc = make_drop(p_drop, rng ? rng[0] : 0ull, rng ? (uint32_t)rng[1] : 0u, site);
   const float sl2 = scale * LOG2E;
 
@@ -195,7 +195,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
   const int ic = valid ? i : Tlen - 1;
   const size_t row0 = (size_t)b * Tlen;
   const int Hd = heads * D;
-  const int Tpad = (Tlen + 3) & ~3;
+  const int Tpad = attn_drop_tpad(Tlen);
   const DropCtx dc = make_drop(p_drop, rng ? rng[0] : 0ull, rng ? (uint32_t)rng[1] : 0u, site);
   const float sl2 = scale * LOG2E;
 
@@ -275,7 +275,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
   const int jc = valid ? j : Tlen - 1;
   const size_t row0 = (size_t)b * Tlen;
   const int Hd = heads * D;
-  const int Tpad = (Tlen + 3) & ~3;
+  const int Tpad = attn_drop_tpad(Tlen);
   const DropCtx dc = make_drop(p_drop, rng ? rng[0] : 0ull, rng ? (uint32_t)rng[1] : 0u, site);
   const float sl2 = scale * LOG2E;
 

@@ -122,6 +122,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
+  pdl_wait();     // q/k/v (and dctx) come from the previous kernel of the step
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -136,7 +138,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Kk{smem_u32(sK), 16, 16384, 0};
   const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV), 16384, 0, 1};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
-  const int Tpad = (T + 3) & ~3;
+  const int Tpad = attn_drop_tpad(T);
   const float sl2 = P.scale * AT_LOG2E;
   uint32_t ph_q = 0, ph_mma = 0;
   // T = 128 n + 1 (the CLS token makes every configured sequence one row longer than a tile): the last query row
@@ -252,18 +254,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float v[32];
       tmem_ld_32x32(my_tmem + cS + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float p4[4];
+      for (int j = 0; j < 32; j += 8) {
+        float kp[8];
+        if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          p4[q] = (c0 + j + q < T) ? exp2f(v[j + q] * sl2 - mxs) : 0.f;
-          sum += p4[q];
+        for (int q = 0; q < 8; ++q) {
+          const float p = (c0 + j + q < T) ? exp2f(v[j + q] * sl2 - mxs) : 0.f;
+          sum += p;
+          v[j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
         }
-        if (dc.on && c0 + j < T) {
-          const float4 kp = drop4(dc, (drow + (uint64_t)(c0 + j)) >> 2);
-          p4[0] *= kp.x; p4[1] *= kp.y; p4[2] *= kp.z; p4[3] *= kp.w;
-        }
-        v[j] = p4[0]; v[j + 1] = p4[1]; v[j + 2] = p4[2]; v[j + 3] = p4[3];
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(at_swz(sP, tid, (c0 >> 3) + c)) = at_pack8(&v[c * 8]);
@@ -342,6 +341,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
+  pdl_wait();     // q/k/v (and dctx) come from the previous kernel of the step
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -358,7 +359,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const AOp Kk{smem_u32(sK), 16, 16384, 0}, Kmn{smem_u32(sK), 16384, 0, 1}, Vk{smem_u32(sV), 16, 16384, 0};
   const AOp DSk{smem_u32(sDS), 16, 16384, 0};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
-  const int Tpad = (T + 3) & ~3;
+  const int Tpad = attn_drop_tpad(T);
   const float sl2 = P.scale * AT_LOG2E;
   uint32_t ph_q = 0, ph_mma = 0;
   const bool side = (T % 128 == 1) && T > 1 && P.cosT == nullptr;  // see the forward kernel
@@ -493,17 +494,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_32x32(my_tmem + cS + c0, s);
       tmem_ld_32x32(my_tmem + cDP + c0, dp);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 kp = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (dc.on && c0 + j < T) kp = drop4(dc, (drow + (uint64_t)(c0 + j)) >> 2);
-        const float kpa[4] = {kp.x, kp.y, kp.z, kp.w};
+      for (int j = 0; j < 32; j += 8) {
+        float kpa[8];
+        if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const bool on = valid && (c0 + j + q < T);
+          const float kq = (c0 + j < T) ? kpa[q] : 0.f;
           const float p = on ? exp2f(s[j + q] * sl2 - lse2) : 0.f;
-          const float ds = p * (dp[j + q] * kpa[q] - Di) * P.scale;
+          const float ds = on ? p * (dp[j + q] * kq - Di) * P.scale : 0.f;  // (columns past KP hold stale TMEM data)
           s[j + q] = ds;               // dS (scale folded in)
-          dp[j + q] = p * kpa[q];      // dropped probabilities
+          dp[j + q] = p * kq;          // dropped probabilities
         }
       }
 #pragma unroll
@@ -625,7 +626,7 @@ extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    attn_tc_fwd_kernel<DD><<<grid, 160, AT_FWD_SMEM, st>>>(tQ, tKV, P);                                \
+    vb_launch_pdl(attn_tc_fwd_kernel<DD>, grid, dim3(160), AT_FWD_SMEM, st, tQ, tKV, P);                                \
   }
   if (d == 16) LAUNCH_F(16) else LAUNCH_F(32)
 #undef LAUNCH_F
@@ -657,7 +658,7 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    attn_tc_bwd_kernel<DD><<<grid, 160, AT_BWD_SMEM, st>>>(tQ, tKV, tDO, P);                           \
+    vb_launch_pdl(attn_tc_bwd_kernel<DD>, grid, dim3(160), AT_BWD_SMEM, st, tQ, tKV, tDO, P);                           \
   }
   if (d == 16) LAUNCH_B(16) else LAUNCH_B(32)
 #undef LAUNCH_B

@@ -20,6 +20,25 @@ namespace vb {
 typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The step is a chain of ~20 short kernels; with a plain launch each one
+// pays launch latency + block scheduling + its own prologue after the previous kernel has drained.  Kernels
+// launched through vb_launch_pdl() may start while their predecessor is still running: they do their
+// data-independent prologue (mbarrier init, descriptor prefetch, weight staging) and then block in pdl_wait()
+// until every earlier kernel of the stream has completed and its writes are visible.
+// Rules: (1) pdl_trigger() is called only AFTER pdl_wait() has returned.  Kernel k+1 can therefore start no earlier
+//            than the moment kernel k got past its own wait, i.e. when kernels <= k-1 have completed: at most two
+//            kernels of the chain are resident at once (k running, k+1 in its prologue).
+//        (2) before pdl_wait() a kernel may only read data that its IMMEDIATE predecessor does not write.  Weights
+//            are written only by the optimizer kernel; the only kernel that can directly follow it is the
+//            embedding kernel, which therefore stages its weights after the wait.  Every other kernel stages
+//            its weights / bias vectors before the wait.
+//        (3) TMEM is allocated after pdl_wait(), so a waiting CTA never holds TMEM that a CTA of the still running
+//            predecessor needs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // 4-wide typed loads/stores (activations are float or bf16; accumulation is always fp32)
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Vec4;
@@ -83,18 +102,19 @@ template <int W> __device__ __forceinline__ float group_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG for dropout.  Masks are never stored: forward and backward
-// regenerate them from (seed, step, site, element index).
+// Philox4x32-7 counter RNG for dropout (7 rounds is the Crush-resistant minimum of Salmon et al. 2011; the extra three
+// rounds of the -10 default are safety margin that costs 30 % of the instructions of the attention epilogues).
+// Masks are never stored: forward and backward regenerate them from (seed, step, site, element index).
 //   key     = seed (64 bit)
-//   counter = { idx4.lo, idx4.hi, site, step }   with idx4 = element_index / 4
-// Element e of a tensor uses word (e & 3) of the block at idx4 = e >> 2.
-// keep(e) <=> uniform(e) >= p  with uniform = word * 2^-32.
+//   counter = { blk.lo, blk.hi, site, step }   with blk = element_index / 8
+// One 128-bit block decides EIGHT elements: element e uses the 16-bit half (e & 1) of word ((e >> 1) & 3) of the block
+// at blk = e >> 3;  keep(e) <=> half >= round(p * 2^16)   (p is honoured to 2^-17: 0.1 -> 0.100006).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
     uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -104,9 +124,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
+// attention-probability masks are indexed [b, head, query, key] with the key axis padded to a multiple of 8
+__host__ __device__ __forceinline__ int attn_drop_tpad(int T) { return (T + 7) & ~7; }
+
 struct DropCtx {
   uint32_t k0, k1, site, step;
-  uint32_t thresh;  // keep <=> word >= thresh ; thresh = p * 2^32
+  uint32_t thresh;  // keep <=> half >= thresh ; thresh = round(p * 2^16)
   float scale;      // 1 / (1 - p)
   bool on;
 };
@@ -115,23 +138,41 @@ __device__ __forceinline__ DropCtx make_drop(float p, uint64_t seed, uint32_t st
   d.on = p > 0.f;
   d.k0 = (uint32_t)seed; d.k1 = (uint32_t)(seed >> 32);
   d.site = site; d.step = step;
-  double t = (double)p * 4294967296.0;
-  d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  const float t = p * 65536.f + 0.5f;
+  d.thresh = t >= 65536.f ? 65536u : (uint32_t)t;   // 65536 => nothing is kept (p = 1)
   d.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   return d;
 }
-// 4 keep-multipliers (0 or 1/(1-p)) for elements [4*idx4, 4*idx4+3]
+__device__ __forceinline__ float2 drop_word(const DropCtx& d, uint32_t w) {
+  return make_float2((w & 0xffffu) >= d.thresh ? d.scale : 0.f, (w >> 16) >= d.thresh ? d.scale : 0.f);
+}
+// 8 keep-multipliers (0 or 1/(1-p)) for elements [8*idx8, 8*idx8+7]
+__device__ __forceinline__ void drop8(const DropCtx& d, uint64_t idx8, float (&k)[8]) {
+  if (!d.on) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i] = 1.f;
+    return;
+  }
+  const uint4 r = philox4x32_7((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.site, d.step, d.k0, d.k1);
+  const float2 a = drop_word(d, r.x), b = drop_word(d, r.y), c = drop_word(d, r.z), e = drop_word(d, r.w);
+  k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y; k[4] = c.x; k[5] = c.y; k[6] = e.x; k[7] = e.y;
+}
+// 4 keep-multipliers for elements [4*idx4, 4*idx4+3]
 __device__ __forceinline__ float4 drop4(const DropCtx& d, uint64_t idx4) {
   if (!d.on) return make_float4(1.f, 1.f, 1.f, 1.f);
-  uint4 r = philox4x32_10((uint32_t)idx4, (uint32_t)(idx4 >> 32), d.site, d.step, d.k0, d.k1);
-  return make_float4(r.x >= d.thresh ? d.scale : 0.f, r.y >= d.thresh ? d.scale : 0.f,
-                     r.z >= d.thresh ? d.scale : 0.f, r.w >= d.thresh ? d.scale : 0.f);
+  const uint64_t idx8 = idx4 >> 1;
+  const uint4 r = philox4x32_7((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.site, d.step, d.k0, d.k1);
+  const float2 a = drop_word(d, (idx4 & 1) ? r.z : r.x), b = drop_word(d, (idx4 & 1) ? r.w : r.y);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 __device__ __forceinline__ float drop1(const DropCtx& d, uint64_t idx) {
   if (!d.on) return 1.f;
-  uint4 r = philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), d.site, d.step, d.k0, d.k1);
-  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  return w >= d.thresh ? d.scale : 0.f;
+  const uint64_t idx8 = idx >> 3;
+  const uint4 r = philox4x32_7((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.site, d.step, d.k0, d.k1);
+  const uint32_t q = (uint32_t)(idx >> 1) & 3u;
+  const uint32_t w = q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;
+  const uint32_t h = (idx & 1) ? (w >> 16) : (w & 0xffffu);
+  return h >= d.thresh ? d.scale : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -182,5 +223,22 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// launch with the programmatic-stream-serialization attribute (see pdl_wait above); the kernel MUST call pdl_wait()
+template <typename... KArgs, typename... Args>
+static inline void vb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace vb

@@ -102,23 +102,25 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   // columns 32..63 of the sD tile are never written by the epilogues: zero them once (MN-major wgrad view reads them)
 #pragma unroll
   for (int c = 4; c < 8; ++c) fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-
-  if (tid == 0) {
+  if (tid == 0) {  // weights are not written inside a step: staged before the dependency wait
     mbar_expect_tx(b_w, 8192 + 16384 + 4096);
     tma_load_2d(sW2, &tmW2, b_w, 0, 0);          // W2 [H rows, I cols]: two {64 cols, H rows} boxes
     tma_load_2d(sW2 + 4096, &tmW2, b_w, 64, 0);
     tma_load_2d(sW1, &tmW1, b_w, 0, 0);          // W1 [I rows, H cols]: one {64 cols (32 valid), 128 rows} box
     tma_load_2d(sWo, &tmWo, b_w, 0, 0);          // Wo [H rows, H cols]
   }
+  pdl_wait();
+  pdl_trigger();
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t aD = smem_u32(sD), aDA = smem_u32(sDA), aM = smem_u32(sM), aU2 = smem_u32(sU2), aCtx = smem_u32(sCtx);
   const uint32_t aW2 = smem_u32(sW2), aW1 = smem_u32(sW1), aWo = smem_u32(sWo);
   // operand views
@@ -373,16 +375,19 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(b_w, 12288);
+    tma_load_2d(sWq, &tmWq, b_w, 0, 0);  // Wqkv [3H rows, H cols]: {64 cols (32 valid), 96 rows}
+  }
+  pdl_wait();
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-  if (tid == 0) {
-    mbar_expect_tx(b_w, 12288);
-    tma_load_2d(sWq, &tmWq, b_w, 0, 0);  // Wqkv [3H rows, H cols]: {64 cols (32 valid), 96 rows}
-  }
   const Opnd DQ_k{smem_u32(sDQ), 16, 16384, 0};        // dqkv tile, K-major (K = 3H = 96: 6 k-steps over 2 k-blocks)
   const Opnd DQ_mn{smem_u32(sDQ), 16384, 0, 1};        // MN-major (MN = 96 of 128)
   const Opnd U_mn{smem_u32(sU), 16384, 0, 1};
@@ -504,12 +509,14 @@ fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
   const int T = P.Np + 1, M = P.B * T;
   const int ntiles = (M + 127) / 128;
   if (tid == 0) { mbar_init(b_mma, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {  // zero both tiles once: unused columns must be finite for the MN-major views
     fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
     fb_swz_store(sX, tid, c, make_uint4(0u, 0u, 0u, 0u));
   }
+  pdl_wait();
+  pdl_trigger();
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -604,6 +611,8 @@ constexpr int EMBED_BWD_SMEM = 16384 + 16384 + 1024 + 16384 + 1024;
 __global__ void __launch_bounds__(256)
 grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, size_t start, size_t n4,
                    float* __restrict__ grad) {
+  pdl_wait();
+  pdl_trigger();
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     const float4* src = reinterpret_cast<const float4*>(gpart + start) + i;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -659,8 +668,8 @@ extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args*
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  fused_bwd_upper_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, UPPER_SMEM, (cudaStream_t)stream>>>(
-      tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm, *a);
+  vb_launch_pdl(fused_bwd_upper_kernel, dim3(vitb200_fused_bwd_grid(M)), dim3(FB_THREADS), UPPER_SMEM, (cudaStream_t)stream,
+                tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -684,8 +693,8 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  fused_bwd_lower_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, LOWER_SMEM, (cudaStream_t)stream>>>(tDQ, tU, tWq, tZ,
-                                                                                                    tDh, *a);
+  vb_launch_pdl(fused_bwd_lower_kernel, dim3(vitb200_fused_bwd_grid(M)), dim3(FB_THREADS), LOWER_SMEM, (cudaStream_t)stream,
+                tDQ, tU, tWq, tZ, tDh, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -705,7 +714,7 @@ extern "C" int vitb200_fused_embed_bwd(const vitb200_embed_bwd_args* a, void* st
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  fused_embed_bwd_kernel<<<vitb200_fused_bwd_grid(M), FB_THREADS, EMBED_BWD_SMEM, (cudaStream_t)stream>>>(*a);
+  vb_launch_pdl(fused_embed_bwd_kernel, dim3(vitb200_fused_bwd_grid(M)), dim3(FB_THREADS), EMBED_BWD_SMEM, (cudaStream_t)stream, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -718,7 +727,7 @@ extern "C" int vitb200_grad_reduce(const float* gpart, int slots, size_t stride,
   const size_t n4 = (end - start) / 4;
   size_t g = (n4 + 255) / 256;
   if (g > 592) g = 592;
-  grad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(gpart, slots, stride, start, n4, grad);
+  vb_launch_pdl(grad_reduce_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, gpart, slots, stride, start, n4, grad);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

@@ -112,24 +112,16 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
     mbar_init(b_in, 1); mbar_init(b_w1, 1); mbar_init(b_w2, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   for (int j = threadIdx.x; j < H; j += FF_THREADS) {
     s_bo[j] = P.b_o[j]; s_g2[j] = P.ln2_g[j]; s_b2ln[j] = P.ln2_b[j]; s_b2[j] = P.b_2[j];
     s_gn[j] = P.lnn_g[j]; s_bn[j] = P.lnn_b[j];
   }
   for (int j = threadIdx.x; j < I; j += FF_THREADS) s_b1[j] = P.b_1[j];
   if (!P.last) for (int j = threadIdx.x; j < 3 * H; j += FF_THREADS) s_bq[j] = P.b_qkv[j];
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-
-  if (tid == 0) {
-    mbar_expect_tx(b_in, SZ_A + SZ_WO);
-    tma_load_2d(sA, &tmCtx, b_in, 0, r0);
-    tma_load_2d(sWo, &tmWo, b_in, 0, 0);
-    mbar_expect_tx(b_w1, SZ_W1);
+  if (tid == 0) {  // weights: not produced inside a step, so they are staged while the previous kernel still runs
+    mbar_expect_tx(b_w1, SZ_WO + SZ_W1);
+    tma_load_2d(sWo, &tmWo, b_w1, 0, 0);
     tma_load_2d(sW1, &tmW1, b_w1, 0, 0);
     mbar_expect_tx(b_w2, SZ_W2);
 #pragma unroll
@@ -138,6 +130,18 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
       mbar_expect_tx(b_wq, SZ_WQ);
       tma_load_2d(sWq, &tmWq, b_wq, 0, 0);
     }
+  }
+  pdl_wait();     // everything below reads what earlier kernels of this step produced
+  pdl_trigger();  // the next kernel may start its prologue now (never earlier: see common.cuh)
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  if (tid == 0) {
+    mbar_expect_tx(b_in, SZ_A);
+    tma_load_2d(sA, &tmCtx, b_in, 0, r0);
   }
   // residual row (overlaps the TMA loads)
   float h[H];
@@ -153,6 +157,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   // ---- 1. attention output projection + dropout + residual, LayerNorm-after ----
   if (tid == 0) {
     mbar_wait(b_in, 0);
+    mbar_wait(b_w1, 0);
     tc_fence_after();
     issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sWo), 0, H, H, b_mma);
   }
@@ -310,6 +315,11 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
     mbar_init(b_wp, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
+  __syncthreads();
+  // The embedding kernel is the FIRST kernel of a step: its predecessor is the previous step's optimizer kernel,
+  // which writes the weights.  So here even the weight staging has to come after pdl_wait().
+  pdl_wait();
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   for (int j = threadIdx.x; j < H; j += FF_THREADS) { s_bp[j] = P.b_p[j]; s_cls[j] = P.cls[j]; s_g[j] = P.ln_g[j]; s_b[j] = P.ln_b[j]; }
   for (int j = threadIdx.x; j < 3 * H; j += FF_THREADS) s_bq[j] = P.b_qkv[j];
@@ -429,7 +439,7 @@ static int launch_layer(const vitb200_layer_fwd_args* a, cudaStream_t st) {
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  kern<<<(M + FF_ROWS - 1) / FF_ROWS, FF_THREADS, layer_smem<H>(), st>>>(tCtx, tWo, tW1, tW2, tWq, *a);
+  vb_launch_pdl(kern, dim3((M + FF_ROWS - 1) / FF_ROWS), dim3(FF_THREADS), layer_smem<H>(), st, tCtx, tWo, tW1, tW2, tWq, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -448,7 +458,7 @@ static int launch_embed(const vitb200_embed_fwd_args* a, cudaStream_t st) {
     if (e != cudaSuccess) return vb_cuda_error(e);
     done = true;
   }
-  kern<<<(M + FF_ROWS - 1) / FF_ROWS, FF_THREADS, embed_smem<H>(), st>>>(tWp, tWq, *a);
+  vb_launch_pdl(kern, dim3((M + FF_ROWS - 1) / FF_ROWS), dim3(FF_THREADS), embed_smem<H>(), st, tWp, tWq, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

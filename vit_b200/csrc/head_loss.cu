@@ -139,7 +139,7 @@ head_dw_kernel(const T* __restrict__ s, const float* __restrict__ logits, const 
 // ------------------------------------------------------------------------------------------------
 // Single-CTA fused variants (the head is a [B, H] x [H, C] problem: one launch instead of two / three)
 // ------------------------------------------------------------------------------------------------
-constexpr int HF_THREADS = 256;
+constexpr int HF_THREADS = 1024;  // 32 warps: two samples per warp at B = 64 (the kernel is a chain of dependent loads)
 constexpr int HF_WARPS = HF_THREADS / 32;
 constexpr int HF_MAXC = 4;
 
@@ -151,6 +151,8 @@ head_fused_fwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const fl
                       int C, int kind) {
   __shared__ float wsum[HF_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
   float acc_loss = 0.f;
   for (int b = warp; b < B; b += HF_WARPS) {
     for (int c = 0; c < C; ++c) {
@@ -185,6 +187,8 @@ head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const fl
                       int kind, int accumulate) {
   extern __shared__ float red[];  // [HF_WARPS][(2 + C) * H + C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
   const float g = gloss ? gloss[0] : 1.f;
   constexpr int HPL = 4;   // columns per lane (H <= 128)
   const int npl = (H + 31) / 32;
@@ -269,9 +273,9 @@ extern "C" int vitb200_head_fused_fwd(const void* s, const void* w, const float*
   if (loss_kind < 0 || loss_kind > 2) return VITB200_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VITB200_F32)
-    head_fused_fwd_kernel<float><<<1, HF_THREADS, 0, st>>>((const float*)s, (const float*)w, bias, labels, logits, loss, B, H, C, loss_kind);
+    vb_launch_pdl(head_fused_fwd_kernel<float>, dim3(1), dim3(HF_THREADS), 0, st, (const float*)s, (const float*)w, bias, labels, logits, loss, B, H, C, loss_kind);
   else if (dtype == VITB200_BF16)
-    head_fused_fwd_kernel<bf16><<<1, HF_THREADS, 0, st>>>((const bf16*)s, (const bf16*)w, bias, labels, logits, loss, B, H, C, loss_kind);
+    vb_launch_pdl(head_fused_fwd_kernel<bf16>, dim3(1), dim3(HF_THREADS), 0, st, (const bf16*)s, (const bf16*)w, bias, labels, logits, loss, B, H, C, loss_kind);
   else
     return VITB200_ERR_ARG;
   VB_CHECK_LAUNCH();
@@ -290,13 +294,13 @@ extern "C" int vitb200_head_fused_bwd(const void* s, const void* w, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)HF_WARPS * ((2 + C) * H + C) * sizeof(float);
   if (dtype == VITB200_F32)
-    head_fused_bwd_kernel<float><<<1, HF_THREADS, smem, st>>>((const float*)s, (const float*)w, logits, labels, gloss, z,
-                                                              z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw,
-                                                              dbias, B, H, C, loss_kind, accumulate);
+    vb_launch_pdl(head_fused_bwd_kernel<float>, dim3(1), dim3(HF_THREADS), smem, st, (const float*)s, (const float*)w, logits,
+                  labels, gloss, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C, loss_kind,
+                  accumulate);
   else if (dtype == VITB200_BF16)
-    head_fused_bwd_kernel<bf16><<<1, HF_THREADS, smem, st>>>((const bf16*)s, (const bf16*)w, logits, labels, gloss, z,
-                                                             z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw,
-                                                             dbias, B, H, C, loss_kind, accumulate);
+    vb_launch_pdl(head_fused_bwd_kernel<bf16>, dim3(1), dim3(HF_THREADS), smem, st, (const bf16*)s, (const bf16*)w, logits,
+                  labels, gloss, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C, loss_kind,
+                  accumulate);
   else
     return VITB200_ERR_ARG;
   VB_CHECK_LAUNCH();

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(OP_THREADS)
 grad_norm_kernel(const float* __restrict__ g, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
                  float* __restrict__ partial, unsigned int* counter) {
   __shared__ float red[OP_THREADS / 32];
+  pdl_wait();
+  pdl_trigger();
   float acc = 0.f;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * OP_THREADS) {
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(OP_THREADS)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, const float* __restrict__ state,
              uint64_t* rng) {
+  pdl_wait();
+  pdl_trigger();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float gmul = hyper[6] * state[2];
   const float bc1 = state[3], bc2 = state[4];
@@ -115,7 +119,7 @@ extern "C" int vitb200_grad_norm(const float* g, size_t n, const float* hyper, f
   if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return VITB200_ERR_ALIGN;
   unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
-  grad_norm_kernel<<<op_grid(n), OP_THREADS, 0, (cudaStream_t)stream>>>(g, n / 4, hyper, state, partial, counter);
+  vb_launch_pdl(grad_norm_kernel, dim3(op_grid(n)), dim3(OP_THREADS), 0, (cudaStream_t)stream, g, n / 4, hyper, state, partial, counter);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -127,7 +131,7 @@ extern "C" int vitb200_adamw(float* p, const float* g, float* m, float* v, void*
   if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
         reinterpret_cast<uintptr_t>(v)) & 15) != 0 || (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
     return VITB200_ERR_ALIGN;
-  adamw_kernel<<<op_grid(n), OP_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow, n / 4, hyper, state, rng);
+  vb_launch_pdl(adamw_kernel, dim3(op_grid(n)), dim3(OP_THREADS), 0, (cudaStream_t)stream, p, g, m, v, (bf16*)shadow, n / 4, hyper, state, rng);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
