@@ -1,11 +1,14 @@
 // Fused backward row-chain kernels (bf16 mode, H = 32).  See include/vit_b200.h.
 //
-// One CTA = 128 threads, thread t owns row t of the current 128-row tile and TMEM lane t.
+// One CTA = 128 rows x 4 column groups = 512 threads (16 warps): warp w reads TMEM lane quarter (w & 3) = rows
+// 32 (w & 3) .. +31 of the current tile and handles column group cg = w >> 2 of every epilogue (see fused_fwd.cu for
+// why: one thread per row left each SM scheduler with a single, latency-bound warp).
 // Every activation-gradient tile (ddelta2, da, ddelta1, dqkv) is written/loaded ONCE into shared memory in
 // the 128B-swizzled row image and then consumed twice by tcgen05.mma:
 //   dgrad  dX = dY . W      : the tile is operand A, K-major view   (contraction over its columns)
 //   wgrad  dW = dY^T . X    : the tile is operand A, MN-major view  (contraction over its 128 rows)
 // wgrad accumulators stay in TMEM across the tiles of a persistent CTA and are written out once.
+// All parameter-gradient reductions run in a fixed order (deterministic=True, basemodule.py:250).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_host.cuh"
@@ -13,9 +16,11 @@
 namespace vb {
 using namespace vb::tc;
 
-constexpr int FB_THREADS = 128;
+constexpr int FB_CG = 4;
+constexpr int FB_THREADS = 128 * FB_CG;
 constexpr int FB_H = 32;
 constexpr int FB_I = 128;
+constexpr int FB_HC = FB_H / FB_CG;   // 8 residual-stream columns per thread
 
 __device__ __forceinline__ uint4 fb_pack8(const float* v) {
   __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -28,13 +33,14 @@ __device__ __forceinline__ uint4 fb_pack8(const float* v) {
 __device__ __forceinline__ void fb_swz_store(uint8_t* tile, int r, int chunk, uint4 v) {
   *reinterpret_cast<uint4*>(tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = v;
 }
-// sum over the 128 rows of column `col` of a swizzled bf16 tile (rows in order => deterministic)
-__device__ __forceinline__ float fb_colsum(const uint8_t* tile, int col) {
+// sum over rows [rb, rb + NR) of column `col` of a swizzled bf16 tile (rows in order => deterministic)
+template <int NR>
+__device__ __forceinline__ float fb_colsum(const uint8_t* tile, int col, int rb) {
   const uint8_t* blk = tile + (col >> 6) * 16384;
   const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
   float s = 0.f;
 #pragma unroll 8
-  for (int r = 0; r < 128; ++r) {
+  for (int r = rb; r < rb + NR; ++r) {
     const bf16 v = *reinterpret_cast<const bf16*>(blk + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
     s += __bfloat162float(v);
   }
@@ -44,6 +50,12 @@ __device__ __forceinline__ float fb_colsum(const uint8_t* tile, int col) {
 // a 128-byte row of a TMA-loaded (128B-swizzled) tile: 16-byte chunk c of row r
 __device__ __forceinline__ const uint8_t* fb_swz_ptr(const uint8_t* tile, int r, int chunk) {
   return tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+}
+// FB_HC = 8 consecutive fp32 values (columns 8 cg .. 8 cg + 7) of row r of a TMA-staged fp32 [128, 32] tile
+__device__ __forceinline__ void fb_ld_f8(const uint8_t* tile, int r, int cg, float (&x)[FB_HC]) {
+  const float4 a = *reinterpret_cast<const float4*>(fb_swz_ptr(tile, r, 2 * cg));
+  const float4 b = *reinterpret_cast<const float4*>(fb_swz_ptr(tile, r, 2 * cg + 1));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 
 // operand view for one tcgen05 GEMM
@@ -63,6 +75,42 @@ __device__ __forceinline__ void fb_issue(uint32_t tmem_d, const Opnd& A, const O
   for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, opnd_desc(A, k), opnd_desc(B, k), idesc, (accumulate || k > 0) ? 1u : 0u);
 }
 
+// LayerNorm backward of one row spread over FB_CG threads: the two row sums are exchanged through shared memory.
+// du: upstream gradient (bf16-rounded), xh: normalised input; on return g = du * gamma and (c1, c2) the row means.
+__device__ __forceinline__ void fb_ln_bwd_sums(const float (&du)[FB_HC], const float (&xh)[FB_HC], const float* s_gamma, int hc0,
+                                               float2* s_ex, int r, int cg, float (&g)[FB_HC], float& c1, float& c2) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < FB_HC; ++j) {
+    g[j] = du[j] * s_gamma[hc0 + j];
+    s1 += g[j];
+    s2 = fmaf(g[j], xh[j], s2);
+  }
+  s_ex[cg * 128 + r] = make_float2(s1, s2);
+  __syncthreads();
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int q = 0; q < FB_CG; ++q) { const float2 p = s_ex[q * 128 + r]; t1 += p.x; t2 += p.y; }
+  c1 = t1 * (1.f / FB_H);
+  c2 = t2 * (1.f / FB_H);
+}
+
+// red[e * 128 + row] (e < NE) -> out(e) = sum over the 128 rows, in a fixed order: 8 threads x 16 rows, then a shuffle tree.
+// Call with all FB_THREADS threads after a __syncthreads(); NE * 8 <= FB_THREADS.
+template <typename F>
+__device__ __forceinline__ void fb_reduce_rows(const float* red, int NE, F&& out) {
+  const int e = threadIdx.x >> 3, part = threadIdx.x & 7;
+  float s = 0.f;
+  if (e < NE) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += red[e * 128 + part * 16 + k];
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (e < NE && part == 0) out(e, s);
+}
+
 // ================================================================================================
 // upper: dz -> [W2 dgrad/wgrad] -> gelu' -> [W1 dgrad/wgrad] -> LN2 bwd -> dh ; [Wo dgrad/wgrad] -> dctx
 // ================================================================================================
@@ -72,11 +120,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWo,
                        const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmHm,
                        const vitb200_layer_bwd_upper_args P) {
-  constexpr int H = FB_H, I = FB_I;
+  constexpr int H = FB_H, I = FB_I, HC = FB_HC;
   // shared memory map (all tile bases 1024-aligned); sD must be directly followed by sDA (see wgrad A views)
   constexpr uint32_t O_D = 0, O_DA = 16384, O_M = O_DA + 32768, O_U2 = O_M + 32768, O_CTX = O_U2 + 16384,
                      O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_ACT = O_WO + 4096,
-                     O_HM = O_ACT + 32768, O_BAR = O_HM + 16384;
+                     O_HM = O_ACT + 32768, O_BAR = O_HM + 16384, O_EX = O_BAR + 1024;
   // TMEM columns
   constexpr uint32_t C_W2 = 0, C_W1 = 128, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -89,8 +137,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* s_g2 = reinterpret_cast<float*>(bars + 8);
+  float2* s_ex = reinterpret_cast<float2*>(base + O_EX);   // [FB_CG][128] row-sum exchange (4 KB)
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);  // row of the tile = TMEM lane
+  const int cg = warp >> 2, hc0 = cg * HC;
   const int M = P.B * P.T;
   const int ntiles = (M + 127) / 128;
 
@@ -103,8 +154,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     fence_barrier_init();
   }
   // columns 32..63 of the sD tile are never written by the epilogues: zero them once (MN-major wgrad view reads them)
-#pragma unroll
-  for (int c = 4; c < 8; ++c) fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
+  fb_swz_store(sD, r, 4 + cg, make_uint4(0u, 0u, 0u, 0u));
   __syncthreads();
   if (tid == 0) {  // weights are not written inside a step: staged before the dependency wait
     mbar_expect_tx(b_w, 8192 + 16384 + 4096);
@@ -120,7 +170,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t aD = smem_u32(sD), aDA = smem_u32(sDA), aM = smem_u32(sM), aU2 = smem_u32(sU2), aCtx = smem_u32(sCtx);
   const uint32_t aW2 = smem_u32(sW2), aW1 = smem_u32(sW1), aWo = smem_u32(sWo);
   // operand views
@@ -139,15 +189,17 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   const DropCtx dc_mlp = make_drop(P.p_drop, seed, step, P.site_mlp);
   const DropCtx dc_proj = make_drop(P.p_drop, seed, step, P.site_proj);
 
-  float acc_g[H], acc_b[H];  // LN2 gamma / beta gradients of this thread's rows
+  float acc_g[HC], acc_b[HC];  // LN2 gamma / beta gradients of this thread's row, columns hc0 .. hc0 + 7
 #pragma unroll
-  for (int j = 0; j < H; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
-  float acc_b2 = 0.f, acc_b1 = 0.f, acc_bo = 0.f;  // bias gradients: thread j owns column j
+  for (int j = 0; j < HC; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
+  // bias gradients = column sums of the gradient tiles; partial per thread:
+  //   H-wide tiles: column tid & 31, rows 8 (tid >> 5) .. +7 ;  I-wide tile: column tid & 127, rows 32 (tid >> 7) .. +31
+  float acc_b2 = 0.f, acc_b1 = 0.f, acc_bo = 0.f;
   uint32_t ph_mma = 0, ph_tile = 0;
   int iter = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-    const int r0 = tile * 128, row = r0 + tid;
+    const int r0 = tile * 128, row = r0 + r;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
     if (tid == 0) {
@@ -162,27 +214,23 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     }
     const float mu = P.mean2[rowc], rs = P.rstd2[rowc];  // issued early, consumed by the LayerNorm stage
     // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
-    float dz[H];
+    float dz[HC];
     {
       // top layer: only the CLS rows carry a gradient (the head reads last_hidden_state[:, 0], specvit.py:78)
       const bool from_cls = P.dz_cls != nullptr;
       const bool nz = !from_cls || (rowc % P.T) == 0;
-      const float4* p = from_cls ? reinterpret_cast<const float4*>(P.dz_cls + (size_t)(rowc / P.T) * H)
-                                 : reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H);
+      const float4* p = from_cls ? reinterpret_cast<const float4*>(P.dz_cls + (size_t)(rowc / P.T) * H + hc0)
+                                 : reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H + hc0);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) {
+      for (int j = 0; j < HC / 4; ++j) {
         float4 t = nz ? p[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w;
       }
-      float d2[H];
+      float kp[8], d2[HC];
+      drop8(dc_mlp, ((size_t)rowc * H + hc0) >> 3, kp);
 #pragma unroll
-      for (int j = 0; j < H; j += 4) {
-        const float4 kp = drop4(dc_mlp, ((size_t)rowc * H + j) >> 2);
-        d2[j] = valid ? bf16_round(dz[j]) * kp.x : 0.f;         d2[j + 1] = valid ? bf16_round(dz[j + 1]) * kp.y : 0.f;
-        d2[j + 2] = valid ? bf16_round(dz[j + 2]) * kp.z : 0.f; d2[j + 3] = valid ? bf16_round(dz[j + 3]) * kp.w : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&d2[c * 8]));
+      for (int j = 0; j < HC; ++j) d2[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
+      fb_swz_store(sD, r, cg, fb_pack8(d2));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -196,19 +244,19 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       fb_issue(tmem + C_W2, D_mn, M_mn, I, 8, iter > 0);          // dW2[h, i]  += sum_rows ddelta2[row,h] m[row,i]
       umma_commit(b_mma);
     }
+    acc_b2 += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);  // overlaps the MMAs
     mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged a / hmid rows below
     ph_tile ^= 1;
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    if (tid < H) acc_b2 += fb_colsum(sD, tid);
     // ---- da = dm * gelu'(a) -> sDA ----
-#pragma unroll 1
-    for (int c0 = 0; c0 < I; c0 += 32) {
+    {
+      const int c0 = cg * 32;
       float v[32];
       tmem_ld_32x32(my_tmem + C_DM + c0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 av = *reinterpret_cast<const uint4*>(fb_swz_ptr(sAct, tid, (c0 >> 3) + q));
+        const uint4 av = *reinterpret_cast<const uint4*>(fb_swz_ptr(sAct, r, (c0 >> 3) + q));
         const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
         float o[8];
 #pragma unroll
@@ -217,7 +265,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
           o[2 * e] = valid ? bf16_round(v[q * 8 + 2 * e]) * gelu_grad_f(f.x) : 0.f;
           o[2 * e + 1] = valid ? bf16_round(v[q * 8 + 2 * e + 1]) * gelu_grad_f(f.y) : 0.f;
         }
-        fb_swz_store(sDA, tid, (c0 >> 3) + q, fb_pack8(o));
+        fb_swz_store(sDA, r, (c0 >> 3) + q, fb_pack8(o));
       }
     }
     fence_proxy_async();
@@ -229,46 +277,35 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       fb_issue(tmem + C_W1, DA_mn, U2_mn, H, 8, iter > 0);        // dW1[i, h]  += sum_rows da[row,i] u2[row,h]
       umma_commit(b_mma);
     }
+    acc_b1 += fb_colsum<32>(sDA, tid & 127, (tid >> 7) * 32);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    acc_b1 += fb_colsum(sDA, tid);  // I = 128 columns = 128 threads
     // ---- LayerNorm-after backward + residual -> dh ; ddelta1 = dropout'(dh) -> sD ----
     {
-      float du[32];
-      tmem_ld_32x32(my_tmem + C_DU2, du);
-      float xh[H], g[H];
-      float s1 = 0.f, s2 = 0.f;
+      float du[HC], xh[HC], g[HC];
+      tmem_ld_32x8(my_tmem + C_DU2 + hc0, du);
+      fb_ld_f8(sHm, r, cg, xh);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) {
-        const float4 t = *reinterpret_cast<const float4*>(fb_swz_ptr(sHm, tid, j));
-        xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
+      for (int j = 0; j < HC; ++j) {
+        xh[j] = (xh[j] - mu) * rs;
+        du[j] = valid ? bf16_round(du[j]) : 0.f;
+        acc_g[j] = fmaf(du[j], xh[j], acc_g[j]);
+        acc_b[j] += du[j];
       }
+      float c1, c2;
+      fb_ln_bwd_sums(du, xh, s_g2, hc0, s_ex, r, cg, g, c1, c2);
 #pragma unroll
-      for (int j = 0; j < H; ++j) {
-        const float d = valid ? bf16_round(du[j]) : 0.f;
-        acc_g[j] = fmaf(d, xh[j], acc_g[j]);
-        acc_b[j] += d;
-        g[j] = d * s_g2[j];
-        s1 += g[j];
-        s2 = fmaf(g[j], xh[j], s2);
-      }
-      const float c1 = s1 * (1.f / H), c2 = s2 * (1.f / H);
-      float d1[H];
-#pragma unroll
-      for (int j = 0; j < H; ++j) dz[j] += rs * (g[j] - c1 - xh[j] * c2);  // dz now holds dh
+      for (int j = 0; j < HC; ++j) dz[j] += rs * (g[j] - c1 - xh[j] * c2);  // dz now holds dh
       if (valid) {
-        float4* op = reinterpret_cast<float4*>(P.dh + (size_t)row * H);
+        float4* op = reinterpret_cast<float4*>(P.dh + (size_t)row * H + hc0);
 #pragma unroll
-        for (int j = 0; j < H / 4; ++j) op[j] = make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]);
+        for (int j = 0; j < HC / 4; ++j) op[j] = make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]);
       }
+      float kp[8], d1[HC];
+      drop8(dc_proj, ((size_t)rowc * H + hc0) >> 3, kp);
 #pragma unroll
-      for (int j = 0; j < H; j += 4) {
-        const float4 kp = drop4(dc_proj, ((size_t)rowc * H + j) >> 2);
-        d1[j] = valid ? bf16_round(dz[j]) * kp.x : 0.f;         d1[j + 1] = valid ? bf16_round(dz[j + 1]) * kp.y : 0.f;
-        d1[j + 2] = valid ? bf16_round(dz[j + 2]) * kp.z : 0.f; d1[j + 3] = valid ? bf16_round(dz[j + 3]) * kp.w : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&d1[c * 8]));
+      for (int j = 0; j < HC; ++j) d1[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
+      fb_swz_store(sD, r, cg, fb_pack8(d1));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -279,17 +316,13 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       fb_issue(tmem + C_WO, D_mn, CTX_mn, H, 8, iter > 0);        // dWo[n, k]  += sum_rows ddelta1[row,n] ctx[row,k]
       umma_commit(b_mma);
     }
+    acc_bo += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    if (tid < H) acc_bo += fb_colsum(sD, tid);
     {
-      float v[32];
-      tmem_ld_32x32(my_tmem + C_DCTX, v);
-      if (valid) {
-        bf16* op = reinterpret_cast<bf16*>(P.dctx) + (size_t)row * H;
-#pragma unroll
-        for (int j = 0; j < H; j += 8) *reinterpret_cast<uint4*>(op + j) = fb_pack8(&v[j]);
-      }
+      float v[HC];
+      tmem_ld_32x8(my_tmem + C_DCTX + hc0, v);
+      if (valid) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.dctx) + (size_t)row * H + hc0) = fb_pack8(v);
     }
     tc_fence_before();
     __syncthreads();  // all reads of sD / TMEM done before the next tile overwrites them
@@ -299,45 +332,44 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
   if (iter > 0) {
-    if (warp == 0) {  // dW2 rows h = lanes 0..31, I columns
-#pragma unroll 1
-      for (int c0 = 0; c0 < I; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(my_tmem + C_W2 + c0, v);
-        float4* op = reinterpret_cast<float4*>(gp + P.off_w2 + (size_t)tid * I + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
+    if ((warp & 3) == 0) {  // dW2 / dWo rows h = lanes 0..31: column group cg of each
       float v[32];
-      tmem_ld_32x32(my_tmem + C_WO, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_wo + (size_t)tid * H);
+      tmem_ld_32x32(my_tmem + C_W2 + cg * 32, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_w2 + (size_t)r * I + cg * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      float w[HC];
+      tmem_ld_32x8(my_tmem + C_WO + hc0, w);
+      float4* oq = reinterpret_cast<float4*>(gp + P.off_wo + (size_t)r * H + hc0);
+      oq[0] = make_float4(w[0], w[1], w[2], w[3]); oq[1] = make_float4(w[4], w[5], w[6], w[7]);
     }
     {  // dW1 rows i = lanes 0..127, H columns
-      float v[32];
-      tmem_ld_32x32(my_tmem + C_W1, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_w1 + (size_t)tid * H);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      float v[HC];
+      tmem_ld_32x8(my_tmem + C_W1 + hc0, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_w1 + (size_t)r * H + hc0);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]); op[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
   } else {  // a CTA without tiles contributes zeros
     for (int e = tid; e < H * I; e += FB_THREADS) { gp[P.off_w2 + e] = 0.f; gp[P.off_w1 + e] = 0.f; }
     for (int e = tid; e < H * H; e += FB_THREADS) gp[P.off_wo + e] = 0.f;
   }
-  gp[P.off_b1 + tid] = acc_b1;
-  if (tid < H) { gp[P.off_b2 + tid] = acc_b2; gp[P.off_bo + tid] = acc_bo; }
-  // LN gamma/beta: reduce the per-thread sums over the 128 threads in thread order (scratch = sDA, 32 KB)
+  // bias and LN gamma/beta gradients: per-thread partials -> shared memory (scratch = sDA, 32 KB) -> fixed-order sums
   tc_fence_before();
   __syncthreads();
-  float* red = reinterpret_cast<float*>(sDA);  // [2][H][128]
+  float* red = reinterpret_cast<float*>(sDA);  // [2 * H][128]
 #pragma unroll
-  for (int j = 0; j < H; ++j) { red[j * 128 + tid] = acc_g[j]; red[(H + j) * 128 + tid] = acc_b[j]; }
+  for (int j = 0; j < HC; ++j) { red[(hc0 + j) * 128 + r] = acc_g[j]; red[(H + hc0 + j) * 128 + r] = acc_b[j]; }
+  float* bsum = reinterpret_cast<float*>(sM);  // [3][512] bias partials
+  bsum[tid] = acc_b2; bsum[512 + tid] = acc_bo; bsum[1024 + tid] = acc_b1;
   __syncthreads();
-  if (tid < 2 * H) {
-    float s = 0.f;
-    for (int t = 0; t < 128; ++t) s += red[tid * 128 + t];
-    if (tid < H) gp[P.off_ln2g + tid] = s; else gp[P.off_ln2b + tid - H] = s;
+  fb_reduce_rows(red, 2 * H, [&](int e, float s) { if (e < H) gp[P.off_ln2g + e] = s; else gp[P.off_ln2b + e - H] = s; });
+  if (tid < H) {
+    float s2 = 0.f, so = 0.f;
+    for (int k = 0; k < 16; ++k) { s2 += bsum[k * 32 + tid]; so += bsum[512 + k * 32 + tid]; }
+    gp[P.off_b2 + tid] = s2; gp[P.off_bo + tid] = so;
+  } else if (tid >= 128 && tid < 128 + I) {
+    const int c = tid - 128;
+    gp[P.off_b1 + c] = (bsum[1024 + c] + bsum[1024 + 128 + c]) + (bsum[1024 + 256 + c] + bsum[1024 + 384 + c]);
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -350,9 +382,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmU,
                        const __grid_constant__ CUtensorMap tmWq, const __grid_constant__ CUtensorMap tmZ,
                        const __grid_constant__ CUtensorMap tmDh, const vitb200_layer_bwd_lower_args P) {
-  constexpr int H = FB_H, Q = 3 * FB_H;
+  constexpr int H = FB_H, Q = 3 * FB_H, HC = FB_HC;
   constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_Z = O_WQ + 12288, O_DH = O_Z + 16384,
-                     O_BAR = O_DH + 16384, O_RED = O_BAR + 1024;
+                     O_BAR = O_DH + 16384, O_RED = O_BAR + 1024, O_EX = O_RED + 32768;
   constexpr uint32_t C_WQ = 0, C_DU = 32, TMEM_COLS = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -362,10 +394,13 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* red = reinterpret_cast<float*>(base + O_RED);  // [2][H][128] floats = 32 KB
+  float2* s_ex = reinterpret_cast<float2*>(base + O_EX);
   const uint8_t *sZ = base + O_Z, *sDh = base + O_DH;   // fp32 rows of z and dh, TMA-staged
   float* s_g1 = reinterpret_cast<float*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);
+  const int cg = warp >> 2, hc0 = cg * HC;
   const int M = P.B * P.T;
   const int ntiles = (M + 127) / 128;
   if (tid < H) s_g1[tid] = P.ln1_g[tid];
@@ -387,20 +422,20 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const Opnd DQ_k{smem_u32(sDQ), 16, 16384, 0};        // dqkv tile, K-major (K = 3H = 96: 6 k-steps over 2 k-blocks)
   const Opnd DQ_mn{smem_u32(sDQ), 16384, 0, 1};        // MN-major (MN = 96 of 128)
   const Opnd U_mn{smem_u32(sU), 16384, 0, 1};
   const Opnd WQ_mn{smem_u32(sWq), 16384, 0, 1};        // B(n = h, k = qkv row): N = H, K = 96 rows
 
-  float acc_g[H], acc_b[H];
+  float acc_g[HC], acc_b[HC];
 #pragma unroll
-  for (int j = 0; j < H; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
-  float acc_bq = 0.f;
+  for (int j = 0; j < HC; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
+  float acc_bq = 0.f;  // column tid & 127 (< 96), rows 32 (tid >> 7) .. +31
   uint32_t ph_mma = 0, ph_tile = 0;
   int iter = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-    const int r0 = tile * 128, row = r0 + tid;
+    const int r0 = tile * 128, row = r0 + r;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
     const float mu = P.mean1[rowc], rs = P.rstd1[rowc];  // issued early
@@ -420,35 +455,27 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     }
     mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-written dqkv tile below
     ph_tile ^= 1;
+    if ((tid & 127) < Q) acc_bq += fb_colsum<32>(sDQ, tid & 127, (tid >> 7) * 32);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    if (tid < Q) acc_bq += fb_colsum(sDQ, tid);
     {
-      float du[32];
-      tmem_ld_32x32(my_tmem + C_DU, du);
-      float xh[H], g[H], dz[H];
-      float s1 = 0.f, s2 = 0.f;
+      float du[HC], xh[HC], g[HC], dz[HC];
+      tmem_ld_32x8(my_tmem + C_DU + hc0, du);
+      fb_ld_f8(sZ, r, cg, xh);
+      fb_ld_f8(sDh, r, cg, dz);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) {
-        const float4 t = *reinterpret_cast<const float4*>(fb_swz_ptr(sZ, tid, j));
-        xh[4 * j] = (t.x - mu) * rs; xh[4 * j + 1] = (t.y - mu) * rs; xh[4 * j + 2] = (t.z - mu) * rs; xh[4 * j + 3] = (t.w - mu) * rs;
-        const float4 d = *reinterpret_cast<const float4*>(fb_swz_ptr(sDh, tid, j));
-        dz[4 * j] = d.x; dz[4 * j + 1] = d.y; dz[4 * j + 2] = d.z; dz[4 * j + 3] = d.w;
+      for (int j = 0; j < HC; ++j) {
+        xh[j] = (xh[j] - mu) * rs;
+        du[j] = valid ? bf16_round(du[j]) : 0.f;
+        acc_g[j] = fmaf(du[j], xh[j], acc_g[j]);
+        acc_b[j] += du[j];
       }
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        const float d = valid ? bf16_round(du[j]) : 0.f;
-        acc_g[j] = fmaf(d, xh[j], acc_g[j]);
-        acc_b[j] += d;
-        g[j] = d * s_g1[j];
-        s1 += g[j];
-        s2 = fmaf(g[j], xh[j], s2);
-      }
-      const float c1 = s1 * (1.f / H), c2 = s2 * (1.f / H);
+      float c1, c2;
+      fb_ln_bwd_sums(du, xh, s_g1, hc0, s_ex, r, cg, g, c1, c2);
       if (valid) {
-        float4* op = reinterpret_cast<float4*>(P.dz + (size_t)row * H);
+        float4* op = reinterpret_cast<float4*>(P.dz + (size_t)row * H + hc0);
 #pragma unroll
-        for (int j = 0; j < H / 4; ++j) {
+        for (int j = 0; j < HC / 4; ++j) {
           float4 o;
           o.x = dz[4 * j] + rs * (g[4 * j] - c1 - xh[4 * j] * c2);
           o.y = dz[4 * j + 1] + rs * (g[4 * j + 1] - c1 - xh[4 * j + 1] * c2);
@@ -464,26 +491,24 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
   if (iter > 0) {
-    if (warp < 3) {  // dWqkv rows n = lanes 0..95
-      float v[32];
-      tmem_ld_32x32(my_tmem + C_WQ, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_wqkv + (size_t)tid * H);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    if ((warp & 3) < 3) {  // dWqkv rows n = lanes 0..95
+      float v[HC];
+      tmem_ld_32x8(my_tmem + C_WQ + hc0, v);
+      float4* op = reinterpret_cast<float4*>(gp + P.off_wqkv + (size_t)r * H + hc0);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]); op[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
   } else {
     for (int e = tid; e < Q * H; e += FB_THREADS) gp[P.off_wqkv + e] = 0.f;
   }
-  if (tid < Q) gp[P.off_bqkv + tid] = acc_bq;
 #pragma unroll
-  for (int j = 0; j < H; ++j) { red[j * 128 + tid] = acc_g[j]; red[(H + j) * 128 + tid] = acc_b[j]; }
+  for (int j = 0; j < HC; ++j) { red[(hc0 + j) * 128 + r] = acc_g[j]; red[(H + hc0 + j) * 128 + r] = acc_b[j]; }
+  float* bsum = reinterpret_cast<float*>(sDQ);  // [4][128] bias partials (the dqkv tile is dead)
   tc_fence_before();
   __syncthreads();
-  if (tid < 2 * H) {
-    float s = 0.f;
-    for (int t = 0; t < 128; ++t) s += red[tid * 128 + t];
-    if (tid < H) gp[P.off_ln1g + tid] = s; else gp[P.off_ln1b + tid - H] = s;
-  }
+  bsum[tid] = acc_bq;
+  __syncthreads();
+  fb_reduce_rows(red, 2 * H, [&](int e, float s) { if (e < H) gp[P.off_ln1g + e] = s; else gp[P.off_ln1b + e - H] = s; });
+  if (tid < Q) gp[P.off_bqkv + tid] = (bsum[tid] + bsum[128 + tid]) + (bsum[256 + tid] + bsum[384 + tid]);
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -493,7 +518,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
 // ================================================================================================
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
-  constexpr int H = FB_H;
+  constexpr int H = FB_H, HC = FB_HC;
   constexpr uint32_t O_D = 0, O_X = 16384, O_BAR = 32768, O_RED = O_BAR + 1024;
   constexpr uint32_t TMEM_COLS = 64;
   extern __shared__ uint8_t smem_raw[];
@@ -506,14 +531,14 @@ fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
   float* red = reinterpret_cast<float*>(base + O_RED);  // [H][128]
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);
+  const int cg = warp >> 2, hc0 = cg * HC;
   const int T = P.Np + 1, M = P.B * T;
   const int ntiles = (M + 127) / 128;
   if (tid == 0) { mbar_init(b_mma, 1); fence_barrier_init(); }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {  // zero both tiles once: unused columns must be finite for the MN-major views
-    fb_swz_store(sD, tid, c, make_uint4(0u, 0u, 0u, 0u));
-    fb_swz_store(sX, tid, c, make_uint4(0u, 0u, 0u, 0u));
-  }
+  // zero both tiles once: unused columns must be finite for the MN-major views
+  fb_swz_store(sD, r, cg, make_uint4(0u, 0u, 0u, 0u));     fb_swz_store(sD, r, 4 + cg, make_uint4(0u, 0u, 0u, 0u));
+  fb_swz_store(sX, r, cg, make_uint4(0u, 0u, 0u, 0u));     fb_swz_store(sX, r, 4 + cg, make_uint4(0u, 0u, 0u, 0u));
   pdl_wait();
   pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -521,47 +546,52 @@ fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const Opnd D_mn{smem_u32(sD), 16384, 0, 1};   // MN group 1 aliases sX: product rows 64..127 are never read
   const Opnd X_mn{smem_u32(sX), 16384, 0, 1};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, VITB200_SITE_EMB);
-  float acc_cls[H];
+  float acc_cls[HC];
 #pragma unroll
-  for (int j = 0; j < H; ++j) acc_cls[j] = 0.f;
-  float acc_bp = 0.f;
+  for (int j = 0; j < HC; ++j) acc_cls[j] = 0.f;
+  float acc_bp = 0.f;  // column tid & 31, rows 8 (tid >> 5) .. +7
   uint32_t ph = 0;
   int iter = 0;
   const int nchunk = P.P / 8;
+  const bool vec = (P.S % 4 == 0) && (P.L % 4 == 0);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-    const int row = tile * 128 + tid;
+    const int row = tile * 128 + r;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
     const int b = rowc / T, t = rowc - b * T;
-    float g[H];
+    float g[HC];
     {
-      const float4* p = reinterpret_cast<const float4*>(P.dz0 + (size_t)rowc * H);
+      const float4* p = reinterpret_cast<const float4*>(P.dz0 + (size_t)rowc * H + hc0);
+      const float4 v0 = p[0], v1 = p[1];
+      float kp[8];
+      drop8(dc, ((size_t)rowc * H + hc0) >> 3, kp);
+      g[0] = v0.x * kp[0]; g[1] = v0.y * kp[1]; g[2] = v0.z * kp[2]; g[3] = v0.w * kp[3];
+      g[4] = v1.x * kp[4]; g[5] = v1.y * kp[5]; g[6] = v1.z * kp[6]; g[7] = v1.w * kp[7];
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) {
-        const float4 v = p[j];
-        const float4 kp = drop4(dc, ((size_t)rowc * H + 4 * j) >> 2);
-        g[4 * j] = valid ? v.x * kp.x : 0.f;         g[4 * j + 1] = valid ? v.y * kp.y : 0.f;
-        g[4 * j + 2] = valid ? v.z * kp.z : 0.f;     g[4 * j + 3] = valid ? v.w * kp.w : 0.f;
-      }
+      for (int j = 0; j < HC; ++j) g[j] = valid ? g[j] : 0.f;
     }
     if (t == 0) {  // CLS row: gradient of cls_token, no patch
 #pragma unroll
-      for (int j = 0; j < H; ++j) { acc_cls[j] += g[j]; g[j] = 0.f; }
+      for (int j = 0; j < HC; ++j) { acc_cls[j] += g[j]; g[j] = 0.f; }
     }
-#pragma unroll
-    for (int c = 0; c < H / 8; ++c) fb_swz_store(sD, tid, c, fb_pack8(&g[c * 8]));
+    fb_swz_store(sD, r, cg, fb_pack8(g));
     {
       const bool has = valid && t >= 1 && (t - 1) < P.n_valid;
       const float* xp = P.x + (size_t)b * P.L + (size_t)(t >= 1 ? t - 1 : 0) * P.S;
-      for (int c = 0; c < nchunk; ++c) {
+      for (int c = cg; c < nchunk; c += FB_CG) {
         float v[8];
+        if (vec && has) {
+          const float4 a0 = *reinterpret_cast<const float4*>(xp + c * 8), a1 = *reinterpret_cast<const float4*>(xp + c * 8 + 4);
+          v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = has ? xp[c * 8 + q] : 0.f;
-        fb_swz_store(sX, tid, c, fb_pack8(v));
+          for (int q = 0; q < 8; ++q) v[q] = has ? xp[c * 8 + q] : 0.f;
+        }
+        fb_swz_store(sX, r, c, fb_pack8(v));
       }
     }
     fence_proxy_async();
@@ -572,35 +602,40 @@ fused_embed_bwd_kernel(const vitb200_embed_bwd_args P) {
       fb_issue(tmem, D_mn, X_mn, P.P, 8, iter > 0);   // dWp[h, j] += sum_rows dtok[row, h] x[row, j]
       umma_commit(b_mma);
     }
+    acc_bp += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);
     mbar_wait(b_mma, ph); ph ^= 1;
     tc_fence_after();
-    if (tid < H) acc_bp += fb_colsum(sD, tid);
     tc_fence_before();
     __syncthreads();
   }
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
-  if (warp == 0) {
+  if ((warp & 3) == 0) {  // dWp rows h = lanes 0..31
     if (iter > 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < P.P; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(my_tmem + c0, v);
-        for (int j = 0; j < 32 && c0 + j < P.P; ++j) gp[P.off_wp + (size_t)tid * P.P + c0 + j] = v[j];
+      for (int c0 = hc0; c0 < P.P; c0 += 8 * FB_CG) {
+        float v[8];
+        tmem_ld_32x8(my_tmem + c0, v);
+        float4* op = reinterpret_cast<float4*>(gp + P.off_wp + (size_t)r * P.P + c0);
+        op[0] = make_float4(v[0], v[1], v[2], v[3]); op[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     } else {
-      for (int e = 0; e < P.P; ++e) gp[P.off_wp + (size_t)tid * P.P + e] = 0.f;
+      for (int e = hc0; e < P.P; e += 8 * FB_CG)
+        for (int q = 0; q < 8; ++q) gp[P.off_wp + (size_t)r * P.P + e + q] = 0.f;
     }
-    gp[P.off_bp + tid] = acc_bp;
   }
 #pragma unroll
-  for (int j = 0; j < H; ++j) red[j * 128 + tid] = acc_cls[j];
+  for (int j = 0; j < HC; ++j) red[(hc0 + j) * 128 + r] = acc_cls[j];
+  float* bsum = reinterpret_cast<float*>(sX);  // [16][32]
   tc_fence_before();
   __syncthreads();
+  bsum[tid] = acc_bp;
+  __syncthreads();
+  fb_reduce_rows(red, H, [&](int e, float s) { gp[P.off_cls + e] = s; });
   if (tid < H) {
     float s = 0.f;
-    for (int k = 0; k < 128; ++k) s += red[tid * 128 + k];
-    gp[P.off_cls + tid] = s;
+    for (int k = 0; k < 16; ++k) s += bsum[k * 32 + tid];
+    gp[P.off_bp + tid] = s;
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -632,8 +667,8 @@ grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, si
   }
 }
 
-constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 32768 + 16384 + 1024 + 1024;
-constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 16384 + 16384 + 1024 + 32768 + 1024;
+constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 32768 + 16384 + 1024 + 4096 + 1024;
+constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 16384 + 16384 + 1024 + 32768 + 4096 + 1024;
 
 }  // namespace vb
 

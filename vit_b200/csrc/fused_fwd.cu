@@ -1,10 +1,13 @@
 // Fused forward row-chain kernels (bf16 mode, H in {32, 64}).  See include/vit_b200.h.
 //
-// One CTA = 128 token rows = 128 threads; thread t owns row t of the tile and TMEM lane t.
-// Thread 0 issues TMA and tcgen05.mma; every GEMM's accumulator sits in TMEM columns [0, N);
-// after each GEMM all threads read their row back (tcgen05.ld), apply the epilogue in registers
-// (a whole row of H values lives in one thread, so LayerNorm needs no shuffles), store what backward
-// needs to HBM, and write the next GEMM's A operand into shared memory in the UMMA K-major / 128B-swizzle
+// One CTA = 128 token rows x 4 column groups = 512 threads (16 warps).  Warp w works on TMEM lane quarter (w & 3)
+// -- rows 32 (w & 3) .. +31 of the tile, the only lanes a warp may read -- and on column group cg = w >> 2: every
+// epilogue splits its columns four ways, so a row's work (bias, Philox dropout, GELU, bf16 packing, stores) is shared
+// by four threads and each SM scheduler has four warps to interleave.  (The first version had one thread per row:
+// 4 warps per SM, 4.7 cycles per issued instruction -- a pure dependent-latency chain.)  LayerNorm statistics of a row
+// are combined across its four threads through shared memory (per-group mean / M2, merged with Chan's formula).
+// Thread 0 issues TMA and tcgen05.mma; every GEMM's accumulator sits in TMEM columns [0, N); the epilogues store what
+// backward needs to HBM and write the next GEMM's A operand into shared memory in the UMMA K-major / 128B-swizzle
 // layout (16-byte chunk c of row r goes to chunk c ^ (r & 7)).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -14,7 +17,8 @@ namespace vb {
 using namespace vb::tc;
 
 constexpr int FF_ROWS = 128;
-constexpr int FF_THREADS = 128;
+constexpr int FF_CG = 4;                       // column groups = threads per row
+constexpr int FF_THREADS = FF_ROWS * FF_CG;    // 512
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -40,20 +44,31 @@ __device__ __forceinline__ void emit_row_bf16(const float (&v)[N], bf16* gdst, b
     if (tile) swz_store(tile, r, chunk0 + (j >> 3), pk);
   }
 }
-template <int H>
-__device__ __forceinline__ void layer_norm_row(const float (&x)[H], const float* __restrict__ g,
-                                               const float* __restrict__ b, float eps, float (&y)[H], float& mu,
-                                               float& rs) {
+// LayerNorm statistics of a row whose H columns are spread over FF_CG threads (HC columns each).
+// Each thread publishes (mean, M2) of its columns; after the barrier every thread merges the four pairs.
+template <int HC>
+__device__ __forceinline__ void row_stats(const float (&x)[HC], float2* s_ln, int r, int cg, float eps, float& mu,
+                                          float& rs) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < H; ++j) s += x[j];
-  mu = s * (1.f / H);
+  for (int j = 0; j < HC; ++j) s += x[j];
+  const float mc = s * (1.f / HC);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < H; ++j) { float d = x[j] - mu; q = fmaf(d, d, q); }
-  rs = rsqrtf(q * (1.f / H) + eps);
+  for (int j = 0; j < HC; ++j) { const float d = x[j] - mc; q = fmaf(d, d, q); }
+  s_ln[cg * FF_ROWS + r] = make_float2(mc, q);
+  __syncthreads();
+  float2 p[FF_CG];
 #pragma unroll
-  for (int j = 0; j < H; ++j) y[j] = bf16_round((x[j] - mu) * rs * g[j] + b[j]);
+  for (int g = 0; g < FF_CG; ++g) p[g] = s_ln[g * FF_ROWS + r];
+  float m = 0.f;
+#pragma unroll
+  for (int g = 0; g < FF_CG; ++g) m += p[g].x;
+  mu = m * (1.f / FF_CG);
+  float m2 = 0.f;
+#pragma unroll
+  for (int g = 0; g < FF_CG; ++g) { const float d = p[g].x - mu; m2 += fmaf(d * d, (float)HC, p[g].y); }
+  rs = rsqrtf(m2 * (1.f / (HC * FF_CG)) + eps);
 }
 // one thread issues a whole K-major x K-major GEMM: D[128, N] = A[128, K] * B[N, K]^T
 __device__ __forceinline__ void issue_gemm_kk(uint32_t tmem_d, uint32_t sA, uint32_t sB, uint32_t b_kblock_bytes, int N,
@@ -78,6 +93,8 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmWq, const vitb200_layer_fwd_args P) {
   constexpr int I = 4 * H;
+  constexpr int HC = H / FF_CG;                    // residual-stream columns per thread (8 / 16)
+  constexpr int IC = I / FF_CG;                    // MLP columns per thread (32 / 64)
   constexpr int KB_I = I / 64;                     // k-blocks of the MLP-down GEMM
   constexpr uint32_t SZ_A = 16384, SZ_M = KB_I * 16384, SZ_WO = H * 128, SZ_W1 = I * 128, SZ_W2 = KB_I * H * 128,
                      SZ_WQ = 3 * H * 128;
@@ -98,11 +115,14 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   float* prm = reinterpret_cast<float*>(bars + 8);
   float *s_bo = prm, *s_g2 = prm + H, *s_b2ln = prm + 2 * H, *s_b2 = prm + 3 * H, *s_gn = prm + 4 * H, *s_bn = prm + 5 * H,
         *s_b1 = prm + 6 * H, *s_bq = prm + 6 * H + I;
+  float2* s_ln = reinterpret_cast<float2*>(prm + 13 * H);  // [FF_CG][128] row-statistics exchange
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);    // row of the tile = TMEM lane
+  const int cg = warp >> 2;                        // column group
   const int M = P.B * P.T;
   const int r0 = blockIdx.x * FF_ROWS;
-  const int row = r0 + tid;
+  const int row = r0 + r;
   const bool valid = row < M;
   const int rowc = valid ? row : M - 1;
 
@@ -138,17 +158,18 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   if (tid == 0) {
     mbar_expect_tx(b_in, SZ_A);
     tma_load_2d(sA, &tmCtx, b_in, 0, r0);
   }
-  // residual row (overlaps the TMA loads)
-  float h[H];
+  // this thread's HC columns of the residual row (overlaps the TMA loads)
+  const int hc0 = cg * HC;
+  float h[HC];
   {
-    const float4* zp = reinterpret_cast<const float4*>(P.z_in + (size_t)rowc * H);
+    const float4* zp = reinterpret_cast<const float4*>(P.z_in + (size_t)rowc * H + hc0);
 #pragma unroll
-    for (int j = 0; j < H / 4; ++j) { float4 t = zp[j]; h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w; }
+    for (int j = 0; j < HC / 4; ++j) { float4 t = zp[j]; h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w; }
   }
   const uint64_t seed = P.rng ? P.rng[0] : 0ull;
   const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
@@ -165,28 +186,27 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   tc_fence_after();
   {
     const DropCtx dc = make_drop(P.p_drop, seed, step, P.site_proj);
+    float v[HC];
+    tmem_ld_cols<HC>(my_tmem + hc0, v);
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(my_tmem + c0, v);
+    for (int j = 0; j < HC; j += 8) {
+      float kp[8];
+      drop8(dc, ((size_t)rowc * H + hc0 + j) >> 3, kp);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
-        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + s_bo[c0 + j + 0]) * kp.x);
-        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + s_bo[c0 + j + 1]) * kp.y);
-        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + s_bo[c0 + j + 2]) * kp.z);
-        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + s_bo[c0 + j + 3]) * kp.w);
-      }
+      for (int e = 0; e < 8; ++e) h[j + e] += bf16_round(bf16_round(v[j + e] + s_bo[hc0 + j + e]) * kp[e]);
     }
-    float u2[H], mu, rs;
-    layer_norm_row<H>(h, s_g2, s_b2ln, P.eps, u2, mu, rs);
+    float mu, rs;
+    row_stats<HC>(h, s_ln, r, cg, P.eps, mu, rs);
+    float u2[HC];
+#pragma unroll
+    for (int j = 0; j < HC; ++j) u2[j] = bf16_round((h[j] - mu) * rs * s_g2[hc0 + j] + s_b2ln[hc0 + j]);
     if (valid) {
-      float4* hp = reinterpret_cast<float4*>(P.hmid + (size_t)row * H);
+      float4* hp = reinterpret_cast<float4*>(P.hmid + (size_t)row * H + hc0);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) hp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-      P.mean2[row] = mu; P.rstd2[row] = rs;
+      for (int j = 0; j < HC / 4; ++j) hp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      if (cg == 0) { P.mean2[row] = mu; P.rstd2[row] = rs; }
     }
-    emit_row_bf16<H>(u2, reinterpret_cast<bf16*>(P.u2) + (size_t)rowc * H, valid, sA, tid, 0);
+    emit_row_bf16<HC>(u2, reinterpret_cast<bf16*>(P.u2) + (size_t)rowc * H + hc0, valid, sA, r, hc0 >> 3);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -195,13 +215,12 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   // ---- 2. MLP up + GELU ----
   if (tid == 0) {
     tc_fence_after();
-    mbar_wait(b_w1, 0);
     issue_gemm_kk(tmem, smem_u32(sA), smem_u32(sW1), 0, I, H, b_mma);
   }
   mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
   tc_fence_after();
 #pragma unroll 1
-  for (int c0 = 0; c0 < I; c0 += 32) {
+  for (int c0 = cg * IC; c0 < (cg + 1) * IC; c0 += 32) {
     float v[32], g[32];
     tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
@@ -210,7 +229,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
       g[j] = gelu_f(v[j]);
     }
     emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.a) + (size_t)rowc * I + c0, valid, nullptr, 0, 0);
-    emit_row_bf16<32>(g, reinterpret_cast<bf16*>(P.m) + (size_t)rowc * I + c0, valid, sM, tid, c0 >> 3);
+    emit_row_bf16<32>(g, reinterpret_cast<bf16*>(P.m) + (size_t)rowc * I + c0, valid, sM, r, c0 >> 3);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -226,33 +245,32 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   tc_fence_after();
   {
     const DropCtx dc = make_drop(P.p_drop, seed, step, P.site_mlp);
+    float v[HC];
+    tmem_ld_cols<HC>(my_tmem + hc0, v);
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(my_tmem + c0, v);
+    for (int j = 0; j < HC; j += 8) {
+      float kp[8];
+      drop8(dc, ((size_t)rowc * H + hc0 + j) >> 3, kp);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
-        h[c0 + j + 0] += bf16_round(bf16_round(v[j + 0] + s_b2[c0 + j + 0]) * kp.x);
-        h[c0 + j + 1] += bf16_round(bf16_round(v[j + 1] + s_b2[c0 + j + 1]) * kp.y);
-        h[c0 + j + 2] += bf16_round(bf16_round(v[j + 2] + s_b2[c0 + j + 2]) * kp.z);
-        h[c0 + j + 3] += bf16_round(bf16_round(v[j + 3] + s_b2[c0 + j + 3]) * kp.w);
-      }
+      for (int e = 0; e < 8; ++e) h[j + e] += bf16_round(bf16_round(v[j + e] + s_b2[hc0 + j + e]) * kp[e]);
     }
     if (valid) {
-      float4* zp = reinterpret_cast<float4*>(P.z_out + (size_t)row * H);
+      float4* zp = reinterpret_cast<float4*>(P.z_out + (size_t)row * H + hc0);
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) zp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      for (int j = 0; j < HC / 4; ++j) zp[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     }
-    float un[H], mu, rs;
-    layer_norm_row<H>(h, s_gn, s_bn, P.eps, un, mu, rs);
+    float mu, rs;
+    row_stats<HC>(h, s_ln, r, cg, P.eps, mu, rs);
+    float un[HC];
+#pragma unroll
+    for (int j = 0; j < HC; ++j) un[j] = bf16_round((h[j] - mu) * rs * s_gn[hc0 + j] + s_bn[hc0 + j]);
     if (!P.last) {
-      if (valid) { P.mean_n[row] = mu; P.rstd_n[row] = rs; }
-      emit_row_bf16<H>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)rowc * H, valid, sA, tid, 0);
+      if (valid && cg == 0) { P.mean_n[row] = mu; P.rstd_n[row] = rs; }
+      emit_row_bf16<HC>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)rowc * H + hc0, valid, sA, r, hc0 >> 3);
     } else if (valid && (row % P.T) == 0) {
       const int b = row / P.T;
-      P.mean_n[b] = mu; P.rstd_n[b] = rs;
-      emit_row_bf16<H>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)b * H, true, nullptr, 0, 0);
+      if (cg == 0) { P.mean_n[b] = mu; P.rstd_n[b] = rs; }
+      emit_row_bf16<HC>(un, reinterpret_cast<bf16*>(P.u_next) + (size_t)b * H + hc0, true, nullptr, 0, 0);
     }
   }
   if (!P.last) {
@@ -268,7 +286,7 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
     mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < 3 * H; c0 += 32) {
+    for (int c0 = cg * 32; c0 < 3 * H; c0 += 32 * FF_CG) {
       float v[32];
       tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
@@ -288,6 +306,7 @@ template <int H>
 __global__ void __launch_bounds__(FF_THREADS, 1)
 fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmWq,
                        const vitb200_embed_fwd_args P) {
+  constexpr int HC = H / FF_CG;
   constexpr uint32_t SZ_A = 16384, SZ_WP = H * 128, SZ_WQ = 3 * H * 128;
   constexpr uint32_t TMEM_COLS = 3 * H <= 128 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -301,11 +320,14 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* prm = reinterpret_cast<float*>(bars + 8);
   float *s_bp = prm, *s_cls = prm + H, *s_g = prm + 2 * H, *s_b = prm + 3 * H, *s_bq = prm + 4 * H;
+  float2* s_ln = reinterpret_cast<float2*>(prm + 7 * H);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);
+  const int cg = warp >> 2;
   const int T = P.Np + 1, M = P.B * T;
   const int r0 = blockIdx.x * FF_ROWS;
-  const int row = r0 + tid;
+  const int row = r0 + r;
   const bool valid = row < M;
   const int rowc = valid ? row : M - 1;
   const int b = rowc / T, t = rowc - b * T;
@@ -327,7 +349,7 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
   if (tid == 0) {
     mbar_expect_tx(b_wp, SZ_WP);
@@ -335,19 +357,26 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
     mbar_expect_tx(b_wq, SZ_WQ);
     tma_load_2d(sWq, &tmWq, b_wq, 0, 0);
   }
-  // A row = the patch window of this token (tokenization.py:45-48); CLS rows and padded windows are zero
+  // A row = the patch window of this token (tokenization.py:45-48); CLS rows and padded windows are zero.
+  // The four threads of a row convert alternate 8-element chunks.
   {
     const bool has = valid && t >= 1 && (t - 1) < P.n_valid;
     const float* xp = P.x + (size_t)b * P.L + (size_t)(t >= 1 ? t - 1 : 0) * P.S;
     const int nchunk = (P.P + 15) / 16 * 2;  // whole 16-element k-steps are read by the MMA
-    for (int c = 0; c < nchunk; ++c) {
+    const bool vec = (P.S % 4 == 0) && (P.L % 4 == 0) && (P.P % 8 == 0);
+    for (int c = cg; c < nchunk; c += FF_CG) {
       float v[8];
+      if (vec && has && c * 8 + 8 <= P.P) {
+        const float4 a0 = *reinterpret_cast<const float4*>(xp + c * 8), a1 = *reinterpret_cast<const float4*>(xp + c * 8 + 4);
+        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+      } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = c * 8 + q;
-        v[q] = (has && j < P.P) ? xp[j] : 0.f;
+        for (int q = 0; q < 8; ++q) {
+          const int j = c * 8 + q;
+          v[q] = (has && j < P.P) ? xp[j] : 0.f;
+        }
       }
-      swz_store(sA, tid, c, pack8_bf16(v));
+      swz_store(sA, r, c, pack8_bf16(v));
     }
   }
   fence_proxy_async();
@@ -365,33 +394,33 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
     const uint64_t seed = P.rng ? P.rng[0] : 0ull;
     const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
     const DropCtx dc = make_drop(P.p_drop, seed, step, VITB200_SITE_EMB);
-    float z[H];
+    const int hc0 = cg * HC;
+    float z[HC], v[HC];
+    tmem_ld_cols<HC>(my_tmem + hc0, v);
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(my_tmem + c0, v);
+    for (int j = 0; j < HC; j += 8) {
+      float kp[8];
+      drop8(dc, ((size_t)rowc * H + hc0 + j) >> 3, kp);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 kp = drop4(dc, ((size_t)rowc * H + c0 + j) >> 2);
-        const float kpa[4] = {kp.x, kp.y, kp.z, kp.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = c0 + j + q;
-          float e = t == 0 ? s_cls[c] : bf16_round(v[j + q] + s_bp[c]);
-          if (P.pos) e += P.pos[(size_t)t * H + c];
-          z[c] = e * kpa[q];
-        }
+      for (int q = 0; q < 8; ++q) {
+        const int c = hc0 + j + q;
+        float e = t == 0 ? s_cls[c] : bf16_round(v[j + q] + s_bp[c]);
+        if (P.pos) e += P.pos[(size_t)t * H + c];
+        z[j + q] = e * kp[q];
       }
     }
-    float u[H], mu, rs;
-    layer_norm_row<H>(z, s_g, s_b, P.eps, u, mu, rs);
-    if (valid) {
-      float4* zp = reinterpret_cast<float4*>(P.z0 + (size_t)row * H);
+    float mu, rs;
+    row_stats<HC>(z, s_ln, r, cg, P.eps, mu, rs);
+    float u[HC];
 #pragma unroll
-      for (int j = 0; j < H / 4; ++j) zp[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-      P.mean[row] = mu; P.rstd[row] = rs;
+    for (int j = 0; j < HC; ++j) u[j] = bf16_round((z[j] - mu) * rs * s_g[hc0 + j] + s_b[hc0 + j]);
+    if (valid) {
+      float4* zp = reinterpret_cast<float4*>(P.z0 + (size_t)row * H + hc0);
+#pragma unroll
+      for (int j = 0; j < HC / 4; ++j) zp[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+      if (cg == 0) { P.mean[row] = mu; P.rstd[row] = rs; }
     }
-    emit_row_bf16<H>(u, reinterpret_cast<bf16*>(P.u) + (size_t)rowc * H, valid, sA, tid, 0);
+    emit_row_bf16<HC>(u, reinterpret_cast<bf16*>(P.u) + (size_t)rowc * H + hc0, valid, sA, r, hc0 >> 3);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -404,7 +433,7 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
   mbar_wait(b_mma, mma_phase); mma_phase ^= 1;
   tc_fence_after();
 #pragma unroll 1
-  for (int c0 = 0; c0 < 3 * H; c0 += 32) {
+  for (int c0 = cg * 32; c0 < 3 * H; c0 += 32 * FF_CG) {
     float v[32];
     tmem_ld_32x32(my_tmem + c0, v);
 #pragma unroll
@@ -417,9 +446,9 @@ fused_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmWp, const __grid_co
 }
 
 template <int H> static constexpr int layer_smem() {
-  return 16384 + (4 * H / 64) * 16384 + H * 128 + 4 * H * 128 + (4 * H / 64) * H * 128 + 3 * H * 128 + 1024 + 64 + (13 * H) * 4 + 64;
+  return 16384 + (4 * H / 64) * 16384 + H * 128 + 4 * H * 128 + (4 * H / 64) * H * 128 + 3 * H * 128 + 1024 + 64 + (13 * H) * 4 + 4096 + 64;
 }
-template <int H> static constexpr int embed_smem() { return 16384 + H * 128 + 3 * H * 128 + 1024 + 64 + (7 * H) * 4 + 64; }
+template <int H> static constexpr int embed_smem() { return 16384 + H * 128 + 3 * H * 128 + 1024 + 64 + (7 * H) * 4 + 4096 + 64; }
 
 template <int H>
 static int launch_layer(const vitb200_layer_fwd_args* a, cudaStream_t st) {
