@@ -1,14 +1,18 @@
-// Multi-head self-attention on tcgen05 for sequences whose keys fit one TMEM tile (T <= 176..208), bf16.
+// Multi-head self-attention on tcgen05 for sequences whose keys fit one TMEM tile (T <= 176), bf16.
 //
-// One CTA (128 threads) per (sample, head).  Q/K/V tiles are TMA-loaded straight out of the fused
-// [B*T, 3H] QKV buffer (box = 64 columns starting at the head's column, so no head-major copy exists);
-// only the first d columns of each 128-byte row take part in the MMAs.
-//   forward : S = Q K^T (UMMA, fp32 in TMEM) -> softmax in registers (thread = query row; exp2 with the
-//             scale folded in; Philox dropout) -> P (bf16) to swizzled smem -> O = P V (UMMA, V as MN-major B)
-//   backward: S and dP = dO V^T by UMMA; thread = query row computes P, dS; dS and dropped P go to smem ONCE and
+// One CTA per (sample, head): 16 MMA-path warps (512 threads) + 1 side-row warp.  Q/K/V tiles are TMA-loaded straight
+// out of the fused [B*T, 3H] QKV buffer (box = 64 columns starting at the head's column, so no head-major copy
+// exists); only the first d columns of each 128-byte row take part in the MMAs.
+// Warp w of the MMA path owns TMEM lane quarter (w & 3) (query rows 32 (w & 3) .. +31 of the tile) and key-column
+// group cg = w >> 2: the softmax row of a query is split over four threads in chunks of 16 keys (chunk c belongs to
+// group c & 3); row max / row sum are merged through shared memory.  (One thread per query row -- the first version --
+// left each SM scheduler a single warp with ~6k dependent instructions: 12 us per launch at 128 CTAs.)
+//   forward : S = Q K^T (UMMA, fp32 in TMEM) -> softmax in registers (exp2 with the scale folded in; Philox dropout)
+//             -> P (bf16) to swizzled smem -> O = P V (UMMA, V as MN-major B)
+//   backward: S and dP = dO V^T by UMMA; P, dS in registers; dS and dropped P go to smem ONCE and
 //             are used as K-major A (dQ = dS K) and as MN-major A (dK = dS^T Q, dV = P^T dO), the latter
 //             accumulating in TMEM over the query tiles.  No atomics: results are bitwise reproducible.
-// Query tiles of 128 rows are looped inside the CTA (T = 129 -> 2 tiles, K/V staged once).
+// Query tiles of 128 rows are looped inside the CTA; K/V are staged once.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_host.cuh"
@@ -16,7 +20,9 @@
 namespace vb {
 using namespace vb::tc;
 
-constexpr int AT_TC_THREADS = 128;
+constexpr int AT_CG = 4;                          // key-column groups = threads per query row
+constexpr int AT_TC_THREADS = 128 * AT_CG;        // MMA-path threads (512)
+constexpr int AT_ALL_THREADS = AT_TC_THREADS + 32;  // + the side-row warp
 constexpr float AT_LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint4 at_pack8(const float* v) {
@@ -70,8 +76,8 @@ __device__ __forceinline__ void at_issue(uint32_t tmem_d, const AOp& A, const AO
   for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, aop_desc(A, k), aop_desc(B, k), idesc, (acc || k > 0) ? 1u : 0u);
 }
 
-__device__ __forceinline__ void bar_main() { asm volatile("bar.sync 1, 128;" ::: "memory"); }     // the 4 MMA-path warps
-__device__ __forceinline__ void bar_all160() { asm volatile("bar.sync 2, 160;" ::: "memory"); }  // + the side-row warp
+__device__ __forceinline__ void bar_main() { asm volatile("bar.sync 1, 512;" ::: "memory"); }    // the 16 MMA-path warps
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 2, 544;" ::: "memory"); }     // + the side-row warp
 __device__ __forceinline__ float warp_allsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -83,6 +89,7 @@ __device__ __forceinline__ float warp_allmax(float v) {
   return v;
 }
 constexpr int AT_SIDE_KEYS = 6;  // keys per lane of the side-row warp: covers T <= 192
+constexpr int AT_MAXCH = 3;      // 16-key chunks per thread: covers KP <= 192
 
 struct AttnTcParams {
   const bf16* qkv;       // q pointer (k = q + H, v = q + 2H inside the same rows)
@@ -97,24 +104,28 @@ struct AttnTcParams {
 // forward
 // ================================================================================================
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(AT_ALL_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  const int KP = P.KP, nblk = (KP + 63) / 64, KW = nblk * 64;
+  const int KP = P.KP, nch = KP / 16;
   const uint32_t kv_bytes = (uint32_t)KP * 128;
   uint8_t* sQ = base;                       // 16 KB
   uint8_t* sK = sQ + 16384;                 // 32 KB reserved
   uint8_t* sV = sK + 32768;                 // 32 KB reserved
-  uint8_t* sP = sV + 32768;                 // nblk x 16 KB
+  uint8_t* sP = sV + 32768;                 // up to 3 x 16 KB (4 reserved)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * 16384);
   uint64_t *b_kv = bars, *b_q = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* s_mx = reinterpret_cast<float*>(bars + 8);   // [AT_CG][128] row-max exchange
+  float* s_sm = s_mx + AT_CG * 128;                   // [AT_CG][128] row-sum exchange
   constexpr uint32_t TMEM_COLS = 512;
   const uint32_t cS = 0, cO = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);   // query row of the tile = TMEM lane
+  const int cg = warp >> 2;                       // key-column group (4 = side-row warp)
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
   if (tid == 0) {
@@ -122,14 +133,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
-  pdl_wait();     // q/k/v (and dctx) come from the previous kernel of the step
+  pdl_wait();     // q/k/v come from the previous kernel of the step
   pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   if (tid == 0) {
     mbar_expect_tx(b_kv, 2 * kv_bytes);
     tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
@@ -142,11 +153,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const float sl2 = P.scale * AT_LOG2E;
   uint32_t ph_q = 0, ph_mma = 0;
   // T = 128 n + 1 (the CLS token makes every configured sequence one row longer than a tile): the last query row
-  // is handled by a 5th warp with plain FMAs, concurrently with the tensor-core tiles, instead of a whole extra tile.
+  // is handled by a 17th warp with plain FMAs, concurrently with the tensor-core tiles, instead of a whole extra tile.
   const bool side = (T % 128 == 1) && T > 1 && P.cosT == nullptr;
   const int nq = side ? T / 128 : (T + 127) / 128;
 
-  if (warp == 4) {
+  if (cg == AT_CG) {
     if (side) {
       const int lane = tid & 31, i = T - 1;
       mbar_wait(b_kv, 0);
@@ -206,7 +217,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
   for (int qt = 0; qt < nq; ++qt) {
-    const int q0 = qt * 128, i = q0 + tid;
+    const int q0 = qt * 128, i = q0 + r;
     const bool valid = i < T;
     if (tid == 0) {
       mbar_expect_tx(b_q, 16384);
@@ -214,16 +225,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     if (qt == 0) mbar_wait(b_kv, 0);
     mbar_wait(b_q, ph_q); ph_q ^= 1;
-    if (P.cosT) {  // rotate this thread's query row (and, once, its key rows) in place
+    if (P.cosT) {  // rotate the query rows (and, once, the key rows) in place
       float x[D];
-      at_load_row<D>(sQ, tid, x);
-      at_rope<D, false>(x, P.cosT, P.sinT, valid ? i : 0);
-      at_store_row<D>(sQ, tid, x);
+      if (cg == 0) {
+        at_load_row<D>(sQ, r, x);
+        at_rope<D, false>(x, P.cosT, P.sinT, valid ? i : 0);
+        at_store_row<D>(sQ, r, x);
+      }
       if (qt == 0) {
-        for (int r = tid; r < KP; r += AT_TC_THREADS) {
-          at_load_row<D>(sK, r, x);
-          at_rope<D, false>(x, P.cosT, P.sinT, r < T ? r : 0);
-          at_store_row<D>(sK, r, x);
+        for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
+          at_load_row<D>(sK, rr, x);
+          at_rope<D, false>(x, P.cosT, P.sinT, rr < T ? rr : 0);
+          at_store_row<D>(sK, rr, x);
         }
       }
       fence_proxy_async();
@@ -237,36 +250,43 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    // ---- softmax over the keys of this thread's row ----
+    // ---- softmax: this thread holds the 16-key chunks cg, cg + 4, cg + 8 of its query row ----
+    float v[AT_MAXCH][16];
     float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < KW; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(my_tmem + cS + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (c0 + j < T) mx = fmaxf(mx, v[j]);
+    for (int k = 0; k < AT_MAXCH; ++k) {
+      const int c0 = (cg + k * AT_CG) * 16;
+      if (cg + k * AT_CG < nch) {
+        tmem_ld_32x16(my_tmem + cS + c0, v[k]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (c0 + j < T) mx = fmaxf(mx, v[k][j]);
+      }
     }
+    s_mx[cg * 128 + r] = mx;
+    bar_main();
+    mx = fmaxf(fmaxf(s_mx[r], s_mx[128 + r]), fmaxf(s_mx[256 + r], s_mx[384 + r]));
     const float mxs = mx * sl2;
     float sum = 0.f;
     const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + (valid ? i : 0)) * (uint64_t)Tpad;
-#pragma unroll 1
-    for (int c0 = 0; c0 < KW; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(my_tmem + cS + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float kp[8];
-        if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+    for (int k = 0; k < AT_MAXCH; ++k) {
+      const int c0 = (cg + k * AT_CG) * 16;
+      if (cg + k * AT_CG < nch) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float p = (c0 + j + q < T) ? exp2f(v[j + q] * sl2 - mxs) : 0.f;
-          sum += p;
-          v[j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
+        for (int j = 0; j < 16; j += 8) {
+          float kp[8];
+          if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float p = (c0 + j + q < T) ? exp2f(v[k][j + q] * sl2 - mxs) : 0.f;
+            sum += p;
+            v[k][j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
+          }
+          *reinterpret_cast<uint4*>(at_swz(sP, r, (c0 + j) >> 3)) = at_pack8(&v[k][j]);
         }
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(at_swz(sP, tid, (c0 >> 3) + c)) = at_pack8(&v[c * 8]);
     }
+    s_sm[cg * 128 + r] = sum;
     fence_proxy_async();
     tc_fence_before();
     bar_main();
@@ -275,20 +295,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       at_issue(tmem + cO, Pk, Vmn, D, KP / 16, false);  // O[i, c] = sum_j P[i, j] v[j, c]
       umma_commit(b_mma);
     }
+    sum = (s_sm[r] + s_sm[128 + r]) + (s_sm[256 + r] + s_sm[384 + r]);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    {
-      float o[32];
-      tmem_ld_32x32(my_tmem + cO, o);  // D <= 32 columns are meaningful
+    if (cg < D / 8) {  // 8 output columns per thread
+      float o[8];
+      tmem_ld_32x8(my_tmem + cO + cg * 8, o);
       if (valid) {
         const float inv = 1.f / sum;
-        float r[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) r[c] = o[c] * inv;
-        bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
-#pragma unroll
-        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&r[c]);
-        P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        for (int c = 0; c < 8; ++c) o[c] *= inv;
+        *reinterpret_cast<uint4*>(P.ctx + (size_t)(row0 + i) * P.H + h * D + cg * 8) = at_pack8(o);
+        if (cg == 0) P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
       }
     }
     tc_fence_before();
@@ -303,13 +321,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // backward
 // ================================================================================================
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(AT_ALL_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const AttnTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  const int KP = P.KP, nblk = (KP + 63) / 64, KW = nblk * 64;
+  const int KP = P.KP, nch = KP / 16;
   const uint32_t kv_bytes = (uint32_t)KP * 128;
   // nblk <= 3 blocks of dS / P~ are written.  The MN-major view of key tile 1 spans blocks 2 and 3; block 3 then aliases
   // the NEXT buffer (sPT block 0, resp. the first 16 KB of sK): finite bf16 data whose product rows (keys >= 192)
@@ -328,12 +346,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* xq = xpt + 256;
   float* xdo = xq + 32;
   constexpr uint32_t TMEM_COLS = 512;
-  // TMEM columns: S and dP take round_up(KP, 32) columns each (the 32-wide reads below may run past KP into the
-  // neighbouring region; those entries are masked), then dQ and the dK / dV accumulators of up to two key tiles
+  // TMEM columns: S and dP take round_up(KP, 32) columns each, then dQ and the dK / dV accumulators of up to two key tiles
   const uint32_t KPa = (uint32_t)((KP + 31) / 32 * 32);
   const uint32_t cS = 0, cDP = KPa, cDQ = 2 * KPa, cDK0 = cDQ + 32, cDK1 = cDK0 + 32, cDV0 = cDK1 + 32, cDV1 = cDV0 + 32;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = ((warp & 3) << 5) | (tid & 31);
+  const int cg = warp >> 2;
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
   if (tid == 0) {
@@ -341,14 +360,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
-  pdl_wait();     // q/k/v (and dctx) come from the previous kernel of the step
+  pdl_wait();     // q/k/v and dctx come from earlier kernels of the step
   pdl_trigger();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   if (tid == 0) {
     mbar_expect_tx(b_kv, 2 * kv_bytes);
     tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
@@ -366,7 +385,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int nq = side ? T / 128 : (T + 127) / 128;
   const int nkt = (KP + 127) / 128;  // key tiles of the dK / dV accumulators (1 or 2)
 
-  if (warp == 4) {
+  if (cg == AT_CG) {
     if (side) {
       // last query row with plain FMAs: dq directly; its rank-1 contributions to dK / dV are handed to the key-row
       // epilogue through shared memory (xds, xpt, xq, xdo)
@@ -422,10 +441,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int c = 0; c < D; ++c) { xq[c] = qf[c]; xdo[c] = dof[c]; }
       }
     }
-    bar_all160();  // side-row results visible to the key-row epilogue
+    bar_all();  // side-row results visible to the key-row epilogue
   } else {
   for (int qt = 0; qt < nq; ++qt) {
-    const int q0 = qt * 128, i = q0 + tid;
+    const int q0 = qt * 128, i = q0 + r;
     const bool valid = i < T;
     const int ic = valid ? i : T - 1;
     if (tid == 0) {
@@ -433,33 +452,41 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
       tma_load_2d(sDO, &tmDO, b_q, h * D, row0 + q0);
     }
+    // row statistics: issued before the waits (lse_i, and the ctx row for D_i = dO_i . O_i)
+    const float lse2 = P.lse[(size_t)(b * P.heads + h) * T + ic] * AT_LOG2E;
+    uint4 oraw[D / 8];
+    {
+      const bf16* op = P.ctx + (size_t)(row0 + ic) * P.H + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) oraw[c] = *reinterpret_cast<const uint4*>(op + c * 8);
+    }
     if (qt == 0) mbar_wait(b_kv, 0);
     mbar_wait(b_q, ph_q); ph_q ^= 1;
     // rows of Q / dO beyond this sample must not leak into the dK / dV contractions: zero them
     float dof[D];
     if (!valid) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        *reinterpret_cast<uint4*>(at_swz(sQ, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(at_swz(sDO, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 2 * cg; c < 2 * cg + 2; ++c) {
+        *reinterpret_cast<uint4*>(at_swz(sQ, r, c)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(at_swz(sDO, r, c)) = make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int c = 0; c < D; ++c) dof[c] = 0.f;
     } else {
-      at_load_row<D>(sDO, tid, dof);
+      at_load_row<D>(sDO, r, dof);
     }
     if (P.cosT) {
       float x[D];
-      if (valid) {
-        at_load_row<D>(sQ, tid, x);
+      if (valid && cg == 0) {
+        at_load_row<D>(sQ, r, x);
         at_rope<D, false>(x, P.cosT, P.sinT, i);
-        at_store_row<D>(sQ, tid, x);
+        at_store_row<D>(sQ, r, x);
       }
       if (qt == 0) {
-        for (int r = tid; r < KP; r += AT_TC_THREADS) {
-          at_load_row<D>(sK, r, x);
-          at_rope<D, false>(x, P.cosT, P.sinT, r < T ? r : 0);
-          at_store_row<D>(sK, r, x);
+        for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
+          at_load_row<D>(sK, rr, x);
+          at_rope<D, false>(x, P.cosT, P.sinT, rr < T ? rr : 0);
+          at_store_row<D>(sK, rr, x);
         }
       }
     }
@@ -472,29 +499,26 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       at_issue(tmem + cDP, DOk, Vk, KP, D / 16, false);  // dP = dO V^T
       umma_commit(b_mma);
     }
-    // D_i = dO_i . O_i (flash-attention backward's row statistic), lse_i
+    // D_i = dO_i . O_i (flash-attention backward's row statistic); every thread of the row computes it
     float Di = 0.f;
-    {
-      const bf16* op = P.ctx + (size_t)(row0 + ic) * P.H + h * D;
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        float o8[8];
-        at_unpack8(*reinterpret_cast<const uint4*>(op + c), o8);
+    for (int c = 0; c < D / 8; ++c) {
+      float o8[8];
+      at_unpack8(oraw[c], o8);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) Di = fmaf(dof[c + q], o8[q], Di);
-      }
+      for (int q = 0; q < 8; ++q) Di = fmaf(dof[c * 8 + q], o8[q], Di);
     }
-    const float lse2 = P.lse[(size_t)(b * P.heads + h) * T + ic] * AT_LOG2E;
     const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + ic) * (uint64_t)Tpad;
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < KW; c0 += 32) {
-      float s[32], dp[32];
-      tmem_ld_32x32(my_tmem + cS + c0, s);
-      tmem_ld_32x32(my_tmem + cDP + c0, dp);
+    for (int ch = cg; ch < nch; ch += AT_CG) {
+      const int c0 = ch * 16;
+      float s[16], dp[16];
+      tmem_ld_32x16(my_tmem + cS + c0, s);
+      tmem_ld_32x16(my_tmem + cDP + c0, dp);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < 16; j += 8) {
         float kpa[8];
         if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
 #pragma unroll
@@ -502,15 +526,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const bool on = valid && (c0 + j + q < T);
           const float kq = (c0 + j < T) ? kpa[q] : 0.f;
           const float p = on ? exp2f(s[j + q] * sl2 - lse2) : 0.f;
-          const float ds = on ? p * (dp[j + q] * kq - Di) * P.scale : 0.f;  // (columns past KP hold stale TMEM data)
+          const float ds = on ? p * (dp[j + q] * kq - Di) * P.scale : 0.f;  // (columns past T hold stale TMEM data)
           s[j + q] = ds;               // dS (scale folded in)
           dp[j + q] = p * kq;          // dropped probabilities
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<uint4*>(at_swz(sDS, tid, (c0 >> 3) + c)) = at_pack8(&s[c * 8]);
-        *reinterpret_cast<uint4*>(at_swz(sPT, tid, (c0 >> 3) + c)) = at_pack8(&dp[c * 8]);
+        *reinterpret_cast<uint4*>(at_swz(sDS, r, (c0 + j) >> 3)) = at_pack8(&s[j]);
+        *reinterpret_cast<uint4*>(at_swz(sPT, r, (c0 + j) >> 3)) = at_pack8(&dp[j]);
       }
     }
     fence_proxy_async();
@@ -528,54 +549,67 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    {
-      float o[32];
-      tmem_ld_32x32(my_tmem + cDQ, o);
-      if (valid) {
-        float r[D];
+    if (P.cosT) {  // the inverse rotation pairs columns c and c + D/2: one thread takes the whole row
+      if (cg == 0) {
+        float o[32];
+        tmem_ld_32x32(my_tmem + cDQ, o);
+        if (valid) {
+          float x[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) r[c] = o[c];
-        if (P.cosT) {
+          for (int c = 0; c < D; ++c) x[c] = bf16_round(o[c]);
+          at_rope<D, true>(x, P.cosT, P.sinT, i);
+          bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
 #pragma unroll
-          for (int c = 0; c < D; ++c) r[c] = bf16_round(r[c]);
-          at_rope<D, true>(r, P.cosT, P.sinT, i);
+          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&x[c]);
         }
-        bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
-#pragma unroll
-        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&r[c]);
       }
+    } else if (cg < D / 8) {
+      float o[8];
+      tmem_ld_32x8(my_tmem + cDQ + cg * 8, o);
+      if (valid) *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D + cg * 8) = at_pack8(o);
     }
     tc_fence_before();
     bar_main();
   }
-  // ---- dK, dV: thread = key row of key tile kt ----
-  bar_all160();
+  // ---- dK, dV: thread = key row of key tile kt; the 2 D/8 eight-column pieces of [dK | dV] are spread over the groups ----
+  bar_all();
   tc_fence_after();
   for (int kt = 0; kt < nkt; ++kt) {
-    const int j = kt * 128 + tid;
-    float dk[32], dv[32];
-    tmem_ld_32x32(my_tmem + (kt ? cDK1 : cDK0), dk);
-    tmem_ld_32x32(my_tmem + (kt ? cDV1 : cDV0), dv);
-    if (j < T) {
-      float r[D];
+    const int j = kt * 128 + r;
+    if (P.cosT) {
+      if (cg < 2) {  // cg 0: dK row (inverse rotation), cg 1: dV row
+        float o[32];
+        tmem_ld_32x32(my_tmem + (cg == 0 ? (kt ? cDK1 : cDK0) : (kt ? cDV1 : cDV0)), o);
+        if (j < T) {
+          float x[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) r[c] = dk[c];
-      if (side) {
-        const float a = xds[j], pt = xpt[j];
+          for (int c = 0; c < D; ++c) x[c] = o[c];
+          if (cg == 0) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) { r[c] = fmaf(a, xq[c], r[c]); dv[c] = fmaf(pt, xdo[c], dv[c]); }
+            for (int c = 0; c < D; ++c) x[c] = bf16_round(x[c]);
+            at_rope<D, true>(x, P.cosT, P.sinT, j);
+          }
+          bf16* dst = P.dqkv + (size_t)(row0 + j) * P.ld_d + (cg == 0 ? P.H : 2 * P.H) + h * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&x[c]);
+        }
       }
-      if (P.cosT) {
+    } else {
+#pragma unroll 1
+      for (int pc = cg; pc < 2 * (D / 8); pc += AT_CG) {
+        const bool is_v = pc >= D / 8;
+        const int c8 = (is_v ? pc - D / 8 : pc) * 8;
+        float o[8];
+        tmem_ld_32x8(my_tmem + (is_v ? (kt ? cDV1 : cDV0) : (kt ? cDK1 : cDK0)) + c8, o);
+        if (j < T) {
+          if (side) {
+            const float a = is_v ? xpt[j] : xds[j];
+            const float* xr = is_v ? xdo : xq;
 #pragma unroll
-        for (int c = 0; c < D; ++c) r[c] = bf16_round(r[c]);
-        at_rope<D, true>(r, P.cosT, P.sinT, j);
-      }
-      bf16* dkp = P.dqkv + (size_t)(row0 + j) * P.ld_d + P.H + h * D;
-      bf16* dvp = P.dqkv + (size_t)(row0 + j) * P.ld_d + 2 * P.H + h * D;
-#pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        *reinterpret_cast<uint4*>(dkp + c) = at_pack8(&r[c]);
-        *reinterpret_cast<uint4*>(dvp + c) = at_pack8(&dv[c]);
+            for (int c = 0; c < 8; ++c) o[c] = fmaf(a, xr[c8 + c], o[c]);
+          }
+          *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + j) * P.ld_d + (is_v ? 2 * P.H : P.H) + h * D + c8) = at_pack8(o);
+        }
       }
     }
   }
@@ -585,7 +619,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 1024;
+constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 64 + 2 * AT_CG * 128 * 4 + 1024;
 constexpr int AT_BWD_SMEM = 16384 + 16384 + 49152 + 49152 + 32768 + 32768 + 1024 + 4096;
 
 static inline int at_kp(int T) { return (T + 15) / 16 * 16; }
@@ -626,7 +660,7 @@ extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    vb_launch_pdl(attn_tc_fwd_kernel<DD>, grid, dim3(160), AT_FWD_SMEM, st, tQ, tKV, P);                                \
+    vb_launch_pdl(attn_tc_fwd_kernel<DD>, grid, dim3(AT_ALL_THREADS), AT_FWD_SMEM, st, tQ, tKV, P);                                \
   }
   if (d == 16) LAUNCH_F(16) else LAUNCH_F(32)
 #undef LAUNCH_F
@@ -658,7 +692,7 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
       if (e != cudaSuccess) return vb_cuda_error(e);                                                             \
       done = true;                                                                                               \
     }                                                                                                            \
-    vb_launch_pdl(attn_tc_bwd_kernel<DD>, grid, dim3(160), AT_BWD_SMEM, st, tQ, tKV, tDO, P);                           \
+    vb_launch_pdl(attn_tc_bwd_kernel<DD>, grid, dim3(AT_ALL_THREADS), AT_BWD_SMEM, st, tQ, tKV, tDO, P);                           \
   }
   if (d == 16) LAUNCH_B(16) else LAUNCH_B(32)
 #undef LAUNCH_B
