@@ -258,31 +258,51 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int c0 = (cg + k * AT_CG) * 16;
       if (cg + k * AT_CG < nch) {
         tmem_ld_32x16(my_tmem + cS + c0, v[k]);
+        if (c0 + 16 <= T) {   // full chunk: no key masking
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (c0 + j < T) mx = fmaxf(mx, v[k][j]);
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[k][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < T) mx = fmaxf(mx, v[k][j]);
+        }
       }
     }
     s_mx[cg * 128 + r] = mx;
     bar_main();
     mx = fmaxf(fmaxf(s_mx[r], s_mx[128 + r]), fmaxf(s_mx[256 + r], s_mx[384 + r]));
-    const float mxs = mx * sl2;
+    const float nmxs = -mx * sl2;
     float sum = 0.f;
     const uint64_t drow = ((uint64_t)(b * P.heads + h) * T + (valid ? i : 0)) * (uint64_t)Tpad;
 #pragma unroll
     for (int k = 0; k < AT_MAXCH; ++k) {
       const int c0 = (cg + k * AT_CG) * 16;
       if (cg + k * AT_CG < nch) {
+        if (c0 + 16 <= T) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-          float kp[8];
-          if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+          for (int j = 0; j < 16; j += 8) {
+            float kp[8];
+            drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float p = (c0 + j + q < T) ? exp2f(v[k][j + q] * sl2 - mxs) : 0.f;
-            sum += p;
-            v[k][j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
+            for (int q = 0; q < 8; ++q) {
+              const float p = ex2_approx(fmaf(v[k][j + q], sl2, nmxs));
+              sum += p;
+              v[k][j + q] = p * kp[q];
+            }
+            *reinterpret_cast<uint4*>(at_swz(sP, r, (c0 + j) >> 3)) = at_pack8(&v[k][j]);
           }
-          *reinterpret_cast<uint4*>(at_swz(sP, r, (c0 + j) >> 3)) = at_pack8(&v[k][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            float kp[8];
+            if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float p = (c0 + j + q < T) ? ex2_approx(fmaf(v[k][j + q], sl2, nmxs)) : 0.f;
+              sum += p;
+              v[k][j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
+            }
+            *reinterpret_cast<uint4*>(at_swz(sP, r, (c0 + j) >> 3)) = at_pack8(&v[k][j]);
+          }
         }
       }
     }
@@ -517,19 +537,37 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float s[16], dp[16];
       tmem_ld_32x16(my_tmem + cS + c0, s);
       tmem_ld_32x16(my_tmem + cDP + c0, dp);
+      if (valid && c0 + 16 <= T) {   // full chunk of a live query row: no masking
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          float kpa[8];
+          drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float p = ex2_approx(fmaf(s[j + q], sl2, -lse2));
+            const float pk = p * kpa[q];                                  // dropped probability
+            s[j + q] = fmaf(dp[j + q], pk, -p * Di);                      // dS / scale (the scale is applied to dQ, dK)
+            dp[j + q] = pk;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          float kpa[8];
+          if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool on = valid && (c0 + j + q < T);
+            const float kq = (c0 + j < T) ? kpa[q] : 0.f;
+            const float p = on ? ex2_approx(fmaf(s[j + q], sl2, -lse2)) : 0.f;
+            const float pk = p * kq;
+            s[j + q] = on ? fmaf(dp[j + q], pk, -p * Di) : 0.f;  // (columns past T hold stale TMEM data)
+            dp[j + q] = pk;
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; j += 8) {
-        float kpa[8];
-        if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const bool on = valid && (c0 + j + q < T);
-          const float kq = (c0 + j < T) ? kpa[q] : 0.f;
-          const float p = on ? exp2f(s[j + q] * sl2 - lse2) : 0.f;
-          const float ds = on ? p * (dp[j + q] * kq - Di) * P.scale : 0.f;  // (columns past T hold stale TMEM data)
-          s[j + q] = ds;               // dS (scale folded in)
-          dp[j + q] = p * kq;          // dropped probabilities
-        }
         *reinterpret_cast<uint4*>(at_swz(sDS, r, (c0 + j) >> 3)) = at_pack8(&s[j]);
         *reinterpret_cast<uint4*>(at_swz(sPT, r, (c0 + j) >> 3)) = at_pack8(&dp[j]);
       }
@@ -556,7 +594,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (valid) {
           float x[D];
 #pragma unroll
-          for (int c = 0; c < D; ++c) x[c] = bf16_round(o[c]);
+          for (int c = 0; c < D; ++c) x[c] = bf16_round(o[c] * P.scale);
           at_rope<D, true>(x, P.cosT, P.sinT, i);
           bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
 #pragma unroll
@@ -566,6 +604,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else if (cg < D / 8) {
       float o[8];
       tmem_ld_32x8(my_tmem + cDQ + cg * 8, o);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] *= P.scale;
       if (valid) *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D + cg * 8) = at_pack8(o);
     }
     tc_fence_before();
@@ -586,7 +626,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int c = 0; c < D; ++c) x[c] = o[c];
           if (cg == 0) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) x[c] = bf16_round(x[c]);
+            for (int c = 0; c < D; ++c) x[c] = bf16_round(x[c] * P.scale);
             at_rope<D, true>(x, P.cosT, P.sinT, j);
           }
           bf16* dst = P.dqkv + (size_t)(row0 + j) * P.ld_d + (cg == 0 ? P.H : 2 * P.H) + h * D;
@@ -602,6 +642,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float o[8];
         tmem_ld_32x8(my_tmem + (is_v ? (kt ? cDV1 : cDV0) : (kt ? cDK1 : cDK0)) + c8, o);
         if (j < T) {
+          if (!is_v) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] *= P.scale;
+          }
           if (side) {
             const float a = is_v ? xpt[j] : xds[j];
             const float* xr = is_v ? xdo : xq;

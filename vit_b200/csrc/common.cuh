@@ -181,22 +181,38 @@ __device__ __forceinline__ float drop1(const DropCtx& d, uint64_t idx) {
 // the surrounding GEMMs): ~14 instructions for both, instead of ~50 for erff + expf.  The GELU epilogues are the
 // longest serial instruction streams of the fused kernels (128 columns per thread), so this matters.
 // ---------------------------------------------------------------------------------------------
+// MUFU wrappers: one instruction each (expf / division without --use_fast_math expand to range-fixup sequences)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ht = 0.5 * erfc(|x| / sqrt 2) = 1 - Phi(|x|)   and   e = exp(-x^2 / 2)
+__device__ __forceinline__ float gelu_half_tail(float x, float& e) {
+  e = ex2_approx(x * x * -0.72134752044448170f);                  // -0.5 * log2(e)
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);   // 0.5 folded into the coefficients
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return p * t * e;
+}
 __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float e = __expf(-z * z);                       // exp(-x^2 / 2)
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_tail = 0.5f * p * t * e;             // 0.5 * (1 - erf(|x| / sqrt 2))
-  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+  float e;
+  const float ht = gelu_half_tail(x, e);
+  cdf = 0.5f + copysignf(0.5f - ht, x);
   pdf = 0.39894228040143268f * e;
 }
+// gelu(x) = x Phi(x) = max(x, 0) - |x| (1 - Phi(|x|))
 __device__ __forceinline__ float gelu_f(float x) {
-  float c, d;
-  gelu_cdf_pdf(x, c, d);
-  return x * c;
+  float e;
+  const float ht = gelu_half_tail(x, e);
+  return fmaf(-fabsf(x), ht, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float c, d;

@@ -262,8 +262,9 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __bfloat1622float2(a2[e]);
-          o[2 * e] = valid ? bf16_round(v[q * 8 + 2 * e]) * gelu_grad_f(f.x) : 0.f;
-          o[2 * e + 1] = valid ? bf16_round(v[q * 8 + 2 * e + 1]) * gelu_grad_f(f.y) : 0.f;
+          const float2 dm = __bfloat1622float2(__floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]));
+          o[2 * e] = valid ? dm.x * gelu_grad_f(f.x) : 0.f;
+          o[2 * e + 1] = valid ? dm.y * gelu_grad_f(f.y) : 0.f;
         }
         fb_swz_store(sDA, r, (c0 >> 3) + q, fb_pack8(o));
       }

@@ -221,15 +221,29 @@ fused_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_c
   tc_fence_after();
 #pragma unroll 1
   for (int c0 = cg * IC; c0 < (cg + 1) * IC; c0 += 32) {
-    float v[32], g[32];
+    float v[32];
     tmem_ld_32x32(my_tmem + c0, v);
+    bf16* ga = reinterpret_cast<bf16*>(P.a) + (size_t)rowc * I + c0;
+    bf16* gm = reinterpret_cast<bf16*>(P.m) + (size_t)rowc * I + c0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = bf16_round(v[j] + s_b1[c0 + j]);
-      g[j] = gelu_f(v[j]);
+    for (int j = 0; j < 32; j += 8) {
+      // pre-activation rounded to bf16 once (packed), GELU evaluated on the rounded value, packed again
+      uint32_t wa[4], wm[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 pa = __floats2bfloat162_rn(v[j + 2 * e] + s_b1[c0 + j + 2 * e], v[j + 2 * e + 1] + s_b1[c0 + j + 2 * e + 1]);
+        const float2 f = __bfloat1622float2(pa);
+        const __nv_bfloat162 pm = __floats2bfloat162_rn(gelu_f(f.x), gelu_f(f.y));
+        wa[e] = *reinterpret_cast<const uint32_t*>(&pa);
+        wm[e] = *reinterpret_cast<const uint32_t*>(&pm);
+      }
+      const uint4 ua = make_uint4(wa[0], wa[1], wa[2], wa[3]), um = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+      if (valid) {
+        *reinterpret_cast<uint4*>(ga + j) = ua;
+        *reinterpret_cast<uint4*>(gm + j) = um;
+      }
+      swz_store(sM, r, (c0 + j) >> 3, um);
     }
-    emit_row_bf16<32>(v, reinterpret_cast<bf16*>(P.a) + (size_t)rowc * I + c0, valid, nullptr, 0, 0);
-    emit_row_bf16<32>(g, reinterpret_cast<bf16*>(P.m) + (size_t)rowc * I + c0, valid, sM, r, c0 >> 3);
   }
   fence_proxy_async();
   tc_fence_before();
