@@ -1,0 +1,57 @@
+"""Per-phase cycle counts of the fused kernels (debug build with clock64 stamps).
+
+    VITB200_TIMELINE=1 python -m vit_b200.build          # builds vit_b200/libvitb200_tl.so (here, no GPU needed)
+    VITB200_TIMELINE=1 python tools/timeline.py          # on the GPU box
+
+Runs a few eager steps of the bench workload, then reads the stamps of the LAST launch of each instrumented
+kernel and prints, per phase, the mean / max over CTAs of the cycle deltas between consecutive stamps.
+"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+assert os.environ.get("VITB200_TIMELINE") == "1", "set VITB200_TIMELINE=1"
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from bench import BASELINE_CFG  # noqa: E402
+from vit_b200 import _lib, get_model  # noqa: E402
+from vit_b200.step import TrainStep  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+dev = torch.device("cuda", 0)
+torch.manual_seed(42)
+m = get_model(json.loads(json.dumps(BASELINE_CFG)), precision="bf16-mixed", device=dev).train()
+st = TrainStep(m, B, lr=1e-3, grad_clip=0.5, use_graph=True, train=True)
+x = torch.rand(B, 4096, device=dev)
+y = torch.rand(B, device=dev)
+for _ in range(5):
+    st.step(x, y)
+torch.cuda.synchronize()
+lib = _lib.load()
+SLOTS, CTAS = 16, 512
+names = {
+    "layer_fwd": ["prologue", "pdl_wait", "tmem+sync", "ctx TMA+MMA1", "epi1 (drop,LN)+sync", "MMA2", "GELU+sync", "MMA3",
+                  "epi3 (drop,LN)", "sync+MMA4", "epi4 (qkv)+sync"],
+    "bwd_upper": ["prologue", "pdl_wait", "tmem+sync", "dz,drop->sD +sync", "tile TMA+MMA1", "gelu'+sync", "MMA2",
+                  "LN bwd+sync", "MMA3", "dctx epi", "grad tail"],
+    "attn_fwd": ["prologue", "pdl_wait", "tmem+sync", "K/V/Q TMA", "rope+bar+MMA S", "max pass+bar", "exp pass+bar", "MMA PV",
+                 "O epi"],
+}
+for key, labels in names.items():
+    buf = (ctypes.c_longlong * (SLOTS * CTAS))()
+    rc = getattr(lib, f"vitb200_tl_{key}")(buf)
+    assert rc == 0
+    a = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)
+    n = len(labels) + 1
+    live = a[:, 0] != 0
+    a = a[live][:, :n]
+    d = np.diff(a, axis=1)
+    print(f"== {key}: {a.shape[0]} CTAs, total mean {d.sum(1).mean():.0f} cycles (max {d.sum(1).max()}) "
+          f"= {d.sum(1).mean() / 1.965e3:.2f} us @1.965 GHz")
+    for i, lab in enumerate(labels):
+        print(f"   {lab:<24} mean {d[:, i].mean():8.0f}   max {d[:, i].max():8d}")

@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+LIB_PATH = os.path.join(_HERE, "libvitb200_tl.so" if os.environ.get("VITB200_TIMELINE") == "1" else "libvitb200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1

@@ -15,15 +15,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libvitb200.so")
+OBJ = os.path.join(CSRC, "build_tl" if os.environ.get("VITB200_TIMELINE") == "1" else "build")
+TIMELINE = os.environ.get("VITB200_TIMELINE") == "1"  # debug variant with phase time stamps (tools/timeline.py)
+LIB = os.path.join(HERE, "libvitb200_tl.so" if TIMELINE else "libvitb200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math" if False else "-DVITB200_NO_FAST_MATH",  # fast-math stays off: fp32 mode has a 1e-4 parity bar
     "-Xcompiler", "-fPIC", "-I", INCLUDE,
-]
+] + (["-DVB_TIMELINE"] if os.environ.get("VITB200_TIMELINE") == "1" else [])
 
 
 def _nvcc() -> str:

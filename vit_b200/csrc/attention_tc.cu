@@ -24,6 +24,7 @@ constexpr int AT_CG = 4;                          // key-column groups = threads
 constexpr int AT_TC_THREADS = 128 * AT_CG;        // MMA-path threads (512)
 constexpr int AT_ALL_THREADS = AT_TC_THREADS + 32;  // + the side-row warp
 constexpr float AT_LOG2E = 1.4426950408889634f;
+VB_TL_DECL(tl_attn_fwd)
 
 __device__ __forceinline__ uint4 at_pack8(const float* v) {
   __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -124,6 +125,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t cS = 0, cO = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  VB_TL(tl_attn_fwd, 0);
   const int r = ((warp & 3) << 5) | (tid & 31);   // query row of the tile = TMEM lane
   const int cg = warp >> 2;                       // key-column group (4 = side-row warp)
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
@@ -133,8 +135,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
+  VB_TL(tl_attn_fwd, 1);
   pdl_wait();     // q/k/v come from the previous kernel of the step
   pdl_trigger();
+  VB_TL(tl_attn_fwd, 2);
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -146,6 +150,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
     tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
   }
+  VB_TL(tl_attn_fwd, 3);
   const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Kk{smem_u32(sK), 16, 16384, 0};
   const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV), 16384, 0, 1};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
@@ -225,6 +230,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     if (qt == 0) mbar_wait(b_kv, 0);
     mbar_wait(b_q, ph_q); ph_q ^= 1;
+  VB_TL(tl_attn_fwd, 4);
     if (P.cosT) {  // rotate the query rows (and, once, the key rows) in place
       float x[D];
       if (cg == 0) {
@@ -249,6 +255,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(b_mma);
     }
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+  VB_TL(tl_attn_fwd, 5);
     tc_fence_after();
     // ---- softmax: this thread holds the 16-key chunks cg, cg + 4, cg + 8 of its query row ----
     float v[AT_MAXCH][16];
@@ -269,6 +276,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     s_mx[cg * 128 + r] = mx;
     bar_main();
+  VB_TL(tl_attn_fwd, 6);
     mx = fmaxf(fmaxf(s_mx[r], s_mx[128 + r]), fmaxf(s_mx[256 + r], s_mx[384 + r]));
     const float nmxs = -mx * sl2;
     float sum = 0.f;
@@ -310,6 +318,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     bar_main();
+  VB_TL(tl_attn_fwd, 7);
     if (tid == 0) {
       tc_fence_after();
       at_issue(tmem + cO, Pk, Vmn, D, KP / 16, false);  // O[i, c] = sum_j P[i, j] v[j, c]
@@ -317,6 +326,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     sum = (s_sm[r] + s_sm[128 + r]) + (s_sm[256 + r] + s_sm[384 + r]);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+  VB_TL(tl_attn_fwd, 8);
     tc_fence_after();
     if (cg < D / 8) {  // 8 output columns per thread
       float o[8];
@@ -333,6 +343,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bar_main();
   }
   }
+  VB_TL(tl_attn_fwd, 9);
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -671,6 +682,8 @@ static inline int at_kp(int T) { return (T + 15) / 16 * 16; }
 }  // namespace vb
 
 using namespace vb;
+
+VB_TL_EXPORT(vitb200_tl_attn_fwd, vb::tl_attn_fwd)
 
 // q, k, v must be the three column blocks of one fused [B*T, 3H] bf16 buffer (k = q + H, v = q + 2H, ld = 3H)
 extern "C" int vitb200_attn_tc_supported(int T, int d, int ld, int H) {

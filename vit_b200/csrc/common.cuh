@@ -39,6 +39,29 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
+// Phase timeline (debug builds only: VITB200_TIMELINE=1 python -m vit_b200.build -> libvitb200_tl.so).
+// Thread 0 of every CTA stamps clock64() at phase boundaries; tools/timeline.py prints the per-phase cycles.
+// ---------------------------------------------------------------------------------------------
+#ifdef VB_TIMELINE
+#define VB_TL_SLOTS 16
+#define VB_TL_CTAS 512
+#define VB_TL_DECL(name) __device__ long long name[VB_TL_CTAS * VB_TL_SLOTS];
+#define VB_TL(name, k)                                                                                        \
+  do {                                                                                                        \
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                     \
+    if (threadIdx.x == 0 && cta_ < VB_TL_CTAS) name[cta_ * VB_TL_SLOTS + (k)] = clock64();                    \
+  } while (0)
+#define VB_TL_EXPORT(fn, name)                                                                                \
+  extern "C" int fn(long long* host) {                                                                        \
+    return cudaMemcpyFromSymbol(host, name, sizeof(long long) * VB_TL_CTAS * VB_TL_SLOTS) == cudaSuccess ? 0 : -1; \
+  }
+#else
+#define VB_TL_DECL(name)
+#define VB_TL(name, k) do { } while (0)
+#define VB_TL_EXPORT(fn, name)
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // 4-wide typed loads/stores (activations are float or bf16; accumulation is always fp32)
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Vec4;

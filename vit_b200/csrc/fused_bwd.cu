@@ -21,6 +21,7 @@ constexpr int FB_THREADS = 128 * FB_CG;
 constexpr int FB_H = 32;
 constexpr int FB_I = 128;
 constexpr int FB_HC = FB_H / FB_CG;   // 8 residual-stream columns per thread
+VB_TL_DECL(tl_bwd_upper)
 
 __device__ __forceinline__ uint4 fb_pack8(const float* v) {
   __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -119,12 +120,13 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
                        const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWo,
                        const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmHm,
-                       const vitb200_layer_bwd_upper_args P) {
+                       const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmDh,
+                       const __grid_constant__ CUtensorMap tmDctx, const vitb200_layer_bwd_upper_args P) {
   constexpr int H = FB_H, I = FB_I, HC = FB_HC;
   // shared memory map (all tile bases 1024-aligned); sD must be directly followed by sDA (see wgrad A views)
   constexpr uint32_t O_D = 0, O_DA = 16384, O_M = O_DA + 32768, O_U2 = O_M + 32768, O_CTX = O_U2 + 16384,
                      O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_ACT = O_WO + 4096,
-                     O_HM = O_ACT + 32768, O_BAR = O_HM + 16384, O_EX = O_BAR + 1024;
+                     O_HM = O_ACT + 32768, O_DZ = O_HM + 16384, O_BAR = O_DZ + 16384, O_EX = O_BAR + 1024;
   // TMEM columns
   constexpr uint32_t C_W2 = 0, C_W1 = 128, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -133,6 +135,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   uint8_t *sD = base + O_D, *sDA = base + O_DA, *sM = base + O_M, *sU2 = base + O_U2, *sCtx = base + O_CTX;
   uint8_t *sW2 = base + O_W2, *sW1 = base + O_W1, *sWo = base + O_WO;
   const uint8_t *sAct = base + O_ACT, *sHm = base + O_HM;  // pre-GELU activations (bf16) and hmid rows (fp32), TMA-staged
+  uint8_t* sDz = base + O_DZ;   // fp32 rows: dz (TMA load) -> dh (TMA store image)
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
   uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
@@ -140,6 +143,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   float2* s_ex = reinterpret_cast<float2*>(base + O_EX);   // [FB_CG][128] row-sum exchange (4 KB)
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  VB_TL(tl_bwd_upper, 0);
   const int r = ((warp & 3) << 5) | (tid & 31);  // row of the tile = TMEM lane
   const int cg = warp >> 2, hc0 = cg * HC;
   const int M = P.B * P.T;
@@ -149,7 +153,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   if (tid == 0) {
     tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmU2); tma_prefetch_desc(&tmCtx);
     tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWo);
-    tma_prefetch_desc(&tmAct); tma_prefetch_desc(&tmHm);
+    tma_prefetch_desc(&tmAct); tma_prefetch_desc(&tmHm); tma_prefetch_desc(&tmDz);
     mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
     fence_barrier_init();
   }
@@ -163,14 +167,17 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     tma_load_2d(sW1, &tmW1, b_w, 0, 0);          // W1 [I rows, H cols]: one {64 cols (32 valid), 128 rows} box
     tma_load_2d(sWo, &tmWo, b_w, 0, 0);          // Wo [H rows, H cols]
   }
+  VB_TL(tl_bwd_upper, 1);
   pdl_wait();
   pdl_trigger();
+  VB_TL(tl_bwd_upper, 2);
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  VB_TL(tl_bwd_upper, 3);
   const uint32_t aD = smem_u32(sD), aDA = smem_u32(sDA), aM = smem_u32(sM), aU2 = smem_u32(sU2), aCtx = smem_u32(sCtx);
   const uint32_t aW2 = smem_u32(sW2), aW1 = smem_u32(sW1), aWo = smem_u32(sWo);
   // operand views
@@ -202,8 +209,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     const int r0 = tile * 128, row = r0 + r;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
+    const bool from_cls = P.dz_cls != nullptr;
     if (tid == 0) {
-      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384);
+      if (iter > 0) tma_store_wait_read<0>();   // the previous tile's dh / dctx images are about to be overwritten
+      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384 + (from_cls ? 0 : 16384));
+      if (!from_cls) tma_load_2d(sDz, &tmDz, b_tile, 0, r0);
       tma_load_2d(sM, &tmM, b_tile, 0, r0);
       tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
       tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
@@ -216,18 +226,22 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
     float dz[HC];
     {
-      // top layer: only the CLS rows carry a gradient (the head reads last_hidden_state[:, 0], specvit.py:78)
-      const bool from_cls = P.dz_cls != nullptr;
-      const bool nz = !from_cls || (rowc % P.T) == 0;
-      const float4* p = from_cls ? reinterpret_cast<const float4*>(P.dz_cls + (size_t)(rowc / P.T) * H + hc0)
-                                 : reinterpret_cast<const float4*>(P.dz + (size_t)rowc * H + hc0);
+      if (from_cls) {
+        // top layer: only the CLS rows carry a gradient (the head reads last_hidden_state[:, 0], specvit.py:78)
+        const bool nz = (rowc % P.T) == 0;
+        const float4* p = reinterpret_cast<const float4*>(P.dz_cls + (size_t)(rowc / P.T) * H + hc0);
 #pragma unroll
-      for (int j = 0; j < HC / 4; ++j) {
-        float4 t = nz ? p[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w;
+        for (int j = 0; j < HC / 4; ++j) {
+          float4 t = nz ? p[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          dz[4 * j] = t.x; dz[4 * j + 1] = t.y; dz[4 * j + 2] = t.z; dz[4 * j + 3] = t.w;
+        }
       }
-      float kp[8], d2[HC];
-      drop8(dc_mlp, ((size_t)rowc * H + hc0) >> 3, kp);
+      float kp[8];
+      drop8(dc_mlp, ((size_t)rowc * H + hc0) >> 3, kp);   // overlaps the tile loads
+      mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged dz / a / hmid rows
+      ph_tile ^= 1;
+      if (!from_cls) fb_ld_f8(sDz, r, cg, dz);
+      float d2[HC];
 #pragma unroll
       for (int j = 0; j < HC; ++j) d2[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
       fb_swz_store(sD, r, cg, fb_pack8(d2));
@@ -235,19 +249,17 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+  VB_TL(tl_bwd_upper, 4);
     if (tid == 0) {
       tc_fence_after();
       if (iter == 0) mbar_wait(b_w, 0);
-      mbar_wait(b_tile, ph_tile);
-      tc_fence_after();
       fb_issue(tmem + C_DM, D_k, W2_mn, I, H / 16, false);        // dm[row, i]  = sum_h ddelta2[row,h] W2[h,i]
       fb_issue(tmem + C_W2, D_mn, M_mn, I, 8, iter > 0);          // dW2[h, i]  += sum_rows ddelta2[row,h] m[row,i]
       umma_commit(b_mma);
     }
     acc_b2 += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);  // overlaps the MMAs
-    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged a / hmid rows below
-    ph_tile ^= 1;
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+  VB_TL(tl_bwd_upper, 5);
     tc_fence_after();
     // ---- da = dm * gelu'(a) -> sDA ----
     {
@@ -274,12 +286,14 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+  VB_TL(tl_bwd_upper, 6);
       fb_issue(tmem + C_DU2, DA_k, W1_mn, H, I / 16, false);      // du2[row, h] = sum_i da[row,i] W1[i,h]
       fb_issue(tmem + C_W1, DA_mn, U2_mn, H, 8, iter > 0);        // dW1[i, h]  += sum_rows da[row,i] u2[row,h]
       umma_commit(b_mma);
     }
     acc_b1 += fb_colsum<32>(sDA, tid & 127, (tid >> 7) * 32);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+  VB_TL(tl_bwd_upper, 7);
     tc_fence_after();
     // ---- LayerNorm-after backward + residual -> dh ; ddelta1 = dropout'(dh) -> sD ----
     {
@@ -297,11 +311,8 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       fb_ln_bwd_sums(du, xh, s_g2, hc0, s_ex, r, cg, g, c1, c2);
 #pragma unroll
       for (int j = 0; j < HC; ++j) dz[j] += rs * (g[j] - c1 - xh[j] * c2);  // dz now holds dh
-      if (valid) {
-        float4* op = reinterpret_cast<float4*>(P.dh + (size_t)row * H + hc0);
-#pragma unroll
-        for (int j = 0; j < HC / 4; ++j) op[j] = make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]);
-      }
+      *reinterpret_cast<float4*>(const_cast<uint8_t*>(fb_swz_ptr(sDz, r, 2 * cg))) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      *reinterpret_cast<float4*>(const_cast<uint8_t*>(fb_swz_ptr(sDz, r, 2 * cg + 1))) = make_float4(dz[4], dz[5], dz[6], dz[7]);
       float kp[8], d1[HC];
       drop8(dc_proj, ((size_t)rowc * H + hc0) >> 3, kp);
 #pragma unroll
@@ -313,22 +324,32 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+  VB_TL(tl_bwd_upper, 8);
       fb_issue(tmem + C_DCTX, D_k, WO_mn, H, H / 16, false);      // dctx[row, k] = sum_n ddelta1[row,n] Wo[n,k]
       fb_issue(tmem + C_WO, D_mn, CTX_mn, H, 8, iter > 0);        // dWo[n, k]  += sum_rows ddelta1[row,n] ctx[row,k]
       umma_commit(b_mma);
+      tma_store_2d(&tmDh, sDz, 0, r0);   // dh leaves through TMA (row-strided st.global costs a tag lookup per row)
+      tma_store_commit();
     }
     acc_bo += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+  VB_TL(tl_bwd_upper, 9);
     tc_fence_after();
     {
       float v[HC];
       tmem_ld_32x8(my_tmem + C_DCTX + hc0, v);
-      if (valid) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.dctx) + (size_t)row * H + hc0) = fb_pack8(v);
+      fb_swz_store(sCtx, r, cg, fb_pack8(v));   // the ctx tile is dead (MMA 3 done): it becomes the dctx store image
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();  // all reads of sD / TMEM done before the next tile overwrites them
+    if (tid == 0) {
+      tma_store_2d(&tmDctx, sCtx, 0, r0);
+      tma_store_commit();
+    }
   }
 
+  VB_TL(tl_bwd_upper, 10);
   // ---- write this CTA's partial parameter gradients ----
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
@@ -373,6 +394,8 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     gp[P.off_b1 + c] = (bsum[1024 + c] + bsum[1024 + 128 + c]) + (bsum[1024 + 256 + c] + bsum[1024 + 384 + c]);
   }
   __syncthreads();
+  VB_TL(tl_bwd_upper, 11);
+  if (tid == 0) tma_store_wait_all();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -382,7 +405,8 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmU,
                        const __grid_constant__ CUtensorMap tmWq, const __grid_constant__ CUtensorMap tmZ,
-                       const __grid_constant__ CUtensorMap tmDh, const vitb200_layer_bwd_lower_args P) {
+                       const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDzOut,
+                       const vitb200_layer_bwd_lower_args P) {
   constexpr int H = FB_H, Q = 3 * FB_H, HC = FB_HC;
   constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_Z = O_WQ + 12288, O_DH = O_Z + 16384,
                      O_BAR = O_DH + 16384, O_RED = O_BAR + 1024, O_EX = O_RED + 32768;
@@ -441,6 +465,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     const int rowc = valid ? row : M - 1;
     const float mu = P.mean1[rowc], rs = P.rstd1[rowc];  // issued early
     if (tid == 0) {
+      if (iter > 0) tma_store_wait_read<0>();   // the previous tile's dz image (sDh) is about to be overwritten
       mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 16384);
       tma_load_2d(sDQ, &tmDQ, b_tile, 0, r0);
       tma_load_2d(sDQ + 16384, &tmDQ, b_tile, 64, r0);
@@ -473,21 +498,23 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
       }
       float c1, c2;
       fb_ln_bwd_sums(du, xh, s_g1, hc0, s_ex, r, cg, g, c1, c2);
-      if (valid) {
-        float4* op = reinterpret_cast<float4*>(P.dz + (size_t)row * H + hc0);
 #pragma unroll
-        for (int j = 0; j < HC / 4; ++j) {
-          float4 o;
-          o.x = dz[4 * j] + rs * (g[4 * j] - c1 - xh[4 * j] * c2);
-          o.y = dz[4 * j + 1] + rs * (g[4 * j + 1] - c1 - xh[4 * j + 1] * c2);
-          o.z = dz[4 * j + 2] + rs * (g[4 * j + 2] - c1 - xh[4 * j + 2] * c2);
-          o.w = dz[4 * j + 3] + rs * (g[4 * j + 3] - c1 - xh[4 * j + 3] * c2);
-          op[j] = o;
-        }
+      for (int j = 0; j < HC / 4; ++j) {   // dz overwrites this thread's piece of the dh tile: the tile is the store image
+        float4 o;
+        o.x = dz[4 * j] + rs * (g[4 * j] - c1 - xh[4 * j] * c2);
+        o.y = dz[4 * j + 1] + rs * (g[4 * j + 1] - c1 - xh[4 * j + 1] * c2);
+        o.z = dz[4 * j + 2] + rs * (g[4 * j + 2] - c1 - xh[4 * j + 2] * c2);
+        o.w = dz[4 * j + 3] + rs * (g[4 * j + 3] - c1 - xh[4 * j + 3] * c2);
+        *reinterpret_cast<float4*>(const_cast<uint8_t*>(fb_swz_ptr(sDh, r, 2 * cg + j))) = o;
       }
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      tma_store_2d(&tmDzOut, sDh, 0, r0);
+      tma_store_commit();
+    }
   }
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
@@ -511,6 +538,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   fb_reduce_rows(red, 2 * H, [&](int e, float s) { if (e < H) gp[P.off_ln1g + e] = s; else gp[P.off_ln1b + e - H] = s; });
   if (tid < Q) gp[P.off_bqkv + tid] = (bsum[tid] + bsum[128 + tid]) + (bsum[256 + tid] + bsum[384 + tid]);
   __syncthreads();
+  if (tid == 0) tma_store_wait_all();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -668,12 +696,14 @@ grad_reduce_kernel(const float* __restrict__ gpart, int slots, size_t stride, si
   }
 }
 
-constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 32768 + 16384 + 1024 + 4096 + 1024;
+constexpr int UPPER_SMEM = 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 16384 + 4096 + 32768 + 16384 + 16384 + 1024 + 4096 + 1024;
 constexpr int LOWER_SMEM = 32768 + 16384 + 12288 + 16384 + 16384 + 1024 + 32768 + 4096 + 1024;
 
 }  // namespace vb
 
 using namespace vb;
+
+VB_TL_EXPORT(vitb200_tl_bwd_upper, vb::tl_bwd_upper)
 
 extern "C" int vitb200_fused_bwd_supported(int H) { return H == FB_H ? 1 : 0; }
 extern "C" int vitb200_fused_bwd_grid(int M) {
@@ -698,6 +728,11 @@ extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args*
   if ((rc = get_tmap(a->w_2, I, H, 64, H, &tW2))) return rc;
   if ((rc = get_tmap(a->w_1, H, I, 64, I, &tW1))) return rc;
   if ((rc = get_tmap(a->w_o, H, H, 64, H, &tWo))) return rc;
+  CUtensorMap tDz, tDh, tDctx;
+  if ((rc = get_tmap(a->dh, 2 * H, M, 64, 128, &tDh))) return rc;
+  if (a->dz) { if ((rc = get_tmap(a->dz, 2 * H, M, 64, 128, &tDz))) return rc; }
+  else tDz = tDh;
+  if ((rc = get_tmap(a->dctx, H, M, 64, 128, &tDctx))) return rc;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(fused_bwd_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPPER_SMEM);
@@ -705,7 +740,7 @@ extern "C" int vitb200_fused_layer_bwd_upper(const vitb200_layer_bwd_upper_args*
     done = true;
   }
   vb_launch_pdl(fused_bwd_upper_kernel, dim3(vitb200_fused_bwd_grid(M)), dim3(FB_THREADS), UPPER_SMEM, (cudaStream_t)stream,
-                tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm, *a);
+                tM, tU2, tCtx, tW2, tW1, tWo, tAct, tHm, tDz, tDh, tDctx, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -723,6 +758,8 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
   if ((rc = get_tmap(a->dqkv, 3 * H, M, 64, 128, &tDQ))) return rc;
   if ((rc = get_tmap(a->u, H, M, 64, 128, &tU))) return rc;
   if ((rc = get_tmap(a->w_qkv, H, 3 * H, 64, 3 * H, &tWq))) return rc;
+  CUtensorMap tDzOut;
+  if ((rc = get_tmap(a->dz, 2 * H, M, 64, 128, &tDzOut))) return rc;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(fused_bwd_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOWER_SMEM);
@@ -730,7 +767,7 @@ extern "C" int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args*
     done = true;
   }
   vb_launch_pdl(fused_bwd_lower_kernel, dim3(vitb200_fused_bwd_grid(M)), dim3(FB_THREADS), LOWER_SMEM, (cudaStream_t)stream,
-                tDQ, tU, tWq, tZ, tDh, *a);
+                tDQ, tU, tWq, tZ, tDh, tDzOut, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
