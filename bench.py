@@ -175,6 +175,9 @@ def call_work(name: str, args: tuple, es: int):
         return 2.0 * B * Np * P * H, 4 * B * L + 4 * B * (Np + 1) * H + 4 * H * P
     if name.startswith("vitb200_fused_") or name.startswith("vitb200_head_fused"):
         return fused_call_work(name, args)
+    if name == "vitb200_clip_adamw_fused":
+        n, slots, start, end = args[5], args[10], args[12], args[13]
+        return 12.0 * n + slots * (end - start), 4.0 * (slots + 1) * (end - start) + 30.0 * n
     if name == "vitb200_grad_reduce":
         slots, start, end = args[1], args[3], args[4]
         return float(slots * (end - start)), 4.0 * (slots + 1) * (end - start)
@@ -224,6 +227,9 @@ def fused_call_work(name: str, args: tuple):
     if name == "vitb200_head_fused_fwd":
         B, H, C = args[6], args[7], args[8]
         return 2.0 * B * H * C, float(B * H * 2 + 8 * B * C)
+    if name == "vitb200_head_fused_fwd_bwd":
+        B, H, C = args[16], args[17], args[18]
+        return 8.0 * B * H * C + 10.0 * B * H, float(B * H * (2 + 4 + 4) + 8 * B * C)
     if name == "vitb200_head_fused_bwd":
         B, H, C = args[15], args[16], args[17]
         return 6.0 * B * H * C + 10.0 * B * H, float(B * H * (2 + 4 + 4) + 8 * B * C)
@@ -292,10 +298,21 @@ def kernel_table(eng, train: bool):
     import torch
 
     es = 2 if eng.act_dtype == torch.bfloat16 else 4
-    eng.forward(train=train, with_labels=True)
-    eng.backward(train=train)
+    fh = eng.can_fuse_head
+    eng.forward(train=train, with_labels=True, head_bwd=fh)
+    eng.backward(train=train, skip_reduce=True, skip_head=fh)
+    eng.optimizer_step(fused_reduce=True)
     torch.cuda.synchronize()
-    progs = [eng._progs[("fwd", train, True)], eng._progs[("bwd", train, None)]]
+    bkey = ("bwd", train, None, True, fh) if eng.fused_bwd else ("bwd", train, None)
+    fkey = ("fwd", train, True, True) if fh else ("fwd", train, True)
+    ar = eng.arena
+    slots, start, end = eng._red if eng.fused_bwd else (0, 0, 0)
+    tail = (eng.lib.vitb200_clip_adamw_fused, (
+        ar.data.data_ptr(), ar.grad.data_ptr(), eng.exp_avg.data_ptr(), eng.exp_avg_sq.data_ptr(),
+        None if ar.shadow is None else ar.shadow.data_ptr(), ar.layout.n_opt, eng.hyper.data_ptr(), eng.state.data_ptr(),
+        eng.rng.data_ptr(), eng.gpart.data_ptr() if slots else None, slots, ar.layout.n_opt, start, end,
+        eng.tail_ws.data_ptr()))
+    progs = [eng._progs[fkey], eng._progs[bkey], [tail]]
     rows = []
     for name, args, sec in time_calls(eng, progs):
         fl, by = call_work(name, args, es)
@@ -384,19 +401,37 @@ def main():
     ms_step = float(t[0]) / args.steps
     value = world * B * 1e3 / ms_step
 
-    # ---- end to end through the public API: pinned host -> H2D -> step -> D2H loss, every step ----
-    for i in range(max(3, args.warmup // 4)):
-        step.step_host(host_x[i % 8], host_y[i % 8])
+    # ---- end to end through the public API: host batches -> H2D -> step -> D2H loss, every step ----
+    # TrainStep.fit_host is the training loop a user calls with an iterable of host batches; it pipelines the copies
+    # around the steps (next batch uploads on a copy stream, the loss is read one step late).  step_host is the
+    # blocking single-step call (H2D, step, D2H, sync); it is reported beside it.
+    def host_batches(n):
+        for i in range(n):
+            yield host_x[i % 8], host_y[i % 8]
+
+    step.fit_host(host_batches(max(3, args.warmup // 4)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step.step_host(host_x[i % 8], host_y[i % 8])
+    e2e_losses = step.fit_host(host_batches(args.steps))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert len(e2e_losses) == args.steps
     te = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te[0])
+    nb = max(10, args.steps // 4)
+    for i in range(3):
+        step.step_host(host_x[i % 8], host_y[i % 8])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(nb):
+        step.step_host(host_x[i % 8], host_y[i % 8])
+    torch.cuda.synchronize()
+    tb = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    e2e_blocking = world * B * nb / float(tb[0])
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -475,7 +510,10 @@ def main():
                    "cuda_graph": not args.no_graph,
                    "l2": f"inputs rotate through a pool of {pool_n} device batches ({pool_n * B * 4096 * 4 / 1e6:.0f} MB > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step.h2d_bytes_per_step,
-                "d2h_bytes_per_step": step.d2h_bytes_per_step, "ms_per_step": 1e3 * float(te[0]) / args.steps},
+                "d2h_bytes_per_step": step.d2h_bytes_per_step, "ms_per_step": 1e3 * float(te[0]) / args.steps,
+                "api": "TrainStep.fit_host(iterable of host batches): per step H2D of the inputs from pinned memory "
+                       "(copy stream, prefetch depth 1), step, D2H of the loss (read one step late)",
+                "blocking_step_host_samples_per_s": e2e_blocking},
         "gpu_launches": step.kernel_launches() * args.steps,
         "launches_per_step": step.kernel_launches(),
         "clocks": clocks,

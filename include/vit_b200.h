@@ -297,6 +297,11 @@ int vitb200_head_fused_bwd(const void* s, const void* w, const float* logits, co
                            const float* z, size_t z_row_stride, const float* mean, const float* rstd, const float* gamma,
                            float* dz_cls, float* dgamma, float* dbeta, float* dw, float* dbias, int B, int H, int C,
                            int loss_kind, int accumulate, int dtype, void* stream);
+/* forward + backward of the head in one launch (training steps: dloss = 1).  Same results as the two calls above. */
+int vitb200_head_fused_fwd_bwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
+                               float* loss, const float* z, size_t z_row_stride, const float* mean, const float* rstd,
+                               const float* gamma, float* dz_cls, float* dgamma, float* dbeta, float* dw, float* dbias,
+                               int B, int H, int C, int loss_kind, int dtype, void* stream);
 
 /* ---- gradient clipping + AdamW ---------------------------------------------------------------------
  * Replaces Lightning's gradient_clip_val -> torch.nn.utils.clip_grad_norm_ (src/basemodule.py:244) and
@@ -310,6 +315,16 @@ size_t vitb200_grad_norm_ws_bytes(size_t n);
 int vitb200_grad_norm(const float* g, size_t n, const float* hyper, float* state, void* ws, void* stream);
 int vitb200_adamw(float* p, const float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
                   const float* state, uint64_t* rng, void* stream);
+/* vitb200_clip_adamw_fused: the whole optimizer tail in ONE launch (the configured model has 40 353 parameters: the
+ * tail is three launch latencies, not bandwidth).  If slots > 0, the gradient of elements [red_start, red_end) is first
+ * formed as the in-order sum of `slots` partial arenas (gpart + s*stride; the per-CTA partials of the fused backward
+ * kernels) and written to g; then norm -> clip_coef -> AdamW exactly as the two calls above.  ws: at least
+ * vitb200_clip_adamw_fused_ws_bytes() bytes, zeroed once by the caller (grid-barrier ticket / epoch + block partials). */
+size_t vitb200_clip_adamw_fused_ws_bytes(void);
+int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                             float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
+                             size_t red_start, size_t red_end, void* ws, void* stream);
+
 /* shadow[i] = bf16(p[i]) (after load_state_dict / an external optimizer touched the fp32 arena) */
 int vitb200_cast_bf16(const float* p, void* shadow, size_t n, void* stream);
 

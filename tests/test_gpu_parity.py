@@ -326,3 +326,71 @@ def test_fused_paths_are_the_ones_tested(golden):
     assert eng64.fused and not eng64.fused_bwd       # H=64: fused forward, unfused (tcgen05 GEMM) backward
     eng32 = _build(fix, "32", dev)._engine(fix["batch"])
     assert not eng32.fused and not eng32.fused_bwd   # fp32 mode: SIMT fp32 kernels (1e-4 parity bar)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
+def test_fit_host_pipeline_matches_blocking_steps(precision):
+    """TrainStep.fit_host (uploads on a copy stream, loss read one step late) must produce exactly the losses and
+    weights of the blocking step_host loop on the same host batches (dropout on: the RNG step counter is part of it)."""
+    from vit_b200 import get_model
+    from vit_b200.step import TrainStep
+
+    dev = _cuda()
+    cfg = {"model": dict(name="vit", task_type="reg", image_size=4096, patch_size=32, hidden_size=32,
+                         num_hidden_layers=3, num_attention_heads=2, stride_size=32, proj_fn="SW"),
+           "loss": {"name": "mae"}, "data": {"param": "log_g"}}
+    batches = []
+    for i in range(7):
+        x, y = vo.synthetic_batch(16, 4096, seed=300 + i, kind="rand")
+        batches.append((x.pin_memory(), y.pin_memory()) if i % 2 else (x, y))   # pinned and pageable inputs
+    runs = []
+    for mode in ("blocking", "pipelined"):
+        torch.manual_seed(7)
+        m = get_model(copy.deepcopy(cfg), precision=precision, device=dev).train()
+        st = TrainStep(m, 16, use_graph=True, train=True)
+        if mode == "blocking":
+            losses = [st.step_host(x, y) for x, y in batches]
+        else:
+            seen = []
+            losses = st.fit_host(iter(batches), on_loss=lambda i, v: seen.append((i, v)))
+            assert [i for i, _ in seen] == list(range(len(batches)))
+        torch.cuda.synchronize()
+        runs.append((losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+    assert runs[0][0] == runs[1][0]
+    for k, v in runs[0][1].items():
+        assert torch.equal(v, runs[1][1][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
+def test_one_launch_tail_and_head_match_separate_kernels(golden, precision):
+    """TrainStep's single-GPU sequence (head backward inside forward's last launch, gradient-partial reduction + clip +
+    AdamW in one launch) vs the separate kernels (grad_reduce, grad_norm, adamw, head_fused_bwd): same gradients,
+    same norm, same updated weights."""
+    dev = _cuda()
+    fix = golden("baseline")
+    x, y = _inputs(fix, dev)
+    res = []
+    for fused in (False, True):
+        m = _build(fix, precision, dev).train()
+        eng = m._engine(fix["batch"])
+        m._stage_inputs(eng, x, y)
+        fh = fused and eng.can_fuse_head
+        eng.forward(train=True, with_labels=True, head_bwd=fh)
+        if fused:
+            eng.backward(train=True, skip_reduce=True, skip_head=fh)
+            eng.optimizer_step(fused_reduce=True)
+        else:
+            eng.backward(train=True)
+            eng.grad_norm()
+            eng.adamw()
+        torch.cuda.synchronize()
+        res.append((eng.arena.grad.clone(), eng.state.clone(), eng.arena.data.clone(), float(eng.loss[0]),
+                    int(eng.rng[1])))
+    (g0, s0, p0, l0, r0), (g1, s1, p1, l1, r1) = res
+    assert l0 == l1 and r0 == r1
+    assert torch.equal(g0, g1)                      # both reductions run in the same fixed order
+    assert rel_err(s1[1], s0[1]) < 1e-6             # grad norm (block partials are summed in a different grouping)
+    assert rel_err(p1, p0) < 1e-6
+    assert float(s1[0]) == float(s0[0]) == 1.0      # optimizer step counter

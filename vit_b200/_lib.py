@@ -108,9 +108,12 @@ SIGNATURES = {
     "vitb200_head_fused_supported": (_i, [_i, _i]),
     "vitb200_head_fused_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vitb200_head_fused_bwd": (_i, [_p, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vitb200_head_fused_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vitb200_grad_norm_ws_bytes": (_sz, [_sz]),
     "vitb200_grad_norm": (_i, [_p, _sz, _p, _p, _p, _p]),
     "vitb200_adamw": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p]),
+    "vitb200_clip_adamw_fused_ws_bytes": (_sz, []),
+    "vitb200_clip_adamw_fused": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p]),
     "vitb200_cast_bf16": (_i, [_p, _p, _sz, _p]),
     "vitb200_gelu_fwd": (_i, [_p, _p, _sz, _i, _p]),
     "vitb200_residual_add": (_i, [_p, _p, _p, _sz, _i, _p]),

@@ -145,14 +145,11 @@ constexpr int HF_MAXC = 4;
 
 // logits + loss in one kernel: warp w handles samples w, w + 8, ... ; loss terms summed in sample order
 template <typename T>
-__global__ void __launch_bounds__(HF_THREADS)
-head_fused_fwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ bias,
-                      const void* __restrict__ labels, float* __restrict__ logits, float* __restrict__ loss, int B, int H,
-                      int C, int kind) {
+__device__ __forceinline__ void head_fwd_body(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ bias,
+                                              const void* __restrict__ labels, float* __restrict__ logits,
+                                              float* __restrict__ loss, int B, int H, int C, int kind) {
   __shared__ float wsum[HF_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_wait();
-  pdl_trigger();
   float acc_loss = 0.f;
   for (int b = warp; b < B; b += HF_WARPS) {
     for (int c = 0; c < C; ++c) {
@@ -173,13 +170,21 @@ head_fused_fwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const fl
     loss[0] = t / (kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
   }
 }
+template <typename T>
+__global__ void __launch_bounds__(HF_THREADS)
+head_fused_fwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ bias,
+                      const void* __restrict__ labels, float* __restrict__ logits, float* __restrict__ loss, int B, int H,
+                      int C, int kind) {
+  pdl_wait();
+  pdl_trigger();
+  head_fwd_body<T>(s, w, bias, labels, logits, loss, B, H, C, kind);
+}
 
 // head backward + final-LayerNorm backward of the CLS rows in one kernel (C <= HF_MAXC):
 //   dl = dloss/dlogits ; ds = dl . W ; dz_cls = LN'(ds) ; dgamma, dbeta, dW, dbias reduced over samples in a
 //   fixed order (warp-strided sample order, then warps in order).
 template <typename T>
-__global__ void __launch_bounds__(HF_THREADS)
-head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ logits,
+__device__ __forceinline__ void head_bwd_body(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ logits,
                       const void* __restrict__ labels, const float* __restrict__ gloss, const float* __restrict__ z,
                       size_t z_row_stride, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, float* __restrict__ dz_cls, float* __restrict__ dgamma,
@@ -187,8 +192,6 @@ head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const fl
                       int kind, int accumulate) {
   extern __shared__ float red[];  // [HF_WARPS][(2 + C) * H + C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_wait();
-  pdl_trigger();
   const float g = gloss ? gloss[0] : 1.f;
   constexpr int HPL = 4;   // columns per lane (H <= 128)
   const int npl = (H + 31) / 32;
@@ -260,6 +263,36 @@ head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const fl
     if (dst) *dst = accumulate ? *dst + t : t;
   }
 }
+template <typename T>
+__global__ void __launch_bounds__(HF_THREADS)
+head_fused_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ logits,
+                      const void* __restrict__ labels, const float* __restrict__ gloss, const float* __restrict__ z,
+                      size_t z_row_stride, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, float* __restrict__ dz_cls, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dbias, int B, int H, int C,
+                      int kind, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  head_bwd_body<T>(s, w, logits, labels, gloss, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C,
+                   kind, accumulate);
+}
+// forward (logits, loss) and backward of the head in one launch: a training step knows dloss/dloss = 1 in advance.
+// Sample b is handled by the same warp in both halves, so the logits only need warp-level ordering.
+template <typename T>
+__global__ void __launch_bounds__(HF_THREADS)
+head_fused_fwd_bwd_kernel(const T* __restrict__ s, const T* __restrict__ w, const float* __restrict__ bias,
+                          const void* __restrict__ labels, float* __restrict__ logits, float* __restrict__ loss,
+                          const float* __restrict__ z, size_t z_row_stride, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dz_cls,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw,
+                          float* __restrict__ dbias, int B, int H, int C, int kind) {
+  pdl_wait();
+  pdl_trigger();
+  head_fwd_body<T>(s, w, bias, labels, logits, loss, B, H, C, kind);
+  __syncthreads();
+  head_bwd_body<T>(s, w, logits, labels, nullptr, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C,
+                   kind, 0);
+}
 
 }  // namespace vb
 
@@ -276,6 +309,28 @@ extern "C" int vitb200_head_fused_fwd(const void* s, const void* w, const float*
     vb_launch_pdl(head_fused_fwd_kernel<float>, dim3(1), dim3(HF_THREADS), 0, st, (const float*)s, (const float*)w, bias, labels, logits, loss, B, H, C, loss_kind);
   else if (dtype == VITB200_BF16)
     vb_launch_pdl(head_fused_fwd_kernel<bf16>, dim3(1), dim3(HF_THREADS), 0, st, (const bf16*)s, (const bf16*)w, bias, labels, logits, loss, B, H, C, loss_kind);
+  else
+    return VITB200_ERR_ARG;
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_head_fused_fwd_bwd(const void* s, const void* w, const float* bias, const void* labels, float* logits,
+                                          float* loss, const float* z, size_t z_row_stride, const float* mean,
+                                          const float* rstd, const float* gamma, float* dz_cls, float* dgamma, float* dbeta,
+                                          float* dw, float* dbias, int B, int H, int C, int loss_kind, int dtype, void* stream) {
+  if (!s || !w || !logits || !labels || !loss || !z || !mean || !rstd || !gamma || !dz_cls || !dgamma || !dbeta || !dw)
+    return VITB200_ERR_ARG;
+  if (B <= 0 || !vitb200_head_fused_supported(H, C)) return VITB200_ERR_SHAPE;
+  if (loss_kind < 0 || loss_kind > 2) return VITB200_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)HF_WARPS * ((2 + C) * H + C) * sizeof(float);
+  if (dtype == VITB200_F32)
+    vb_launch_pdl(head_fused_fwd_bwd_kernel<float>, dim3(1), dim3(HF_THREADS), smem, st, (const float*)s, (const float*)w, bias,
+                  labels, logits, loss, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C, loss_kind);
+  else if (dtype == VITB200_BF16)
+    vb_launch_pdl(head_fused_fwd_bwd_kernel<bf16>, dim3(1), dim3(HF_THREADS), smem, st, (const bf16*)s, (const bf16*)w, bias,
+                  labels, logits, loss, z, z_row_stride, mean, rstd, gamma, dz_cls, dgamma, dbeta, dw, dbias, B, H, C, loss_kind);
   else
     return VITB200_ERR_ARG;
   VB_CHECK_LAUNCH();

@@ -158,7 +158,7 @@ class ViTEngine:
         return self.stats[i].data_ptr()
 
     # ---- programs -----------------------------------------------------------------------------
-    def _build_forward_fused(self, train: bool, with_labels: bool) -> List[Tuple[Callable, tuple]]:
+    def _build_forward_fused(self, train: bool, with_labels: bool, head_bwd: bool = False) -> List[Tuple[Callable, tuple]]:
         """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L."""
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, Lh, M = self.B, c.tokens, c.hidden_size, c.num_hidden_layers, self.M
@@ -210,12 +210,34 @@ class ViTEngine:
             self._keep.append(la)
             prog.append((lib.vitb200_fused_layer_fwd, (ctypes.addressof(la),)))
         hd = self.arena.layout.head_name
+        if head_bwd:  # training step: logits, loss AND the head / final-LayerNorm backward in one launch
+            self._alloc_backward()
+            self._ensure_dz_cls()
+            prog.append((lib.vitb200_head_fused_fwd_bwd, (
+                P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"), P_(self.labels), P_(self.logits),
+                P_(self.loss), P_(self.z[Lh]), T * H, self._stat(fin), self._stat(fin + 1),
+                self._p("vit.layernorm.weight"), P_(self.dz_cls), self._g("vit.layernorm.weight"),
+                self._g("vit.layernorm.bias"), self._g(hd + ".weight"), self._g(hd + ".bias"), B, H, c.num_labels,
+                self.loss_kind, dt)))
+            return prog
         head_fn = lib.vitb200_head_fused_fwd if lib.vitb200_head_fused_supported(H, c.num_labels) else lib.vitb200_head_loss_fwd
         prog.append((head_fn, (
             P_(self.s_cls), self._w(hd + ".weight"), self._p(hd + ".bias"),
             P_(self.labels) if with_labels else None, P_(self.logits), P_(self.loss), B, H, c.num_labels,
             self.loss_kind, dt)))
         return prog
+
+    def _ensure_dz_cls(self) -> None:
+        if not hasattr(self, "dz_cls"):
+            c = self.cfg
+            self.dz_cls = torch.zeros(self.B, c.hidden_size, dtype=torch.float32, device=self.device)
+
+    @property
+    def can_fuse_head(self) -> bool:
+        """forward's last launch can also do the head backward (fused programs, CLS-row top gradient, known dloss = 1)."""
+        c = self.cfg
+        return bool(self.fused and self.fused_bwd and self.lib.vitb200_head_fused_supported(c.hidden_size, c.num_labels)
+                    and self.loss_kind in (_lib.LOSS_MSE, _lib.LOSS_L1, _lib.LOSS_CE))
 
     def _build_forward(self, train: bool, with_labels: bool) -> List[Tuple[Callable, tuple]]:
         if self.fused:
@@ -288,7 +310,8 @@ class ViTEngine:
             self.loss_kind, dt)))
         return prog
 
-    def _build_backward_fused(self, train: bool, gloss_ptr: Optional[int], given: bool):
+    def _build_backward_fused(self, train: bool, gloss_ptr: Optional[int], given: bool, skip_reduce: bool = False,
+                              skip_head: bool = False):
         """head -> final LN -> [upper, attention bwd, lower] x L -> embed -> reduce of the per-CTA partials."""
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
@@ -313,10 +336,11 @@ class ViTEngine:
         gl = None if given else gloss_ptr
         cur, other = self.dzA, self.dzB
         top_cls = bool(lib.vitb200_head_fused_supported(H, c.num_labels))
-        if top_cls:
+        if top_cls and skip_head:
+            self._ensure_dz_cls()          # written by forward's vitb200_head_fused_fwd_bwd
+        elif top_cls:
             # head backward + final-LayerNorm backward of the CLS rows in one launch; only those rows carry a gradient
-            if not hasattr(self, "dz_cls"):
-                self.dz_cls = torch.zeros(B, H, dtype=torch.float32, device=self.device)
+            self._ensure_dz_cls()
             prog.append((lib.vitb200_head_fused_bwd, (
                 P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), lab_ptr, gl, P_(self.z[Lh]), T * H,
                 self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"), P_(self.dz_cls),
@@ -380,13 +404,15 @@ class ViTEngine:
                 self._g(emb + "patch_embeddings.projection.bias"), self._g(emb + "cls_token"), dpos, B, c.image_size,
                 c.patch_size, c.stride, c.num_patches, c.n_valid, H, ph, rng, SITE_EMB, 0, dt, ws)))
         end = lay.buckets[Lh][2]           # end of the last encoder layer
-        prog.append((lib.vitb200_grad_reduce, (gp, G, lay.n_opt, start, end, self.arena.grad.data_ptr())))
+        self._red = (G, start, end)        # partial slots and the arena range they cover
+        if not skip_reduce:                # (TrainStep folds this reduction into the one-launch optimizer tail)
+            prog.append((lib.vitb200_grad_reduce, (gp, G, lay.n_opt, start, end, self.arena.grad.data_ptr())))
         return prog
 
     def _build_backward(self, train: bool, gloss_ptr: Optional[int] = None,
-                        given: bool = False) -> List[Tuple[Callable, tuple]]:
+                        given: bool = False, skip_reduce: bool = False, skip_head: bool = False) -> List[Tuple[Callable, tuple]]:
         if self.fused_bwd:
-            return self._build_backward_fused(train, gloss_ptr, given)
+            return self._build_backward_fused(train, gloss_ptr, given, skip_reduce, skip_head)
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
@@ -505,13 +531,25 @@ class ViTEngine:
         _lib.check(self.lib.vitb200_cast_bf16(ar.data.data_ptr(), ar.shadow.data_ptr(), ar.layout.n_total, st), "cast")
         ar.mark_shadow_fresh()
 
-    def forward(self, train: bool, with_labels: bool = True) -> None:
+    def forward(self, train: bool, with_labels: bool = True, head_bwd: bool = False) -> None:
+        """head_bwd (training steps, needs can_fuse_head): the last launch also runs the head / final-LayerNorm backward
+        with dloss = 1; the caller must then use backward(skip_head=True)."""
         self.refresh_shadow()
-        self._run(("fwd", train, with_labels), lambda: self._build_forward(train, with_labels))
+        if head_bwd:
+            assert with_labels and self.can_fuse_head
+            self._run(("fwd", train, True, True), lambda: self._build_forward_fused(train, True, head_bwd=True))
+        else:
+            self._run(("fwd", train, with_labels), lambda: self._build_forward(train, with_labels))
 
-    def backward(self, train: bool, gloss: Optional[torch.Tensor] = None) -> None:
+    def backward(self, train: bool, gloss: Optional[torch.Tensor] = None, skip_reduce: bool = False,
+                 skip_head: bool = False) -> None:
+        """skip_reduce (fused programs only): leave the layer / embedding gradients as per-CTA partials; the caller
+        must follow with optimizer_step(fused_reduce=True), which sums them inside the optimizer kernel."""
         gp = None if gloss is None else gloss.data_ptr()
-        self._run(("bwd", train, gp), lambda: self._build_backward(train, gp))
+        skip = bool(skip_reduce and self.fused_bwd)
+        sh = bool(skip_head and self.fused_bwd)
+        self._run(("bwd", train, gp, skip, sh) if (skip or sh) else ("bwd", train, gp),
+                  lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh))
 
     def backward_from_dlogits(self, train: bool, dlogits: torch.Tensor) -> None:
         """Backward when the caller computed its own loss from `logits` (labels=None forward)."""
@@ -545,9 +583,22 @@ class ViTEngine:
         if ar.shadow is not None:
             ar.mark_shadow_fresh()
 
-    def optimizer_step(self) -> None:
-        self.grad_norm()
-        self.adamw()
+    def optimizer_step(self, fused_reduce: bool = False) -> None:
+        """clip_grad_norm_ + AdamW.step in ONE launch (vitb200_clip_adamw_fused).  fused_reduce: the backward ran with
+        skip_reduce=True, so the kernel first sums the per-CTA gradient partials."""
+        self._ensure_opt_state()
+        ar = self.arena
+        if not hasattr(self, "tail_ws"):
+            self.tail_ws = torch.zeros(int(self.lib.vitb200_clip_adamw_fused_ws_bytes()), dtype=torch.uint8, device=self.device)
+        slots, start, end = (self._red if (fused_reduce and self.fused_bwd) else (0, 0, 0))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vitb200_clip_adamw_fused(
+            ar.data.data_ptr(), ar.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            None if ar.shadow is None else ar.shadow.data_ptr(), ar.layout.n_opt, self.hyper.data_ptr(),
+            self.state.data_ptr(), self.rng.data_ptr(), self.gpart.data_ptr() if slots else None, slots,
+            ar.layout.n_opt, start, end, self.tail_ws.data_ptr(), st), "clip_adamw_fused")
+        if ar.shadow is not None:
+            ar.mark_shadow_fresh()
 
     def advance_rng(self) -> None:
         self.rng[1] += 1
@@ -591,15 +642,20 @@ class ViTEngine:
         _lib.check(self.lib.vitb200_dropout_mask(out.data_ptr(), n, p, self.rng.data_ptr(), site, st), "mask")
         return out
 
-    def kernel_launches(self, train: bool = True) -> int:
-        """Kernel launches of one fwd+bwd+update step (for bench.py's gpu_launches), counted from the programs."""
-        if ("fwd", train, True) not in self._progs:
-            self._progs[("fwd", train, True)] = self._build_forward(train, True)
-        if ("bwd", train, None) not in self._progs:
-            self._progs[("bwd", train, None)] = self._build_backward(train, None)
+    def kernel_launches(self, train: bool = True, fused_tail: bool = False) -> int:
+        """Kernel launches of one fwd+bwd+update step (for bench.py's gpu_launches), counted from the programs.
+        fused_tail: the TrainStep single-GPU sequence (gradient-partial reduction folded into the optimizer kernel)."""
+        skip = bool(fused_tail and self.fused_bwd)
+        sh = bool(skip and self.can_fuse_head)
+        fkey = ("fwd", train, True, True) if sh else ("fwd", train, True)
+        if fkey not in self._progs:
+            self._progs[fkey] = self._build_forward_fused(train, True, head_bwd=True) if sh else self._build_forward(train, True)
+        bkey = ("bwd", train, None, skip, sh) if (skip or sh) else ("bwd", train, None)
+        if bkey not in self._progs:
+            self._progs[bkey] = self._build_backward(train, None, skip_reduce=skip, skip_head=sh)
         per_call = {"vitb200_head_loss_fwd": 2, "vitb200_head_loss_bwd": 2, "vitb200_patch_embed_bwd": 2}
-        n = 2  # grad_norm + adamw
-        for key in (("fwd", train, True), ("bwd", train, None)):
+        n = 1  # clip + AdamW (one launch)
+        for key in (fkey, bkey):
             for fn, args in self._progs[key]:
                 k = per_call.get(fn.__name__, 1)
                 if fn.__name__ == "vitb200_linear_wgrad" and self.dt == BF16 and \

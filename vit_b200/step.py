@@ -44,12 +44,16 @@ class TrainStep:
     # ---- one step's kernel sequence (also what gets captured) ---------------------------------
     def _launch(self) -> None:
         eng = self.eng
-        eng.forward(train=self.train, with_labels=True)
         if self.world > 1:
-            self._backward_overlapped()
+            eng.forward(train=self.train, with_labels=True)
+            self._backward_overlapped()   # gradients are summed across ranks before the optimizer kernel reads them
+            eng.optimizer_step()
         else:
-            eng.backward(train=self.train)
-        eng.optimizer_step()
+            # single GPU: head backward rides on forward's last launch, the gradient-partial reduction on the optimizer's
+            fh = eng.can_fuse_head
+            eng.forward(train=self.train, with_labels=True, head_bwd=fh)
+            eng.backward(train=self.train, skip_reduce=True, skip_head=fh)
+            eng.optimizer_step(fused_reduce=True)
 
     def _backward_overlapped(self) -> None:
         """Backward + gradient all-reduce (SUM; the 1/world mean is folded into the optimizer's grad_scale).
@@ -142,14 +146,99 @@ class TrainStep:
             self._launch()
         return eng.loss[0]
 
+    def _pinned(self, flux_host: torch.Tensor, labels_host: torch.Tensor, slot_x: torch.Tensor, slot_y: torch.Tensor):
+        """Host batch -> page-locked memory (batches that already are pinned, e.g. from a DataLoader with
+        pin_memory=True -- src/basemodule.py:76-85 -- are used in place)."""
+        if flux_host.is_pinned() and flux_host.dtype == torch.float32 and flux_host.is_contiguous():
+            hx = flux_host
+        else:
+            slot_x.copy_(flux_host)
+            hx = slot_x
+        ly = labels_host.reshape(slot_y.shape)
+        if ly.is_pinned() and ly.dtype == slot_y.dtype and ly.is_contiguous():
+            hy = ly
+        else:
+            slot_y.copy_(ly)
+            hy = slot_y
+        return hx, hy
+
     def step_host(self, flux_host: torch.Tensor, labels_host: torch.Tensor) -> float:
         """End-to-end step: host inputs -> pinned staging -> H2D -> step -> D2H loss (blocking)."""
-        self.h_x.copy_(flux_host)
-        self.h_y.copy_(labels_host.reshape(self.h_y.shape))
-        loss = self.step(self.h_x, self.h_y)
+        hx, hy = self._pinned(flux_host, labels_host, self.h_x, self.h_y)
+        loss = self.step(hx, hy)
         self.h_loss.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream(self.eng.device).synchronize()
         return float(self.h_loss[0])
+
+    def fit_host(self, batches, on_loss=None) -> list:
+        """The training loop over an iterable of HOST batches `(flux [B, L], labels)` -- what Lightning's fit loop does
+        with the reference's in-RAM dataset (src/dataloader/base.py:219-245): every step copies its inputs host ->
+        device and reads its loss back, but the copies are pipelined around the step instead of serialised with it:
+
+          * batch i+1 goes pinned host -> device staging slot on a COPY stream while step i runs;
+          * the loss of step i is copied to pinned memory behind the step and read by the host after step i+1 has
+            been enqueued (one step late, like a logger), so the GPU never waits for the host round trip.
+
+        Returns the list of per-step losses (floats); `on_loss(i, loss)` is called as each one becomes available."""
+        eng = self.eng
+        dev = eng.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_pipe", None) is None:
+            c = self.model.config
+            self._pipe = dict(
+                copy=torch.cuda.Stream(device=dev),
+                d_x=[torch.empty(self.B, c.image_size, dtype=torch.float32, device=dev) for _ in range(2)],
+                d_y=[torch.empty_like(eng.labels) for _ in range(2)],
+                h_x=[torch.empty(self.B, c.image_size, dtype=torch.float32, pin_memory=True) for _ in range(2)],
+                h_y=[torch.empty(eng.labels.shape, dtype=eng.labels.dtype, pin_memory=True) for _ in range(2)],
+                h_loss=[torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(2)],
+                ev_in=[torch.cuda.Event() for _ in range(2)],     # staging slot filled (copy stream)
+                ev_free=[torch.cuda.Event() for _ in range(2)],   # staging slot consumed (main stream)
+                ev_loss=[torch.cuda.Event() for _ in range(2)],   # loss of the step landed in pinned memory
+            )
+        P = self._pipe
+        copy = P["copy"]
+        losses = []
+
+        def upload(i, batch):
+            s = i & 1
+            if i >= 2:
+                P["ev_free"][s].synchronize()   # the host slot / device slot of step i-2 are reusable
+            hx, hy = self._pinned(batch[0], batch[1], P["h_x"][s], P["h_y"][s])
+            with torch.cuda.stream(copy):
+                P["d_x"][s].copy_(hx, non_blocking=True)
+                P["d_y"][s].copy_(hy, non_blocking=True)
+                P["ev_in"][s].record(copy)
+
+        def collect(i):
+            s = i & 1
+            P["ev_loss"][s].synchronize()
+            v = float(P["h_loss"][s][0])
+            losses.append(v)
+            if on_loss is not None:
+                on_loss(i, v)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            upload(0, nxt)
+        while nxt is not None:
+            s = i & 1
+            main.wait_event(P["ev_in"][s])
+            loss = self.step(P["d_x"][s], P["d_y"][s])
+            P["ev_free"][s].record(main)
+            P["h_loss"][s].copy_(loss.reshape(1), non_blocking=True)
+            P["ev_loss"][s].record(main)
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(i + 1, nxt)       # overlaps step i
+            if i >= 1:
+                collect(i - 1)           # one step late: never stalls the GPU
+            i += 1
+        if i >= 1:
+            collect(i - 1)
+        return losses
 
     @property
     def h2d_bytes_per_step(self) -> int:
@@ -163,7 +252,8 @@ class TrainStep:
         self.eng.set_lr(lr)
 
     def kernel_launches(self) -> int:
-        return self.eng.kernel_launches(self.train)
+        """Our kernels per step (+2 device-to-device staging copies of the inputs done by torch in step())."""
+        return self.eng.kernel_launches(self.train, fused_tail=self.world == 1)
 
 
 class EvalStep:
