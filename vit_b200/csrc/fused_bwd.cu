@@ -128,7 +128,8 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
                      O_W2 = O_CTX + 16384, O_W1 = O_W2 + 8192, O_WO = O_W1 + 16384, O_ACT = O_WO + 4096,
                      O_HM = O_ACT + 32768, O_DZ = O_HM + 16384, O_BAR = O_DZ + 16384, O_EX = O_BAR + 1024;
   // TMEM columns
-  constexpr uint32_t C_W2 = 0, C_W1 = 128, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, TMEM_COLS = 512;
+  // (dW1 is 48 columns wide: column H is the bias gradient db1, produced by a column of ones in the u2 tile)
+  constexpr uint32_t C_W2 = 0, C_WO = 160, C_DM = 192, C_DU2 = 320, C_DCTX = 352, C_W1 = 384, TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -137,7 +138,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   const uint8_t *sAct = base + O_ACT, *sHm = base + O_HM;  // pre-GELU activations (bf16) and hmid rows (fp32), TMA-staged
   uint8_t* sDz = base + O_DZ;   // fp32 rows: dz (TMA load) -> dh (TMA store image)
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
-  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
+  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2, *b_dz = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* s_g2 = reinterpret_cast<float*>(bars + 8);
   float2* s_ex = reinterpret_cast<float2*>(base + O_EX);   // [FB_CG][128] row-sum exchange (4 KB)
@@ -154,7 +155,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmU2); tma_prefetch_desc(&tmCtx);
     tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWo);
     tma_prefetch_desc(&tmAct); tma_prefetch_desc(&tmHm); tma_prefetch_desc(&tmDz);
-    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
+    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1); mbar_init(b_dz, 1);
     fence_barrier_init();
   }
   // columns 32..63 of the sD tile are never written by the epilogues: zero them once (MN-major wgrad view reads them)
@@ -201,7 +202,7 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   for (int j = 0; j < HC; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
   // bias gradients = column sums of the gradient tiles; partial per thread:
   //   H-wide tiles: column tid & 31, rows 8 (tid >> 5) .. +7 ;  I-wide tile: column tid & 127, rows 32 (tid >> 7) .. +31
-  float acc_b2 = 0.f, acc_b1 = 0.f, acc_bo = 0.f;
+  float acc_b2 = 0.f, acc_bo = 0.f;
   uint32_t ph_mma = 0, ph_tile = 0;
   int iter = 0;
 
@@ -212,8 +213,11 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     const bool from_cls = P.dz_cls != nullptr;
     if (tid == 0) {
       if (iter > 0) tma_store_wait_read<0>();   // the previous tile's dh / dctx images are about to be overwritten
-      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384 + (from_cls ? 0 : 16384));
-      if (!from_cls) tma_load_2d(sDz, &tmDz, b_tile, 0, r0);
+      if (!from_cls) {   // dz gates the first stage: it gets its own barrier and goes first
+        mbar_expect_tx(b_dz, 16384);
+        tma_load_2d(sDz, &tmDz, b_dz, 0, r0);
+      }
+      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384);
       tma_load_2d(sM, &tmM, b_tile, 0, r0);
       tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
       tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
@@ -238,9 +242,10 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       }
       float kp[8];
       drop8(dc_mlp, ((size_t)rowc * H + hc0) >> 3, kp);   // overlaps the tile loads
-      mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged dz / a / hmid rows
-      ph_tile ^= 1;
-      if (!from_cls) fb_ld_f8(sDz, r, cg, dz);
+      if (!from_cls) {
+        mbar_wait(b_dz, ph_tile);
+        fb_ld_f8(sDz, r, cg, dz);
+      }
       float d2[HC];
 #pragma unroll
       for (int j = 0; j < HC; ++j) d2[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
@@ -254,10 +259,16 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       tc_fence_after();
       if (iter == 0) mbar_wait(b_w, 0);
       fb_issue(tmem + C_DM, D_k, W2_mn, I, H / 16, false);        // dm[row, i]  = sum_h ddelta2[row,h] W2[h,i]
+      umma_commit(b_mma);                                         // the gelu' stage only needs dm
+      mbar_wait(b_tile, ph_tile);
+      tc_fence_after();
       fb_issue(tmem + C_W2, D_mn, M_mn, I, 8, iter > 0);          // dW2[h, i]  += sum_rows ddelta2[row,h] m[row,i]
-      umma_commit(b_mma);
-    }
+    }                                                             // (completion is covered by the next commit)
     acc_b2 += fb_colsum<8>(sD, tid & 31, (tid >> 5) * 8);  // overlaps the MMAs
+    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-staged a / hmid rows below
+    ph_tile ^= 1;
+    // a column of ones next to u2 (columns H..63 of the tile are TMA zero fill): the dW1 MMA then also emits db1
+    if (cg == 0) *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(fb_swz_ptr(sU2, r, H / 8))) = 0x00003F80u;   // bf16 {1, 0}
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
   VB_TL(tl_bwd_upper, 5);
     tc_fence_after();
@@ -288,10 +299,9 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
       tc_fence_after();
   VB_TL(tl_bwd_upper, 6);
       fb_issue(tmem + C_DU2, DA_k, W1_mn, H, I / 16, false);      // du2[row, h] = sum_i da[row,i] W1[i,h]
-      fb_issue(tmem + C_W1, DA_mn, U2_mn, H, 8, iter > 0);        // dW1[i, h]  += sum_rows da[row,i] u2[row,h]
+      fb_issue(tmem + C_W1, DA_mn, U2_mn, H + 16, 8, iter > 0);   // dW1[i, h]  += sum_rows da[row,i] u2[row,h] ; column H: db1[i]
       umma_commit(b_mma);
     }
-    acc_b1 += fb_colsum<32>(sDA, tid & 127, (tid >> 7) * 32);
     mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
   VB_TL(tl_bwd_upper, 7);
     tc_fence_after();
@@ -351,47 +361,60 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
 
   VB_TL(tl_bwd_upper, 10);
   // ---- write this CTA's partial parameter gradients ----
+  // TMEM rows are parameter rows: a direct st.global would touch one 128-byte line per lane.  The tiles go through
+  // shared memory (16-byte pieces, XOR-swizzled so that neither side has bank conflicts) and leave as coalesced float4s.
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
+  float4* t_w1 = reinterpret_cast<float4*>(sM);            // [128 rows][8 pieces]   dW1 (16 KB)
+  float4* t_w2 = reinterpret_cast<float4*>(sM + 16384);    // [32 rows][32 pieces]   dW2 (16 KB)
+  float4* t_wo = reinterpret_cast<float4*>(sDA);           // [32 rows][8 pieces]    dWo (4 KB)
+  float* t_b1 = reinterpret_cast<float*>(sDA + 4096);      // [128]                  db1
+  float* red = reinterpret_cast<float*>(base + O_ACT);     // [2 * H][128]           LN gamma / beta partials (32 KB)
+  float* bsum = reinterpret_cast<float*>(sDA + 8192);      // [2][512]               db2 / dbo partials
   if (iter > 0) {
     if ((warp & 3) == 0) {  // dW2 / dWo rows h = lanes 0..31: column group cg of each
       float v[32];
       tmem_ld_32x32(my_tmem + C_W2 + cg * 32, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_w2 + (size_t)r * I + cg * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j) t_w2[r * 32 + ((cg * 8 + j) ^ (r & 31))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       float w[HC];
       tmem_ld_32x8(my_tmem + C_WO + hc0, w);
-      float4* oq = reinterpret_cast<float4*>(gp + P.off_wo + (size_t)r * H + hc0);
-      oq[0] = make_float4(w[0], w[1], w[2], w[3]); oq[1] = make_float4(w[4], w[5], w[6], w[7]);
+      t_wo[r * 8 + ((2 * cg) ^ (r & 7))] = make_float4(w[0], w[1], w[2], w[3]);
+      t_wo[r * 8 + ((2 * cg + 1) ^ (r & 7))] = make_float4(w[4], w[5], w[6], w[7]);
     }
-    {  // dW1 rows i = lanes 0..127, H columns
+    {  // dW1 rows i = lanes 0..127, H columns (+ db1 in column H)
       float v[HC];
       tmem_ld_32x8(my_tmem + C_W1 + hc0, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_w1 + (size_t)r * H + hc0);
-      op[0] = make_float4(v[0], v[1], v[2], v[3]); op[1] = make_float4(v[4], v[5], v[6], v[7]);
+      t_w1[r * 8 + ((2 * cg) ^ (r & 7))] = make_float4(v[0], v[1], v[2], v[3]);
+      t_w1[r * 8 + ((2 * cg + 1) ^ (r & 7))] = make_float4(v[4], v[5], v[6], v[7]);
+      if (cg == 0) {
+        float b8[8];
+        tmem_ld_32x8(my_tmem + C_W1 + H, b8);
+        t_b1[r] = b8[0];
+      }
     }
-  } else {  // a CTA without tiles contributes zeros
-    for (int e = tid; e < H * I; e += FB_THREADS) { gp[P.off_w2 + e] = 0.f; gp[P.off_w1 + e] = 0.f; }
-    for (int e = tid; e < H * H; e += FB_THREADS) gp[P.off_wo + e] = 0.f;
   }
-  // bias and LN gamma/beta gradients: per-thread partials -> shared memory (scratch = sDA, 32 KB) -> fixed-order sums
-  tc_fence_before();
-  __syncthreads();
-  float* red = reinterpret_cast<float*>(sDA);  // [2 * H][128]
 #pragma unroll
   for (int j = 0; j < HC; ++j) { red[(hc0 + j) * 128 + r] = acc_g[j]; red[(H + hc0 + j) * 128 + r] = acc_b[j]; }
-  float* bsum = reinterpret_cast<float*>(sM);  // [3][512] bias partials
-  bsum[tid] = acc_b2; bsum[512 + tid] = acc_bo; bsum[1024 + tid] = acc_b1;
+  bsum[tid] = acc_b2; bsum[512 + tid] = acc_bo;
+  tc_fence_before();
   __syncthreads();
+  {
+    float4* o_w1 = reinterpret_cast<float4*>(gp + P.off_w1);
+    float4* o_w2 = reinterpret_cast<float4*>(gp + P.off_w2);
+    float4* o_wo = reinterpret_cast<float4*>(gp + P.off_wo);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);   // a CTA without tiles contributes zeros
+    for (int e = tid; e < 128 * 8; e += FB_THREADS) { const int rr = e >> 3, c = e & 7; o_w1[e] = iter > 0 ? t_w1[rr * 8 + (c ^ (rr & 7))] : z4; }
+    for (int e = tid; e < 32 * 32; e += FB_THREADS) { const int rr = e >> 5, c = e & 31; o_w2[e] = iter > 0 ? t_w2[rr * 32 + (c ^ (rr & 31))] : z4; }
+    for (int e = tid; e < 32 * 8; e += FB_THREADS) { const int rr = e >> 3, c = e & 7; o_wo[e] = iter > 0 ? t_wo[rr * 8 + (c ^ (rr & 7))] : z4; }
+    if (tid < I) gp[P.off_b1 + tid] = iter > 0 ? t_b1[tid] : 0.f;
+  }
   fb_reduce_rows(red, 2 * H, [&](int e, float s) { if (e < H) gp[P.off_ln2g + e] = s; else gp[P.off_ln2b + e - H] = s; });
-  if (tid < H) {
-    float s2 = 0.f, so = 0.f;
-    for (int k = 0; k < 16; ++k) { s2 += bsum[k * 32 + tid]; so += bsum[512 + k * 32 + tid]; }
-    gp[P.off_b2 + tid] = s2; gp[P.off_bo + tid] = so;
-  } else if (tid >= 128 && tid < 128 + I) {
+  if (tid >= 128 && tid < 128 + H) {
     const int c = tid - 128;
-    gp[P.off_b1 + c] = (bsum[1024 + c] + bsum[1024 + 128 + c]) + (bsum[1024 + 256 + c] + bsum[1024 + 384 + c]);
+    float s2 = 0.f, so = 0.f;
+    for (int k = 0; k < 16; ++k) { s2 += bsum[k * 32 + c]; so += bsum[512 + k * 32 + c]; }
+    gp[P.off_b2 + c] = s2; gp[P.off_bo + c] = so;
   }
   __syncthreads();
   VB_TL(tl_bwd_upper, 11);
@@ -410,13 +433,13 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   constexpr int H = FB_H, Q = 3 * FB_H, HC = FB_HC;
   constexpr uint32_t O_DQ = 0, O_U = 32768, O_WQ = O_U + 16384, O_Z = O_WQ + 12288, O_DH = O_Z + 16384,
                      O_BAR = O_DH + 16384, O_RED = O_BAR + 1024, O_EX = O_RED + 32768;
-  constexpr uint32_t C_WQ = 0, C_DU = 32, TMEM_COLS = 64;
+  constexpr uint32_t C_WQ = 0, C_DU = 64, TMEM_COLS = 128;   // dWqkv is 48 columns: column H = dbqkv (ones column in the u tile)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t *sDQ = base + O_DQ, *sU = base + O_U, *sWq = base + O_WQ;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + O_BAR);
-  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2;
+  uint64_t *b_w = bars, *b_tile = bars + 1, *b_mma = bars + 2, *b_wg = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* red = reinterpret_cast<float*>(base + O_RED);  // [2][H][128] floats = 32 KB
   float2* s_ex = reinterpret_cast<float2*>(base + O_EX);
@@ -432,7 +455,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   if (tid == 0) {
     tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmWq);
     tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmDh);
-    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1);
+    mbar_init(b_w, 1); mbar_init(b_tile, 1); mbar_init(b_mma, 1); mbar_init(b_wg, 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -456,7 +479,6 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   float acc_g[HC], acc_b[HC];
 #pragma unroll
   for (int j = 0; j < HC; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; }
-  float acc_bq = 0.f;  // column tid & 127 (< 96), rows 32 (tid >> 7) .. +31
   uint32_t ph_mma = 0, ph_tile = 0;
   int iter = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
@@ -476,13 +498,20 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
       mbar_wait(b_tile, ph_tile);
       tc_fence_after();
       fb_issue(tmem + C_DU, DQ_k, WQ_mn, H, Q / 16, false);      // du[row, h]   = sum_n dqkv[row,n] Wqkv[n,h]
-      fb_issue(tmem + C_WQ, DQ_mn, U_mn, H, 8, iter > 0);         // dWqkv[n, h] += sum_rows dqkv[row,n] u[row,h]
-      umma_commit(b_mma);
+      umma_commit(b_mma);                                         // the LayerNorm stage only needs du
     }
-    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-written dqkv tile below
+    mbar_wait(b_tile, ph_tile);  // every thread reads the TMA-written z / dh rows below
     ph_tile ^= 1;
-    if ((tid & 127) < Q) acc_bq += fb_colsum<32>(sDQ, tid & 127, (tid >> 7) * 32);
-    mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
+    // a column of ones next to u (columns H..63 are TMA zero fill): the dWqkv MMA then also emits dbqkv in column H
+    if (cg == 0) *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(fb_swz_ptr(sU, r, H / 8))) = 0x00003F80u;   // bf16 {1, 0}
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      fb_issue(tmem + C_WQ, DQ_mn, U_mn, H + 16, 8, iter > 0);   // dWqkv[n, h] += sum_rows dqkv[row,n] u[row,h] ; column H: dbqkv[n]
+      umma_commit(b_wg);
+    }
+    mbar_wait(b_mma, ph_mma);
     tc_fence_after();
     {
       float du[HC], xh[HC], g[HC], dz[HC];
@@ -510,6 +539,7 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     }
     fence_proxy_async();
     tc_fence_before();
+    mbar_wait(b_wg, ph_mma); ph_mma ^= 1;   // the wgrad MMA has finished reading the dqkv / u tiles (long done by now)
     __syncthreads();
     if (tid == 0) {
       tma_store_2d(&tmDzOut, sDh, 0, r0);
@@ -518,25 +548,30 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   }
   float* gp = P.gpart + (size_t)blockIdx.x * P.n_opt;
   tc_fence_after();
-  if (iter > 0) {
-    if ((warp & 3) < 3) {  // dWqkv rows n = lanes 0..95
-      float v[HC];
-      tmem_ld_32x8(my_tmem + C_WQ + hc0, v);
-      float4* op = reinterpret_cast<float4*>(gp + P.off_wqkv + (size_t)r * H + hc0);
-      op[0] = make_float4(v[0], v[1], v[2], v[3]); op[1] = make_float4(v[4], v[5], v[6], v[7]);
+  float4* t_wq = reinterpret_cast<float4*>(sDQ);            // [96 rows][8 pieces] dWqkv (12 KB; the dqkv tile is dead)
+  float* t_bq = reinterpret_cast<float*>(sDQ + 16384);      // [96] dbqkv
+  if (iter > 0 && (warp & 3) < 3) {  // dWqkv rows n = lanes 0..95
+    float v[HC];
+    tmem_ld_32x8(my_tmem + C_WQ + hc0, v);
+    t_wq[r * 8 + ((2 * cg) ^ (r & 7))] = make_float4(v[0], v[1], v[2], v[3]);
+    t_wq[r * 8 + ((2 * cg + 1) ^ (r & 7))] = make_float4(v[4], v[5], v[6], v[7]);
+    if (cg == 0) {
+      float b8[8];
+      tmem_ld_32x8(my_tmem + C_WQ + H, b8);
+      t_bq[r] = b8[0];
     }
-  } else {
-    for (int e = tid; e < Q * H; e += FB_THREADS) gp[P.off_wqkv + e] = 0.f;
   }
 #pragma unroll
   for (int j = 0; j < HC; ++j) { red[(hc0 + j) * 128 + r] = acc_g[j]; red[(H + hc0 + j) * 128 + r] = acc_b[j]; }
-  float* bsum = reinterpret_cast<float*>(sDQ);  // [4][128] bias partials (the dqkv tile is dead)
   tc_fence_before();
   __syncthreads();
-  bsum[tid] = acc_bq;
-  __syncthreads();
+  {
+    float4* o_wq = reinterpret_cast<float4*>(gp + P.off_wqkv);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < Q * 8; e += FB_THREADS) { const int rr = e >> 3, c = e & 7; o_wq[e] = iter > 0 ? t_wq[rr * 8 + (c ^ (rr & 7))] : z4; }
+    if (tid < Q) gp[P.off_bqkv + tid] = iter > 0 ? t_bq[tid] : 0.f;
+  }
   fb_reduce_rows(red, 2 * H, [&](int e, float s) { if (e < H) gp[P.off_ln1g + e] = s; else gp[P.off_ln1b + e - H] = s; });
-  if (tid < Q) gp[P.off_bqkv + tid] = (bsum[tid] + bsum[128 + tid]) + (bsum[256 + tid] + bsum[384 + tid]);
   __syncthreads();
   if (tid == 0) tma_store_wait_all();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);

@@ -125,6 +125,13 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
       const float4* src = reinterpret_cast<const float4*>(gpart) + i;
       s = make_float4(0.f, 0.f, 0.f, 0.f);
       int z = 0;
+      for (; z + 16 <= slots; z += 16) {   // 16 independent L2 reads in flight per thread, summed in slot order
+        float4 t[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t[q] = __ldcg(src + (size_t)(z + q) * stride4);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+      }
       for (; z + 4 <= slots; z += 4) {
         float4 t[4];
 #pragma unroll
