@@ -101,7 +101,11 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 64):
     import torch
     from oracle import vit_oracle as vo
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        ncpu = len(os.sched_getaffinity(0))   # the cores this process may actually use (cgroup / affinity aware)
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))       # torchrun exports OMP_NUM_THREADS=1: override it for the CPU arm
     spec = vo.spec_from_config(BASELINE_CFG)
     tr = vo.OracleTrainer(spec, vo.init_params(spec, seed=42))
     x, y = vo.synthetic_batch(batch, 4096, seed=0, kind="dummy")
@@ -354,7 +358,7 @@ def main():
     B = args.batch
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only
         r = cpu_reference_run(steps=60, warmup=3)
         cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
@@ -437,6 +441,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            step.close()   # a live graph with captured NCCL collectives would block destroy_process_group()
             dist.destroy_process_group()
         return
 
@@ -450,8 +455,13 @@ def main():
         bound, achieved, peak, unit = "tensor", top["flops"] / (top["us"] * 1e-6) / 1e12, peaks["tf_sustained"], "TFLOP/s"
     else:
         bound, achieved, peak, unit = "hbm", top["bytes"] / (top["us"] * 1e-6) / 1e9, peaks["hbm"], "GB/s"
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if B == 64 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(top["call"])
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": None, "kernel": top["call"], "kernel_us": top["us"], "peak_source": peaks["source"],
+                "traffic": traffic, "algorithmic_bytes": top["bytes"], "algorithmic_flops": top["flops"],
+                "kernel": top["call"], "kernel_us": top["us"], "peak_source": peaks["source"],
                 "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
                 "share_of_step": top["us"] / max(ksum_us, 1e-9),
                 "note": "algorithmic bytes (or flops) of the call / its mean device time, timed alone as a CUDA graph "
@@ -530,6 +540,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        step.close()
         dist.destroy_process_group()
 
 

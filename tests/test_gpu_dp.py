@@ -50,6 +50,7 @@ assert d < tol, d
 if rank == 0:
     print("DP_OK", json.dumps({"world": world, "param_rel_diff": d, "losses_rank0": losses, "losses_single": l1}))
 dist.barrier()
+step.close()   # the graph holds captured NCCL collectives: it must go before the communicator
 dist.destroy_process_group()
 '''
 

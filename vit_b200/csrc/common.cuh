@@ -15,6 +15,8 @@
 
 int vb_cuda_error(cudaError_t e);  // records the message for vitb200_last_cuda_error(), returns VITB200_ERR_CUDA
 
+#include <stdlib.h>
+
 namespace vb {
 
 typedef __nv_bfloat16 bf16;
@@ -275,8 +277,9 @@ static inline void vb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("VITB200_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

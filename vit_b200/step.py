@@ -251,6 +251,17 @@ class TrainStep:
     def set_lr(self, lr: float) -> None:
         self.eng.set_lr(lr)
 
+    def close(self) -> None:
+        """Release the captured CUDA graph (and the host pipeline).  Data-parallel runs MUST call this before
+        torch.distributed.destroy_process_group(): NCCL (2.28) does not finish destroying a communicator while a live
+        CUDA graph still holds collectives captured on it -- the call blocks forever on every rank."""
+        import gc
+
+        self.graph = None
+        self._pipe = None
+        gc.collect()
+        torch.cuda.synchronize(self.eng.device)
+
     def kernel_launches(self) -> int:
         """Our kernels per step (+2 device-to-device staging copies of the inputs done by torch in step())."""
         return self.eng.kernel_launches(self.train, fused_tail=self.world == 1)
