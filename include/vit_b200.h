@@ -325,6 +325,25 @@ int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, void* shado
                              float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
                              size_t red_start, size_t red_end, void* ws, void* stream);
 
+/* Data-parallel optimizer tail: the DDP gradient all-reduce (implicit in the reference: strategy='ddp',
+ * src/hardware_utils.py:86-95) is fused INTO the kernel.  Each rank owns one exchange buffer
+ * (vitb200_peer_buffer_bytes(n) bytes: flags + two gradient copies, double-buffered by launch parity) allocated with
+ * vitb200_peer_alloc, which also returns a 64-byte CUDA IPC handle; the ranks of one node exchange handles (host side)
+ * and map each other's buffers with vitb200_peer_open (NVLink / NVSwitch peer access).  peer_bufs is a DEVICE array of
+ * `world` pointers in rank order (entry `rank` = the local buffer).  Per launch: publish the locally reduced gradient,
+ * raise this rank's flag in every rank's buffer, wait for all flags, sum the ranks' gradients in rank order (bit-identical
+ * on every rank), then norm -> clip -> AdamW as vitb200_clip_adamw_fused.  Every rank must launch it the same number of
+ * times.  grad_scale (hyper[6]) carries the 1/world mean. */
+size_t vitb200_peer_buffer_bytes(size_t n);
+int vitb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int vitb200_peer_open(const unsigned char* handle64, void** ptr);
+int vitb200_peer_close(void* ptr);
+int vitb200_peer_free(void* ptr);
+int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                                float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
+                                size_t red_start, size_t red_end, void* ws, void* const* peer_bufs, int rank, int world,
+                                void* stream);
+
 /* shadow[i] = bf16(p[i]) (after load_state_dict / an external optimizer touched the fp32 arena) */
 int vitb200_cast_bf16(const float* p, void* shadow, size_t n, void* stream);
 

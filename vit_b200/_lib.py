@@ -114,6 +114,12 @@ SIGNATURES = {
     "vitb200_adamw": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p]),
     "vitb200_clip_adamw_fused_ws_bytes": (_sz, []),
     "vitb200_clip_adamw_fused": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p]),
+    "vitb200_peer_buffer_bytes": (_sz, [_sz]),
+    "vitb200_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
+    "vitb200_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vitb200_peer_close": (_i, [_p]),
+    "vitb200_peer_free": (_i, [_p]),
+    "vitb200_clip_adamw_fused_dp": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p, _i, _i, _p]),
     "vitb200_cast_bf16": (_i, [_p, _p, _sz, _p]),
     "vitb200_gelu_fwd": (_i, [_p, _p, _sz, _i, _p]),
     "vitb200_residual_add": (_i, [_p, _p, _p, _sz, _i, _p]),

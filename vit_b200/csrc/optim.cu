@@ -1,5 +1,7 @@
 // Gradient-norm clipping + AdamW over one flat fp32 parameter arena (HBM-bound streaming kernels),
 // bf16 shadow refresh for BF16-mode GEMM operands, and the dropout-mask test helper.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -97,6 +99,30 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // reduces the partials in block order (deterministic), writes the state and bumps the epoch that the others poll.
 // Each thread keeps its (<= TAIL_KEEP) reduced gradient vectors in registers across the barrier.
 // ------------------------------------------------------------------------------------------------
+// ---- peer (NVLink) exchange buffer of the data-parallel optimizer tail ------------------------------------------
+// layout: [1024 B header: uint32 flags[world]] [parity 0: xfloats fp32] [parity 1: xfloats fp32]
+struct PeerX {
+  void* const* bufs;   // DEVICE array [world]: every rank's exchange buffer (own entry = local memory)
+  int rank, world;     // world <= 1: no exchange
+  size_t xfloats;
+};
+__device__ __forceinline__ unsigned int* peer_flags(void* buf) { return reinterpret_cast<unsigned int*>(buf); }
+__device__ __forceinline__ float* peer_data(void* buf, unsigned int parity, size_t xfloats) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(buf) + 1024) + (size_t)parity * xfloats;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 constexpr int TAIL_THREADS = 256;
 constexpr int TAIL_KEEP = 4;
 constexpr int TAIL_MAX_BLOCKS = 148;
@@ -105,7 +131,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
 clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
                         uint64_t* rng, const float* __restrict__ gpart, int slots, size_t stride4, size_t red_lo4,
-                        size_t red_hi4, float* __restrict__ partial, unsigned int* sync) {
+                        size_t red_hi4, float* __restrict__ partial, unsigned int* sync, const PeerX X) {
   __shared__ float red[TAIL_THREADS / 32];
   __shared__ bool is_last;
   pdl_wait();
@@ -113,6 +139,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   unsigned int* ticket = sync;
   volatile unsigned int* epoch = sync + 1;
   const unsigned int my_epoch = *epoch;   // read BEFORE this block's ticket: the epoch cannot move until every block arrived
+  const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): exchange tag
   float4* g4 = reinterpret_cast<float4*>(g);
   const size_t gstride = (size_t)gridDim.x * TAIL_THREADS;
   const size_t i0 = (size_t)blockIdx.x * TAIL_THREADS + threadIdx.x;
@@ -147,8 +174,50 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     } else {
       s = g4[i];
     }
+    if (X.world > 1) {   // data parallel: publish the local gradient, the sum over ranks is formed below
+      reinterpret_cast<float4*>(peer_data(X.bufs[X.rank], seq & 1u, X.xfloats))[i] = s;
+      continue;
+    }
     if (k < TAIL_KEEP) keep[k] = s;
     acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
+  }
+  if (X.world > 1) {
+    // ---- gradient all-reduce over NVLink peer memory, fused into this kernel (no NCCL launch on the step's critical
+    // path).  1. every block fences its slice of the published gradient and takes a ticket; the last one raises this
+    // rank's flag (= seq) in EVERY rank's buffer.  2. all blocks wait until all `world` flags in the local buffer
+    // reached seq.  3. each element is summed over the ranks' buffers in rank order -- every rank computes bit-identical
+    // sums, so the replicas cannot drift.  Buffers are double-buffered by launch parity: a rank can only overwrite
+    // parity p two launches later, after a full flag round in between proved that every peer finished reading it.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tk = atomicAdd(ticket, 1u);
+      if (tk == gridDim.x - 1) {
+        *ticket = 0u;
+        __threadfence_system();
+        for (int q = 0; q < X.world; ++q) st_release_sys(peer_flags(X.bufs[q]) + X.rank, seq);
+      }
+    }
+    if (threadIdx.x < X.world) {
+      const unsigned int* f = peer_flags(X.bufs[X.rank]) + threadIdx.x;
+      unsigned int spins = 0;
+      while ((int)(ld_acquire_sys(f) - seq) < 0) {
+        if (++spins > (1u << 28)) __trap();   // a dead peer traps instead of hanging the device
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    k = 0;
+    for (size_t i = i0; i < n4; i += gstride, ++k) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < X.world; ++q) {
+        const float4 t = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(peer_data(X.bufs[q], seq & 1u, X.xfloats)) + i);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      g4[i] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
+      if (k < TAIL_KEEP) keep[k] = s;
+      acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -179,6 +248,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     state[4] = (float)(1.0 - pow((double)hyper[2], (double)step));
     if (rng) rng[1] += 1ull;
     *ticket = 0u;
+    sync[2] = seq;
     __threadfence();
     *epoch = my_epoch + 1u;   // release
   }
@@ -286,7 +356,65 @@ extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, 
   unsigned int* sync = reinterpret_cast<unsigned int*>(ws);   // {ticket, epoch}: zero-initialised by the caller once
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
   vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, p, g, m, v,
-                (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync);
+                (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
+                PeerX{nullptr, 0, 1, 0});
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+// ---- data-parallel variant: the gradient all-reduce runs inside the kernel over peer memory ---------------------
+extern "C" size_t vitb200_peer_buffer_bytes(size_t n) { return 1024 + 2 * n * sizeof(float); }
+
+extern "C" int vitb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return VITB200_ERR_ARG;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return vb_cuda_error(e);
+  if ((e = cudaMemset(*ptr, 0, bytes)) != cudaSuccess) return vb_cuda_error(e);
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, *ptr)) != cudaSuccess) return vb_cuda_error(e);
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return vb_cuda_error(e);
+  return VITB200_OK;
+}
+extern "C" int vitb200_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return VITB200_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return vb_cuda_error(e);
+  return VITB200_OK;
+}
+extern "C" int vitb200_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? VITB200_OK : vb_cuda_error(e);
+}
+extern "C" int vitb200_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? VITB200_OK : vb_cuda_error(e);
+}
+
+extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                                           float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
+                                           size_t red_start, size_t red_end, void* ws, void* const* peer_bufs, int rank,
+                                           int world, void* stream) {
+  if (!p || !g || !m || !v || !hyper || !state || !ws || !peer_bufs) return VITB200_ERR_ARG;
+  if (world < 2 || world > TAIL_THREADS || rank < 0 || rank >= world) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if (slots > 0 && (!gpart || (stride | red_start | red_end) % 4 != 0 || red_end < red_start || red_end > n)) return VITB200_ERR_ARG;
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(gpart)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
+    return VITB200_ERR_ALIGN;
+  const size_t n4 = n / 4;
+  size_t grid = (n4 + TAIL_THREADS - 1) / TAIL_THREADS;
+  if (grid > TAIL_MAX_BLOCKS) grid = TAIL_MAX_BLOCKS;
+  if (grid < 1) grid = 1;
+  unsigned int* sync = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, p, g, m, v,
+                (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
+                PeerX{peer_bufs, rank, world, n});
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

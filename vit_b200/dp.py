@@ -68,3 +68,51 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
 def broadcast_parameters(flat_data: torch.Tensor, group=None, src: int = 0) -> None:
     """Replicate rank `src`'s parameter arena (DDP's constructor does the same)."""
     dist.broadcast(flat_data, src=src, group=group)
+
+
+class PeerExchange:
+    """Per-rank exchange buffers for the in-kernel gradient all-reduce (vitb200_clip_adamw_fused_dp).
+
+    Every rank cudaMalloc's one buffer, the 64-byte CUDA IPC handles are all-gathered (host side, once), and each rank
+    maps its peers' buffers (NVLink / NVSwitch peer access inside one node, one process per GPU).  `table` is the device
+    array of the `world` buffer pointers in rank order that the kernel receives.  There is no NCCL call per step."""
+
+    def __init__(self, n_floats: int, device: torch.device, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        nbytes = int(self.lib.vitb200_peer_buffer_bytes(n_floats))
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.vitb200_peer_alloc(nbytes, ctypes.byref(own), handle), "peer_alloc")
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.opened = []
+        ptrs = []
+        for q, h in enumerate(handles):
+            if q == self.rank:
+                ptrs.append(self.own)
+                continue
+            p = ctypes.c_void_p()
+            _lib.check(self.lib.vitb200_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "peer_open")
+            self.opened.append(p.value)
+            ptrs.append(p.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)   # every rank has mapped every buffer before the first launch touches them
+
+    def close(self) -> None:
+        if self.own is None:
+            return
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()          # nobody unmaps while a peer's last kernel may still read
+        for p in self.opened:
+            self.lib.vitb200_peer_close(p)
+        self.lib.vitb200_peer_free(self.own)
+        self.own, self.opened = None, []

@@ -21,7 +21,7 @@ from .model import MyViT
 class TrainStep:
     def __init__(self, model: MyViT, batch_size: int, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, grad_clip: float = 0.5, use_graph: bool = True, process_group=None,
-                 world_size: int = 1, noise_level: float = 0.0, train: bool = True):
+                 world_size: int = 1, noise_level: float = 0.0, train: bool = True, peer_allreduce: bool = True):
         self.model = model
         model._opt_hyper = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=grad_clip)
         model._engines.pop(batch_size, None)
@@ -32,6 +32,9 @@ class TrainStep:
         self.group = process_group
         if self.world > 1:
             self.eng.set_grad_scale(1.0 / self.world)
+            # fused programs: the gradient all-reduce runs inside the optimizer kernel over NVLink peer memory
+            if self.eng.fused_bwd and peer_allreduce:
+                self.eng.peer = _dp.PeerExchange(self.eng.arena.layout.n_opt, self.eng.device, group=process_group)
         self.noise_level = float(noise_level)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -44,9 +47,9 @@ class TrainStep:
     # ---- one step's kernel sequence (also what gets captured) ---------------------------------
     def _launch(self) -> None:
         eng = self.eng
-        if self.world > 1:
+        if self.world > 1 and getattr(eng, "peer", None) is None:
             eng.forward(train=self.train, with_labels=True)
-            self._backward_overlapped()   # gradients are summed across ranks before the optimizer kernel reads them
+            self._backward_overlapped()   # NCCL: gradients are summed across ranks before the optimizer kernel reads them
             eng.optimizer_step()
         else:
             # single GPU: head backward rides on forward's last launch, the gradient-partial reduction on the optimizer's
@@ -261,10 +264,13 @@ class TrainStep:
         self._pipe = None
         gc.collect()
         torch.cuda.synchronize(self.eng.device)
+        if getattr(self.eng, "peer", None) is not None:
+            self.eng.peer.close()
+            self.eng.peer = None
 
     def kernel_launches(self) -> int:
         """Our kernels per step (+2 device-to-device staging copies of the inputs done by torch in step())."""
-        return self.eng.kernel_launches(self.train, fused_tail=self.world == 1)
+        return self.eng.kernel_launches(self.train, fused_tail=self.world == 1 or getattr(self.eng, "peer", None) is not None)
 
 
 class EvalStep:
