@@ -530,6 +530,53 @@ def main():
             except Exception as ex:  # noqa: BLE001
                 sweep[f"batch_{b2}"] = {"error": str(ex)[:200]}
 
+    # ---- the other BASELINE.json configs, measured beside the headline (N = 1 only; not the bench line's value) ----
+    other = None
+    if not args.no_sweep and world == 1:
+        from vit_b200.step import EvalStep
+        other = {}
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(n):
+                fn()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+
+        def variant(**kw):
+            c = json.loads(json.dumps(BASELINE_CFG))
+            c["model"].update(kw)
+            return c
+
+        cases = [
+            ("config_yaml_2layers_train_b64", variant(num_hidden_layers=2), 64, "train", 50),
+            ("eval_forward_b1024", variant(), 1024, "eval", 20),
+            ("eval_forward_b8192", variant(), 8192, "eval", 5),
+            ("long_seq_x4_stride8_T510_train_b64", variant(stride_size=8), 64, "train", 5),
+        ]
+        for name, cfg2, b2, mode, n2 in cases:
+            try:
+                m2 = get_model(cfg2, precision=args.precision, device=dev)
+                x2 = torch.rand(b2, 4096, device=dev); y2 = torch.rand(b2, device=dev)
+                if mode == "train":
+                    s2 = TrainStep(m2.train(), b2, use_graph=not args.no_graph, train=True)
+                    msb = timed(lambda: s2.step(x2, y2), n2)
+                else:
+                    s2 = EvalStep(m2.eval(), b2, use_graph=not args.no_graph)
+                    msb = timed(lambda: s2.forward(x2), n2)
+                eng2 = s2.eng
+                other[name] = {"samples_per_s": b2 * 1e3 / msb, "ms": msb, "tokens": int(m2.config.tokens),
+                               "fused_fwd": bool(eng2.fused), "fused_bwd": bool(eng2.fused_bwd)}
+                del s2, m2, x2, y2, eng2
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                other[name] = {"error": str(ex)[:200]}
+
     line = {
         "metric": "train samples/sec (baseline.yaml shape)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -555,6 +602,7 @@ def main():
         "kernel_time_sum_us": ksum_us,
         "kernels": kernels[:8],
         "sweep": sweep,
+        "other_configs": other,
         "tc_gemm_probe": probe,
         "final_loss": loss_last,
     }

@@ -149,6 +149,9 @@ def get_model(config: dict, precision: Any = None, device: Any = None):
                       precision=precision, device=device)
         print("[builder] Created vanilla ViT model")
         return model
-    from .preprocessor import build_preprocessor_model
-
-    return build_preprocessor_model(config, precision=precision, device=device)
+    # SURVEY.md 8(f) rank 3 ("next" row): the LinearPreprocessor / PrefilledAttention input stage
+    # (src/models/builder.py:43-133) is not part of this round's hot path.  Fail loudly instead of building a model
+    # that silently ignores the preprocessor.
+    raise NotImplementedError(
+        f"vit_b200: warmup.preprocessor={preproc_type!r} (src/models/builder.py:43-133) is not implemented yet; "
+        "only the vanilla ViT step (warmup.preprocessor: null) is available")

@@ -139,17 +139,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_wait();     // q/k/v come from the previous kernel of the step
   pdl_trigger();
   VB_TL(tl_attn_fwd, 2);
+  if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
+    mbar_expect_tx(b_kv, 2 * kv_bytes);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+    mbar_expect_tx(b_q, 16384);                       // first query tile
+    tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
+  }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  if (tid == 0) {
-    mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
-  }
   VB_TL(tl_attn_fwd, 3);
   const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Kk{smem_u32(sK), 16, 16384, 0};
   const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV), 16384, 0, 1};
@@ -224,7 +226,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   for (int qt = 0; qt < nq; ++qt) {
     const int q0 = qt * 128, i = q0 + r;
     const bool valid = i < T;
-    if (tid == 0) {
+    if (tid == 0 && qt > 0) {
       mbar_expect_tx(b_q, 16384);
       tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
     }
@@ -393,17 +395,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   pdl_wait();     // q/k/v and dctx come from earlier kernels of the step
   pdl_trigger();
+  if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
+    mbar_expect_tx(b_kv, 2 * kv_bytes);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+    mbar_expect_tx(b_q, 32768);                       // first query / dO tiles
+    tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
+    tma_load_2d(sDO, &tmDO, b_q, h * D, row0);
+  }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  if (tid == 0) {
-    mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
-  }
   const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Qmn{smem_u32(sQ), 16384, 0, 1};
   const AOp DOk{smem_u32(sDO), 16, 16384, 0}, DOmn{smem_u32(sDO), 16384, 0, 1};
   const AOp Kk{smem_u32(sK), 16, 16384, 0}, Kmn{smem_u32(sK), 16384, 0, 1}, Vk{smem_u32(sV), 16, 16384, 0};
@@ -478,7 +483,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int q0 = qt * 128, i = q0 + r;
     const bool valid = i < T;
     const int ic = valid ? i : T - 1;
-    if (tid == 0) {
+    if (tid == 0 && qt > 0) {
       mbar_expect_tx(b_q, 32768);
       tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
       tma_load_2d(sDO, &tmDO, b_q, h * D, row0 + q0);

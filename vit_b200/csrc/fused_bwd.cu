@@ -172,6 +172,22 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
   pdl_wait();
   pdl_trigger();
   VB_TL(tl_bwd_upper, 2);
+  const bool from_cls = P.dz_cls != nullptr;
+  auto load_tile = [&](int r0) {   // thread 0: all TMA loads of one 128-row tile
+    if (!from_cls) {   // dz gates the first stage: it gets its own barrier and goes first
+      mbar_expect_tx(b_dz, 16384);
+      tma_load_2d(sDz, &tmDz, b_dz, 0, r0);
+    }
+    mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384);
+    tma_load_2d(sM, &tmM, b_tile, 0, r0);
+    tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
+    tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
+    tma_load_2d(sCtx, &tmCtx, b_tile, 0, r0);
+    tma_load_2d(base + O_ACT, &tmAct, b_tile, 0, r0);
+    tma_load_2d(base + O_ACT + 16384, &tmAct, b_tile, 64, r0);
+    tma_load_2d(base + O_HM, &tmHm, b_tile, 0, r0);
+  };
+  if (tid == 0 && (int)blockIdx.x < ntiles) load_tile(blockIdx.x * 128);   // first tile: in flight while TMEM is allocated
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -210,21 +226,9 @@ fused_bwd_upper_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_con
     const int r0 = tile * 128, row = r0 + r;
     const bool valid = row < M;
     const int rowc = valid ? row : M - 1;
-    const bool from_cls = P.dz_cls != nullptr;
-    if (tid == 0) {
-      if (iter > 0) tma_store_wait_read<0>();   // the previous tile's dh / dctx images are about to be overwritten
-      if (!from_cls) {   // dz gates the first stage: it gets its own barrier and goes first
-        mbar_expect_tx(b_dz, 16384);
-        tma_load_2d(sDz, &tmDz, b_dz, 0, r0);
-      }
-      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 32768 + 16384);
-      tma_load_2d(sM, &tmM, b_tile, 0, r0);
-      tma_load_2d(sM + 16384, &tmM, b_tile, 64, r0);
-      tma_load_2d(sU2, &tmU2, b_tile, 0, r0);
-      tma_load_2d(sCtx, &tmCtx, b_tile, 0, r0);
-      tma_load_2d(base + O_ACT, &tmAct, b_tile, 0, r0);
-      tma_load_2d(base + O_ACT + 16384, &tmAct, b_tile, 64, r0);
-      tma_load_2d(base + O_HM, &tmHm, b_tile, 0, r0);
+    if (tid == 0 && iter > 0) {
+      tma_store_wait_read<0>();   // the previous tile's dh / dctx images are about to be overwritten
+      load_tile(r0);
     }
     const float mu = P.mean2[rowc], rs = P.rstd2[rowc];  // issued early, consumed by the LayerNorm stage
     // ---- ddelta2 = dropout'(dz) (bf16) -> sD ----
@@ -465,6 +469,15 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
   }
   pdl_wait();
   pdl_trigger();
+  auto load_tile = [&](int r0) {   // thread 0: all TMA loads of one 128-row tile
+    mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 16384);
+    tma_load_2d(sDQ, &tmDQ, b_tile, 0, r0);
+    tma_load_2d(sDQ + 16384, &tmDQ, b_tile, 64, r0);
+    tma_load_2d(sU, &tmU, b_tile, 0, r0);
+    tma_load_2d(base + O_Z, &tmZ, b_tile, 0, r0);
+    tma_load_2d(base + O_DH, &tmDh, b_tile, 0, r0);
+  };
+  if (tid == 0 && (int)blockIdx.x < ntiles) load_tile(blockIdx.x * 128);   // first tile: in flight while TMEM is allocated
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -487,13 +500,10 @@ fused_bwd_lower_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_co
     const int rowc = valid ? row : M - 1;
     const float mu = P.mean1[rowc], rs = P.rstd1[rowc];  // issued early
     if (tid == 0) {
-      if (iter > 0) tma_store_wait_read<0>();   // the previous tile's dz image (sDh) is about to be overwritten
-      mbar_expect_tx(b_tile, 32768 + 16384 + 16384 + 16384);
-      tma_load_2d(sDQ, &tmDQ, b_tile, 0, r0);
-      tma_load_2d(sDQ + 16384, &tmDQ, b_tile, 64, r0);
-      tma_load_2d(sU, &tmU, b_tile, 0, r0);
-      tma_load_2d(base + O_Z, &tmZ, b_tile, 0, r0);
-      tma_load_2d(base + O_DH, &tmDh, b_tile, 0, r0);
+      if (iter > 0) {
+        tma_store_wait_read<0>();   // the previous tile's dz image (sDh) is about to be overwritten
+        load_tile(r0);
+      }
       if (iter == 0) mbar_wait(b_w, 0);
       mbar_wait(b_tile, ph_tile);
       tc_fence_after();
