@@ -394,3 +394,57 @@ def test_one_launch_tail_and_head_match_separate_kernels(golden, precision):
     assert rel_err(s1[1], s0[1]) < 1e-6             # grad norm (block partials are summed in a different grouping)
     assert rel_err(p1, p0) < 1e-6
     assert float(s1[0]) == float(s0[0]) == 1.0      # optimizer step counter
+
+
+@pytest.mark.gpu
+def test_large_batch_multi_tile_persistent_ctas():
+    """B = 296 (38 184 token rows = 299 row tiles on 148 persistent CTAs: up to three tiles per CTA, a partial last
+    tile, TMEM-resident weight-gradient accumulation across tiles, smem store images reused between tiles).
+    Size-independent properties instead of a CPU replay: the mean-loss gradient of the full batch equals the mean of
+    the gradients of its 8 chunks of 37 samples (each chunk runs the one-tile-per-CTA path), the per-sample logits
+    are identical, and two runs are bitwise equal (fixed-order reductions) -- dropout ON with the same masks."""
+    from vit_b200 import get_model
+
+    dev = _cuda()
+    cfg = {"model": dict(name="vit", task_type="reg", image_size=4096, patch_size=32, hidden_size=32,
+                         num_hidden_layers=3, num_attention_heads=2, stride_size=32, proj_fn="SW"),
+           "loss": {"name": "mae"}, "data": {"param": "log_g"}}
+    torch.manual_seed(5)
+    m = get_model(copy.deepcopy(cfg), precision="bf16-mixed", device=dev)
+    B, C = 296, 8
+    x, y = vo.synthetic_batch(B, 4096, seed=21, kind="rand")
+    x, y = x.to(dev), y.to(dev)
+
+    def run(xx, yy, train):
+        eng = m._engine(xx.shape[0])
+        eng.rng[1] = 11
+        m._stage_inputs(eng, xx, yy)
+        eng.forward(train=train, with_labels=True)
+        eng.backward(train=train)
+        torch.cuda.synchronize()
+        return eng.arena.grad[:eng.arena.layout.n_opt].clone(), eng.logits.clone(), float(eng.loss[0])
+
+    assert m._engine(B).fused_bwd
+    # bitwise reproducibility of the multi-tile path, dropout on
+    g1, l1, s1 = run(x, y, True)
+    g2, l2, s2 = run(x, y, True)
+    assert torch.equal(g1, g2) and torch.equal(l1, l2) and s1 == s2
+    # full batch vs chunks, dropout off (the masks are indexed by row within the batch, so chunks would draw others)
+    gf, lf, sf = run(x, y, False)
+    gc = torch.zeros_like(gf)
+    lc, sc = [], 0.0
+    n = B // C
+    for c in range(C):
+        g, l, s = run(x[c * n:(c + 1) * n], y[c * n:(c + 1) * n], False)
+        gc += g / C
+        lc.append(l)
+        sc += s / C
+    assert torch.equal(torch.cat(lc), lf)                       # rows are independent: identical logits
+    assert abs(sf - sc) < 1e-5 * max(1.0, abs(sc))
+    assert rel_err(gf, gc) < 5e-3, rel_err(gf, gc)              # same bf16 products, different fp32 summation order
+    lay = m._arena.layout
+    for name in ("vit.encoder.layer.0.intermediate.dense.weight", "vit.encoder.layer.2.attention.attention.query.bias",
+                 "vit.embeddings.cls_token", "vit.encoder.layer.1.layernorm_after.weight"):
+        e = lay.entries[name]
+        a, b = gf[e.offset:e.offset + e.numel], gc[e.offset:e.offset + e.numel]
+        assert rel_err(a, b) < 1e-2, (name, rel_err(a, b))
