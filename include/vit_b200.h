@@ -317,7 +317,7 @@ int vitb200_adamw(float* p, const float* g, float* m, float* v, void* shadow, si
                   const float* state, uint64_t* rng, void* stream);
 /* vitb200_clip_adamw_fused: the whole optimizer tail in ONE launch (the configured model has 40 353 parameters: the
  * tail is three launch latencies, not bandwidth).  If slots > 0, the gradient of elements [red_start, red_end) is first
- * formed as the in-order sum of `slots` partial arenas (gpart + s*stride; the per-CTA partials of the fused backward
+ * formed as a fixed-order sum of `slots` partial arenas (gpart + s*stride; the per-CTA partials of the fused backward
  * kernels) and written to g; then norm -> clip_coef -> AdamW exactly as the two calls above.  ws: at least
  * vitb200_clip_adamw_fused_ws_bytes() bytes, zeroed once by the caller (grid-barrier ticket / epoch + block partials). */
 size_t vitb200_clip_adamw_fused_ws_bytes(void);

@@ -390,7 +390,7 @@ def test_one_launch_tail_and_head_match_separate_kernels(golden, precision):
                     int(eng.rng[1])))
     (g0, s0, p0, l0, r0), (g1, s1, p1, l1, r1) = res
     assert l0 == l1 and r0 == r1
-    assert torch.equal(g0, g1)                      # both reductions run in the same fixed order
+    assert rel_err(g1, g0) < 1e-6                   # fixed-order sums on both sides, grouped differently (4 lanes x slots)
     assert rel_err(s1[1], s0[1]) < 1e-6             # grad norm (block partials are summed in a different grouping)
     assert rel_err(p1, p0) < 1e-6
     assert float(s1[0]) == float(s0[0]) == 1.0      # optimizer step counter

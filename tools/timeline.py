@@ -39,6 +39,7 @@ names = {
                   "epi3 (drop,LN)", "sync+MMA4", "epi4 (qkv)+sync"],
     "bwd_upper": ["prologue", "pdl_wait", "tmem+sync", "dz,drop->sD +sync", "tile TMA+MMA1", "gelu'+sync", "MMA2",
                   "LN bwd+sync", "MMA3", "dctx epi", "grad tail"],
+    "tail": ["pdl_wait", "reduce partial slots", "block sum + ticket + wait", "norm, coef, bias corrections", "AdamW"],
     "attn_fwd": ["prologue", "pdl_wait", "tmem+sync", "K/V/Q TMA", "rope+bar+MMA S", "max pass+bar", "exp pass+bar", "MMA PV",
                  "O epi"],
 }

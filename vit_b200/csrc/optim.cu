@@ -94,13 +94,14 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 // ------------------------------------------------------------------------------------------------
 // One-launch optimizer tail:  [sum of the per-CTA gradient partials] -> global L2 norm -> clip -> AdamW.
-// The norm is a grid-wide dependency; the grid is at most one CTA per SM (all co-resident), so a ticket + epoch flag
-// in global memory is a safe grid barrier: block b publishes its partial sum, takes a ticket; the last arrival
-// reduces the partials in block order (deterministic), writes the state and bumps the epoch that the others poll.
+// The norm is a grid-wide dependency; the grid is at most one CTA per SM (all co-resident), so a ticket counter in
+// global memory is a safe grid barrier: block b publishes its partial sum and takes a ticket; once all tickets of this
+// launch are in, every block reduces the partials in the same fixed order (deterministic, identical in all blocks).
 // Each thread keeps its (<= TAIL_KEEP) reduced gradient vectors in registers across the barrier.
 // ------------------------------------------------------------------------------------------------
 // ---- peer (NVLink) exchange buffer of the data-parallel optimizer tail ------------------------------------------
-// layout: [1024 B header: uint32 flags[world]] [parity 0: xfloats fp32] [parity 1: xfloats fp32]
+// layout: [16 KB header: uint32 flags[world][148 blocks]] [parity 0: xfloats fp32] [parity 1: xfloats fp32]
+constexpr size_t PEER_HEADER = 16384;   // >= 4 * world * 148 for world <= 27
 struct PeerX {
   void* const* bufs;   // DEVICE array [world]: every rank's exchange buffer (own entry = local memory)
   int rank, world;     // world <= 1: no exchange
@@ -108,7 +109,7 @@ struct PeerX {
 };
 __device__ __forceinline__ unsigned int* peer_flags(void* buf) { return reinterpret_cast<unsigned int*>(buf); }
 __device__ __forceinline__ float* peer_data(void* buf, unsigned int parity, size_t xfloats) {
-  return reinterpret_cast<float*>(reinterpret_cast<char*>(buf) + 1024) + (size_t)parity * xfloats;
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(buf) + PEER_HEADER) + (size_t)parity * xfloats;
 }
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -118,88 +119,93 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+VB_TL_DECL(tl_tail)
 constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_EPB = TAIL_THREADS / 4;   // float4 elements per block pass: FOUR lanes share one element, so the
+                                             // 40 k-parameter arena of the configured model spreads over all 148 SMs
 constexpr int TAIL_KEEP = 4;
 constexpr int TAIL_MAX_BLOCKS = 148;
 
+// Thread (e, j): float4 element e of the arena, lane j = tid & 3.
+//   reduction of the gradient partials: lane j sums slots j, j+4, ... (independent 16-byte L2 reads), the four partial
+//     float4s are combined by a two-level butterfly (fixed order) and lane j keeps component j;
+//   everything after that (peer exchange, norm, AdamW) is scalar work on element 4 e + j: consecutive lanes touch
+//     consecutive floats, so all accesses stay coalesced and four times more threads hide the L2 / NVLink latency.
 __global__ void __launch_bounds__(TAIL_THREADS)
 clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
                         uint64_t* rng, const float* __restrict__ gpart, int slots, size_t stride4, size_t red_lo4,
                         size_t red_hi4, float* __restrict__ partial, unsigned int* sync, const PeerX X) {
   __shared__ float red[TAIL_THREADS / 32];
-  __shared__ bool is_last;
+  VB_TL(tl_tail, 0);
   pdl_wait();
   pdl_trigger();
+  VB_TL(tl_tail, 1);
   unsigned int* ticket = sync;
-  volatile unsigned int* epoch = sync + 1;
-  const unsigned int my_epoch = *epoch;   // read BEFORE this block's ticket: the epoch cannot move until every block arrived
-  const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): exchange tag
-  float4* g4 = reinterpret_cast<float4*>(g);
-  const size_t gstride = (size_t)gridDim.x * TAIL_THREADS;
-  const size_t i0 = (size_t)blockIdx.x * TAIL_THREADS + threadIdx.x;
-  float4 keep[TAIL_KEEP];
+  // read BEFORE this block's ticket: block 0 rewrites them only after every block of this launch took its ticket
+  const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): barrier / exchange tag
+  const float step_prev = *(volatile float*)state;
+  const int lane4 = threadIdx.x & 3;
+  const size_t estride = (size_t)gridDim.x * TAIL_EPB;
+  const size_t e0 = (size_t)blockIdx.x * TAIL_EPB + (threadIdx.x >> 2);
+  float keep[TAIL_KEEP];
   float acc = 0.f;
+  float* mine = X.world > 1 ? peer_data(X.bufs[X.rank], seq & 1u, X.xfloats) : nullptr;
   int k = 0;
-  for (size_t i = i0; i < n4; i += gstride, ++k) {
-    float4 s;
-    if (slots > 0 && i >= red_lo4 && i < red_hi4) {   // gradient = sum over the CTA partial slots, in slot order
-      const float4* src = reinterpret_cast<const float4*>(gpart) + i;
-      s = make_float4(0.f, 0.f, 0.f, 0.f);
-      int z = 0;
-      for (; z + 16 <= slots; z += 16) {   // 16 independent L2 reads in flight per thread, summed in slot order
-        float4 t[16];
+  for (size_t e = e0; e < n4; e += estride, ++k) {
+    float gj;
+    if (slots > 0 && e >= red_lo4 && e < red_hi4) {
+      const float4* src = reinterpret_cast<const float4*>(gpart) + e;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      int z = lane4;
+      for (; z + 28 < slots; z += 32) {   // 8 independent reads in flight
+        float4 t[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) t[q] = __ldcg(src + (size_t)(z + q) * stride4);
+        for (int q = 0; q < 8; ++q) t[q] = __ldcg(src + (size_t)(z + 4 * q) * stride4);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+        for (int q = 0; q < 8; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
       }
-      for (; z + 4 <= slots; z += 4) {
-        float4 t[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t[q] = __ldcg(src + (size_t)(z + q) * stride4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
-      }
-      for (; z < slots; ++z) {
+      for (; z < slots; z += 4) {
         const float4 t = __ldcg(src + (size_t)z * stride4);
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
       }
-      g4[i] = s;   // the flat gradient arena stays the public result (p.grad views, DDP, tests)
+      // the four lanes of an element are adjacent lanes of one warp and always take this branch together
+      const unsigned gm = 0xFu << (threadIdx.x & 28);
+      s.x += __shfl_xor_sync(gm, s.x, 1); s.y += __shfl_xor_sync(gm, s.y, 1);
+      s.z += __shfl_xor_sync(gm, s.z, 1); s.w += __shfl_xor_sync(gm, s.w, 1);
+      s.x += __shfl_xor_sync(gm, s.x, 2); s.y += __shfl_xor_sync(gm, s.y, 2);
+      s.z += __shfl_xor_sync(gm, s.z, 2); s.w += __shfl_xor_sync(gm, s.w, 2);
+      gj = lane4 == 0 ? s.x : lane4 == 1 ? s.y : lane4 == 2 ? s.z : s.w;
     } else {
-      s = g4[i];
+      gj = g[4 * e + lane4];
     }
     if (X.world > 1) {   // data parallel: publish the local gradient, the sum over ranks is formed below
-      reinterpret_cast<float4*>(peer_data(X.bufs[X.rank], seq & 1u, X.xfloats))[i] = s;
+      mine[4 * e + lane4] = gj;
       continue;
     }
-    if (k < TAIL_KEEP) keep[k] = s;
-    acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
+    g[4 * e + lane4] = gj;   // the flat gradient arena stays the public result (p.grad views, tests)
+    if (k < TAIL_KEEP) keep[k] = gj;
+    acc = fmaf(gj, gj, acc);
   }
   if (X.world > 1) {
     // ---- gradient all-reduce over NVLink peer memory, fused into this kernel (no NCCL launch on the step's critical
-    // path).  1. every block fences its slice of the published gradient and takes a ticket; the last one raises this
-    // rank's flag (= seq) in EVERY rank's buffer.  2. all blocks wait until all `world` flags in the local buffer
-    // reached seq.  3. each element is summed over the ranks' buffers in rank order -- every rank computes bit-identical
-    // sums, so the replicas cannot drift.  Buffers are double-buffered by launch parity: a rank can only overwrite
-    // parity p two launches later, after a full flag round in between proved that every peer finished reading it.
+    // path).  Block b handles the same elements on every rank, so the exchange is block-to-block: 1. block b fences its
+    // slice of the published gradient and raises flag [rank][b] (= seq) in EVERY rank's buffer; 2. it waits until the
+    // flags [q][b] of all ranks q in the local buffer reached seq; 3. each element is summed over the ranks' buffers in
+    // rank order -- every rank computes bit-identical sums, so the replicas cannot drift.  Buffers are double-buffered
+    // by launch parity: a rank can only overwrite parity p two launches later, after a full flag round in between
+    // proved that every peer finished reading it.
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int tk = atomicAdd(ticket, 1u);
-      if (tk == gridDim.x - 1) {
-        *ticket = 0u;
-        __threadfence_system();
-        for (int q = 0; q < X.world; ++q) st_release_sys(peer_flags(X.bufs[q]) + X.rank, seq);
-      }
-    }
+    if (threadIdx.x < X.world)
+      st_release_sys(peer_flags(X.bufs[threadIdx.x]) + (size_t)X.rank * TAIL_MAX_BLOCKS + blockIdx.x, seq);
     if (threadIdx.x < X.world) {
-      const unsigned int* f = peer_flags(X.bufs[X.rank]) + threadIdx.x;
+      const unsigned int* f = peer_flags(X.bufs[X.rank]) + (size_t)threadIdx.x * TAIL_MAX_BLOCKS + blockIdx.x;
       unsigned int spins = 0;
       while ((int)(ld_acquire_sys(f) - seq) < 0) {
         if (++spins > (1u << 28)) __trap();   // a dead peer traps instead of hanging the device
@@ -208,87 +214,96 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     }
     __syncthreads();
     k = 0;
-    for (size_t i = i0; i < n4; i += gstride, ++k) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < X.world; ++q) {
-        const float4 t = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(peer_data(X.bufs[q], seq & 1u, X.xfloats)) + i);
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-      }
-      g4[i] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
+    for (size_t e = e0; e < n4; e += estride, ++k) {
+      float s = 0.f;
+      for (int q = 0; q < X.world; ++q) s += ld_relaxed_sys_f32(peer_data(X.bufs[q], seq & 1u, X.xfloats) + 4 * e + lane4);
+      g[4 * e + lane4] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
       if (k < TAIL_KEEP) keep[k] = s;
-      acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
+      acc = fmaf(s, s, acc);
     }
   }
+  VB_TL(tl_tail, 2);
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < TAIL_THREADS / 32; ++w) t += red[w];
-    partial[blockIdx.x] = t;
-    __threadfence();
-    const unsigned int tk = atomicAdd(ticket, 1u);
-    is_last = (tk == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    double tot = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) tot += (double)__ldcg(&partial[b]);
-    const float gs = hyper[6];
-    const float norm = (float)sqrt(tot) * fabsf(gs);
-    const float max_norm = hyper[5];
-    float coef = 1.f;
-    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
-    const float step = state[0] + 1.f;
-    state[0] = step;
-    state[1] = norm;
-    state[2] = coef;
-    state[3] = (float)(1.0 - pow((double)hyper[1], (double)step));
-    state[4] = (float)(1.0 - pow((double)hyper[2], (double)step));
-    if (rng) rng[1] += 1ull;
-    *ticket = 0u;
-    sync[2] = seq;
-    __threadfence();
-    *epoch = my_epoch + 1u;   // release
-  }
-  if (threadIdx.x == 0) {
-    unsigned int spins = 0;
-    while (*epoch == my_epoch) {
-      if (++spins > (1u << 28)) __trap();   // a mis-sized grid traps instead of hanging the device
+  // ---- grid barrier + norm.  Tickets only ever count up: launch number seq is complete when the counter reaches
+  // seq * gridDim (the workspace belongs to one arena, so the grid is the same at every launch).  EVERY block then sums
+  // the block partials itself (same fixed order => same bits) and derives coef / bias corrections: there is no serial
+  // "last block computes, everybody polls a second flag" hop.  Block 0 alone records the results.
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < TAIL_THREADS / 32; ++w) t += red[w];
+      partial[blockIdx.x] = t;
+      __threadfence();
+      atomicAdd(ticket, 1u);
+      const unsigned int target = seq * gridDim.x;
+      unsigned int spins = 0;
+      while ((int)(*(volatile unsigned int*)ticket - target) < 0) {
+        if (++spins > (1u << 28)) __trap();   // a mis-sized grid traps instead of hanging the device
+      }
+      __threadfence();
     }
-    __threadfence();
+    __syncwarp();
+    VB_TL(tl_tail, 3);
+    double tot = 0.0;   // lane l sums partial[l], partial[l + 32], ... then a fixed shuffle tree (deterministic)
+    for (unsigned int bb = threadIdx.x; bb < gridDim.x; bb += 32) tot += (double)__ldcg(&partial[bb]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (threadIdx.x == 0) {
+      const float norm = (float)sqrt(tot) * fabsf(hyper[6]);
+      const float max_norm = hyper[5];
+      float coef = 1.f;
+      if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
+      const float step = step_prev + 1.f;
+      // beta^step: a double pow() is ~2 us of dependent FP64; the running products {beta1^t, beta2^t, t, beta1, beta2} are
+      // kept next to the barrier words (two copies, by launch parity, so block 0 can write while the others read) and
+      // only recomputed when the step counter was changed behind our back (restore / load_state)
+      const double* cur = reinterpret_cast<const double*>(sync + 16) + ((seq - 1u) & 1u) * 8;
+      const double b1d = (double)hyper[1], b2d = (double)hyper[2];
+      double p1, p2;
+      if (cur[2] == (double)step_prev && cur[3] == b1d && cur[4] == b2d && step_prev > 0.f) {
+        p1 = cur[0] * b1d; p2 = cur[1] * b2d;
+      } else {
+        p1 = pow(b1d, (double)step); p2 = pow(b2d, (double)step);
+      }
+      red[0] = coef;
+      red[1] = (float)(1.0 - p1);
+      red[2] = (float)(1.0 - p2);
+      if (blockIdx.x == 0) {
+        double* nxt = reinterpret_cast<double*>(sync + 16) + (seq & 1u) * 8;
+        nxt[0] = p1; nxt[1] = p2; nxt[2] = (double)step; nxt[3] = b1d; nxt[4] = b2d;
+        state[0] = step;
+        state[1] = norm;
+        state[2] = coef;
+        state[3] = red[1];
+        state[4] = red[2];
+        if (rng) rng[1] += 1ull;
+        sync[2] = seq;
+      }
+    }
   }
   __syncthreads();
+  VB_TL(tl_tail, 4);
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
-  const float gmul = hyper[6] * __ldcg(&state[2]);
-  const float bc1 = __ldcg(&state[3]), bc2 = __ldcg(&state[4]);
+  const float gmul = hyper[6] * red[0];
+  const float bc1 = red[1], bc2 = red[2];
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
   const float decay = 1.f - lr * wd;
-  float4* p4 = reinterpret_cast<float4*>(p);
-  float4* m4 = reinterpret_cast<float4*>(m);
-  float4* v4 = reinterpret_cast<float4*>(v);
   k = 0;
-  for (size_t i = i0; i < n4; i += gstride, ++k) {
-    const float4 gg = k < TAIL_KEEP ? keep[k] : __ldcg(&g4[i]);
-    float4 pp = p4[i], mm = m4[i], vv = v4[i];
-    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
-    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float gr = ga[q] * gmul;
-      pa[q] *= decay;
-      ma[q] = fmaf(1.f - b1, gr - ma[q], ma[q]);          // exp_avg.lerp_(grad, 1 - beta1)
-      va[q] = fmaf(1.f - b2, gr * gr, b2 * va[q]);         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-      const float denom = sqrtf(va[q]) * inv_sqrt_bc2 + eps;
-      pa[q] -= step_size * (ma[q] / denom);
-    }
-    p4[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-    m4[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
-    v4[i] = make_float4(va[0], va[1], va[2], va[3]);
-    if (shadow) Vec4<bf16>::st(shadow + i * 4, make_float4(pa[0], pa[1], pa[2], pa[3]));
+  for (size_t e = e0; e < n4; e += estride, ++k) {
+    const size_t i = 4 * e + lane4;
+    const float gr = (k < TAIL_KEEP ? keep[k] : __ldcg(&g[i])) * gmul;
+    float pa = p[i] * decay, ma = m[i], va = v[i];
+    ma = fmaf(1.f - b1, gr - ma, ma);            // exp_avg.lerp_(grad, 1 - beta1)
+    va = fmaf(1.f - b2, gr * gr, b2 * va);       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = sqrtf(va) * inv_sqrt_bc2 + eps;
+    pa -= step_size * (ma / denom);
+    p[i] = pa; m[i] = ma; v[i] = va;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pa);
   }
+  VB_TL(tl_tail, 5);
 }
 
 __global__ void __launch_bounds__(OP_THREADS)
@@ -337,6 +352,8 @@ extern "C" int vitb200_adamw(float* p, const float* g, float* m, float* v, void*
   return VITB200_OK;
 }
 
+VB_TL_EXPORT(vitb200_tl_tail, vb::tl_tail)
+
 extern "C" size_t vitb200_clip_adamw_fused_ws_bytes(void) { return 4096 + TAIL_MAX_BLOCKS * sizeof(float); }
 
 extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
@@ -350,10 +367,10 @@ extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, 
       (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
     return VITB200_ERR_ALIGN;
   const size_t n4 = n / 4;
-  size_t grid = (n4 + TAIL_THREADS - 1) / TAIL_THREADS;
+  size_t grid = (n4 + TAIL_EPB - 1) / TAIL_EPB;
   if (grid > TAIL_MAX_BLOCKS) grid = TAIL_MAX_BLOCKS;   // <= one CTA per SM: the in-kernel grid barrier needs co-residency
   if (grid < 1) grid = 1;
-  unsigned int* sync = reinterpret_cast<unsigned int*>(ws);   // {ticket, epoch}: zero-initialised by the caller once
+  unsigned int* sync = reinterpret_cast<unsigned int*>(ws);   // {ticket, -, launch count, ..., beta powers}: zeroed by the caller once
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
   vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, p, g, m, v,
                 (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
@@ -363,7 +380,7 @@ extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, 
 }
 
 // ---- data-parallel variant: the gradient all-reduce runs inside the kernel over peer memory ---------------------
-extern "C" size_t vitb200_peer_buffer_bytes(size_t n) { return 1024 + 2 * n * sizeof(float); }
+extern "C" size_t vitb200_peer_buffer_bytes(size_t n) { return PEER_HEADER + 2 * n * sizeof(float); }
 
 extern "C" int vitb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
   if (!ptr || !handle64 || bytes == 0) return VITB200_ERR_ARG;
@@ -399,7 +416,7 @@ extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* 
                                            size_t red_start, size_t red_end, void* ws, void* const* peer_bufs, int rank,
                                            int world, void* stream) {
   if (!p || !g || !m || !v || !hyper || !state || !ws || !peer_bufs) return VITB200_ERR_ARG;
-  if (world < 2 || world > TAIL_THREADS || rank < 0 || rank >= world) return VITB200_ERR_ARG;
+  if (world < 2 || world > 27 || rank < 0 || rank >= world) return VITB200_ERR_ARG;
   if (n % 4 != 0) return VITB200_ERR_SHAPE;
   if (slots > 0 && (!gpart || (stride | red_start | red_end) % 4 != 0 || red_end < red_start || red_end > n)) return VITB200_ERR_ARG;
   if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -407,7 +424,7 @@ extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* 
       (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
     return VITB200_ERR_ALIGN;
   const size_t n4 = n / 4;
-  size_t grid = (n4 + TAIL_THREADS - 1) / TAIL_THREADS;
+  size_t grid = (n4 + TAIL_EPB - 1) / TAIL_EPB;
   if (grid > TAIL_MAX_BLOCKS) grid = TAIL_MAX_BLOCKS;
   if (grid < 1) grid = 1;
   unsigned int* sync = reinterpret_cast<unsigned int*>(ws);
