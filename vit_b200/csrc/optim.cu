@@ -125,9 +125,9 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
   return v;
 }
 VB_TL_DECL(tl_tail)
-constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_EPB = TAIL_THREADS / 4;   // float4 elements per block pass: FOUR lanes share one element, so the
-                                             // 40 k-parameter arena of the configured model spreads over all 148 SMs
+constexpr int TAIL_MAX_THREADS = 512;         // block size is chosen per arena: four lanes share one float4 element and
+                                              // the launcher picks 4 * ceil(n4 / 148) threads (a multiple of 32), so the
+                                              // 40 k-parameter arena of the configured model is ONE pass over 148 SMs
 constexpr int TAIL_KEEP = 4;
 constexpr int TAIL_MAX_BLOCKS = 148;
 
@@ -136,12 +136,12 @@ constexpr int TAIL_MAX_BLOCKS = 148;
 //     float4s are combined by a two-level butterfly (fixed order) and lane j keeps component j;
 //   everything after that (peer exchange, norm, AdamW) is scalar work on element 4 e + j: consecutive lanes touch
 //     consecutive floats, so all accesses stay coalesced and four times more threads hide the L2 / NVLink latency.
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_MAX_THREADS)
 clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
                         uint64_t* rng, const float* __restrict__ gpart, int slots, size_t stride4, size_t red_lo4,
                         size_t red_hi4, float* __restrict__ partial, unsigned int* sync, const PeerX X) {
-  __shared__ float red[TAIL_THREADS / 32];
+  __shared__ float red[TAIL_MAX_THREADS / 32];
   VB_TL(tl_tail, 0);
   pdl_wait();
   pdl_trigger();
@@ -151,8 +151,9 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): barrier / exchange tag
   const float step_prev = *(volatile float*)state;
   const int lane4 = threadIdx.x & 3;
-  const size_t estride = (size_t)gridDim.x * TAIL_EPB;
-  const size_t e0 = (size_t)blockIdx.x * TAIL_EPB + (threadIdx.x >> 2);
+  const size_t epb = blockDim.x >> 2;   // float4 elements per block pass
+  const size_t estride = (size_t)gridDim.x * epb;
+  const size_t e0 = (size_t)blockIdx.x * epb + (threadIdx.x >> 2);
   float keep[TAIL_KEEP];
   float acc = 0.f;
   float* mine = X.world > 1 ? peer_data(X.bufs[X.rank], seq & 1u, X.xfloats) : nullptr;
@@ -163,12 +164,19 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
       const float4* src = reinterpret_cast<const float4*>(gpart) + e;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       int z = lane4;
-      for (; z + 28 < slots; z += 32) {   // 8 independent reads in flight
-        float4 t[8];
+      for (; z + 60 < slots; z += 64) {   // 16 independent reads in flight
+        float4 t[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = __ldcg(src + (size_t)(z + 4 * q) * stride4);
+        for (int q = 0; q < 16; ++q) t[q] = __ldcg(src + (size_t)(z + 4 * q) * stride4);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+        for (int q = 0; q < 16; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+      }
+      for (; z + 12 < slots; z += 16) {
+        float4 t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = __ldcg(src + (size_t)(z + 4 * q) * stride4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
       }
       for (; z < slots; z += 4) {
         const float4 t = __ldcg(src + (size_t)z * stride4);
@@ -233,7 +241,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0) {
       float t = 0.f;
-      for (int w = 0; w < TAIL_THREADS / 32; ++w) t += red[w];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
       partial[blockIdx.x] = t;
       __threadfence();
       atomicAdd(ticket, 1u);
@@ -352,6 +360,20 @@ extern "C" int vitb200_adamw(float* p, const float* g, float* m, float* v, void*
   return VITB200_OK;
 }
 
+// block size / grid of the tail kernel: <= one CTA per SM (the in-kernel grid barrier needs co-residency), and, when the
+// arena is small enough, exactly one pass (no block does two rounds while the others wait at the barrier)
+static inline void tail_launch_shape(size_t n4, int* threads, int* grid) {
+  size_t per = (n4 + TAIL_MAX_BLOCKS - 1) / TAIL_MAX_BLOCKS;   // float4 elements per block for one pass
+  size_t t = ((per * 4 + 31) / 32) * 32;
+  if (t < 128) t = 128;
+  if (t > TAIL_MAX_THREADS) t = TAIL_MAX_THREADS;
+  size_t g = (n4 + t / 4 - 1) / (t / 4);
+  if (g > TAIL_MAX_BLOCKS) g = TAIL_MAX_BLOCKS;
+  if (g < 1) g = 1;
+  *threads = (int)t;
+  *grid = (int)g;
+}
+
 VB_TL_EXPORT(vitb200_tl_tail, vb::tl_tail)
 
 extern "C" size_t vitb200_clip_adamw_fused_ws_bytes(void) { return 4096 + TAIL_MAX_BLOCKS * sizeof(float); }
@@ -367,12 +389,11 @@ extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, 
       (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
     return VITB200_ERR_ALIGN;
   const size_t n4 = n / 4;
-  size_t grid = (n4 + TAIL_EPB - 1) / TAIL_EPB;
-  if (grid > TAIL_MAX_BLOCKS) grid = TAIL_MAX_BLOCKS;   // <= one CTA per SM: the in-kernel grid barrier needs co-residency
-  if (grid < 1) grid = 1;
+  int threads, grid;
+  tail_launch_shape(n4, &threads, &grid);
   unsigned int* sync = reinterpret_cast<unsigned int*>(ws);   // {ticket, -, launch count, ..., beta powers}: zeroed by the caller once
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
-  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, p, g, m, v,
+  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3((unsigned)threads), 0, (cudaStream_t)stream, p, g, m, v,
                 (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
                 PeerX{nullptr, 0, 1, 0});
   VB_CHECK_LAUNCH();
@@ -424,12 +445,11 @@ extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* 
       (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
     return VITB200_ERR_ALIGN;
   const size_t n4 = n / 4;
-  size_t grid = (n4 + TAIL_EPB - 1) / TAIL_EPB;
-  if (grid > TAIL_MAX_BLOCKS) grid = TAIL_MAX_BLOCKS;
-  if (grid < 1) grid = 1;
+  int threads, grid;
+  tail_launch_shape(n4, &threads, &grid);
   unsigned int* sync = reinterpret_cast<unsigned int*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
-  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, p, g, m, v,
+  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3((unsigned)threads), 0, (cudaStream_t)stream, p, g, m, v,
                 (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
                 PeerX{peer_bufs, rank, world, n});
   VB_CHECK_LAUNCH();
