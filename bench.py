@@ -558,6 +558,7 @@ def main():
             ("eval_forward_b1024", variant(), 1024, "eval", 20),
             ("eval_forward_b8192", variant(), 8192, "eval", 5),
             ("long_seq_x4_stride8_T510_train_b64", variant(stride_size=8), 64, "train", 5),
+            ("long_seq_x16_stride2_T2034_train_b64", variant(stride_size=2), 64, "train", 2),
         ]
         for name, cfg2, b2, mode, n2 in cases:
             try:

@@ -97,8 +97,14 @@ struct AttnTcParams {
   bf16* ctx; float* lse;
   const bf16* dctx; bf16* dqkv; int ld_d;
   const float* cosT; const float* sinT;
-  int B, T, heads, H, ld, KP;   // KP = keys padded to a multiple of 16
+  int B, T, heads, H, ld, KP;   // KP = keys (of this launch) padded to a multiple of 16
   float scale, p_drop; const uint64_t* rng; uint32_t site;
+  // key-blocked mode (long sequences): this launch handles keys [key0, key0 + Tk) of every sample only.
+  //   forward : writes the block-normalised output (fp32) and the block log-sum-exp; attn_tc_combine_kernel merges blocks
+  //   backward: dK / dV of the block's keys are complete; dQ is accumulated over the launches in an fp32 buffer
+  //             (first: store, otherwise add; last: the bf16 dq rows are written)
+  int kb, key0, Tk, first, last;
+  float* o_part; float* lse_part; float* dq_acc;
 };
 
 // ================================================================================================
@@ -130,6 +136,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int cg = warp >> 2;                       // key-column group (4 = side-row warp)
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
+  const int key0 = P.kb ? P.key0 : 0, Tk = P.kb ? P.Tk : T;   // keys of this launch: [key0, key0 + Tk)
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
@@ -141,8 +148,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VB_TL(tl_attn_fwd, 2);
   if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
     mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0 + key0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0 + key0);
     mbar_expect_tx(b_q, 16384);                       // first query tile
     tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
   }
@@ -180,7 +187,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
         const int j = lane + 32 * jj;
         float acc = -INFINITY;
-        if (j < T) {
+        if (j < Tk) {
           float kr[D];
           at_load_row<D>(sK, j, kr);
           acc = 0.f;
@@ -198,10 +205,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
         const int j = lane + 32 * jj;
-        if (j < T) {
+        if (j < Tk) {
           float p = exp2f((sc[jj] - mx) * sl2);
           sum += p;
-          p *= drop1(dc, drow + (uint64_t)j);
+          p *= drop1(dc, drow + (uint64_t)(key0 + j));
           p = bf16_round(p);
           float vr[D];
           at_load_row<D>(sV, j, vr);
@@ -216,10 +223,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float inv = 1.f / sum;
 #pragma unroll
         for (int c = 0; c < D; ++c) o[c] *= inv;
-        bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
+        if (P.kb) {
+          float* dst = P.o_part + (size_t)(row0 + i) * P.H + h * D;
 #pragma unroll
-        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&o[c]);
-        P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+          for (int c = 0; c < D; ++c) dst[c] = o[c];
+          P.lse_part[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        } else {
+          bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&o[c]);
+          P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        }
       }
     }
   } else {
@@ -243,7 +257,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (qt == 0) {
         for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
           at_load_row<D>(sK, rr, x);
-          at_rope<D, false>(x, P.cosT, P.sinT, rr < T ? rr : 0);
+          at_rope<D, false>(x, P.cosT, P.sinT, rr < Tk ? key0 + rr : 0);
           at_store_row<D>(sK, rr, x);
         }
       }
@@ -267,12 +281,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int c0 = (cg + k * AT_CG) * 16;
       if (cg + k * AT_CG < nch) {
         tmem_ld_32x16(my_tmem + cS + c0, v[k]);
-        if (c0 + 16 <= T) {   // full chunk: no key masking
+        if (c0 + 16 <= Tk) {   // full chunk: no key masking
 #pragma unroll
           for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[k][j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (c0 + j < T) mx = fmaxf(mx, v[k][j]);
+          for (int j = 0; j < 16; ++j) if (c0 + j < Tk) mx = fmaxf(mx, v[k][j]);
         }
       }
     }
@@ -287,11 +301,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int k = 0; k < AT_MAXCH; ++k) {
       const int c0 = (cg + k * AT_CG) * 16;
       if (cg + k * AT_CG < nch) {
-        if (c0 + 16 <= T) {
+        if (c0 + 16 <= Tk) {
 #pragma unroll
           for (int j = 0; j < 16; j += 8) {
             float kp[8];
-            drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+            drop8(dc, (drow + (uint64_t)(key0 + c0 + j)) >> 3, kp);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float p = ex2_approx(fmaf(v[k][j + q], sl2, nmxs));
@@ -304,12 +318,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; j += 8) {
             float kp[8];
-            if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kp);
+            if (c0 + j < Tk) drop8(dc, (drow + (uint64_t)(key0 + c0 + j)) >> 3, kp);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float p = (c0 + j + q < T) ? ex2_approx(fmaf(v[k][j + q], sl2, nmxs)) : 0.f;
+              const float p = (c0 + j + q < Tk) ? ex2_approx(fmaf(v[k][j + q], sl2, nmxs)) : 0.f;
               sum += p;
-              v[k][j + q] = (c0 + j < T) ? p * kp[q] : 0.f;
+              v[k][j + q] = (c0 + j < Tk) ? p * kp[q] : 0.f;
             }
             *reinterpret_cast<uint4*>(at_swz(sP, r, (c0 + j) >> 3)) = at_pack8(&v[k][j]);
           }
@@ -337,8 +351,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float inv = 1.f / sum;
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] *= inv;
-        *reinterpret_cast<uint4*>(P.ctx + (size_t)(row0 + i) * P.H + h * D + cg * 8) = at_pack8(o);
-        if (cg == 0) P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        if (P.kb) {
+          float4* dst = reinterpret_cast<float4*>(P.o_part + (size_t)(row0 + i) * P.H + h * D + cg * 8);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          if (cg == 0) P.lse_part[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        } else {
+          *reinterpret_cast<uint4*>(P.ctx + (size_t)(row0 + i) * P.H + h * D + cg * 8) = at_pack8(o);
+          if (cg == 0) P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
+        }
       }
     }
     tc_fence_before();
@@ -388,6 +408,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int cg = warp >> 2;
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
+  const int key0 = P.kb ? P.key0 : 0, Tk = P.kb ? P.Tk : T;   // keys of this launch: [key0, key0 + Tk)
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
@@ -397,8 +418,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_trigger();
   if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
     mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0);
+    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0 + key0);
+    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0 + key0);
     mbar_expect_tx(b_q, 32768);                       // first query / dO tiles
     tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
     tma_load_2d(sDO, &tmDO, b_q, h * D, row0);
@@ -451,7 +472,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int jj = 0; jj < AT_SIDE_KEYS; ++jj) {
         const int j = lane + 32 * jj;
-        if (j < T) {
+        if (j < Tk) {
           float kr[D], vr[D];
           at_load_row<D>(sK, j, kr);
           at_load_row<D>(sV, j, vr);
@@ -459,7 +480,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int c = 0; c < D; ++c) { sdot = fmaf(qf[c], kr[c], sdot); dp = fmaf(dof[c], vr[c], dp); }
           const float p = exp2f(sdot * sl2 - lse2);
-          const float keep = drop1(dc, drow + (uint64_t)j);
+          const float keep = drop1(dc, drow + (uint64_t)(key0 + j));
           const float ds = bf16_round(p * (dp * keep - Di) * P.scale);
           xds[j] = ds;
           xpt[j] = bf16_round(p * keep);
@@ -470,9 +491,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < D; ++c) dq[c] = warp_allsum(dq[c]);
       if (lane == 0) {
-        bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+        if (P.kb) {
+          float* acc = P.dq_acc + (size_t)(row0 + i) * P.H + h * D;
 #pragma unroll
-        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&dq[c]);
+          for (int c = 0; c < D; ++c) { if (!P.first) dq[c] += acc[c]; if (!P.last) acc[c] = dq[c]; }
+        }
+        if (!P.kb || P.last) {
+          bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&dq[c]);
+        }
 #pragma unroll
         for (int c = 0; c < D; ++c) { xq[c] = qf[c]; xdo[c] = dof[c]; }
       }
@@ -521,7 +549,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (qt == 0) {
         for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
           at_load_row<D>(sK, rr, x);
-          at_rope<D, false>(x, P.cosT, P.sinT, rr < T ? rr : 0);
+          at_rope<D, false>(x, P.cosT, P.sinT, rr < Tk ? key0 + rr : 0);
           at_store_row<D>(sK, rr, x);
         }
       }
@@ -553,11 +581,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float s[16], dp[16];
       tmem_ld_32x16(my_tmem + cS + c0, s);
       tmem_ld_32x16(my_tmem + cDP + c0, dp);
-      if (valid && c0 + 16 <= T) {   // full chunk of a live query row: no masking
+      if (valid && c0 + 16 <= Tk) {   // full chunk of a live query row: no masking
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
           float kpa[8];
-          drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
+          drop8(dc, (drow + (uint64_t)(key0 + c0 + j)) >> 3, kpa);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float p = ex2_approx(fmaf(s[j + q], sl2, -lse2));
@@ -570,11 +598,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
           float kpa[8];
-          if (c0 + j < T) drop8(dc, (drow + (uint64_t)(c0 + j)) >> 3, kpa);
+          if (c0 + j < Tk) drop8(dc, (drow + (uint64_t)(key0 + c0 + j)) >> 3, kpa);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const bool on = valid && (c0 + j + q < T);
-            const float kq = (c0 + j < T) ? kpa[q] : 0.f;
+            const bool on = valid && (c0 + j + q < Tk);
+            const float kq = (c0 + j < Tk) ? kpa[q] : 0.f;
             const float p = on ? ex2_approx(fmaf(s[j + q], sl2, -lse2)) : 0.f;
             const float pk = p * kq;
             s[j + q] = on ? fmaf(dp[j + q], pk, -p * Di) : 0.f;  // (columns past T hold stale TMEM data)
@@ -610,11 +638,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (valid) {
           float x[D];
 #pragma unroll
-          for (int c = 0; c < D; ++c) x[c] = bf16_round(o[c] * P.scale);
-          at_rope<D, true>(x, P.cosT, P.sinT, i);
-          bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+          for (int c = 0; c < D; ++c) x[c] = o[c] * P.scale;
+          if (P.kb) {
+            float* acc = P.dq_acc + (size_t)(row0 + i) * P.H + h * D;
 #pragma unroll
-          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&x[c]);
+            for (int c = 0; c < D; ++c) { if (!P.first) x[c] += acc[c]; if (!P.last) acc[c] = x[c]; }
+          }
+          if (!P.kb || P.last) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) x[c] = bf16_round(x[c]);
+            at_rope<D, true>(x, P.cosT, P.sinT, i);
+            bf16* dst = P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D;
+#pragma unroll
+            for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&x[c]);
+          }
         }
       }
     } else if (cg < D / 8) {
@@ -622,7 +659,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_32x8(my_tmem + cDQ + cg * 8, o);
 #pragma unroll
       for (int c = 0; c < 8; ++c) o[c] *= P.scale;
-      if (valid) *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D + cg * 8) = at_pack8(o);
+      if (valid && P.kb) {
+        float4* acc = reinterpret_cast<float4*>(P.dq_acc + (size_t)(row0 + i) * P.H + h * D + cg * 8);
+        if (!P.first) {
+          const float4 a0 = acc[0], a1 = acc[1];
+          o[0] += a0.x; o[1] += a0.y; o[2] += a0.z; o[3] += a0.w; o[4] += a1.x; o[5] += a1.y; o[6] += a1.z; o[7] += a1.w;
+        }
+        if (!P.last) { acc[0] = make_float4(o[0], o[1], o[2], o[3]); acc[1] = make_float4(o[4], o[5], o[6], o[7]); }
+      }
+      if (valid && (!P.kb || P.last))
+        *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + i) * P.ld_d + h * D + cg * 8) = at_pack8(o);
     }
     tc_fence_before();
     bar_main();
@@ -636,16 +682,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (cg < 2) {  // cg 0: dK row (inverse rotation), cg 1: dV row
         float o[32];
         tmem_ld_32x32(my_tmem + (cg == 0 ? (kt ? cDK1 : cDK0) : (kt ? cDV1 : cDV0)), o);
-        if (j < T) {
+        if (j < Tk) {
           float x[D];
 #pragma unroll
           for (int c = 0; c < D; ++c) x[c] = o[c];
           if (cg == 0) {
 #pragma unroll
             for (int c = 0; c < D; ++c) x[c] = bf16_round(x[c] * P.scale);
-            at_rope<D, true>(x, P.cosT, P.sinT, j);
+            at_rope<D, true>(x, P.cosT, P.sinT, key0 + j);
           }
-          bf16* dst = P.dqkv + (size_t)(row0 + j) * P.ld_d + (cg == 0 ? P.H : 2 * P.H) + h * D;
+          bf16* dst = P.dqkv + (size_t)(row0 + key0 + j) * P.ld_d + (cg == 0 ? P.H : 2 * P.H) + h * D;
 #pragma unroll
           for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&x[c]);
         }
@@ -657,7 +703,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int c8 = (is_v ? pc - D / 8 : pc) * 8;
         float o[8];
         tmem_ld_32x8(my_tmem + (is_v ? (kt ? cDV1 : cDV0) : (kt ? cDK1 : cDK0)) + c8, o);
-        if (j < T) {
+        if (j < Tk) {
           if (!is_v) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] *= P.scale;
@@ -668,7 +714,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = fmaf(a, xr[c8 + c], o[c]);
           }
-          *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + j) * P.ld_d + (is_v ? 2 * P.H : P.H) + h * D + c8) = at_pack8(o);
+          *reinterpret_cast<uint4*>(P.dqkv + (size_t)(row0 + key0 + j) * P.ld_d + (is_v ? 2 * P.H : P.H) + h * D + c8) = at_pack8(o);
         }
       }
     }
@@ -678,6 +724,43 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
+
+// merge of the key-blocked forward: ctx = sum_blk exp(lse_blk - lse) O_blk,  lse = log sum_blk exp(lse_blk).
+// One thread per (row, head, 8 columns).
+__global__ void __launch_bounds__(256)
+attn_tc_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ lse_part, bf16* __restrict__ ctx,
+                       float* __restrict__ lse, int B, int T, int heads, int D, int nblk) {
+  pdl_wait();
+  pdl_trigger();
+  const int H = heads * D, cpr = H / 8;
+  const size_t M = (size_t)B * T, BHT = (size_t)B * heads * T;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= M * cpr) return;
+  const size_t row = idx / cpr;
+  const int c8 = (int)(idx - row * cpr) * 8, h = c8 / D;
+  const size_t b = row / T, t = row - b * T;
+  const size_t li = (b * heads + h) * T + t;
+  float mx = -INFINITY;
+  for (int k = 0; k < nblk; ++k) mx = fmaxf(mx, lse_part[(size_t)k * BHT + li]);
+  float se = 0.f, o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = 0.f;
+  for (int k = 0; k < nblk; ++k) {
+    const float w = __expf(lse_part[(size_t)k * BHT + li] - mx);
+    se += w;
+    const float4* src = reinterpret_cast<const float4*>(o_part + ((size_t)k * M + row) * H + c8);
+    const float4 a0 = src[0], a1 = src[1];
+    o[0] = fmaf(w, a0.x, o[0]); o[1] = fmaf(w, a0.y, o[1]); o[2] = fmaf(w, a0.z, o[2]); o[3] = fmaf(w, a0.w, o[3]);
+    o[4] = fmaf(w, a1.x, o[4]); o[5] = fmaf(w, a1.y, o[5]); o[6] = fmaf(w, a1.z, o[6]); o[7] = fmaf(w, a1.w, o[7]);
+  }
+  const float inv = 1.f / se;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] *= inv;
+  *reinterpret_cast<uint4*>(ctx + row * H + c8) = at_pack8(o);
+  if ((c8 % D) == 0) lse[li] = mx + logf(se);
+}
+
+constexpr int AT_KB = 128;   // keys per launch in key-blocked mode
 
 constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 64 + 2 * AT_CG * 128 * 4 + 1024;
 constexpr int AT_BWD_SMEM = 16384 + 16384 + 49152 + 49152 + 32768 + 32768 + 1024 + 4096;
@@ -711,7 +794,7 @@ extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const
   if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
   if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
   AttnTcParams P{(const bf16*)qkv, (bf16*)ctx, lse, nullptr, nullptr, 0, rope_cos, rope_sin, B, T, heads, H, ld, KP,
-                 scale, p_drop, rng, site};
+                 scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr};
   dim3 grid(heads, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_F(DD)                                                                                             \
@@ -743,7 +826,8 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
   if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
   if ((rc = get_tmap(dctx, H, M, 64, 128, &tDO))) return rc;
   AttnTcParams P{(const bf16*)qkv, (bf16*)const_cast<void*>(ctx), const_cast<float*>(lse), (const bf16*)dctx, (bf16*)dqkv,
-                 ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site};
+                 ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr, nullptr,
+                 nullptr};
   dim3 grid(heads, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_B(DD)                                                                                             \
@@ -759,5 +843,106 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
   if (d == 16) LAUNCH_B(16) else LAUNCH_B(32)
 #undef LAUNCH_B
   VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+// ---- key-blocked mode: any sequence length (the long-sequence sweep: T = 510 / 513 / 2034 / 2049) -------------------
+// The single-tile kernels above keep a whole key range in one TMEM tile.  Longer sequences are handled by launching
+// them once per block of 128 keys: forward writes block-normalised partial outputs + block log-sum-exps and one merge
+// kernel combines them (split-KV flash attention); backward recomputes P from the merged lse, so dK / dV of a block are
+// complete and dQ is accumulated over the launches in fp32.  Same math, same dropout masks, same tolerances.
+extern "C" int vitb200_attn_tc_blocked_supported(int T, int d, int ld, int H) {
+  if (!(d == 16 || d == 32)) return 0;
+  if (ld != 3 * H || (ld % 8) != 0 || (H % 8) != 0) return 0;
+  return T > 0 ? 1 : 0;
+}
+extern "C" size_t vitb200_attn_tc_blocked_ws_bytes(int B, int T, int heads, int d) {
+  const size_t nblk = (size_t)(T + AT_KB - 1) / AT_KB, M = (size_t)B * T, H = (size_t)heads * d;
+  const size_t nl = (nblk * (size_t)B * heads * T + 3) / 4 * 4;   // keeps the fp32 dq accumulator 16-byte aligned
+  return sizeof(float) * (nblk * M * H + nl + M * H) + 256;
+}
+static inline void at_blocked_ws(void* ws, int B, int T, int heads, int d, float** o_part, float** lse_part, float** dq_acc) {
+  const size_t nblk = (size_t)(T + AT_KB - 1) / AT_KB, M = (size_t)B * T, H = (size_t)heads * d;
+  float* p = reinterpret_cast<float*>(ws);
+  *o_part = p;
+  *lse_part = p + nblk * M * H;
+  *dq_acc = *lse_part + (nblk * (size_t)B * heads * T + 3) / 4 * 4;
+}
+
+extern "C" int vitb200_attn_tc_blocked_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin,
+                                           int B, int T, int heads, int d, float scale, float p_drop, const uint64_t* rng,
+                                           uint32_t site, void* ws, void* stream) {
+  if (!qkv || !ctx || !lse || !ws || B <= 0 || T <= 0 || heads <= 0) return VITB200_ERR_ARG;
+  const int H = heads * d, ld = 3 * H;
+  if (!vitb200_attn_tc_blocked_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return VITB200_ERR_ALIGN;
+  const int M = B * T, nblk = (T + AT_KB - 1) / AT_KB;
+  float *o_part, *lse_part, *dq_acc;
+  at_blocked_ws(ws, B, T, heads, d, &o_part, &lse_part, &dq_acc);
+  CUtensorMap tQ, tKV;
+  int rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
+  dim3 grid(heads, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool done16 = false, done32 = false;
+  bool& done = d == 16 ? done16 : done32;
+  if (!done) {
+    cudaError_t e = d == 16 ? cudaFuncSetAttribute(attn_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM)
+                            : cudaFuncSetAttribute(attn_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int key0 = kb * AT_KB, Tk = T - key0 < AT_KB ? T - key0 : AT_KB, KP = at_kp(Tk);
+    if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
+    AttnTcParams P{(const bf16*)qkv, (bf16*)ctx, lse, nullptr, nullptr, 0, rope_cos, rope_sin, B, T, heads, H, ld, KP,
+                   scale, p_drop, rng, site, 1, key0, Tk, kb == 0, kb == nblk - 1,
+                   o_part + (size_t)kb * M * H, lse_part + (size_t)kb * B * heads * T, dq_acc};
+    if (d == 16) vb_launch_pdl(attn_tc_fwd_kernel<16>, grid, dim3(AT_ALL_THREADS), AT_FWD_SMEM, st, tQ, tKV, P);
+    else vb_launch_pdl(attn_tc_fwd_kernel<32>, grid, dim3(AT_ALL_THREADS), AT_FWD_SMEM, st, tQ, tKV, P);
+    VB_CHECK_LAUNCH();
+  }
+  const size_t items = (size_t)M * (H / 8);
+  vb_launch_pdl(attn_tc_combine_kernel, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st, (const float*)o_part,
+                (const float*)lse_part, (bf16*)ctx, lse, B, T, heads, d, nblk);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                                           const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d,
+                                           float scale, float p_drop, const uint64_t* rng, uint32_t site, void* ws,
+                                           void* stream) {
+  if (!qkv || !ctx || !dctx || !lse || !dqkv || !ws || B <= 0 || T <= 0 || heads <= 0) return VITB200_ERR_ARG;
+  const int H = heads * d, ld = 3 * H;
+  if (!vitb200_attn_tc_blocked_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return VITB200_ERR_ALIGN;
+  const int M = B * T, nblk = (T + AT_KB - 1) / AT_KB;
+  float *o_part, *lse_part, *dq_acc;
+  at_blocked_ws(ws, B, T, heads, d, &o_part, &lse_part, &dq_acc);
+  CUtensorMap tQ, tKV, tDO;
+  int rc;
+  if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
+  if ((rc = get_tmap(dctx, H, M, 64, 128, &tDO))) return rc;
+  dim3 grid(heads, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool done16 = false, done32 = false;
+  bool& done = d == 16 ? done16 : done32;
+  if (!done) {
+    cudaError_t e = d == 16 ? cudaFuncSetAttribute(attn_tc_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BWD_SMEM)
+                            : cudaFuncSetAttribute(attn_tc_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BWD_SMEM);
+    if (e != cudaSuccess) return vb_cuda_error(e);
+    done = true;
+  }
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int key0 = kb * AT_KB, Tk = T - key0 < AT_KB ? T - key0 : AT_KB, KP = at_kp(Tk);
+    if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
+    AttnTcParams P{(const bf16*)qkv, (bf16*)const_cast<void*>(ctx), const_cast<float*>(lse), (const bf16*)dctx, (bf16*)dqkv,
+                   ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site, 1, key0, Tk, kb == 0,
+                   kb == nblk - 1, nullptr, nullptr, dq_acc};
+    if (d == 16) vb_launch_pdl(attn_tc_bwd_kernel<16>, grid, dim3(AT_ALL_THREADS), AT_BWD_SMEM, st, tQ, tKV, tDO, P);
+    else vb_launch_pdl(attn_tc_bwd_kernel<32>, grid, dim3(AT_ALL_THREADS), AT_BWD_SMEM, st, tQ, tKV, tDO, P);
+    VB_CHECK_LAUNCH();
+  }
   return VITB200_OK;
 }

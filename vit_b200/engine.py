@@ -158,6 +158,53 @@ class ViTEngine:
         return self.stats[i].data_ptr()
 
     # ---- programs -----------------------------------------------------------------------------
+    # ---- attention call selection ----------------------------------------------------------------
+    def _attn_blocked(self) -> bool:
+        """bf16 sequences too long for the single-tile tcgen05 kernels run them once per block of 128 keys
+        (vitb200_attn_tc_blocked_*) instead of falling back to the SIMT kernels."""
+        c = self.cfg
+        if self.dt != BF16:
+            return False
+        if self.lib.vitb200_attn_tc_supported(c.tokens, c.head_dim, 3 * c.hidden_size, c.hidden_size):
+            return False
+        if not self.lib.vitb200_attn_tc_blocked_supported(c.tokens, c.head_dim, 3 * c.hidden_size, c.hidden_size):
+            return False
+        if not hasattr(self, "attn_ws"):
+            nbytes = int(self.lib.vitb200_attn_tc_blocked_ws_bytes(self.B, c.tokens, c.num_attention_heads, c.head_dim))
+            self.attn_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return True
+
+    def _attn_fwd_call(self, l: int, pa: float, es: int):
+        c, P_ = self.cfg, self._ptr
+        H, T = c.hidden_size, c.tokens
+        qkv = self.qkv[l].data_ptr()
+        scale = 1.0 / math.sqrt(c.head_dim)
+        rng = self.rng.data_ptr()
+        if self._attn_blocked():
+            return (self.lib.vitb200_attn_tc_blocked_fwd, (
+                qkv, P_(self.ctx[l]), P_(self.lse[l]), P_(self.rope_cos), P_(self.rope_sin), self.B, T,
+                c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), P_(self.attn_ws)))
+        return (self.lib.vitb200_attn_fwd, (
+            qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
+            P_(self.rope_cos), P_(self.rope_sin), self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
+            site_attn(l), self.dt))
+
+    def _attn_bwd_call(self, l: int, pa: float, es: int):
+        c, P_ = self.cfg, self._ptr
+        H, T = c.hidden_size, c.tokens
+        qkv = self.qkv[l].data_ptr()
+        dqkv = self.dqkv.data_ptr()
+        scale = 1.0 / math.sqrt(c.head_dim)
+        rng = self.rng.data_ptr()
+        if self._attn_blocked():
+            return (self.lib.vitb200_attn_tc_blocked_bwd, (
+                qkv, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]), dqkv, P_(self.rope_cos), P_(self.rope_sin),
+                self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), P_(self.attn_ws)))
+        return (self.lib.vitb200_attn_bwd, (
+            qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
+            P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
+            self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), self.dt))
+
     def _build_forward_fused(self, train: bool, with_labels: bool, head_bwd: bool = False) -> List[Tuple[Callable, tuple]]:
         """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L."""
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
@@ -185,10 +232,7 @@ class ViTEngine:
             last = l == Lh - 1
             nxt = "" if last else f"vit.encoder.layer.{l + 1}."
             qkv = self.qkv[l].data_ptr()
-            prog.append((lib.vitb200_attn_fwd, (
-                qkv, qkv + H * 2, qkv + 2 * H * 2, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
-                P_(self.rope_cos), P_(self.rope_sin), B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
-                site_attn(l), dt)))
+            prog.append(self._attn_fwd_call(l, pa, 2))
             la = _lib.LayerFwdArgs(
                 B=B, T=T, H=H, last=1 if last else 0, eps=eps, p_drop=ph, rng=rng, site_proj=site_proj(l),
                 site_mlp=site_mlp(l), ctx=P_(self.ctx[l]), z_in=P_(self.z[l]),
@@ -274,10 +318,7 @@ class ViTEngine:
             prog.append((lib.vitb200_linear_fwd, (
                 P_(self.u[l]), self._w(pre + "attention.attention.query.weight"),
                 self._p(pre + "attention.attention.query.bias"), qkv, None, M, 3 * H, H, ACT_NONE, dt)))
-            prog.append((lib.vitb200_attn_fwd, (
-                qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
-                P_(self.rope_cos), P_(self.rope_sin), B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
-                site_attn(l), dt)))
+            prog.append(self._attn_fwd_call(l, pa, es))
             prog.append((lib.vitb200_linear_fwd, (
                 P_(self.ctx[l]), self._w(pre + "attention.output.dense.weight"),
                 self._p(pre + "attention.output.dense.bias"), P_(self.delta), None, M, H, H, ACT_NONE, dt)))
@@ -372,10 +413,7 @@ class ViTEngine:
                 off_wo=lay.off(pre + "attention.output.dense.weight"), off_bo=lay.off(pre + "attention.output.dense.bias"))
             self._keep.append(ua)
             prog.append((lib.vitb200_fused_layer_bwd_upper, (ctypes.addressof(ua),)))
-            prog.append((lib.vitb200_attn_bwd, (
-                qkv, qkv + H * 2, qkv + 2 * H * 2, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
-                P_(self.dsum), dqkv, dqkv + H * 2, dqkv + 2 * H * 2, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
-                B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), dt)))
+            prog.append(self._attn_bwd_call(l, pa, 2))
             la = _lib.LayerBwdLowerArgs(
                 B=B, T=T, H=H, dqkv=dqkv, u=P_(self.u[l]), z=P_(self.z[l]), mean1=self._stat(4 * l),
                 rstd1=self._stat(4 * l + 1), ln1_g=self._p(pre + "layernorm_before.weight"), dh=P_(other),
@@ -477,10 +515,7 @@ class ViTEngine:
                 self._g(pre + "attention.output.dense.bias"), M, H, H, acc, dt, ws)))
             prog.append((lib.vitb200_linear_dgrad, (
                 P_(self.ddelta), self._w(pre + "attention.output.dense.weight"), None, P_(self.dctx), M, H, H, dt)))
-            prog.append((lib.vitb200_attn_bwd, (
-                qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
-                P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
-                B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), dt)))
+            prog.append(self._attn_bwd_call(l, pa, es))
             # fused QKV projection
             prog.append((lib.vitb200_linear_wgrad, (
                 dqkv, P_(self.u[l]), self._g(pre + "attention.attention.query.weight"),
@@ -672,6 +707,9 @@ class ViTEngine:
                 if fn.__name__ == "vitb200_linear_wgrad" and self.dt == BF16 and \
                         self.lib.vitb200_tc_supported(args[4], args[5], args[6]):
                     k = 2  # column-sum (bias gradient) kernel + tensor-core wgrad
+                if fn.__name__.startswith("vitb200_attn_tc_blocked"):
+                    nb = (self.cfg.tokens + 127) // 128
+                    k = nb + 1 if fn.__name__.endswith("fwd") else nb   # one launch per key block (+ the merge kernel)
                 if fn.__name__ == "vitb200_attn_bwd":
                     tc = self.dt == BF16 and self.lib.vitb200_attn_tc_supported(
                         self.cfg.tokens, self.cfg.head_dim, 3 * self.cfg.hidden_size, self.cfg.hidden_size)
