@@ -208,8 +208,12 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     // rank order -- every rank computes bit-identical sums, so the replicas cannot drift.  Buffers are double-buffered
     // by launch parity: a rank can only overwrite parity p two launches later, after a full flag round in between
     // proved that every peer finished reading it.
-    __threadfence_system();
+    // Memory ordering: the block's gradient stores are ordered before the flag by bar.sync + st.release.sys (release is
+    // cumulative over what the releasing thread observed through the barrier); the consumer's ld.acquire.sys + bar.sync
+    // orders its peer loads after the flag.  No thread executes a stand-alone fence.sys: 40 k of them cost ~6 us each way.
+    VB_TL(tl_tail, 6);
     __syncthreads();
+    VB_TL(tl_tail, 7);
     if (threadIdx.x < X.world)
       st_release_sys(peer_flags(X.bufs[threadIdx.x]) + (size_t)X.rank * TAIL_MAX_BLOCKS + blockIdx.x, seq);
     if (threadIdx.x < X.world) {
@@ -218,13 +222,21 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
       while ((int)(ld_acquire_sys(f) - seq) < 0) {
         if (++spins > (1u << 28)) __trap();   // a dead peer traps instead of hanging the device
       }
-      __threadfence_system();
     }
     __syncthreads();
+    VB_TL(tl_tail, 8);
     k = 0;
     for (size_t e = e0; e < n4; e += estride, ++k) {
+      // all peer loads of an element are issued before the first add: one NVLink round trip per 8 ranks, not one per rank
       float s = 0.f;
-      for (int q = 0; q < X.world; ++q) s += ld_relaxed_sys_f32(peer_data(X.bufs[q], seq & 1u, X.xfloats) + 4 * e + lane4);
+      for (int q0 = 0; q0 < X.world; q0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          t[u] = q0 + u < X.world ? ld_relaxed_sys_f32(peer_data(X.bufs[q0 + u], seq & 1u, X.xfloats) + 4 * e + lane4) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += t[u];   // rank order (absent ranks add +0)
+      }
       g[4 * e + lane4] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
       if (k < TAIL_KEEP) keep[k] = s;
       acc = fmaf(s, s, acc);
