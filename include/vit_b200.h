@@ -366,6 +366,37 @@ int vitb200_cast_bf16(const float* p, void* shadow, size_t n, void* stream);
 int vitb200_gelu_fwd(const void* x, void* y, size_t n, int dtype, void* stream);
 int vitb200_residual_add(const float* z, const void* delta, float* out, size_t n, int dtype, void* stream);
 
+/* ---- either side of the step: input stage, dataset hand-off, evaluation metrics --------
+ * dst[i] = float(src_bf16[i]).  The input preprocessor (LinearPreprocessor / PrefilledLinear.forward,
+ * src/models/preprocessor.py:107-108, src/models/layers.py:62-63; PrefilledAttention 2-D branch,
+ * src/models/attention.py:81-82) is vitb200_linear_fwd on [B, D_in] x [D_out, D_in]^T; in BF16 mode its bf16 output is
+ * widened with this call into the fp32 pixel buffer the embedding kernels read. */
+int vitb200_cast_f32(const void* src, float* dst, size_t n, void* stream);
+/* Gradient of the patch embedding w.r.t. its input pixels -- what autograd hands to a TRAINABLE preprocessor
+ * (PrefilledLinear.freeze(False), src/models/layers.py:51-60):
+ *   dx[b, l] = sum_{n : n*S <= l < n*S+P, n < n_valid} sum_h drop'(dz[b, 1+n, h]) * w[h, l - n*S]
+ * dz [B, Np+1, H] f32 = gradient w.r.t. the embedding output (same tensor vitb200_patch_embed_bwd takes, same dropout
+ * site); w [H, P] (dtype); dx [B, L] f32, fully written. */
+int vitb200_patch_embed_dgrad(const float* dz, const void* w, float* dx, int B, int L, int P, int S, int Np,
+                              int n_valid, int H, float p_drop, const uint64_t* rng, uint32_t site, int dtype,
+                              void* stream);
+/* Batch assembly from a DEVICE-resident dataset (replaces DataLoader collation + H2D of the in-RAM tensors of
+ * src/dataloader/base.py:219-245,299-300 and the noise injection of src/vit.py:86-88):
+ *   x[i, :] = flux[idx[i], :] (+ N(0,1) * error[idx[i], :] * noise_level when noise_level > 0 and error != NULL)
+ *   y[i]    = labels[idx[i]]   (rows of label_bytes raw bytes: fp32 [C] or int64; labels/y may both be NULL)
+ * flux, error [n_rows, L] f32 (L % 4 == 0); idx [B] int64 on the device (NULL: rows 0..B-1); rng = {seed, step}. */
+int vitb200_gather_batch(const float* flux, const float* error, const void* labels, const int64_t* idx, float* x,
+                         void* y, int B, int L, int label_bytes, long long n_rows, float noise_level,
+                         const uint64_t* rng, void* stream);
+/* Running evaluation metrics on the device (replaces the per-batch torchmetrics updates of src/vit.py:94-125:
+ * MeanAbsoluteError, MeanSquaredError, R2Score, Accuracy).  acc: DEVICE doubles, zeroed by the caller at epoch start,
+ * at least 2 + 4*C entries:  acc[0] += B, acc[1] += B*loss[0] (loss may be NULL),
+ *   regression     (is_cls = 0, labels f32 [B, C], C <= 16): acc[2+4c+{0,1,2,3}] += sum_b {|e|, e^2, y, y^2}, e = logits - y
+ *   classification (is_cls = 1, labels int64 [B]):           acc[2] += #(argmax_c logits[b, c] == labels[b])
+ * One CTA, fixed summation order (deterministic). */
+int vitb200_eval_metrics_accum(const float* logits, const void* labels, const float* loss, double* acc, int B, int C,
+                               int is_cls, void* stream);
+
 /* ---- test support ----------------------------------------------------------------------------------
  * mask[i] = 1 if element i of dropout site `site` is kept.  For the attention site the element index
  * is ((b*heads+h)*T + i) * round_up(T,4) + j; for every other site it is the linear index. */

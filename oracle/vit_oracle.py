@@ -179,6 +179,72 @@ def init_params(spec: VitSpec, seed: int = 42, dtype=torch.float32) -> Dict[str,
 
 
 # ----------------------------------------------------------------------------------------------
+# input preprocessor (src/models/preprocessor.py:12-90, src/models/builder.py:43-133, src/models/attention.py:58-72)
+# ----------------------------------------------------------------------------------------------
+def zca_matrix(eigvecs, eigvals, eps=1e-5, r=None, shrinkage=0.0):
+    """preprocessor.py:12-72.  Shrinkage towards the mean eigenvalue first; full rank: V diag(1/sqrt(lam+eps)) V^T;
+    rank r: signal subspace whitened, orthogonal complement scaled by 1/sqrt(lam0+eps), lam0 = median of the tail
+    eigenvalues (the r-th one if there is no tail), floored at 1e-3 * mean(lam[:r])."""
+    lam = eigvals if shrinkage <= 0.0 else (1.0 - shrinkage) * eigvals + shrinkage * eigvals.mean()
+    if r is None:
+        return eigvecs @ torch.diag(1.0 / torch.sqrt(lam + eps)) @ eigvecs.t()
+    Vr = eigvecs[:, :r]
+    tail = lam[r:]
+    lam0 = tail.median() if tail.numel() > 0 else lam[r - 1]
+    lam0 = torch.clamp(lam0, min=1e-3 * lam[:r].mean())
+    s_perp = 1.0 / torch.sqrt(lam0 + eps)
+    ident = torch.eye(eigvecs.shape[0], dtype=eigvecs.dtype)
+    return (Vr * torch.rsqrt(lam[:r] + eps)) @ Vr.t() + s_perp * (ident - Vr @ Vr.t())
+
+
+def preprocessor_tensors(warmup: dict, stats: dict) -> dict:
+    """warmup config + covariance statistics -> dict(tensors keyed by state_dict name, out_dim, prefix, frozen) following
+    builder.py:43-133: 'zca' / 'pca' give `preprocessor.linear.{weight,bias}` with bias = -mean @ P^T (unless
+    warmup.bias is false), frozen iff freeze_epochs != 0 (builder.py:168); 'attention' gives q_lin / k_lin prefilled with
+    the (optionally 1/sqrt(lam+eps)-scaled) leading eigenvectors, always Parameters (but see the quirk below)."""
+    kind = warmup["preprocessor"]
+    V, mean, r = stats["eigvecs"], stats.get("mean"), warmup.get("r")
+    fe = warmup.get("freeze_epochs", 0)
+    fz = "perm" if fe == -1 else str(fe)
+    if kind in ("zca", "pca"):
+        use_bias = warmup.get("bias", True)
+        if kind == "zca":
+            sh = warmup.get("shrinkage", 0.0)
+            P = zca_matrix(V, stats["eigvals"], eps=warmup.get("eps", 1e-5), r=r, shrinkage=sh)
+            prefix = ("ZCA" if r is None else f"ZCA{r}") + f"_fz{fz}" + (f"_s{int(sh * 10)}" if sh > 0 else "")
+        else:
+            P = V.t() if r is None else V[:, :r].t()      # preprocessor.py:75-90
+            prefix = ("PCA" if r is None else f"PCA{r}") + f"_fz{fz}"
+        prefix += "" if use_bias else "_nobias"
+        t = {"preprocessor.linear.weight": P.to(torch.float32)}
+        if use_bias and mean is not None:
+            t["preprocessor.linear.bias"] = (-mean @ P.t()).to(torch.float32)
+        return dict(tensors=t, out_dim=P.shape[0], prefix=prefix, frozen=fe != 0)
+    if kind == "attention":
+        D = V.shape[0]
+        rr = r if r is not None else V.shape[1]
+        basis = V[:, :rr].t().contiguous()
+        lam = stats.get("eigvals")
+        scaled = warmup.get("scale_by_eigvals", True) and lam is not None
+        if scaled:
+            basis = basis * torch.rsqrt(lam[:rr] + warmup.get("eps", 1e-5)).unsqueeze(1)
+        if rr < D:
+            W = basis
+        else:
+            W = torch.zeros(D, D)
+            W[:rr] = basis
+        prefix = f"Attn{r if r else 'Full'}" + ("_scaled" if scaled else "") + f"_fz{fz}"
+        # QUIRK (pinned by the pre_attn_r64 fixture): the prefill does not survive model construction.  MyViT.__init__
+        # ends with self.init_weights() (specvit.py:57) and HF's _init_weights re-draws every nn.Linear below MyViT --
+        # q_lin / k_lin / v_lin included -- from trunc_normal(0, initializer_range=0.02).  So the state_dict holds random
+        # matrices (`reinit`), and `prefill` is only what attention.py:58-72 computed before that.
+        return dict(tensors={}, prefill={"preprocessor.q_lin.weight": W.clone(), "preprocessor.k_lin.weight": W.clone()},
+                    reinit=("preprocessor.q_lin.weight", "preprocessor.k_lin.weight", "preprocessor.v_lin.weight"),
+                    out_dim=(r if r is not None else D), prefix=prefix, frozen=False)
+    raise ValueError(f"Unknown preprocessor type: '{kind}'")
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic inputs (src/utils.py:131-139; datasets clip flux >= 0, src/dataloader/base.py:236)
 # ----------------------------------------------------------------------------------------------
 def make_dummy_spectra(n: int = 512, length: int = 4096, seed: int = 0) -> torch.Tensor:
@@ -265,6 +331,11 @@ def forward(
     reference/HF code calls, so autocast makes the same per-op dtype choices."""
     H, a, d = spec.hidden, spec.heads, spec.head_dim
     p = params
+    if preproc is None:  # preprocessor tensors carried in `params` under their state_dict names
+        if "preprocessor.linear.weight" in p:      # LinearPreprocessor (preprocessor.py:107-108)
+            preproc = (p["preprocessor.linear.weight"], p.get("preprocessor.linear.bias"))
+        elif "preprocessor.q_lin.weight" in p:     # PrefilledAttention, 2-D input: q_lin only (attention.py:81-82)
+            preproc = (p["preprocessor.q_lin.weight"], None)
     if preproc is not None:  # layers.py:62-63
         x = F.linear(x, preproc[0], preproc[1])
     B = x.shape[0]
@@ -358,9 +429,10 @@ class OracleTrainer:
     """Lightning-free restatement of the reference training step on CPU (the CPU baseline)."""
 
     def __init__(self, spec: VitSpec, params: Dict[str, torch.Tensor], lr=1e-3, wd=0.0, clip=0.5,
-                 autocast_bf16: bool = False):
+                 autocast_bf16: bool = False, frozen=()):
+        """frozen: name prefixes of tensors that are buffers, not parameters (a frozen preprocessor, layers.py:21-24)."""
         self.spec = spec
-        self.params = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        self.params = {k: v.clone().requires_grad_(not any(k.startswith(f) for f in frozen)) for k, v in params.items()}
         self.m = {k: torch.zeros_like(v) for k, v in params.items()}
         self.v = {k: torch.zeros_like(v) for k, v in params.items()}
         self.steps = {k: 0 for k in params}

@@ -10,6 +10,24 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_VARIANTS = ["baseline", "config2", "rope", "learned", "cnn", "stride8", "pad48", "cls", "l1",
                    "h64multi", "h128d64rope"]
+# input-preprocessor variants (src/models/builder.py:43-133): the fixture also carries the covariance statistics
+PRE_VARIANTS = ["pre_zca_full", "pre_zca_r32", "pre_pca_r128", "pre_attn_r64"]
+
+
+def config_with_cov(fix, tmp_path):
+    """The fixture's config with warmup.cov_path pointing at a statistics file written from the fixture."""
+    import copy
+
+    import torch
+
+    cfg = copy.deepcopy(fix["config"])
+    st = dict(fix["stats"])
+    d = st["eigvecs"].shape[0]
+    st["cov"] = torch.zeros(d, d)   # required key (src/utils.py:64); the builder never reads it
+    path = os.path.join(str(tmp_path), "cov.pt")
+    torch.save(st, path)
+    cfg["warmup"]["cov_path"] = path
+    return cfg
 
 
 def pytest_configure(config):

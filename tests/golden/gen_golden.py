@@ -61,12 +61,49 @@ def variants():
     c = base_cfg(image_size=2048, hidden_size=128, num_attention_heads=2, num_hidden_layers=1,
                  pos_encoding_type="rope", stride_size=16)
     v["h128d64rope"] = (c, 2, "rand")
+    # input preprocessors (src/models/builder.py:43-133) on seeded covariance statistics of 256-pixel spectra
+    for name, warm in (
+        ("pre_zca_full", dict(preprocessor="zca", freeze_epochs=-1)),                           # frozen buffers
+        ("pre_zca_r32", dict(preprocessor="zca", r=32, shrinkage=0.1, freeze_epochs=0)),        # trainable, low rank
+        ("pre_pca_r128", dict(preprocessor="pca", r=128, freeze_epochs=2)),                     # image_size 256 -> 128
+        ("pre_attn_r64", dict(preprocessor="attention", r=64)),                                 # q_lin only, trainable
+    ):
+        c = base_cfg(image_size=256, patch_size=16, stride_size=16)
+        c["warmup"] = warm
+        v[name] = (c, 4, "rand")
     return v
+
+
+def cov_stats(dim: int, seed: int = 11) -> dict:
+    """Seeded stand-in for the offline covariance statistics file (src/prepca/precompute_pca.py writes mean, cov,
+    eigvals, eigvecs sorted by descending eigenvalue): smooth correlated 'spectra' so that the spectrum decays."""
+    g = torch.Generator().manual_seed(seed)
+    n = 4 * dim
+    basis = torch.randn(24, dim, generator=g).cumsum(1) / dim ** 0.5
+    X = torch.randn(n, 24, generator=g) @ basis + 0.05 * torch.randn(n, dim, generator=g) + 0.5
+    mean = X.mean(0)
+    Xc = (X - mean).double()
+    cov = (Xc.t() @ Xc / (n - 1))
+    lam, V = torch.linalg.eigh(cov)
+    lam, V = lam.flip(0).clamp_min(0).float(), V.flip(1).float().contiguous()
+    return dict(mean=mean.float(), cov=cov.float(), eigvals=lam, eigvecs=V)
 
 
 def run_variant(name, cfg, batch, kind):
     torch.manual_seed(42)
+    stats = None
+    if cfg.get("warmup"):
+        import tempfile
+
+        stats = cov_stats(cfg["model"]["image_size"])
+        tmp = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
+        torch.save(stats, tmp.name)
+        cfg = copy.deepcopy(cfg)
+        cfg["warmup"]["cov_path"] = tmp.name
     model = ref_shims.reference_get_model(cfg)
+    if stats is not None:
+        os.unlink(cfg["warmup"]["cov_path"])
+        cfg["warmup"].pop("cov_path")
     model.eval()  # dropout off; grads still flow
     spec_len = cfg["model"]["image_size"]
     x, y = synthetic_batch(batch, spec_len, seed=7, kind=kind)
@@ -82,8 +119,8 @@ def run_variant(name, cfg, batch, kind):
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
     ev = dict(loss=out.loss.detach().clone(), logits=out.logits.detach().clone(),
               hidden_states=[h[0].detach().clone() for h in out.hidden_states])
-    with torch.no_grad():
-        last = model.vit(x).last_hidden_state
+    with torch.no_grad():  # model.vit takes preprocessed pixels (src/viz/viz_callback.py:574-579)
+        last = model.vit(x if model.preprocessor is None else model.preprocessor(x)).last_hidden_state
     ev["last_hidden_cls"] = last[:, 0].clone()
 
     model.zero_grad()
@@ -110,6 +147,11 @@ def run_variant(name, cfg, batch, kind):
     fix = dict(config=copy.deepcopy(cfg), state_dict=sd0, batch=batch, x_seed=7, x_kind=kind, labels=y,
                eval=ev, grads=grads, bf16=bf, train3=tr, model_name=model.name, loss_name=model.loss_name,
                torch_version=torch.__version__)
+    if stats is not None:   # what the builder needs to rebuild the preprocessor (the covariance itself is not used)
+        fix["stats"] = {k: stats[k].clone() for k in ("mean", "eigvals", "eigvecs")}
+        fix["param_names"] = [k for k, _ in model.named_parameters()]
+        with torch.no_grad():
+            fix["eval"]["preprocessed"] = model.preprocessor(x).clone()
     path = os.path.join(OUT, f"{name}.pt")
     torch.save(fix, path)
     print(f"{name}: loss={float(ev['loss']):.6f} bf16={float(bf['loss']):.6f} name={model.name} "

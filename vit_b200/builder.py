@@ -149,9 +149,69 @@ def get_model(config: dict, precision: Any = None, device: Any = None):
                       precision=precision, device=device)
         print("[builder] Created vanilla ViT model")
         return model
-    # SURVEY.md 8(f) rank 3 ("next" row): the LinearPreprocessor / PrefilledAttention input stage
-    # (src/models/builder.py:43-133) is not part of this round's hot path.  Fail loudly instead of building a model
-    # that silently ignores the preprocessor.
-    raise NotImplementedError(
-        f"vit_b200: warmup.preprocessor={preproc_type!r} (src/models/builder.py:43-133) is not implemented yet; "
-        "only the vanilla ViT step (warmup.preprocessor: null) is available")
+    # ---- input preprocessor (builder.py:152-197) ----
+    from .preprocessor import load_cov_stats
+
+    cov_path = warmup_cfg.get("cov_path", None)
+    if cov_path is None:
+        raise ValueError(f"preprocessor='{preproc_type}' requires 'cov_path' in warmup config")
+    stats = load_cov_stats(cov_path)
+    input_dim = stats["eigvecs"].shape[0]
+    original_image_size = config["model"]["image_size"]
+    if input_dim != original_image_size:
+        raise ValueError(f"Mismatch: eigvecs dimension {input_dim} != image_size {original_image_size}")
+    freeze_epochs = warmup_cfg.get("freeze_epochs", 0)
+    preprocessor, output_dim, name_prefix, desc = build_preprocessor(
+        preproc_type, warmup_cfg, stats, input_dim, initial_freeze=freeze_epochs != 0)
+    if output_dim != original_image_size:
+        print(f"[builder] Auto-adjusting image_size: {original_image_size} -> {output_dim}")
+        config["model"]["image_size"] = output_dim
+    vit_config = get_vit_config(config)
+    print(f"[builder] Created {desc} preprocessor")
+    if freeze_epochs == -1:
+        print("[builder] Preprocessor will be PERMANENTLY FROZEN (never trained)")
+    elif freeze_epochs > 0:
+        print(f"[builder] Preprocessor will be frozen for first {freeze_epochs} epochs")
+    else:
+        print("[builder] Preprocessor is trainable from start")
+    model = MyViT(vit_config, loss_name=loss_name, model_name=f"{name_prefix}_ViT", preprocessor=preprocessor,
+                  full_config=config, precision=precision, device=device)
+    print(f"[builder] Created {model._model_name} with {preproc_type} preprocessor")
+    return model
+
+
+def build_preprocessor(preproc_type: str, warmup_cfg: dict, stats: dict, input_dim: int, initial_freeze: bool):
+    """(preprocessor, output_dim, model-name prefix, description) for warmup.preprocessor in {'zca','pca','attention'}
+    (builder.py:43-133): matrices from the covariance statistics, centering bias = -mean @ P^T unless warmup.bias is
+    false, names `ZCA{r}_fz{..}[_s{..}][_nobias]`, `PCA{r}_fz{..}[_nobias]`, `Attn{r|Full}[_scaled]_fz{..}`."""
+    from .preprocessor import LinearPreprocessor, PrefilledAttention, compute_pca_matrix, compute_zca_matrix
+
+    eigvecs = stats["eigvecs"]
+    mean = stats.get("mean", None)
+    r = warmup_cfg.get("r", None)
+    fe = warmup_cfg.get("freeze_epochs", 0)
+    fz = "perm" if fe == -1 else str(fe)
+    kind = str(preproc_type)
+    if kind in ("zca", "pca"):
+        use_bias = warmup_cfg.get("bias", True)
+        if kind == "zca":
+            eps = warmup_cfg.get("eps", 1e-5)
+            shrinkage = warmup_cfg.get("shrinkage", 0.0)
+            P = compute_zca_matrix(eigvecs, stats["eigvals"], eps=eps, r=r, shrinkage=shrinkage)
+            shrink = f"_s{int(shrinkage * 10)}" if shrinkage > 0 else ""
+            prefix = f"{'ZCA' + str(r) if r is not None else 'ZCA'}_fz{fz}{shrink}{'' if use_bias else '_nobias'}"
+            desc = f"{'low-rank' if r else 'full-rank'} ZCA, eps={eps}, shrinkage={shrinkage}, bias={use_bias}"
+        else:
+            P = compute_pca_matrix(eigvecs, r=r)
+            prefix = f"{'PCA' + str(r) if r is not None else 'PCA'}_fz{fz}{'' if use_bias else '_nobias'}"
+            desc = f"PCA with r={r}, bias={use_bias}" if r else f"full-rank PCA, bias={use_bias}"
+        bias = -mean @ P.t() if (use_bias and mean is not None) else None   # y = (x - mean) P^T
+        return LinearPreprocessor(P, bias=bias, freeze=initial_freeze), P.shape[0], prefix, desc
+    if kind == "attention":
+        eigvals = stats.get("eigvals", None)
+        scale = warmup_cfg.get("scale_by_eigvals", True)
+        pre = PrefilledAttention(input_dim=input_dim, eigvecs=eigvecs, eigvals=eigvals, r=r, scale_by_eigvals=scale,
+                                 eps=warmup_cfg.get("eps", 1e-5))
+        prefix = f"Attn{r if r else 'Full'}{'_scaled' if scale and eigvals is not None else ''}_fz{fz}"
+        return pre, (r if r is not None else input_dim), prefix, f"Attention preprocessor with r={r}, scale_by_eigvals={scale}"
+    raise ValueError(f"Unknown preprocessor type: '{preproc_type}'")

@@ -595,6 +595,21 @@ class ViTEngine:
         self.dlogits.copy_(dlogits.reshape(self.dlogits.shape))
         self._run(key, lambda: None)
 
+    def pixel_grad(self, train: bool) -> torch.Tensor:
+        """d loss / d pixel_values [B, L] (fp32) of the backward that just ran: the embedding kernels' input gradient,
+        needed only when a trainable preprocessor (src/models/layers.py:51-60) produced the pixels.  Both backward
+        programs leave d loss / d z0 in `dzA`; the dropout mask of the embedding site is regenerated from the same
+        (seed, step)."""
+        c = self.cfg
+        dx = torch.empty(self.B, c.image_size, dtype=torch.float32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        ph = float(c.hidden_dropout_prob) if train else 0.0
+        _lib.check(self.lib.vitb200_patch_embed_dgrad(
+            self.dzA.data_ptr(), self._w("vit.embeddings.patch_embeddings.projection.weight"), dx.data_ptr(), self.B,
+            c.image_size, c.patch_size, c.stride, c.num_patches, c.n_valid, c.hidden_size, ph, self.rng.data_ptr(),
+            SITE_EMB, self.dt, st), "patch_embed_dgrad")
+        return dx
+
     def _ensure_opt_state(self):
         if self.exp_avg is None:
             n = self.arena.layout.n_total

@@ -281,6 +281,7 @@ class _FusedViTFunction(torch.autograd.Function):
         ctx.token = eng._fwd_token
         ctx.has_labels = labels is not None
         ctx.n_params = len(params)
+        ctx.want_dx = bool(ctx.needs_input_grad[2])   # a trainable input preprocessor sits in front of the encoder
         loss = eng.loss[0].clone() if labels is not None else eng.loss.new_zeros(())
         return loss, eng.logits.clone()
 
@@ -307,7 +308,8 @@ class _FusedViTFunction(torch.autograd.Function):
         for n in ctx.names:
             e = lay.entries[n]
             grads.append(flat[e.offset:e.offset + e.numel].view(e.shape) if e.offset < lay.n_opt else None)
-        return (None, None, None, None, None, None, *grads)
+        dx = eng.pixel_grad(ctx.train) if ctx.want_dx else None
+        return (None, None, dx, None, None, None, *grads)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -346,6 +348,8 @@ class MyViT(nn.Module):
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self._bind_arena(ParamArena(self._layout, device, with_shadow=True), init=True)
+        if self.preprocessor is not None:
+            self.preprocessor.to(device)
         for m in self.modules():
             m.__dict__["_owner"] = self
 
@@ -357,6 +361,12 @@ class MyViT(nn.Module):
     @property
     def loss_name(self):
         return self._loss_name
+
+    @property
+    def input_dim(self) -> int:
+        """Length of the raw spectra `forward` takes: the preprocessor's input size, else config.image_size."""
+        pre = self.preprocessor
+        return int(pre.in_features) if pre is not None and hasattr(pre, "in_features") else int(self.config.image_size)
 
     def compute_loss(self, *args, **kwargs):
         return self.forward(*args, **kwargs).loss
@@ -423,6 +433,16 @@ class MyViT(nn.Module):
                 w = torch.empty(p.shape)
                 nn.init.trunc_normal_(w, mean=0.0, std=std)
                 p.copy_(w)
+        if self.preprocessor is not None:
+            # Reference quirk, reproduced on purpose: MyViT.__init__ ends with self.init_weights() (specvit.py:57), and HF's
+            # _init_weights reaches EVERY nn.Linear below MyViT -- including PrefilledAttention's q_lin / k_lin / v_lin, whose
+            # eigenvector prefill (attention.py:58-72) is therefore overwritten by trunc_normal(0, 0.02).  PrefilledLinear
+            # (ZCA / PCA) is not an nn.Linear and keeps its matrix.
+            for mod in self.preprocessor.modules():
+                if isinstance(mod, nn.Linear):
+                    nn.init.trunc_normal_(mod.weight, mean=0.0, std=std)
+                    if mod.bias is not None:
+                        mod.bias.zero_()
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn)
@@ -453,10 +473,14 @@ class MyViT(nn.Module):
         return eng
 
     def _stage_inputs(self, eng: ViTEngine, x: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
+        """(already preprocessed) pixels and labels -> the engine's input buffers."""
         c = self.config
         if x.dim() != 2 or x.shape[1] != c.image_size:
             raise ValueError(f"expected pixel_values of shape [B, {c.image_size}], got {tuple(x.shape)}")
         eng.x.copy_(x, non_blocking=True)
+        self._stage_labels(eng, labels)
+
+    def _stage_labels(self, eng: ViTEngine, labels: Optional[torch.Tensor]) -> None:
         if labels is not None:
             if self._loss_kind == _lib.LOSS_CE:
                 eng.labels.copy_(labels.reshape(-1), non_blocking=True)
@@ -465,6 +489,36 @@ class MyViT(nn.Module):
                 if lab.numel() != eng.labels.numel():
                     raise ValueError(f"labels have {lab.numel()} elements, expected {eng.labels.numel()}")
                 eng.labels.copy_(lab, non_blocking=True)  # copy_ casts to float like labels.view(-1).float()
+
+    def _raw_buffer(self, eng: ViTEngine) -> torch.Tensor:
+        """Where RAW spectra go for `eng`: the pixel buffer itself, or -- with a (frozen) preprocessor in front -- a
+        [B, input_dim] staging buffer that `preprocessor.forward_into(raw, eng.x)` turns into pixels."""
+        pre = self.preprocessor
+        if pre is None:
+            return eng.x
+        if not hasattr(pre, "forward_into"):
+            raise NotImplementedError(f"vit_b200: no kernel path for preprocessor {type(pre).__name__}")
+        if not pre.is_frozen:
+            raise NotImplementedError(
+                "vit_b200: TrainStep/EvalStep run a FROZEN preprocessor (warmup.freeze_epochs != 0 or "
+                "model.set_preprocessor_trainable(False)); train an unfrozen one through MyViT.forward / ViTLModule "
+                "with a torch optimizer (its matrix lives outside the fused parameter arena)")
+        raw = eng.__dict__.get("x_raw")
+        if raw is None:
+            raw = eng.x_raw = torch.empty(eng.B, self.input_dim, dtype=torch.float32, device=eng.device)
+        return raw
+
+    def _stage_raw(self, eng: ViTEngine, x: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
+        """RAW spectra -> [frozen preprocessor GEMM ->] the engine's pixel buffer (TrainStep / EvalStep, which drive the
+        engine without autograd).  A trainable preprocessor needs autograd through MyViT.forward instead."""
+        if self.preprocessor is None:
+            return self._stage_inputs(eng, x, labels)
+        raw = self._raw_buffer(eng)
+        if x.dim() != 2 or x.shape[1] != self.input_dim:
+            raise ValueError(f"expected spectra of shape [B, {self.input_dim}], got {tuple(x.shape)}")
+        raw.copy_(x, non_blocking=True)
+        self.preprocessor.forward_into(raw, eng.x)
+        self._stage_labels(eng, labels)
 
     def _has_inner_hooks(self) -> bool:
         for m in self.modules():

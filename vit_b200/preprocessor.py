@@ -1,0 +1,366 @@
+"""Input preprocessors of the reference (SURVEY.md 8a rows a2/a2', 8f rank 3) on the B200 kernels.
+
+Same classes, attribute names and `state_dict` keys as the reference:
+
+  * `compute_zca_matrix`, `compute_pca_matrix`   src/models/preprocessor.py:12-90   (one-time, at model build)
+  * `PrefilledLinear`                            src/models/layers.py:12-63        (buffer when frozen, Parameter when not)
+  * `LinearPreprocessor`                         src/models/preprocessor.py:93-111
+  * `PrefilledAttention`                         src/models/attention.py:13-124    (2-D inputs: `q_lin(x)` only)
+  * `load_cov_stats`                             src/utils.py:17-71
+
+The per-step work -- `x @ P^T + b` on `[B, D_in]` -- runs on `vitb200_linear_fwd` (fp32: SIMT fp32 GEMM; bf16-mixed: the
+tcgen05/TMA GEMM on a bf16 copy of the matrix, bf16 output widened to the fp32 pixel buffer, as autocast does), and for a
+trainable preprocessor `vitb200_linear_wgrad` / `vitb200_linear_dgrad` in backward.  There is no PyTorch fallback: CPU
+tensors raise.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ACT_NONE, BF16, F32
+
+__all__ = ["LinearPreprocessor", "PrefilledLinear", "PrefilledAttention", "compute_zca_matrix", "compute_pca_matrix",
+           "load_cov_stats", "clear_cov_cache"]
+
+
+# ----------------------------------------------------------------------------------------------
+# statistics -> matrices (host side, once per model build)
+# ----------------------------------------------------------------------------------------------
+def compute_zca_matrix(eigvecs: torch.Tensor, eigvals: torch.Tensor, eps: float = 1e-5, r: int | None = None,
+                       shrinkage: float = 0.1) -> torch.Tensor:
+    """ZCA whitening matrix (preprocessor.py:12-72).  Full rank: V diag((lam_hat + eps)^-1/2) V^T.  Low rank r:
+    (Vr * (lam_hat_r + eps)^-1/2) Vr^T + s_perp (I - Vr Vr^T) with s_perp from the median tail eigenvalue, floored at
+    1e-3 x the mean of the leading r."""
+    lam = eigvals
+    if shrinkage > 0.0:
+        lam = (1.0 - shrinkage) * eigvals + shrinkage * eigvals.mean()
+    if r is None:
+        return eigvecs @ torch.diag(1.0 / torch.sqrt(lam + eps)) @ eigvecs.t()
+    Vr = eigvecs[:, :r]
+    inv_sqrt_r = torch.rsqrt(lam[:r] + eps)
+    tail = lam[r:]
+    lam0 = tail.median() if tail.numel() > 0 else lam[r - 1]
+    lam0 = torch.clamp(lam0, min=1e-3 * lam[:r].mean())
+    s_perp = 1.0 / torch.sqrt(lam0 + eps)
+    D = eigvecs.shape[0]
+    eye = torch.eye(D, dtype=eigvecs.dtype, device=eigvecs.device)
+    return (Vr * inv_sqrt_r) @ Vr.t() + s_perp * (eye - Vr @ Vr.t())
+
+
+def compute_pca_matrix(eigvecs: torch.Tensor, r: int | None = None) -> torch.Tensor:
+    """PCA projection V[:, :r]^T (preprocessor.py:75-90)."""
+    return eigvecs.t() if r is None else eigvecs[:, :r].t()
+
+
+_COV_CACHE: Dict[Path, dict] = {}
+
+
+def load_cov_stats(cov_path) -> dict:
+    """src/utils.py:17-71: a torch-saved dict with 'mean', 'cov', 'eigvals', 'eigvecs' (cached per path)."""
+    path = Path(cov_path).resolve()
+    if path in _COV_CACHE:
+        return _COV_CACHE[path]
+    if not path.exists():
+        raise FileNotFoundError(f"Covariance file not found: {path}")
+    stats = torch.load(path, map_location="cpu", weights_only=True)
+    if not isinstance(stats, dict):
+        raise ValueError(f"Expected dict from {cov_path}, got {type(stats)}")
+    missing = {"mean", "cov", "eigvals", "eigvecs"} - set(stats.keys())
+    if missing:
+        raise ValueError(f"Missing required keys in {cov_path}: {missing}")
+    _COV_CACHE[path] = stats
+    return stats
+
+
+def clear_cov_cache() -> None:
+    _COV_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# the GEMM on the device
+# ----------------------------------------------------------------------------------------------
+def _precision_of(mod: nn.Module) -> str:
+    owner = mod.__dict__.get("_owner")
+    return getattr(owner, "precision", None) or mod.__dict__.get("_precision", "fp32")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def _bf16_copy(mod: nn.Module, weight: torch.Tensor) -> torch.Tensor:
+    """bf16 GEMM operand of the matrix, refreshed when the fp32 tensor was written (optimizer step, load_state_dict,
+    .to()): keyed by storage pointer + version counter, like the parameter arena's shadow."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    cached = mod.__dict__.get("_w16")
+    if cached is None or cached[0] != key:
+        w32 = _aligned(weight.detach().to(torch.float32))
+        w16 = torch.empty(w32.shape, dtype=torch.bfloat16, device=w32.device)
+        _lib.check(_lib.load().vitb200_cast_bf16(w32.data_ptr(), w16.data_ptr(), w32.numel(), _stream(w32)), "cast_bf16")
+        cached = (key, w16)
+        mod.__dict__["_w16"] = cached
+    return cached[1]
+
+
+def _check_input(x: torch.Tensor, weight: torch.Tensor) -> None:
+    if not x.is_cuda or not weight.is_cuda:
+        raise RuntimeError("vit_b200 has no CPU path: the preprocessor and its input must live on a CUDA (sm_100a) device")
+    if x.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise ValueError(f"expected input of shape [B, {weight.shape[1]}], got {tuple(x.shape)}")
+    if weight.shape[0] % 4 or weight.shape[1] % 4:
+        raise ValueError("vit_b200 preprocessor: input and output dimensions must be multiples of 4")
+
+
+def linear_forward(mod: nn.Module, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                   out: Optional[torch.Tensor] = None):
+    """y[B, N] (fp32) = x[B, K] . weight[N, K]^T + bias.  Returns (y, x_operand) -- the operand copy of x is what backward
+    needs.  `out`: write into this fp32 [B, N] buffer (the engine's pixel buffer) instead of allocating."""
+    _check_input(x, weight)
+    lib = _lib.load()
+    B, K = x.shape
+    N = weight.shape[0]
+    st = _stream(x)
+    xin = _aligned(x.detach().to(torch.float32))
+    y = out if out is not None else torch.empty(B, N, dtype=torch.float32, device=x.device)
+    bptr = None if bias is None else _aligned(bias.detach().to(torch.float32)).data_ptr()
+    if _precision_of(mod) == "bf16":
+        xb = torch.empty(B, K, dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.vitb200_cast_bf16(xin.data_ptr(), xb.data_ptr(), B * K, st), "cast_bf16")
+        wb = _bf16_copy(mod, weight)
+        yb = torch.empty(B, N, dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.vitb200_linear_fwd(xb.data_ptr(), wb.data_ptr(), bptr, yb.data_ptr(), None, B, N, K, ACT_NONE, BF16,
+                                          st), "preprocessor linear_fwd")
+        _lib.check(lib.vitb200_cast_f32(yb.data_ptr(), y.data_ptr(), B * N, st), "cast_f32")
+        return y, xb
+    w32 = _aligned(weight.detach().to(torch.float32))
+    _lib.check(lib.vitb200_linear_fwd(xin.data_ptr(), w32.data_ptr(), bptr, y.data_ptr(), None, B, N, K, ACT_NONE, F32, st),
+               "preprocessor linear_fwd")
+    return y, xin
+
+
+class _PreLinearFunction(torch.autograd.Function):
+    """Autograd node of a TRAINABLE preprocessor matrix: dW = dy^T x, db = column sums of dy (vitb200_linear_wgrad) and,
+    if the raw input itself requires a gradient, dx = dy W (vitb200_linear_dgrad)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, weight, bias):
+        y, x_op = linear_forward(mod, x, weight, bias)
+        ctx.mod, ctx.x_op = mod, x_op
+        ctx.save_for_backward(weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mod = ctx.mod
+        (weight,) = ctx.saved_tensors
+        lib = _lib.load()
+        x_op = ctx.x_op
+        B, K = x_op.shape
+        N = weight.shape[0]
+        st = _stream(dy)
+        bf = x_op.dtype == torch.bfloat16
+        dt = BF16 if bf else F32
+        dy32 = _aligned(dy.to(torch.float32))
+        if bf:
+            dy_op = torch.empty(B, N, dtype=torch.bfloat16, device=dy.device)
+            _lib.check(lib.vitb200_cast_bf16(dy32.data_ptr(), dy_op.data_ptr(), B * N, st), "cast_bf16")
+        else:
+            dy_op = dy32
+        dw = db = dx = None
+        if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+            ws = mod.__dict__.get("_wgrad_ws")
+            need = int(lib.vitb200_linear_wgrad_ws_bytes(B, N, K)) + 4096
+            if ws is None or ws.numel() < need or ws.device != dy.device:
+                ws = torch.zeros(need, dtype=torch.uint8, device=dy.device)
+                mod.__dict__["_wgrad_ws"] = ws
+            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+            db = torch.empty(N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            _lib.check(lib.vitb200_linear_wgrad(dy_op.data_ptr(), x_op.data_ptr(), dw.data_ptr(),
+                                                None if db is None else db.data_ptr(), B, N, K, 0, dt, ws.data_ptr(), st),
+                       "preprocessor linear_wgrad")
+            if not ctx.needs_input_grad[2]:
+                dw = None
+            if not (ctx.has_bias and ctx.needs_input_grad[3]):
+                db = None
+        if ctx.needs_input_grad[1]:
+            w_op = _bf16_copy(mod, weight) if bf else _aligned(weight.detach().to(torch.float32))
+            dx_op = torch.empty(B, K, dtype=x_op.dtype, device=dy.device)
+            _lib.check(lib.vitb200_linear_dgrad(dy_op.data_ptr(), w_op.data_ptr(), None, dx_op.data_ptr(), B, N, K, dt, st),
+                       "preprocessor linear_dgrad")
+            if bf:
+                dx = torch.empty(B, K, dtype=torch.float32, device=dy.device)
+                _lib.check(lib.vitb200_cast_f32(dx_op.data_ptr(), dx.data_ptr(), B * K, st), "cast_f32")
+            else:
+                dx = dx_op
+        return None, dx, dw, db
+
+
+def _apply_linear(mod: nn.Module, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    needs = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                         (bias is not None and bias.requires_grad))
+    if needs:
+        return _PreLinearFunction.apply(mod, x, weight, bias)
+    return linear_forward(mod, x, weight, bias)[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# modules (reference surface)
+# ----------------------------------------------------------------------------------------------
+class PrefilledLinear(nn.Module):
+    """Linear layer initialised from a matrix (ZCA, PCA, ...), optional centering bias (layers.py:12-63).  Frozen: weight
+    and bias are buffers; unfrozen: Parameters -- `freeze()` converts between the two at run time (layers.py:36-60)."""
+
+    def __init__(self, matrix: torch.Tensor, bias: torch.Tensor | None = None, freeze: bool = True) -> None:
+        super().__init__()
+        weight = matrix.to(torch.float32)
+        if freeze:
+            self.register_buffer("weight", weight)
+            self._is_frozen = True
+        else:
+            self.weight = nn.Parameter(weight)
+            self._is_frozen = False
+        if bias is not None:
+            bias = bias.to(torch.float32)
+            if freeze:
+                self.register_buffer("bias", bias)
+            else:
+                self.bias = nn.Parameter(bias)
+        else:
+            self.register_buffer("bias", None)
+
+    @property
+    def in_features(self) -> int:
+        return self.weight.shape[1]
+
+    @property
+    def out_features(self) -> int:
+        return self.weight.shape[0]
+
+    def freeze(self, freeze: bool = True) -> None:
+        if freeze and not self._is_frozen:
+            weight_data = self.weight.data.clone()
+            del self.weight
+            self.register_buffer("weight", weight_data)
+            if hasattr(self, "bias") and isinstance(self.bias, nn.Parameter):
+                bias_data = self.bias.data.clone()
+                del self.bias
+                self.register_buffer("bias", bias_data)
+            self._is_frozen = True
+        elif not freeze and self._is_frozen:
+            weight_data = self.weight.clone()
+            delattr(self, "weight")
+            self.weight = nn.Parameter(weight_data)
+            if self.bias is not None:
+                bias_data = self.bias.clone()
+                delattr(self, "bias")
+                self.bias = nn.Parameter(bias_data)
+            self._is_frozen = False
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _apply_linear(self, x, self.weight, self.bias)
+
+
+class LinearPreprocessor(nn.Module):
+    """x -> x P^T + bias: ZCA whitening (P [D, D]) or PCA projection (P [r, D]) (preprocessor.py:93-111)."""
+
+    def __init__(self, matrix: torch.Tensor, bias: torch.Tensor | None = None, freeze: bool = True) -> None:
+        super().__init__()
+        self.linear = PrefilledLinear(matrix, bias=bias, freeze=freeze)
+
+    @property
+    def in_features(self) -> int:
+        return self.linear.in_features
+
+    @property
+    def out_features(self) -> int:
+        return self.linear.out_features
+
+    @property
+    def is_frozen(self) -> bool:
+        return self.linear._is_frozen
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.linear(x)
+
+    def forward_into(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        """No-grad forward straight into the engine's pixel buffer (TrainStep / EvalStep with a frozen preprocessor)."""
+        linear_forward(self.linear, x, self.linear.weight, self.linear.bias, out=out)
+
+    def freeze(self, freeze: bool = True) -> None:
+        self.linear.freeze(freeze)
+
+
+class _KernelLinear(nn.Linear):
+    """nn.Linear parameter holder whose forward runs the vit_b200 GEMM (bias-free q_lin of PrefilledAttention)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _apply_linear(self, x, self.weight, self.bias)
+
+
+class PrefilledAttention(nn.Module):
+    """Attention layer whose query/key projections are prefilled from an eigenbasis (attention.py:13-124).  The model feeds
+    it 2-D inputs `[B, D]`, for which the reference evaluates `q_lin(x)` only (attention.py:81-82); `k_lin` / `v_lin` exist
+    for `state_dict` compatibility (and get the reference's initialisation), the 3-D attention branch is not on this path."""
+
+    def __init__(self, input_dim: int, eigvecs: torch.Tensor, eigvals: torch.Tensor | None = None, r: int | None = None,
+                 low_rank: bool | None = None, scale_by_eigvals: bool = True, eps: float = 1e-5) -> None:
+        super().__init__()
+        self.input_dim = input_dim
+        self.r = r if r is not None else eigvecs.shape[1]
+        self.low_rank = low_rank if low_rank is not None else (self.r < input_dim)
+        self.scale_by_eigvals = scale_by_eigvals and eigvals is not None
+        out = self.r if self.low_rank else input_dim
+        self.q_lin = _KernelLinear(input_dim, out, bias=False)
+        self.k_lin = nn.Linear(input_dim, out, bias=False)
+        self.v_lin = nn.Linear(input_dim, input_dim, bias=False)
+        V = eigvecs[:, :self.r].t().contiguous()
+        if self.scale_by_eigvals:
+            V = V * torch.rsqrt(eigvals[:self.r] + eps).unsqueeze(1)
+        with torch.no_grad():
+            for layer in (self.q_lin, self.k_lin):
+                if self.low_rank:
+                    layer.weight.copy_(V)
+                else:
+                    layer.weight.zero_()
+                    layer.weight[:V.shape[0], :].copy_(V)
+        nn.init.kaiming_uniform_(self.v_lin.weight, a=math.sqrt(5))
+        self.softmax = nn.Softmax(dim=-1)
+
+    @property
+    def in_features(self) -> int:
+        return self.input_dim
+
+    @property
+    def out_features(self) -> int:
+        return self.q_lin.weight.shape[0]
+
+    @property
+    def is_frozen(self) -> bool:
+        return not self.q_lin.weight.requires_grad
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 2:
+            return self.q_lin(x)
+        raise NotImplementedError("vit_b200: PrefilledAttention is only evaluated on 2-D inputs [B, D] by the model "
+                                  "(src/models/attention.py:81-82); the 3-D attention branch is not on the hot path")
+
+    def forward_into(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        linear_forward(self.q_lin, x, self.q_lin.weight, None, out=out)
+
+    def set_qk_trainable(self, trainable: bool = True) -> None:
+        for p in self.q_lin.parameters():
+            p.requires_grad = trainable
+        for p in self.k_lin.parameters():
+            p.requires_grad = trainable

@@ -39,7 +39,7 @@ class TrainStep:
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         c = model.config
-        self.h_x = torch.empty(batch_size, c.image_size, dtype=torch.float32, pin_memory=True)
+        self.h_x = torch.empty(batch_size, model.input_dim, dtype=torch.float32, pin_memory=True)
         self.h_y = torch.empty(self.eng.labels.shape, dtype=self.eng.labels.dtype, pin_memory=True)
         self.h_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
         self._segments = None
@@ -139,15 +139,57 @@ class TrainStep:
         if self.noise_level > 0 and error is not None:  # src/vit.py:86-88
             flux = flux.to(eng.device, non_blocking=True)
             flux = flux + torch.randn_like(flux) * error.to(eng.device, non_blocking=True) * self.noise_level
-        self.model._stage_inputs(eng, flux, labels)
+        self.model._stage_raw(eng, flux, labels)
+        self._run_staged()
+        return eng.loss[0]
+
+    def _run_staged(self) -> None:
+        """One step on the inputs already sitting in the engine's buffers."""
         if self.use_graph:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
         else:
-            eng.refresh_shadow()
+            self.eng.refresh_shadow()
             self._launch()
-        return eng.loss[0]
+
+    def fit_device(self, dataset, epochs: int = 1, shuffle: bool = True, seed: int = 0, tail: str = "wrap",
+                   start_epoch: int = 0) -> list:
+        """The training loop over a DEVICE-resident dataset (`vit_b200.data.DeviceDataset`): per step
+        one gather kernel assembles the batch (row gather by the epoch's permutation, noise injection when
+        noise_level > 0, labels) directly in the engine's input buffers, then the step graph runs; the loss of every
+        step is kept on the device.  No host<->device traffic and no host synchronisation inside an epoch.  Data-parallel
+        runs take rank r's share of the permutation (DistributedSampler semantics, vit_b200.data.epoch_indices).
+        Returns one device tensor of per-step losses per epoch."""
+        from .data import epoch_indices
+
+        eng, model = self.eng, self.model
+        if dataset.length != model.input_dim:
+            raise ValueError(f"dataset spectra have {dataset.length} pixels, the model expects {model.input_dim}")
+        if dataset.labels is None:
+            raise ValueError("fit_device needs a dataset with labels")
+        pre = model.preprocessor
+        x_dst = model._raw_buffer(eng)    # eng.x, or the staging buffer in front of a frozen preprocessor
+        rank = 0
+        if self.world > 1:
+            import torch.distributed as dist
+
+            rank = dist.get_rank(self.group)
+        out = []
+        B = self.B
+        for ep in range(start_epoch, start_epoch + epochs):
+            order = epoch_indices(len(dataset), ep, seed=seed, shuffle=shuffle, rank=rank, world=self.world, batch=B,
+                                  tail=tail).to(eng.device, non_blocking=True)
+            nb = order.numel() // B
+            losses = torch.empty(nb, dtype=torch.float32, device=eng.device)
+            for i in range(nb):
+                dataset.gather(order[i * B:(i + 1) * B], x_dst, eng.labels, noise_level=self.noise_level, rng=eng.rng)
+                if pre is not None:
+                    pre.forward_into(x_dst, eng.x)
+                self._run_staged()
+                losses[i:i + 1].copy_(eng.loss, non_blocking=True)
+            out.append(losses)
+        return out
 
     def _pinned(self, flux_host: torch.Tensor, labels_host: torch.Tensor, slot_x: torch.Tensor, slot_y: torch.Tensor):
         """Host batch -> page-locked memory (batches that already are pinned, e.g. from a DataLoader with
@@ -190,9 +232,9 @@ class TrainStep:
             c = self.model.config
             self._pipe = dict(
                 copy=torch.cuda.Stream(device=dev),
-                d_x=[torch.empty(self.B, c.image_size, dtype=torch.float32, device=dev) for _ in range(2)],
+                d_x=[torch.empty(self.B, self.model.input_dim, dtype=torch.float32, device=dev) for _ in range(2)],
                 d_y=[torch.empty_like(eng.labels) for _ in range(2)],
-                h_x=[torch.empty(self.B, c.image_size, dtype=torch.float32, pin_memory=True) for _ in range(2)],
+                h_x=[torch.empty(self.B, self.model.input_dim, dtype=torch.float32, pin_memory=True) for _ in range(2)],
                 h_y=[torch.empty(eng.labels.shape, dtype=eng.labels.dtype, pin_memory=True) for _ in range(2)],
                 h_loss=[torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(2)],
                 ev_in=[torch.cuda.Event() for _ in range(2)],     # staging slot filled (copy stream)
@@ -252,6 +294,7 @@ class TrainStep:
         return 4
 
     def set_lr(self, lr: float) -> None:
+        self.model._opt_hyper["lr"] = float(lr)
         self.eng.set_lr(lr)
 
     def close(self) -> None:
@@ -274,37 +317,50 @@ class TrainStep:
 
 
 class EvalStep:
-    """scripts/test.py semantics: model.eval(), no_grad, forward only (one forward per batch)."""
+    """scripts/test.py semantics: model.eval(), no_grad, forward only -- ONE forward per batch (the reference's
+    validation/test steps run the model twice per batch, src/vit.py:127-150,194-215) with the metrics accumulated on the
+    device (`evaluate`)."""
 
     def __init__(self, model: MyViT, batch_size: int, use_graph: bool = True):
         self.model = model
         self.eng = model._engine(batch_size)
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = {}
         c = model.config
-        self.h_x = torch.empty(batch_size, c.image_size, dtype=torch.float32, pin_memory=True)
+        self.h_x = torch.empty(batch_size, model.input_dim, dtype=torch.float32, pin_memory=True)
         self.h_logits = torch.empty(batch_size, c.num_labels, dtype=torch.float32, pin_memory=True)
 
-    def forward(self, flux: torch.Tensor) -> torch.Tensor:
+    @property
+    def graph(self):
+        return self.graphs.get(False)
+
+    def _run(self, with_labels: bool) -> None:
         eng = self.eng
-        self.model._stage_inputs(eng, flux, None)
-        if self.use_graph:
-            if self.graph is None:
-                eng.refresh_shadow()
-                side = torch.cuda.Stream(device=eng.device)
-                side.wait_stream(torch.cuda.current_stream(eng.device))
-                with torch.cuda.stream(side):
-                    eng.forward(train=False, with_labels=False)
-                torch.cuda.current_stream(eng.device).wait_stream(side)
-                torch.cuda.synchronize(eng.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    eng.forward(train=False, with_labels=False)
-                self.graph = g
-            self.graph.replay()
+        if not self.use_graph:
+            eng.forward(train=False, with_labels=with_labels)
+            return
+        g = self.graphs.get(with_labels)
+        if g is None:
+            eng.refresh_shadow()
+            side = torch.cuda.Stream(device=eng.device)
+            side.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side):
+                eng.forward(train=False, with_labels=with_labels)
+            torch.cuda.current_stream(eng.device).wait_stream(side)
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                eng.forward(train=False, with_labels=with_labels)
+            self.graphs[with_labels] = g
         else:
-            eng.forward(train=False, with_labels=False)
-        return eng.logits
+            eng.refresh_shadow()
+        g.replay()
+
+    def forward(self, flux: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Logits [B, num_labels] (device, no host sync); with labels the loss is left in `eng.loss`."""
+        self.model._stage_raw(self.eng, flux, labels)
+        self._run(labels is not None)
+        return self.eng.logits
 
     def forward_host(self, flux_host: torch.Tensor) -> torch.Tensor:
         self.h_x.copy_(flux_host)
@@ -312,3 +368,43 @@ class EvalStep:
         self.h_logits.copy_(logits, non_blocking=True)
         torch.cuda.current_stream(self.eng.device).synchronize()
         return self.h_logits
+
+    def evaluate(self, dataset, return_preds: bool = True) -> dict:
+        """One pass over a device-resident dataset in order: loss, MAE / MSE / R2 (regression) or accuracy
+        (classification) accumulated on the device, predictions kept on the device; ONE host read at the end.  The last
+        partial batch runs on a second engine of that size (no padding, so the metrics are exact)."""
+        from .data import EvalMetrics
+
+        model, eng = self.model, self.eng
+        if dataset.labels is None:
+            raise ValueError("evaluate needs a dataset with labels")
+        if dataset.length != model.input_dim:
+            raise ValueError(f"dataset spectra have {dataset.length} pixels, the model expects {model.input_dim}")
+        N, B, C = len(dataset), eng.B, model.config.num_labels
+        dev = eng.device
+        is_cls = model.task_type == "cls"
+        metrics = EvalMetrics(C, is_cls, dev)
+        preds = torch.empty(N, C, dtype=torch.float32, device=dev) if return_preds else None
+        idx = torch.arange(N, dtype=torch.int64, device=dev)
+        pre = model.preprocessor
+
+        def run(step: "EvalStep", lo: int, hi: int) -> None:
+            e = step.eng
+            dst = model._raw_buffer(e)
+            dataset.gather(idx[lo:hi], dst, e.labels)
+            if pre is not None:
+                pre.forward_into(dst, e.x)
+            step._run(True)
+            metrics.update(e.logits, e.labels, e.loss)
+            if preds is not None:
+                preds[lo:hi].copy_(e.logits, non_blocking=True)
+
+        nb = N // B
+        for i in range(nb):
+            run(self, i * B, (i + 1) * B)
+        if N - nb * B:
+            run(EvalStep(model, N - nb * B, use_graph=False), nb * B, N)
+        out = metrics.compute()
+        out["preds"] = preds
+        out["labels"] = dataset.labels
+        return out
