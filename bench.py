@@ -578,6 +578,69 @@ def main():
             except Exception as ex:  # noqa: BLE001
                 other[name] = {"error": str(ex)[:200]}
 
+    # ---- rows either side of the step: device-resident hand-off, frozen ZCA stage, on-device evaluation ----
+    if other is not None:
+        from vit_b200.data import DeviceDataset
+        from vit_b200.step import EvalStep
+
+        def ev_timed(fn):
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            r = fn()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1), r
+
+        try:   # one epoch over a device-resident dataset: gather kernel + step graph per batch, no host traffic
+            nds = 12800
+            gd = torch.Generator(device="cpu").manual_seed(7)
+            ds = DeviceDataset(torch.rand(nds, 4096, generator=gd), torch.rand(nds, generator=gd), device=dev)
+            m3 = get_model(json.loads(json.dumps(BASELINE_CFG)), precision=args.precision, device=dev).train()
+            s3 = TrainStep(m3, B, use_graph=not args.no_graph, train=True)
+            s3.fit_device(ds, epochs=1, seed=0)
+            ms3, _ = ev_timed(lambda: s3.fit_device(ds, epochs=1, seed=1, start_epoch=1))
+            other["fit_device_resident_dataset_b64"] = {"samples_per_s": nds * 1e3 / ms3, "ms_per_step": ms3 / (nds // B),
+                                                        "dataset_mb": ds.nbytes / 1e6, "steps": nds // B}
+            e3 = EvalStep(m3.eval(), 1024, use_graph=not args.no_graph)
+            e3.evaluate(ds, return_preds=True)
+            ms4, r4 = ev_timed(lambda: e3.evaluate(ds, return_preds=True))
+            other["evaluate_on_device_metrics_b1024"] = {"samples_per_s": nds * 1e3 / ms4, "ms": ms4, "n": r4["n"],
+                                                         "mae": r4.get("mae"), "r2": r4.get("r2")}
+            del ds, m3, s3, e3
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            other["fit_device_resident_dataset_b64"] = {"error": str(ex)[:200]}
+        try:   # frozen 4096 x 4096 ZCA-shaped preprocessor in front of the same model (2.1 GFLOP / step at B = 64)
+            from vit_b200.builder import get_vit_config
+            from vit_b200.model import MyViT
+            from vit_b200.preprocessor import LinearPreprocessor
+
+            gd = torch.Generator(device="cpu").manual_seed(8)
+            Pm = torch.randn(4096, 4096, generator=gd) / 64.0
+            cz = json.loads(json.dumps(BASELINE_CFG))
+            m5 = MyViT(get_vit_config(cz), loss_name="mae", model_name="ZCA_fzperm_ViT",
+                       preprocessor=LinearPreprocessor(Pm, bias=torch.zeros(4096), freeze=True), full_config=cz,
+                       precision=args.precision, device=dev).train()
+            s5 = TrainStep(m5, B, use_graph=not args.no_graph, train=True)
+            x5 = torch.rand(B, 4096, device=dev); y5 = torch.rand(B, device=dev)
+            ms5 = timed(lambda: s5.step(x5, y5), 50)
+            raw = m5._raw_buffer(s5.eng)
+            # device time of the preprocessor alone: 20 back-to-back calls in one CUDA graph (no host launch overhead)
+            g5 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g5):
+                for _ in range(20):
+                    m5.preprocessor.forward_into(raw, s5.eng.x)
+            ms6 = timed(g5.replay, 10) / 20
+            wbytes = 4096 * 4096 * (2 if "bf16" in args.precision else 4)
+            other["zca4096_frozen_train_b64"] = {"samples_per_s": B * 1e3 / ms5, "ms": ms5, "preprocessor_ms": ms6,
+                                                 "preprocessor_gbs": wbytes / (ms6 * 1e-3) / 1e9,
+                                                 "preprocessor_tflops": 2.0 * B * 4096 * 4096 / (ms6 * 1e-3) / 1e12}
+            del m5, s5, Pm
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            other["zca4096_frozen_train_b64"] = {"error": str(ex)[:200]}
+
     line = {
         "metric": "train samples/sec (baseline.yaml shape)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

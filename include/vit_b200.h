@@ -372,6 +372,14 @@ int vitb200_residual_add(const float* z, const void* delta, float* out, size_t n
  * src/models/attention.py:81-82) is vitb200_linear_fwd on [B, D_in] x [D_out, D_in]^T; in BF16 mode its bf16 output is
  * widened with this call into the fp32 pixel buffer the embedding kernels read. */
 int vitb200_cast_f32(const void* src, float* dst, size_t n, void* stream);
+/* The same Linear specialised for the preprocessor's shape (M = batch rows << N, K: the 4096 x 4096 ZCA matrix is 32 MB of
+ * bf16 that every step has to stream): bf16 x [M,K] and w [N,K] on tcgen05 with the contraction split across CTAs so
+ * that one wave of <= 148 CTAs pulls the matrix at HBM rate; deterministic fixed-order sum of the splits; output
+ * y [M,N] fp32 holding bf16-rounded values (autocast's bf16 output, widened) written straight into the pixel buffer.
+ * N % 8 == 0, K % 8 == 0, 16-byte aligned pointers.  ws: vitb200_tc_prelinear_ws_bytes() bytes, first 4096 zeroed once. */
+size_t vitb200_tc_prelinear_ws_bytes(int M, int N, int K);
+int vitb200_tc_prelinear_fwd(const void* x, const void* w, const float* bias, float* y, int M, int N, int K, void* ws,
+                             void* stream);
 /* Gradient of the patch embedding w.r.t. its input pixels -- what autograd hands to a TRAINABLE preprocessor
  * (PrefilledLinear.freeze(False), src/models/layers.py:51-60):
  *   dx[b, l] = sum_{n : n*S <= l < n*S+P, n < n_valid} sum_h drop'(dz[b, 1+n, h]) * w[h, l - n*S]

@@ -112,6 +112,10 @@ def run_variant(name, cfg, batch, kind):
     elif model.config.num_labels > 1:
         y = torch.rand(batch, model.config.num_labels, generator=torch.Generator().manual_seed(3))
     sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    preprocessed = None
+    if model.preprocessor is not None:   # with the INITIAL weights (the train3 section below updates a trainable matrix)
+        with torch.no_grad():
+            preprocessed = model.preprocessor(x).clone()
 
     out = model(x, labels=y, output_hidden_states=True)
     model.zero_grad()
@@ -150,8 +154,7 @@ def run_variant(name, cfg, batch, kind):
     if stats is not None:   # what the builder needs to rebuild the preprocessor (the covariance itself is not used)
         fix["stats"] = {k: stats[k].clone() for k in ("mean", "eigvals", "eigvecs")}
         fix["param_names"] = [k for k, _ in model.named_parameters()]
-        with torch.no_grad():
-            fix["eval"]["preprocessed"] = model.preprocessor(x).clone()
+        fix["eval"]["preprocessed"] = preprocessed
     path = os.path.join(OUT, f"{name}.pt")
     torch.save(fix, path)
     print(f"{name}: loss={float(ev['loss']):.6f} bf16={float(bf['loss']):.6f} name={model.name} "

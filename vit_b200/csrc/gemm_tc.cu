@@ -127,6 +127,21 @@ struct TcEpiWgrad {  // fp32 output [M_out = N_w, N_out = K_w]; split over the c
   }
 };
 
+// fp32 output y[m, n] = bf16_round(acc + bias[n]): the input-preprocessor GEMM (few rows, a large weight matrix).  It is
+// weight-streaming bound, so the contraction is split across CTAs until the grid covers the SMs (kSplit); the fp32 result
+// carries bf16-rounded values, exactly what autocast's bf16 Linear output widened to fp32 holds.
+struct TcEpiBiasF32 {
+  static constexpr bool kSplit = true;
+  float* y; const float* bias; int ldy;
+  __device__ __forceinline__ void apply1(int m, int n, float v) const {
+    y[(size_t)m * ldy + n] = bf16_round(v + (bias ? bias[n] : 0.f));
+  }
+  __device__ __forceinline__ void row(int m, int n0, const float (&v)[32], int M, int N) const {
+    if (m >= M) return;
+    for (int j = 0; j < 32 && n0 + j < N; ++j) apply1(m, n0 + j, v[j]);
+  }
+};
+
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epi epi, int M, int N,
@@ -219,7 +234,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi.row(m, n0 + c0, v, M, N);
       } else if (m < M) {
         float* dst = partial + (size_t)blockIdx.z * M * N + (size_t)m * N + n0 + c0;
-        for (int j = 0; j < 32 && n0 + c0 + j < N; ++j) dst[j] = v[j];
+        if (n0 + c0 + 32 <= N && (N & 3) == 0) {   // 16-byte stores: a quarter of the store instructions
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && n0 + c0 + j < N; ++j) dst[j] = v[j];
+        }
       }
     }
     tc_fence_before();
@@ -234,6 +255,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const size_t MN = (size_t)M * N;
       const int tm = min(TC_BM, M - m0), tn = min(BN, N - n0);
       const unsigned int Z = gridDim.z;
+      if ((tn & 3) == 0 && (N & 3) == 0) {
+        // four columns per thread, the splits' loads batched (the scalar loop below is a chain of dependent L2 latencies
+        // when Z is small); same z-ascending summation order, so the result is bit-identical to it
+        const int tn4 = tn >> 2;
+        for (int e = threadIdx.x; e < tm * tn4; e += TC_THREADS) {
+          const int mm = m0 + e / tn4, nn = n0 + (e % tn4) * 4;
+          const float* src = partial + (size_t)mm * N + nn;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          unsigned int z = 0;
+          for (; z + 4 <= Z; z += 4) {
+            float4 t[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) t[qq] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + qq) * MN));
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) { acc.x += t[qq].x; acc.y += t[qq].y; acc.z += t[qq].z; acc.w += t[qq].w; }
+          }
+          for (; z < Z; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * MN));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          epi.apply1(mm, nn, acc.x); epi.apply1(mm, nn + 1, acc.y);
+          epi.apply1(mm, nn + 2, acc.z); epi.apply1(mm, nn + 3, acc.w);
+        }
+        return;
+      }
       for (int e = threadIdx.x; e < tm * tn; e += TC_THREADS) {
         const int mm = m0 + e / tn, nn = n0 + e % tn;
         const float* src = partial + (size_t)mm * N + nn;
@@ -352,6 +398,40 @@ extern "C" int vitb200_tc_linear_fwd(const void* x, const void* w, const float* 
   }
   if ((rc = get_tmap(w, K, N, 64, 128, &tb))) return rc;
   return launch_tc<128, false, false>(ta, tb, epi, M, N, K, 1, nullptr, nullptr, st);
+}
+
+// Skinny-M Linear with fp32 output (the input preprocessor, src/models/layers.py:62-63): splits the contraction so that
+// tiles x splits <= 148 CTAs stream the weight matrix in one wave.
+static int tc_prelinear_splits(int M, int N, int K) {
+  const long long tiles = (long long)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
+  const int total_kb = (K + TC_BK - 1) / TC_BK;
+  long long s = tiles >= 148 ? 1 : 148 / tiles;
+  const int max_by_k = (total_kb + 3) / 4;   // at least four k-blocks (one pipeline depth) per split
+  if (s > max_by_k) s = max_by_k;
+  if (s > 32) s = 32;
+  if (tiles > 1024) s = 1;                   // one ticket counter per tile lives in the first 4096 bytes of ws
+  return s < 1 ? 1 : (int)s;
+}
+
+extern "C" size_t vitb200_tc_prelinear_ws_bytes(int M, int N, int K) {
+  const int splits = tc_prelinear_splits(M, N, K);
+  return 4096 + (splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0);
+}
+
+extern "C" int vitb200_tc_prelinear_fwd(const void* x, const void* w, const float* bias, float* y, int M, int N, int K,
+                                        void* ws, void* stream) {
+  if (!x || !w || !y || !ws || M <= 0 || N <= 0 || K <= 0) return VITB200_ERR_ARG;
+  if (N % 8 || K % 8) return VITB200_ERR_SHAPE;
+  if (!tc_ok_ptr(x) || !tc_ok_ptr(w) || !tc_ok_ptr(y)) return VITB200_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(x, K, M, 64, TC_BM, &ta);
+  if (rc) return rc;
+  if ((rc = get_tmap(w, K, N, 64, 128, &tb))) return rc;
+  TcEpiBiasF32 epi{y, bias, N};
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  return launch_tc<128, false, false>(ta, tb, epi, M, N, K, tc_prelinear_splits(M, N, K), partial, counters, st);
 }
 
 // dx[M, K] = dy[M, N] . w[N, K]  (optionally * gelu'(pre_act))

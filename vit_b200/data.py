@@ -61,8 +61,8 @@ class DeviceDataset:
         dev = torch.device(device) if device is not None else flux.device
         if dev.type != "cuda":
             raise RuntimeError("vit_b200 has no CPU path: a DeviceDataset lives on a CUDA (sm_100a) device")
-        self.device = dev
         self.flux = flux.to(dev, torch.float32).contiguous()
+        self.device = dev = self.flux.device      # normalised ('cuda' -> 'cuda:0')
         self.error = None if error is None else error.to(dev, torch.float32).contiguous()
         if self.error is not None and self.error.shape != self.flux.shape:
             raise ValueError("error must have the shape of flux")

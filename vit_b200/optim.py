@@ -40,6 +40,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
         lib = _lib.load()
         s = self._buffers()
         ar = s["arena"]
+        inside = {id(p) for p in self.model._param_list}
+        outside = [p for p in self.param_groups[0]["params"] if id(p) not in inside and p.requires_grad]
+        if outside:
+            raise NotImplementedError(
+                "vit_b200: FusedClipAdamW updates the flat parameter arena only; this model has trainable parameters "
+                "outside it (an unfrozen input preprocessor) -- use torch.optim.AdamW over model.parameters(), or "
+                "freeze the preprocessor (model.set_preprocessor_trainable(False))")
         if ar.data.device.type != "cuda":
             raise RuntimeError("vit_b200 has no CPU path")
         g = self.param_groups[0]

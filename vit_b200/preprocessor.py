@@ -125,7 +125,8 @@ def _check_input(x: torch.Tensor, weight: torch.Tensor) -> None:
 def linear_forward(mod: nn.Module, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                    out: Optional[torch.Tensor] = None):
     """y[B, N] (fp32) = x[B, K] . weight[N, K]^T + bias.  Returns (y, x_operand) -- the operand copy of x is what backward
-    needs.  `out`: write into this fp32 [B, N] buffer (the engine's pixel buffer) instead of allocating."""
+    needs.  `out`: write into this fp32 [B, N] buffer (the engine's pixel buffer) instead of allocating; that is the
+    no-grad step path, which also re-uses its bf16 staging buffer from call to call."""
     _check_input(x, weight)
     lib = _lib.load()
     B, K = x.shape
@@ -135,9 +136,23 @@ def linear_forward(mod: nn.Module, x: torch.Tensor, weight: torch.Tensor, bias: 
     y = out if out is not None else torch.empty(B, N, dtype=torch.float32, device=x.device)
     bptr = None if bias is None else _aligned(bias.detach().to(torch.float32)).data_ptr()
     if _precision_of(mod) == "bf16":
-        xb = torch.empty(B, K, dtype=torch.bfloat16, device=x.device)
+        xb = mod.__dict__.get("_x16") if out is not None else None
+        if xb is None or xb.shape != (B, K) or xb.device != x.device:
+            xb = torch.empty(B, K, dtype=torch.bfloat16, device=x.device)
+            if out is not None:
+                mod.__dict__["_x16"] = xb
         _lib.check(lib.vitb200_cast_bf16(xin.data_ptr(), xb.data_ptr(), B * K, st), "cast_bf16")
         wb = _bf16_copy(mod, weight)
+        if N % 8 == 0 and K % 8 == 0 and y.data_ptr() % 16 == 0:
+            # few rows x a large matrix: split-K tcgen05 GEMM sized to one wave of CTAs, fp32 (bf16-rounded) output
+            need = int(lib.vitb200_tc_prelinear_ws_bytes(B, N, K))
+            ws = mod.__dict__.get("_fwd_ws")
+            if ws is None or ws.numel() < need or ws.device != x.device:
+                ws = torch.zeros(need, dtype=torch.uint8, device=x.device)
+                mod.__dict__["_fwd_ws"] = ws
+            _lib.check(lib.vitb200_tc_prelinear_fwd(xb.data_ptr(), wb.data_ptr(), bptr, y.data_ptr(), B, N, K,
+                                                    ws.data_ptr(), st), "preprocessor prelinear_fwd")
+            return y, xb
         yb = torch.empty(B, N, dtype=torch.bfloat16, device=x.device)
         _lib.check(lib.vitb200_linear_fwd(xb.data_ptr(), wb.data_ptr(), bptr, yb.data_ptr(), None, B, N, K, ACT_NONE, BF16,
                                           st), "preprocessor linear_fwd")
