@@ -8,10 +8,11 @@ Same classes, attribute names and `state_dict` keys as the reference:
   * `PrefilledAttention`                         src/models/attention.py:13-124    (2-D inputs: `q_lin(x)` only)
   * `load_cov_stats`                             src/utils.py:17-71
 
-The per-step work -- `x @ P^T + b` on `[B, D_in]` -- runs on `vitb200_linear_fwd` (fp32: SIMT fp32 GEMM; bf16-mixed: the
-tcgen05/TMA GEMM on a bf16 copy of the matrix, bf16 output widened to the fp32 pixel buffer, as autocast does), and for a
-trainable preprocessor `vitb200_linear_wgrad` / `vitb200_linear_dgrad` in backward.  There is no PyTorch fallback: CPU
-tensors raise.
+The per-step work -- `x @ P^T + b` on `[B, D_in]` -- runs on the B200 kernels: fp32 mode `vitb200_linear_fwd` (SIMT fp32
+GEMM); bf16-mixed `vitb200_tc_prelinear_fwd`, a tcgen05/TMA GEMM on a bf16 copy of the matrix whose contraction is split
+over one wave of CTAs (the few-rows x large-matrix shape is weight-streaming bound) and whose fp32 output holds
+bf16-rounded values, as autocast's bf16 Linear output does.  A trainable preprocessor adds `vitb200_linear_wgrad` /
+`vitb200_linear_dgrad` in backward.  There is no PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
