@@ -437,7 +437,16 @@ def main():
     if world > 1:
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
     e2e_blocking = world * B * nb / float(tb[0])
+    # the timed regions last ~0.1 s, nvidia-smi samples every 100 ms: keep the SAME step running (untimed) for about one
+    # more second so that the clock / throttle-reason samples describe this load.  The count derives from the all-reduced
+    # step time, so every rank runs the same number of steps (the in-kernel gradient exchange needs that).
+    extra = max(0, min(8000, int(1.0 / max(ms_step * 1e-3, 1e-6))))
+    for i in range(extra):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    barrier()
     clocks = sampler.stop() if sampler is not None else None
+    if clocks is not None:
+        clocks["window"] = f"timed regions + {extra} more untimed steps of the same workload"
     launches_all = step.kernel_launches()
     if world > 1:
         dist.barrier()
