@@ -240,21 +240,21 @@ class PrefilledLinear(nn.Module):
 
     def __init__(self, matrix: torch.Tensor, bias: torch.Tensor | None = None, freeze: bool = True) -> None:
         super().__init__()
-        weight = matrix.to(torch.float32)
-        if freeze:
-            self.register_buffer("weight", weight)
-            self._is_frozen = True
+        self._is_frozen = bool(freeze)
+        self._install("weight", matrix.to(torch.float32), as_param=not freeze)
+        # a missing bias is registered as a None buffer, so `state_dict` has no bias key (layers.py:34-35)
+        self._install("bias", None if bias is None else bias.to(torch.float32), as_param=not freeze)
+
+    def _install(self, name: str, value: Optional[torch.Tensor], as_param: bool) -> None:
+        """(Re-)register `name` as a Parameter (trainable) or as a buffer (frozen / absent)."""
+        if name in self._parameters:
+            del self._parameters[name]
+        if name in self._buffers:
+            del self._buffers[name]
+        if value is not None and as_param:
+            self.register_parameter(name, nn.Parameter(value))
         else:
-            self.weight = nn.Parameter(weight)
-            self._is_frozen = False
-        if bias is not None:
-            bias = bias.to(torch.float32)
-            if freeze:
-                self.register_buffer("bias", bias)
-            else:
-                self.bias = nn.Parameter(bias)
-        else:
-            self.register_buffer("bias", None)
+            self.register_buffer(name, value)
 
     @property
     def in_features(self) -> int:
@@ -265,24 +265,14 @@ class PrefilledLinear(nn.Module):
         return self.weight.shape[0]
 
     def freeze(self, freeze: bool = True) -> None:
-        if freeze and not self._is_frozen:
-            weight_data = self.weight.data.clone()
-            del self.weight
-            self.register_buffer("weight", weight_data)
-            if hasattr(self, "bias") and isinstance(self.bias, nn.Parameter):
-                bias_data = self.bias.data.clone()
-                del self.bias
-                self.register_buffer("bias", bias_data)
-            self._is_frozen = True
-        elif not freeze and self._is_frozen:
-            weight_data = self.weight.clone()
-            delattr(self, "weight")
-            self.weight = nn.Parameter(weight_data)
-            if self.bias is not None:
-                bias_data = self.bias.clone()
-                delattr(self, "bias")
-                self.bias = nn.Parameter(bias_data)
-            self._is_frozen = False
+        """Run-time switch between buffers and Parameters (layers.py:36-60): the tensors keep their values but change
+        their role, so `parameters()` -- and what an optimizer built afterwards sees -- changes with it."""
+        if bool(freeze) == self._is_frozen:
+            return
+        for name in ("weight", "bias"):
+            cur = getattr(self, name)
+            self._install(name, None if cur is None else cur.detach().clone(), as_param=not freeze)
+        self._is_frozen = bool(freeze)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _apply_linear(self, x, self.weight, self.bias)
