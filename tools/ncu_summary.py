@@ -18,11 +18,23 @@ want = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_pct"),
     ("smsp__inst_executed.sum", "inst"),
     ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
-    ("sm__pipe_tensor_subpipe_mma_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
-    ("sm__inst_executed_pipe_tensor_subpipe_mma.sum", "tensor_inst"),
+    # tensor-pipe utilisation: share of elapsed cycles with the tensor pipe active (tcgen05.mma shows up in the hmma
+    # sub-pipe counters), and the share of cycles the tensor-memory (TMEM) path is busy
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor_pct"),
+    ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "hmma_cyc"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tmem_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit"),
 ]
-idx = [(hdr.index(k), n) for k, n in want if k in hdr]
+
+
+def find(key):   # section-qualified columns look like "TPC.TriageCompute.<metric>"
+    for i, c in enumerate(hdr):
+        if c == key or c.endswith("." + key):
+            return i
+    return None
+
+
+idx = [(find(k), n) for k, n in want if find(k) is not None]
 units = rows[1]
 lines = [[n for _, n in idx]]
 for r in rows[2:]:
@@ -42,6 +54,16 @@ for r in rows[2:]:
             v = f"{f * mult:.2f}us"
         line.append(v)
     lines.append(line)
+# derived: tensor-pipe active share of the kernel = hmma sub-pipe active cycles / busiest SM's active cycles
+names = lines[0]
+if "hmma_cyc" in names and "sm_cyc_max" in names and "tensor_active_pct" not in names:
+    a, b = names.index("hmma_cyc"), names.index("sm_cyc_max")
+    names.append("tensor_active_pct")
+    for l in lines[1:]:
+        try:
+            l.append(f"{100.0 * float(l[a].replace(',', '')) / max(float(l[b].replace(',', '')), 1.0):.1f}")
+        except ValueError:
+            l.append("")
 w = [max(len(l[c]) for l in lines) for c in range(len(lines[0]))]
 txt = "\n".join("  ".join(v.ljust(w[c]) for c, v in enumerate(l)) for l in lines)
 print(txt)
