@@ -59,3 +59,53 @@ def test_device_dataset_has_no_cpu_path():
         DeviceDataset(torch.rand(4, 16), torch.rand(4))
     with pytest.raises(ValueError, match="multiple of 4"):
         DeviceDataset(torch.rand(4, 18), torch.rand(4), device="cuda")
+
+
+def test_lightning_eval_hooks_single_forward_and_epoch_statistics():
+    """validation_step / test_step keep the outputs of their ONE forward (the reference runs the model twice per batch,
+    src/vit.py:127-150) and on_validation_epoch_end logs median bias / p90 / slope per output (src/vit.py:157-192)."""
+    import numpy as np
+
+    from vit_b200.lightning_module import ViTLModule
+    from vit_b200.model import ModelOutput
+
+    cfg = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                         num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"},
+           "data": {"param": "a,b"}}
+
+    class Dummy(torch.nn.Module):
+        loss_name = "l2"
+
+    lm = ViTLModule(model=Dummy(), config=cfg)
+    calls = []
+    g = torch.Generator().manual_seed(0)
+
+    def fake_forward(flux, labels, loss_only=True):
+        calls.append(flux.shape[0])
+        logits = labels + 0.1 * torch.randn(labels.shape, generator=g)
+        out = ModelOutput(loss=((logits - labels) ** 2).mean(), logits=logits, hidden_states=None, attentions=None)
+        return out.loss if loss_only else out
+
+    lm.forward = fake_forward
+    lm.on_validation_start()
+    ys, ps = [], []
+    for i in range(3):
+        y = torch.rand(5, 2, generator=g)
+        lm.validation_step((torch.zeros(5, 256), torch.zeros(5, 256), y), i)
+        ys.append(y)
+        ps.append(lm._last_outputs.logits)
+    assert calls == [5, 5, 5]                       # one forward per batch
+    assert abs(float(lm._logged["val_mae"]) - float((ps[-1] - ys[-1]).abs().mean())) < 1e-6
+    assert len(lm.val_dict["preds"]) == 3
+    lm.on_validation_epoch_end()
+    P, Y = torch.cat(ps).numpy(), torch.cat(ys).numpy()
+    for i in range(2):
+        r = P[:, i] - Y[:, i]
+        assert abs(lm._logged[f"val_bias_median_{i}"] - float(np.median(r))) < 1e-6
+        assert abs(lm._logged[f"val_p90_{i}"] - float(np.percentile(np.abs(r), 90))) < 1e-6
+        assert abs(lm._logged[f"val_beta_{i}"] - float(np.polyfit(Y[:, i], P[:, i], 1)[0])) < 1e-6
+    assert lm.val_dict == {"preds": [], "labels": []}
+    lm.on_test_start()
+    lm.test_step((torch.zeros(4, 256), torch.zeros(4, 256), torch.zeros(4, 256), torch.rand(4, 2, generator=g)), 0)
+    assert len(lm.test_dict["preds"]) == 1 and calls[-1] == 4
+    lm.on_test_epoch_end()                          # no src.viz here: returns quietly

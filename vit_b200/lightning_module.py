@@ -86,11 +86,74 @@ class ViTLModule(_Base):
         self._last_outputs = outputs
         return loss
 
+    # The reference's validation_step / test_step run the model a SECOND time per batch just to get the predictions for
+    # the epoch-level statistics (src/vit.py:127-150,194-215).  Here the outputs of the one forward in
+    # `_shared_eval_step` are kept, so every batch costs one forward.
+    def _collect(self, store: str, batch) -> None:
+        if self.task_type != "reg" or not hasattr(self, store):
+            return
+        preds = self._last_outputs.logits.squeeze()
+        getattr(self, store)["preds"].append(preds.detach().cpu())
+        getattr(self, store)["labels"].append(batch[-1].detach().cpu())
+
     def validation_step(self, batch, batch_idx):
-        return self._shared_eval_step(batch, "val")
+        loss = self._shared_eval_step(batch, "val")
+        self._collect("val_dict", batch)
+        return loss
+
+    def on_validation_start(self):  # src/vit.py:152-155
+        if self.task_type == "reg":
+            self.val_dict = {"preds": [], "labels": []}
+
+    def on_validation_epoch_end(self):
+        """Epoch-level regression statistics per output (src/vit.py:157-192): median residual, 90th percentile of
+        |residual|, slope of the linear fit pred = a + beta * label."""
+        if self.task_type != "reg" or not getattr(self, "val_dict", None) or not self.val_dict["preds"]:
+            return
+        import numpy as np
+
+        preds = torch.cat([p.reshape(p.shape[0] if p.dim() else 1, -1) for p in self.val_dict["preds"]], dim=0).numpy()
+        labels = torch.cat([l.reshape(l.shape[0] if l.dim() else 1, -1) for l in self.val_dict["labels"]], dim=0).numpy()
+        for i in range(preds.shape[1]):
+            res = preds[:, i] - labels[:, i]
+            beta = float(np.polyfit(labels[:, i], preds[:, i], 1)[0])
+            suffix = "" if preds.shape[1] == 1 else f"_{i}"
+            self.log(f"val_bias_median{suffix}", float(np.median(res)), on_epoch=True)
+            self.log(f"val_p90{suffix}", float(np.percentile(np.abs(res), 90)), on_epoch=True)
+            self.log(f"val_beta{suffix}", beta, on_epoch=True)
+        self.val_dict = {"preds": [], "labels": []}
+
+    def on_test_start(self):  # src/vit.py:194-197
+        if self.task_type == "reg":
+            self.test_dict = {"preds": [], "labels": []}
 
     def test_step(self, batch, batch_idx):
-        return self._shared_eval_step(batch, "test")
+        loss = self._shared_eval_step(batch, "test")
+        self._collect("test_dict", batch)
+        return loss
+
+    def on_test_epoch_end(self):
+        """src/vit.py:216-296: hand the collected predictions to the reference's RegressionPlotter when this module runs
+        inside the reference repository (plotting itself is the reference's code, not part of the hot path)."""
+        if self.task_type != "reg" or not getattr(self, "test_dict", None) or not self.test_dict["preds"]:
+            return
+        try:
+            from src.viz import RegressionPlotter  # the reference package, when present
+        except Exception:  # noqa: BLE001
+            return
+        preds = torch.cat(self.test_dict["preds"], dim=0).numpy()
+        labels = torch.cat(self.test_dict["labels"], dim=0).numpy()
+        n_out = preds.shape[1] if preds.ndim > 1 else 1
+        names = (self.config.get("model", {}) or {}).get("param_names", ["Teff", "log_g", "M_H"][:n_out])
+        norm = {}
+        ds = getattr(getattr(getattr(self, "trainer", None), "datamodule", None), "test", None)
+        if ds is not None:
+            norm["label_norm"] = getattr(ds, "label_norm", None)
+            for k in ("label_mean", "label_std", "label_min", "label_max"):
+                norm[k] = getattr(ds, k, None)
+        RegressionPlotter(predictions=preds, labels=labels, param_names=names, logger=getattr(self, "logger", None),
+                          save_dir=(self.config.get("train", {}) or {}).get("plot_dir", "plots"), **norm
+                          ).generate_all_plots(quick_mode=(self.config.get("plotting", {}) or {}).get("quick_mode", False))
 
     def configure_optimizers(self):  # src/basemodule.py:152-182 + src/opt/optimizer.py:37-172
         opt = {**(self.config.get("opt", {}) or {})}
