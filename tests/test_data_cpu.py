@@ -109,3 +109,49 @@ def test_lightning_eval_hooks_single_forward_and_epoch_statistics():
     lm.test_step((torch.zeros(4, 256), torch.zeros(4, 256), torch.zeros(4, 256), torch.rand(4, 2, generator=g)), 0)
     assert len(lm.test_dict["preds"]) == 1 and calls[-1] == 4
     lm.on_test_epoch_end()                          # no src.viz here: returns quietly
+
+
+def test_configure_optimizers_mirrors_optmodule():
+    """Same optimizer / scheduler selection and Lightning dicts as OptModule (src/opt/optimizer.py:37-172)."""
+    import copy
+
+    from vit_b200.lightning_module import ViTLModule
+
+    base = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                          num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"},
+            "data": {"param": "g", "val_path": "v.h5", "num_samples": 1000}, "train": {"batch_size": 64, "ep": 7}}
+    S = torch.optim.lr_scheduler
+
+    def make(**opt):
+        cfg = copy.deepcopy(base)
+        cfg["opt"] = opt
+        from vit_b200 import get_model
+
+        return ViTLModule(model=get_model(copy.deepcopy(cfg), device="cpu"), config=cfg).configure_optimizers()
+
+    o = make(type="AdamW", lr=2e-3)
+    assert isinstance(o, torch.optim.AdamW) and o.param_groups[0]["lr"] == 2e-3 and o.param_groups[0]["weight_decay"] == 0
+    assert isinstance(make(lr=1e-3), torch.optim.Adam)                       # default type 'adam'
+    d = make(type="adamw", lr_sch="plateau", factor=0.8, patience=10)     # configs/config.yaml
+    assert isinstance(d["lr_scheduler"]["scheduler"], S.ReduceLROnPlateau)
+    assert d["lr_scheduler"]["monitor"] == "val_mae" and d["lr_scheduler"]["reduce_on_plateau"] and not d["lr_scheduler"]["strict"]
+    assert d["lr_scheduler"]["scheduler"].factor == 0.8 and d["lr_scheduler"]["scheduler"].patience == 10
+    d = make(type="adamw", lr_sch="cosine", ep=50, eta_min=1e-6)
+    assert isinstance(d["lr_scheduler"]["scheduler"], S.CosineAnnealingLR) and d["lr_scheduler"]["scheduler"].T_max == 50
+    assert d["lr_scheduler"]["interval"] == "epoch"
+    d = make(type="adamw", lr=1e-3, lr_sch="onecycle", pct_start=0.2)
+    sch = d["lr_scheduler"]["scheduler"]
+    assert isinstance(sch, S.OneCycleLR) and sch.total_steps == 7 * 16 and d["lr_scheduler"]["interval"] == "step"
+    d = make(type="sgd", lr_sch="constant", factor=0.5, total_iters=3)
+    assert isinstance(d["optimizer"], torch.optim.SGD) and isinstance(d["lr_scheduler"]["scheduler"], S.ConstantLR)
+    d = make(type="adamw", lr_sch="cosine", ep=20, warmup_ratio=0.1)
+    assert isinstance(d["lr_scheduler"]["scheduler"], S.SequentialLR)
+    with pytest.raises(ValueError, match="Unknown scheduler"):
+        make(type="adamw", lr_sch="step")
+    cfg = copy.deepcopy(base)
+    cfg["data"].pop("val_path")                                            # plateau without validation data: disabled
+    cfg["opt"] = {"type": "adamw", "lr_sch": "plateau"}
+    from vit_b200 import get_model
+
+    assert isinstance(ViTLModule(model=get_model(copy.deepcopy(cfg), device="cpu"), config=cfg).configure_optimizers(),
+                      torch.optim.AdamW)

@@ -155,11 +155,21 @@ class ViTLModule(_Base):
                           save_dir=(self.config.get("train", {}) or {}).get("plot_dir", "plots"), **norm
                           ).generate_all_plots(quick_mode=(self.config.get("plotting", {}) or {}).get("quick_mode", False))
 
-    def configure_optimizers(self):  # src/basemodule.py:152-182 + src/opt/optimizer.py:37-172
+    def configure_optimizers(self):
+        """src/basemodule.py:152-182 + OptModule (src/opt/optimizer.py:37-172): same config keys (`opt.type`, `lr`,
+        `weight_decay`, `lr_sch` in {plateau, cosine*, onecycle, constant*}, `warmup`/`warmup_ratio`/`warmup_epochs`, scheduler
+        arguments) and the same Lightning scheduler dicts.  `opt.fused: true` with AdamW selects the one-arena fused
+        optimizer instead of torch's."""
         opt = {**(self.config.get("opt", {}) or {})}
-        lr = float(opt.get("lr", 1e-3))
+        data_cfg = self.config.get("data", {}) or {}
+        lr = opt.get("lr", 1e-3)
         wd = opt.get("weight_decay", 0)
         kind = str(opt.get("type", "adam")).lower()
+        sch = str(opt.get("lr_sch", "") or "").lower()
+        if "plateau" in sch and not bool(data_cfg.get("val_path")):
+            print("[WARNING] ReduceLROnPlateau requires validation data ('data.val_path' in config) but none configured.")
+            print("[WARNING] Disabling learning rate scheduler.")
+            sch = ""
         if opt.get("fused", False) and kind == "adamw":
             from .optim import FusedClipAdamW
 
@@ -168,19 +178,48 @@ class ViTLModule(_Base):
             fns = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD,
                    "rmsprop": torch.optim.RMSprop, "adagrad": torch.optim.Adagrad}
             optimizer = fns[kind](self.model.parameters(), lr=lr, weight_decay=wd)
-        sch = str(opt.get("lr_sch", "") or "").lower()
-        has_val = bool((self.config.get("data", {}) or {}).get("val_path"))
-        if not sch or ("plateau" in sch and not has_val):
+        if not sch:
             return optimizer
-        if "plateau" in sch:
-            scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=opt.get("factor", 0.1),
-                                                                   patience=opt.get("patience", 10))
-            cfg = {"scheduler": scheduler, "monitor": f"val_{self.monitor_metric}", "reduce_on_plateau": True,
-                   "strict": False}
-        elif "cosine" in sch:
-            scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(
-                optimizer, T_max=opt.get("T_max", opt.get("ep", 100)), eta_min=opt.get("eta_min", 0.0))
-            cfg = {"scheduler": scheduler, "monitor": f"val_{self.monitor_metric}", "interval": "epoch", "frequency": 1}
+        S = torch.optim.lr_scheduler
+        table = {"cosine": S.CosineAnnealingLR, "cosineannealinglr": S.CosineAnnealingLR, "onecycle": S.OneCycleLR,
+                 "constant": S.ConstantLR, "constantlr": S.ConstantLR, "plateau": S.ReduceLROnPlateau}
+        if sch not in table:
+            raise ValueError(f"Unknown scheduler: {sch}")
+        kw = {}
+        if "cosine" in sch:
+            kw["T_max"] = opt.get("T_max", opt.get("ep", 100))
+            if "eta_min" in opt:
+                kw["eta_min"] = opt["eta_min"]
+        elif "onecycle" in sch:   # steps_per_epoch / epochs from the train + data config (src/basemodule.py:167-179)
+            train_cfg = self.config.get("train", {}) or {}
+            bs = train_cfg.get("batch_size", 64)
+            kw.update(max_lr=lr, steps_per_epoch=(data_cfg.get("num_samples", 32000) + bs - 1) // bs,
+                      epochs=train_cfg.get("ep", 100))
+            for k in ("pct_start", "div_factor", "final_div_factor"):
+                if k in opt:
+                    kw[k] = opt[k]
+        elif "constant" in sch:
+            kw.update(factor=opt.get("factor", 1.0), total_iters=opt.get("total_iters", 1))
+        elif "plateau" in sch:
+            kw.update(factor=opt.get("factor", 0.1), patience=opt.get("patience", 10))
+            if "mode" in opt:
+                kw["mode"] = opt["mode"]
+        wcfg = opt.get("warmup", {}) or {}
+        w_ratio = wcfg.get("ratio", opt.get("warmup_ratio", 0.0))
+        w_epochs = wcfg.get("epochs", opt.get("warmup_epochs", None))
+        if (w_ratio > 0 or w_epochs is not None) and "onecycle" not in sch:
+            if w_epochs is None:
+                w_epochs = max(1, int(kw.get("T_max", kw.get("epochs", 100)) * w_ratio))
+            scheduler = S.SequentialLR(optimizer, schedulers=[S.LinearLR(optimizer, start_factor=0.1, total_iters=w_epochs),
+                                                               table[sch](optimizer, **kw)], milestones=[w_epochs])
+            print(f"[Warmup] Using {w_epochs} warmup epochs before {sch}")
         else:
-            return optimizer
+            scheduler = table[sch](optimizer, **kw)
+        cfg = {"scheduler": scheduler, "monitor": f"val_{self.monitor_metric}"}
+        if "plateau" in sch:
+            cfg.update(reduce_on_plateau=True, strict=False)
+        elif "onecycle" in sch:
+            cfg.update(interval="step", frequency=1)
+        else:
+            cfg.update(interval="epoch", frequency=1)
         return {"optimizer": optimizer, "lr_scheduler": cfg}
