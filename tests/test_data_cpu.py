@@ -155,3 +155,56 @@ def test_configure_optimizers_mirrors_optmodule():
 
     assert isinstance(ViTLModule(model=get_model(copy.deepcopy(cfg), device="cpu"), config=cfg).configure_optimizers(),
                       torch.optim.AdamW)
+
+
+_GLOO_SAMPLER_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VIT_ROOT"])
+from vit_b200 import dp
+from vit_b200.data import epoch_indices
+from oracle import vit_oracle as vo
+rank, local, world = dp.init_from_env("gloo")
+cfg = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                     num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"}, "data": {"param": "g"}}
+spec = vo.spec_from_config(cfg)
+params = vo.init_params(spec, seed=5)
+N, B = 21, 4
+x, y = vo.synthetic_batch(N, 256, seed=3, kind="rand")
+mine = epoch_indices(N, 2, seed=9, rank=rank, world=world, batch=B)
+both = [epoch_indices(N, 2, seed=9, rank=r, world=world, batch=B) for r in range(world)]
+assert mine.numel() % B == 0 and all(b.numel() == mine.numel() for b in both)
+assert set(torch.cat(both).tolist()) == set(range(N))           # the ranks together visit every sample
+def grads_of(idx):
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    vo.forward(p, x[idx], spec, labels=y[idx])["loss"].backward()
+    return torch.cat([t.grad.reshape(-1) for k, t in p.items() if t.grad is not None])
+for i in range(mine.numel() // B):
+    g = grads_of(mine[i * B:(i + 1) * B])
+    dist.all_reduce(g)                                           # SUM; the optimizer kernel's grad_scale is 1/world
+    g /= world
+    union = torch.cat([b[i * B:(i + 1) * B] for b in both])      # what one process with batch world*B would see
+    full = grads_of(union)
+    err = float((g - full).abs().max() / full.abs().max())
+    assert err < 1e-5, (i, err)
+if rank == 0: print("SAMPLER_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_fit_device_sharding_equals_global_batch_gloo_world2(tmp_path):
+    """world_size 2 over gloo: stepping on rank r's share of the epoch permutation (what TrainStep.fit_device does) and
+    averaging the gradients over ranks == one process stepping on the union batch (Lightning DDP + DistributedSampler)."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_SAMPLER_WORKER)
+    env = dict(os.environ, VIT_ROOT=ROOT, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "SAMPLER_OK" in r.stdout
