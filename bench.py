@@ -325,6 +325,66 @@ def kernel_table(eng, train: bool):
     return rows
 
 
+def dp_parity_check(dev, rank, world, precision, B=16, steps=2):
+    """Data-parallel correctness, proven inside the run that prints the scaling numbers: the same TrainStep the timed
+    loop uses (in-kernel peer exchange, CUDA graph), dropout off, `steps` steps with rank r holding shard r of a global
+    batch; then (1) every replica's parameter arena must be BIT-identical, (2) on rank 0 the oracle takes the same steps
+    on the UNION batch and the mean of the rank losses / the AdamW first moments (= the clipped mean gradient) must agree
+    within the precision's tolerance."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vit_oracle as vo
+    from vit_b200 import dp, get_model
+    from vit_b200.step import TrainStep
+
+    cfg = json.loads(json.dumps(BASELINE_CFG))
+    torch.manual_seed(7)
+    m = get_model(cfg, precision=precision, device=dev).eval()
+    dp.broadcast_parameters(m._arena.data)
+    p0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    st = TrainStep(m, B, use_graph=True, world_size=world, train=False)
+    x, y = vo.synthetic_batch(B * world, 4096, seed=5, kind="rand")
+    lo, hi = rank * B, (rank + 1) * B
+    xs, ys = x[lo:hi].to(dev), y[lo:hi].to(dev)
+    losses = [st.step(xs, ys).clone() for _ in range(steps)]
+    torch.cuda.synchronize()
+    flat = m._arena.data[:m._arena.layout.n_opt]
+    # (1) bitwise replica equality: a 64-bit checksum of the raw bits + a max over |p - p_rank0|
+    bits = flat.view(torch.int32).to(torch.int64)
+    chk = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+    allchk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    identical = all(bool(torch.equal(c, allchk[0])) for c in allchk)
+    lt = torch.stack(losses).reshape(1, steps)
+    alll = [torch.zeros_like(lt) for _ in range(world)]
+    dist.all_gather(alll, lt)
+    out = {"world": world, "shard_batch": B, "steps": steps, "replicas_bit_identical": identical}
+    if rank == 0:
+        tol = 2e-2 if "bf16" in precision else 1e-4
+        spec = vo.spec_from_config(cfg)
+        ref = vo.OracleTrainer(spec, p0, autocast_bf16="bf16" in precision)
+        ref_losses = [ref.step(x, y, train=False) for _ in range(steps)]
+        mine = torch.cat(alll, 0).mean(0).cpu()
+        lerr = max(abs(float(mine[i]) - ref_losses[i]) / max(1.0, abs(ref_losses[i])) for i in range(steps))
+        eng, lay = st.eng, m._arena.layout
+        gmax = max(float(v.abs().max()) for k, v in ref.m.items() if "pooler" not in k)
+        merr = 0.0
+        for k, v in ref.m.items():
+            e = lay.entries.get(k)
+            if e is None or e.offset >= lay.n_opt:
+                continue
+            got = eng.exp_avg[e.offset:e.offset + e.numel].reshape(e.shape).cpu()
+            merr = max(merr, float((got - v).abs().max()) / max(float(v.abs().max()), 1e-2 * gmax))
+        out.update(oracle="CPU oracle, union batch of %d samples, %s" % (B * world, "autocast bf16" if "bf16" in precision else "fp32"),
+                   loss_rel_err=lerr, exp_avg_rel_err=merr, tol_loss=tol, tol_exp_avg=2 * tol if "bf16" in precision else 2e-3,
+                   peer_exchange=getattr(eng, "peer", None) is not None)
+        out["ok"] = bool(identical and lerr < out["tol_loss"] and merr < out["tol_exp_avg"])
+    dist.barrier()
+    st.close()
+    del st, m
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -363,6 +423,8 @@ def main():
         r = cpu_reference_run(steps=60, warmup=3)
         cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    dp_parity = dp_parity_check(dev, rank, world, args.precision) if world > 1 else None
+
     torch.manual_seed(42)
     cfg = json.loads(json.dumps(BASELINE_CFG))
     model = get_model(cfg, precision=args.precision, device=dev)
@@ -393,8 +455,15 @@ def main():
     sampler = ClockSampler(local).start() if rank == 0 else None
     stream = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The ranks leave the host barrier up to ~1 ms apart.  In a data-parallel run every step ends at the slowest rank
+    # (gradient exchange), so timing from the barrier would charge that one-off host skew to the K timed steps.  A few
+    # untimed steps first let the in-kernel exchange align the GPUs (and fill the launch queue); the events then bracket
+    # exactly K steps of steady state on the launching stream.  Same code path at N = 1.
+    lead = 8
+    for i in range(lead):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(lead, lead + args.steps):
         step.step(pool_x[i % pool_n], pool_y[i % pool_n])
     e1.record(stream)
     barrier()
@@ -447,6 +516,34 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
     if clocks is not None:
         clocks["window"] = f"timed regions + {extra} more untimed steps of the same workload"
+    # ---- BASELINE config 5 at N GPUs: scripts/test.py semantics (eval mode, forward only, large batch), N independent
+    # replicas over a batch-sharded set, no collective on the data path; device time, max over ranks ----
+    eval_replicas = None
+    try:
+        from vit_b200.step import EvalStep
+        eb = 1024
+        es_ = EvalStep(model.eval(), eb, use_graph=not args.no_graph)
+        ex = torch.rand(4, eb, 4096, generator=g).to(dev)
+        for i in range(3):
+            es_.forward(ex[i % 4])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_ev = 20
+        a0.record(stream)
+        for i in range(n_ev):
+            es_.forward(ex[i % 4])
+        a1.record(stream)
+        barrier()
+        tev = torch.tensor([a0.elapsed_time(a1) / n_ev], device=dev)
+        if world > 1:
+            dist.all_reduce(tev, op=dist.ReduceOp.MAX)
+        eval_replicas = {"samples_per_s": world * eb * 1e3 / float(tev[0]), "ms_per_batch": float(tev[0]),
+                         "per_gpu_batch": eb, "replicas": world, "collective": "none (replicas only)"}
+        model.train()
+        del es_, ex
+    except Exception as ex_:  # noqa: BLE001
+        eval_replicas = {"error": str(ex_)[:200]}
+        model.train()
     launches_all = step.kernel_launches()
     if world > 1:
         dist.barrier()
@@ -563,6 +660,7 @@ def main():
             return c
 
         cases = [
+            ("fp32_train_b64", variant(), 64, "train32", 50),
             ("config_yaml_2layers_train_b64", variant(num_hidden_layers=2), 64, "train", 50),
             ("eval_forward_b1024", variant(), 1024, "eval", 20),
             ("eval_forward_b8192", variant(), 8192, "eval", 5),
@@ -571,9 +669,9 @@ def main():
         ]
         for name, cfg2, b2, mode, n2 in cases:
             try:
-                m2 = get_model(cfg2, precision=args.precision, device=dev)
+                m2 = get_model(cfg2, precision="32" if mode == "train32" else args.precision, device=dev)
                 x2 = torch.rand(b2, 4096, device=dev); y2 = torch.rand(b2, device=dev)
-                if mode == "train":
+                if mode in ("train", "train32"):
                     s2 = TrainStep(m2.train(), b2, use_graph=not args.no_graph, train=True)
                     msb = timed(lambda: s2.step(x2, y2), n2)
                 else:
@@ -679,6 +777,11 @@ def main():
         "tc_gemm_probe": probe,
         "final_loss": loss_last,
     }
+    line["eval_forward_replicas"] = eval_replicas
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity
+        if not dp_parity.get("ok", False):
+            print("bench.py: DATA-PARALLEL PARITY CHECK FAILED: " + json.dumps(dp_parity), file=sys.stderr, flush=True)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -14,7 +14,8 @@ Writes `tests/golden/<variant>.pt`, each a dict:
     grads         fp32, dropout off: d loss / d param for every param that received a grad
     bf16          the same under torch.autocast('cpu', bfloat16): loss, logits, grads
     train3        3 steps of clip_grad_norm_(0.5) + torch.optim.AdamW(lr=1e-3) with dropout off:
-                  losses, grad norms and the final weights
+                  losses, grad norms, AdamW first moments and the final weights
+    train3_bf16   the same 3 steps under torch.autocast('cpu', bfloat16) (Lightning precision='bf16-mixed')
 """
 from __future__ import annotations
 
@@ -61,6 +62,9 @@ def variants():
     c = base_cfg(image_size=2048, hidden_size=128, num_attention_heads=2, num_hidden_layers=1,
                  pos_encoding_type="rope", stride_size=16)
     v["h128d64rope"] = (c, 2, "rand")
+    # BASELINE config 4, the long-sequence sweep at its full spectrum length: x4 tokens (T = 510) and x16 (T = 2034)
+    v["long510"] = (base_cfg(stride_size=8), 2, "rand")
+    v["long2034"] = (base_cfg(stride_size=2, num_hidden_layers=2), 1, "rand")
     # input preprocessors (src/models/builder.py:43-133) on seeded covariance statistics of 256-pixel spectra
     for name, warm in (
         ("pre_zca_full", dict(preprocessor="zca", freeze_epochs=-1)),                           # frozen buffers
@@ -145,11 +149,34 @@ def run_variant(name, cfg, batch, kind):
         norms.append(torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5).detach().clone())
         opt.step()
         losses.append(loss.detach().clone())
-    tr = dict(losses=torch.stack(losses), grad_norms=torch.stack(norms),
+    names = [k for k, _ in model.named_parameters()]
+
+    def moments(o):
+        return {names[i]: st["exp_avg"].detach().clone() for i, st in o.state_dict()["state"].items()}
+
+    tr = dict(losses=torch.stack(losses), grad_norms=torch.stack(norms), exp_avg=moments(opt),
               state_dict={k: v.detach().clone() for k, v in model.state_dict().items()})
 
+    # the same 3 steps under Lightning's precision='bf16-mixed' (= torch.autocast(bf16) around forward), from the initial
+    # weights again.  Adam normalises every update to ~lr, so post-step WEIGHTS of elements whose gradient sits at the bf16
+    # noise level are not comparable across implementations; the first moments (clipped gradients, EMA) are.
+    model.load_state_dict(sd0)
+    model.zero_grad()
+    optb = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0)
+    lossesb, normsb = [], []
+    for _ in range(3):
+        optb.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            lossb = model(x, labels=y).loss
+        lossb.backward()
+        normsb.append(torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5).detach().clone())
+        optb.step()
+        lossesb.append(lossb.detach().float().clone())
+    trb = dict(losses=torch.stack(lossesb), grad_norms=torch.stack(normsb), exp_avg=moments(optb),
+               state_dict={k: v.detach().clone() for k, v in model.state_dict().items()})
+
     fix = dict(config=copy.deepcopy(cfg), state_dict=sd0, batch=batch, x_seed=7, x_kind=kind, labels=y,
-               eval=ev, grads=grads, bf16=bf, train3=tr, model_name=model.name, loss_name=model.loss_name,
+               eval=ev, grads=grads, bf16=bf, train3=tr, train3_bf16=trb, model_name=model.name, loss_name=model.loss_name,
                torch_version=torch.__version__)
     if stats is not None:   # what the builder needs to rebuild the preprocessor (the covariance itself is not used)
         fix["stats"] = {k: stats[k].clone() for k in ("mean", "eigvals", "eigvecs")}

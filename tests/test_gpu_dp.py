@@ -37,6 +37,7 @@ rank, local, world = dp.init_from_env("nccl")
 torch.manual_seed(7)
 m = get_model(cfg, precision=prec, device=dev)
 dp.broadcast_parameters(m._arena.data)
+p0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
 step = TrainStep(m, B, use_graph=use_graph, world_size=world, train=False)
 lo, hi = rank * B, (rank + 1) * B
 losses = [float(step.step(x[lo:hi].to(dev), y[lo:hi].to(dev))) for _ in range(3)]
@@ -47,8 +48,34 @@ assert torch.equal(ref, flat), "replicas diverged"
 d = float((ref_flat - flat).abs().max() / ref_flat.abs().max())
 tol = 2e-3 if prec == "32" else 2e-2
 assert d < tol, d
+# ... and the ORACLE on the union batch (CPU restatement of the reference step): mean of the rank losses, AdamW first
+# moments (= clipped mean gradients) and, in fp32, the parameters themselves
+lt = torch.tensor(losses, device=dev).reshape(1, -1)
+alll = [torch.zeros_like(lt) for _ in range(world)]
+dist.all_gather(alll, lt)
 if rank == 0:
-    print("DP_OK", json.dumps({"world": world, "param_rel_diff": d, "losses_rank0": losses, "losses_single": l1}))
+    spec = vo.spec_from_config(cfg)
+    ora = vo.OracleTrainer(spec, p0, autocast_bf16=prec != "32")
+    ol = [ora.step(x, y, train=False) for _ in range(3)]
+    mine = torch.cat(alll, 0).mean(0).cpu()
+    ltol = 1e-4 if prec == "32" else 2e-2
+    for i in range(3):
+        assert abs(float(mine[i]) - ol[i]) <= ltol * max(1.0, abs(ol[i])), (i, float(mine[i]), ol[i])
+    lay, eng = m._arena.layout, step.eng
+    gmax = max(float(v.abs().max()) for k, v in ora.m.items() if "pooler" not in k)
+    merr = perr = 0.0
+    for k, v in ora.m.items():
+        e = lay.entries.get(k)
+        if e is None or e.offset >= lay.n_opt:
+            continue
+        got = eng.exp_avg[e.offset:e.offset + e.numel].reshape(e.shape).cpu()
+        merr = max(merr, float((got - v).abs().max()) / max(float(v.abs().max()), 1e-2 * gmax))
+        gp = flat[e.offset:e.offset + e.numel].reshape(e.shape).cpu()
+        perr = max(perr, float((gp - ora.params[k].detach()).abs().max()) / max(float(ora.params[k].abs().max()), 3e-3))
+    assert merr < (2e-3 if prec == "32" else 4e-2), merr
+    assert prec != "32" or perr < 1e-3, perr
+    print("DP_OK", json.dumps({"world": world, "param_rel_diff_vs_single_gpu": d, "exp_avg_rel_err_vs_oracle": merr,
+                               "param_rel_err_vs_oracle": perr, "losses_mean": mine.tolist(), "losses_oracle": ol}))
 dist.barrier()
 step.close()   # the graph holds captured NCCL collectives: it must go before the communicator
 dist.destroy_process_group()

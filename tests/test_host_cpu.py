@@ -184,3 +184,75 @@ def test_dp_gradient_mean_equals_full_batch_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_shadow_goes_stale_after_to_and_foreign_updates():
+    """after model.to()/_apply the Parameters keep their own version counters; updates through them
+    (torch.optim step, load_state_dict, in-place ops) must still mark the bf16 operand copy stale."""
+    from vit_b200 import get_model
+
+    cfg = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                         num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"}}
+    m = get_model(cfg, precision="bf16-mixed", device="cpu")
+    m._apply(lambda t: t.clone())          # what .to(device) / .cuda() do
+    ar = m._arena
+    assert ar.shadow is not None
+    ar.mark_shadow_fresh()
+    assert not ar.shadow_stale()
+    with torch.no_grad():
+        next(m.parameters()).add_(1.0)
+    assert ar.shadow_stale()
+    ar.mark_shadow_fresh()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert ar.shadow_stale()
+    ar.mark_shadow_fresh()
+    m.load_state_dict(m.state_dict())
+    assert ar.shadow_stale()
+
+
+def test_fused_optimizer_state_dict_is_torch_adamw_format():
+    """FusedClipAdamW.state_dict()/load_state_dict() carry the flat moments in torch.optim.AdamW's
+    per-parameter layout (what Lightning's ModelCheckpoint stores and the reference resumes from)."""
+    from vit_b200 import get_model
+    from vit_b200.optim import FusedClipAdamW
+
+    cfg = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                         num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"}}
+    m = get_model(cfg, device="cpu")
+    ref = torch.optim.AdamW(m.parameters(), lr=2e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.0)
+    torch.manual_seed(0)
+    for _ in range(2):
+        for n, p in m.named_parameters():
+            p.grad = None if "pooler" in n else torch.randn_like(p)
+        ref.step()
+    want = ref.state_dict()
+    opt = FusedClipAdamW(m, lr=1e-3)
+    assert opt.state_dict()["state"] == {}
+    opt.load_state_dict(want)
+    got = opt.state_dict()
+    assert sorted(got["state"]) == sorted(want["state"])
+    for i, st in want["state"].items():
+        assert float(got["state"][i]["step"]) == float(st["step"]) == 2.0
+        assert torch.equal(got["state"][i]["exp_avg"], st["exp_avg"])
+        assert torch.equal(got["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+    g = got["param_groups"][0]
+    assert g["lr"] == 2e-3 and tuple(g["betas"]) == (0.8, 0.95) and g["eps"] == 1e-7
+    # a stock AdamW accepts it
+    torch.optim.AdamW(m.parameters()).load_state_dict({"state": got["state"], "param_groups": [
+        {k: v for k, v in g.items() if k != "max_norm"}]})
+
+
+def test_lightning_checkpoint_has_no_empty_loops_key():
+    """Lightning's restore_loops() indexes ckpt['loops']['fit_loop'] whenever 'loops' exists."""
+    from vit_b200 import get_model
+    from vit_b200.checkpoint import save_lightning_checkpoint
+
+    cfg = {"model": dict(task_type="reg", image_size=256, patch_size=32, hidden_size=32, num_hidden_layers=1,
+                         num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"}}
+    ck = save_lightning_checkpoint(get_model(cfg, device="cpu"), epoch=3, global_step=17,
+                                   lr_schedulers=[{"best": 0.5, "num_bad_epochs": 2}])
+    assert "loops" not in ck and ck["epoch"] == 3 and ck["global_step"] == 17
+    assert ck["lr_schedulers"] == [{"best": 0.5, "num_bad_epochs": 2}]

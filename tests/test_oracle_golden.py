@@ -68,6 +68,24 @@ def test_oracle_train_steps(golden, name):
         assert rel_err(tr.params[k], v, 3e-3) < 1e-4, k   # floor = 3 steps x lr (key.bias has a zero gradient)
 
 
+@pytest.mark.parametrize("name", ["baseline", "cls"])
+def test_oracle_train_steps_bf16_autocast(golden, name):
+    """The autocast-bf16 oracle trainer vs the reference's own 3 autocast steps: losses, grad norms and AdamW first
+    moments (the quantity the GPU bf16 train-step tests pin; post-step weights are not comparable in bf16)."""
+    fix = golden(name)
+    spec = vo.spec_from_config(fix["config"])
+    x, y = _inputs(fix)
+    tr = vo.OracleTrainer(spec, fix["state_dict"], autocast_bf16=True)
+    ref = fix["train3_bf16"]
+    for i in range(3):
+        loss = tr.step(x, y, train=False)
+        assert abs(loss - float(ref["losses"][i])) < 2e-2 * max(1.0, abs(loss))
+        assert rel_err(tr.last_grad_norm, ref["grad_norms"][i]) < 0.2
+    gmax = max(float(v.abs().max()) for v in ref["exp_avg"].values())
+    for k, v in ref["exp_avg"].items():
+        assert rel_err(tr.m[k], v, 1e-2 * gmax) < 4e-2, (k, rel_err(tr.m[k], v, 1e-2 * gmax))
+
+
 def test_spec_quirks():
     cfg = {"model": dict(task_type="reg", image_size=4096, patch_size=32, hidden_size=32, num_hidden_layers=3,
                          num_attention_heads=2, stride_size=32, proj_fn="SW"), "loss": {"name": "mae"},

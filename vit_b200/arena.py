@@ -105,6 +105,7 @@ class ParamArena:
         self.shadow = (torch.zeros(layout.n_total, dtype=torch.bfloat16, device=self.device)
                        if with_shadow else None)
         self._shadow_version = -1
+        self.watch = []   # the module Parameters that alias `data` (set by MyViT._bind_arena)
 
     def view(self, name: str, buf: torch.Tensor | None = None) -> torch.Tensor:
         e = self.layout.entries[name]
@@ -121,8 +122,14 @@ class ParamArena:
         return new
 
     # ---- bf16 shadow maintenance -------------------------------------------------------------
+    def _version(self) -> int:
+        # Parameters rebound with `p.data = view` (MyViT._apply after .to()/.cuda()) keep their OWN version counters:
+        # an in-place update through such a Parameter (torch.optim step, load_state_dict) does not bump data._version.
+        # The sum over both moves whenever any alias is written.
+        return self.data._version + sum(p._version for p in self.watch)
+
     def shadow_stale(self) -> bool:
-        return self.shadow is not None and self._shadow_version != self.data._version
+        return self.shadow is not None and self._shadow_version != self._version()
 
     def mark_shadow_fresh(self) -> None:
-        self._shadow_version = self.data._version
+        self._shadow_version = self._version()

@@ -102,7 +102,7 @@ def load_lightning_checkpoint(model, ckpt, train_step=None, strict: bool = True)
         sd = strip_prefix(sd)
     model.load_state_dict(sd, strict=strict)
     info = {"epoch": ckpt.get("epoch"), "global_step": ckpt.get("global_step"), "step": None,
-            "extra_optimizer_state": {}}
+            "extra_optimizer_state": {}, "lr_schedulers": list(ckpt.get("lr_schedulers") or [])}
     opt_states = ckpt.get("optimizer_states") or []
     if train_step is not None and opt_states:
         eng = train_step.eng
@@ -129,13 +129,16 @@ def load_lightning_checkpoint(model, ckpt, train_step=None, strict: bool = True)
 
 
 def save_lightning_checkpoint(model, path=None, train_step=None, epoch: int = 0, global_step: Optional[int] = None,
-                              hyper_parameters: Optional[dict] = None) -> dict:
+                              hyper_parameters: Optional[dict] = None, lr_schedulers: Optional[list] = None) -> dict:
     """Write (and return) a dict the reference's Lightning trainer can load: `model.`-prefixed state_dict, and -- with
     `train_step` -- the AdamW state in torch's per-parameter layout."""
     sd = {PREFIX + k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     ckpt = {"epoch": int(epoch), "global_step": 0 if global_step is None else int(global_step),
-            "pytorch-lightning_version": "2.0.0", "state_dict": sd, "loops": {}, "callbacks": {},
-            "optimizer_states": [], "lr_schedulers": [], "hyper_parameters": {"config": hyper_parameters or {}}}
+            "pytorch-lightning_version": "2.0.0", "state_dict": sd, "callbacks": {},
+            "optimizer_states": [], "lr_schedulers": list(lr_schedulers or []),
+            "hyper_parameters": {"config": hyper_parameters or {}}}
+    # No "loops" key on purpose: Lightning's _CheckpointConnector.restore_loops() reads ckpt["loops"]["fit_loop"] whenever
+    # the key exists, and falls back to the plain epoch / global_step fields (the pre-1.6 format) when it does not.
     if train_step is not None:
         eng = train_step.eng
         eng._ensure_opt_state()

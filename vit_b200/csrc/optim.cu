@@ -220,7 +220,10 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
       const unsigned int* f = peer_flags(X.bufs[X.rank]) + (size_t)threadIdx.x * TAIL_MAX_BLOCKS + blockIdx.x;
       unsigned int spins = 0;
       while ((int)(ld_acquire_sys(f) - seq) < 0) {
-        if (++spins > (1u << 28)) __trap();   // a dead peer traps instead of hanging the device
+        // a peer that never arrives (crashed rank) must not hang the device, and must not poison the context of the
+        // surviving ranks either: give up after ~minutes, record the failure in state[7] (the host checks it,
+        // PeerExchange.check()) and carry on with whatever the buffer holds
+        if (++spins > (1u << 30)) { state[7] = 1.f; break; }
       }
     }
     __syncthreads();

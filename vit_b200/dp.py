@@ -70,6 +70,10 @@ def broadcast_parameters(flat_data: torch.Tensor, group=None, src: int = 0) -> N
     dist.broadcast(flat_data, src=src, group=group)
 
 
+class PeerUnavailable(RuntimeError):
+    """The ranks cannot map each other's memory (different nodes, P2P disabled): use the NCCL all-reduce."""
+
+
 class PeerExchange:
     """Per-rank exchange buffers for the in-kernel gradient all-reduce (vitb200_clip_adamw_fused_dp).
 
@@ -94,24 +98,48 @@ class PeerExchange:
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         self.opened = []
         ptrs = []
+        ok = 1
         for q, h in enumerate(handles):
             if q == self.rank:
                 ptrs.append(self.own)
                 continue
             p = ctypes.c_void_p()
-            _lib.check(self.lib.vitb200_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "peer_open")
+            if self.lib.vitb200_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)) != 0:
+                ok = 0      # no CUDA IPC / peer access to that rank (another node, or P2P disabled)
+                break
             self.opened.append(p.value)
             ptrs.append(p.value)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag[0]) == 0:   # every rank takes the same decision: the caller falls back to the NCCL all-reduce
+            for p in self.opened:
+                self.lib.vitb200_peer_close(p)
+            self.lib.vitb200_peer_free(self.own)
+            self.own, self.opened = None, []
+            raise PeerUnavailable("CUDA IPC peer mapping failed on at least one rank")
         self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        # the optimizer kernel's barrier / launch-count words live and die with the exchange buffers: the flag protocol
+        # compares peer flags with the local launch count, so a re-zeroed workspace next to surviving buffers (or the
+        # reverse) would let a wait pass on stale flags
+        self.tail_ws = torch.zeros(int(self.lib.vitb200_clip_adamw_fused_ws_bytes()), dtype=torch.uint8, device=device)
+        self.group = group
         torch.cuda.synchronize(device)
         dist.barrier(group=group)   # every rank has mapped every buffer before the first launch touches them
+
+    @staticmethod
+    def check(state: torch.Tensor) -> None:
+        """Raise if an optimizer launch gave up waiting for a peer (state[7] is set by the kernel; one host read --
+        call it at epoch / checkpoint boundaries, not per step)."""
+        if float(state[7]) != 0.0:
+            raise RuntimeError("vit_b200: a data-parallel optimizer launch timed out waiting for a peer rank's gradients; "
+                               "the replicas are no longer consistent")
 
     def close(self) -> None:
         if self.own is None:
             return
         torch.cuda.synchronize()
         if dist.is_initialized():
-            dist.barrier()          # nobody unmaps while a peer's last kernel may still read
+            dist.barrier(group=self.group)   # nobody unmaps while a peer's last kernel may still read
         for p in self.opened:
             self.lib.vitb200_peer_close(p)
         self.lib.vitb200_peer_free(self.own)

@@ -644,11 +644,12 @@ class ViTEngine:
         st = torch.cuda.current_stream(self.device).cuda_stream
         if getattr(self, "peer", None) is not None:   # data parallel: gradient all-reduce over peer memory, in-kernel
             pr = self.peer
+            tail_ws = pr.tail_ws
             _lib.check(self.lib.vitb200_clip_adamw_fused_dp(
                 ar.data.data_ptr(), ar.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                 None if ar.shadow is None else ar.shadow.data_ptr(), ar.layout.n_opt, self.hyper.data_ptr(),
                 self.state.data_ptr(), self.rng.data_ptr(), self.gpart.data_ptr() if slots else None, slots,
-                ar.layout.n_opt, start, end, self.tail_ws.data_ptr(), pr.table.data_ptr(), pr.rank, pr.world, st),
+                ar.layout.n_opt, start, end, tail_ws.data_ptr(), pr.table.data_ptr(), pr.rank, pr.world, st),
                 "clip_adamw_fused_dp")
             if ar.shadow is not None:
                 ar.mark_shadow_fresh()

@@ -411,6 +411,7 @@ class MyViT(nn.Module):
                 setattr(mod, attr, nn.Parameter(view))
         self._param_names = [n for n, _ in self.named_parameters() if n in self._layout.entries]
         self._param_list = [p for n, p in self.named_parameters() if n in self._layout.entries]
+        arena.watch = self._param_list
         if init:
             self.init_weights()
 

@@ -34,7 +34,10 @@ class TrainStep:
             self.eng.set_grad_scale(1.0 / self.world)
             # fused programs: the gradient all-reduce runs inside the optimizer kernel over NVLink peer memory
             if self.eng.fused_bwd and peer_allreduce:
-                self.eng.peer = _dp.PeerExchange(self.eng.arena.layout.n_opt, self.eng.device, group=process_group)
+                try:
+                    self.eng.peer = _dp.PeerExchange(self.eng.arena.layout.n_opt, self.eng.device, group=process_group)
+                except _dp.PeerUnavailable:
+                    self.eng.peer = None    # collective decision (all ranks): NCCL all-reduce of the gradient arena
         self.noise_level = float(noise_level)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
