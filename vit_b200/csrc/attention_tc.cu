@@ -43,15 +43,16 @@ __device__ __forceinline__ uint8_t* at_swz(uint8_t* tile, int r, int chunk) {
   return tile + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
 }
 // row r (of a tile whose rows are 128 B) holds d values in chunks 0..d/8-1: load / store them
+// (c0 = first 16-byte chunk of the head inside the 64-column TMA box: the box starts at a multiple of 64 columns)
 template <int D>
-__device__ __forceinline__ void at_load_row(uint8_t* tile, int r, float (&x)[D]) {
+__device__ __forceinline__ void at_load_row(uint8_t* tile, int r, float (&x)[D], int c0 = 0) {
 #pragma unroll
-  for (int c = 0; c < D / 8; ++c) at_unpack8(*reinterpret_cast<const uint4*>(at_swz(tile, r, c)), &x[c * 8]);
+  for (int c = 0; c < D / 8; ++c) at_unpack8(*reinterpret_cast<const uint4*>(at_swz(tile, r, c0 + c)), &x[c * 8]);
 }
 template <int D>
-__device__ __forceinline__ void at_store_row(uint8_t* tile, int r, const float (&x)[D]) {
+__device__ __forceinline__ void at_store_row(uint8_t* tile, int r, const float (&x)[D], int c0 = 0) {
 #pragma unroll
-  for (int c = 0; c < D / 8; ++c) *reinterpret_cast<uint4*>(at_swz(tile, r, c)) = at_pack8(&x[c * 8]);
+  for (int c = 0; c < D / 8; ++c) *reinterpret_cast<uint4*>(at_swz(tile, r, c0 + c)) = at_pack8(&x[c * 8]);
 }
 // RoPE on a full head row held by one thread (rope.py:60-98); INV = transpose (for gradients)
 template <int D, bool INV>
@@ -137,6 +138,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
   const int key0 = P.kb ? P.key0 : 0, Tk = P.kb ? P.Tk : T;   // keys of this launch: [key0, key0 + Tk)
+  // TMA boxes are 64 columns wide and start at multiples of 64 columns; a head's d columns sit at 16-byte chunk
+  // cq / ck / cv inside the 128-byte rows (UMMA descriptors and row accessors start there: the 128B swizzle is a
+  // function of the address bits, so a start offset inside the swizzle atom selects the columns)
+  const int colQ = h * D, colK = P.H + h * D, colV = 2 * P.H + h * D;
+  const int cq = (colQ & 63) >> 3, ck = (colK & 63) >> 3, cv = (colV & 63) >> 3;
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
@@ -148,10 +154,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VB_TL(tl_attn_fwd, 2);
   if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
     mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0 + key0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0 + key0);
+    tma_load_2d(sK, &tmKV, b_kv, colK & ~63, row0 + key0);
+    tma_load_2d(sV, &tmKV, b_kv, colV & ~63, row0 + key0);
     mbar_expect_tx(b_q, 16384);                       // first query tile
-    tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
+    tma_load_2d(sQ, &tmQ, b_q, colQ & ~63, row0);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -160,8 +166,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   VB_TL(tl_attn_fwd, 3);
-  const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Kk{smem_u32(sK), 16, 16384, 0};
-  const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV), 16384, 0, 1};
+  const AOp Qk{smem_u32(sQ) + cq * 16, 16, 16384, 0}, Kk{smem_u32(sK) + ck * 16, 16, 16384, 0};
+  const AOp Pk{smem_u32(sP), 16, 16384, 0}, Vmn{smem_u32(sV) + cv * 16, 16384, 0, 1};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
   const int Tpad = attn_drop_tpad(T);
   const float sl2 = P.scale * AT_LOG2E;
@@ -189,7 +195,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float acc = -INFINITY;
         if (j < Tk) {
           float kr[D];
-          at_load_row<D>(sK, j, kr);
+          at_load_row<D>(sK, j, kr, ck);
           acc = 0.f;
 #pragma unroll
           for (int c = 0; c < D; ++c) acc = fmaf(qf[c], kr[c], acc);
@@ -211,7 +217,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           p *= drop1(dc, drow + (uint64_t)(key0 + j));
           p = bf16_round(p);
           float vr[D];
-          at_load_row<D>(sV, j, vr);
+          at_load_row<D>(sV, j, vr, cv);
 #pragma unroll
           for (int c = 0; c < D; ++c) o[c] = fmaf(p, vr[c], o[c]);
         }
@@ -242,7 +248,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool valid = i < T;
     if (tid == 0 && qt > 0) {
       mbar_expect_tx(b_q, 16384);
-      tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
+      tma_load_2d(sQ, &tmQ, b_q, colQ & ~63, row0 + q0);
     }
     if (qt == 0) mbar_wait(b_kv, 0);
     mbar_wait(b_q, ph_q); ph_q ^= 1;
@@ -250,15 +256,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (P.cosT) {  // rotate the query rows (and, once, the key rows) in place
       float x[D];
       if (cg == 0) {
-        at_load_row<D>(sQ, r, x);
+        at_load_row<D>(sQ, r, x, cq);
         at_rope<D, false>(x, P.cosT, P.sinT, valid ? i : 0);
-        at_store_row<D>(sQ, r, x);
+        at_store_row<D>(sQ, r, x, cq);
       }
       if (qt == 0) {
         for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
-          at_load_row<D>(sK, rr, x);
+          at_load_row<D>(sK, rr, x, ck);
           at_rope<D, false>(x, P.cosT, P.sinT, rr < Tk ? key0 + rr : 0);
-          at_store_row<D>(sK, rr, x);
+          at_store_row<D>(sK, rr, x, ck);
         }
       }
       fence_proxy_async();
@@ -409,6 +415,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int h = blockIdx.x, b = blockIdx.y, T = P.T;
   const int row0 = b * T;
   const int key0 = P.kb ? P.key0 : 0, Tk = P.kb ? P.Tk : T;   // keys of this launch: [key0, key0 + Tk)
+  const int colQ = h * D, colK = P.H + h * D, colV = 2 * P.H + h * D;   // see the forward kernel
+  const int cq = (colQ & 63) >> 3, ck = (colK & 63) >> 3, cv = (colV & 63) >> 3;
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
     mbar_init(b_kv, 1); mbar_init(b_q, 1); mbar_init(b_mma, 1);
@@ -418,11 +426,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_trigger();
   if (tid == 0) {    // loads first (same thread that initialised the barriers): they fly while TMEM is allocated
     mbar_expect_tx(b_kv, 2 * kv_bytes);
-    tma_load_2d(sK, &tmKV, b_kv, P.H + h * D, row0 + key0);
-    tma_load_2d(sV, &tmKV, b_kv, 2 * P.H + h * D, row0 + key0);
+    tma_load_2d(sK, &tmKV, b_kv, colK & ~63, row0 + key0);
+    tma_load_2d(sV, &tmKV, b_kv, colV & ~63, row0 + key0);
     mbar_expect_tx(b_q, 32768);                       // first query / dO tiles
-    tma_load_2d(sQ, &tmQ, b_q, h * D, row0);
-    tma_load_2d(sDO, &tmDO, b_q, h * D, row0);
+    tma_load_2d(sQ, &tmQ, b_q, colQ & ~63, row0);
+    tma_load_2d(sDO, &tmDO, b_q, colQ & ~63, row0);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -430,9 +438,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const AOp Qk{smem_u32(sQ), 16, 16384, 0}, Qmn{smem_u32(sQ), 16384, 0, 1};
-  const AOp DOk{smem_u32(sDO), 16, 16384, 0}, DOmn{smem_u32(sDO), 16384, 0, 1};
-  const AOp Kk{smem_u32(sK), 16, 16384, 0}, Kmn{smem_u32(sK), 16384, 0, 1}, Vk{smem_u32(sV), 16, 16384, 0};
+  const AOp Qk{smem_u32(sQ) + cq * 16, 16, 16384, 0}, Qmn{smem_u32(sQ) + cq * 16, 16384, 0, 1};
+  const AOp DOk{smem_u32(sDO) + cq * 16, 16, 16384, 0}, DOmn{smem_u32(sDO) + cq * 16, 16384, 0, 1};
+  const AOp Kk{smem_u32(sK) + ck * 16, 16, 16384, 0}, Kmn{smem_u32(sK) + ck * 16, 16384, 0, 1};
+  const AOp Vk{smem_u32(sV) + cv * 16, 16, 16384, 0};
   const AOp DSk{smem_u32(sDS), 16, 16384, 0};
   const DropCtx dc = make_drop(P.p_drop, P.rng ? P.rng[0] : 0ull, P.rng ? (uint32_t)P.rng[1] : 0u, P.site);
   const int Tpad = attn_drop_tpad(T);
@@ -474,8 +483,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int j = lane + 32 * jj;
         if (j < Tk) {
           float kr[D], vr[D];
-          at_load_row<D>(sK, j, kr);
-          at_load_row<D>(sV, j, vr);
+          at_load_row<D>(sK, j, kr, ck);
+          at_load_row<D>(sV, j, vr, cv);
           float sdot = 0.f, dp = 0.f;
 #pragma unroll
           for (int c = 0; c < D; ++c) { sdot = fmaf(qf[c], kr[c], sdot); dp = fmaf(dof[c], vr[c], dp); }
@@ -513,8 +522,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int ic = valid ? i : T - 1;
     if (tid == 0 && qt > 0) {
       mbar_expect_tx(b_q, 32768);
-      tma_load_2d(sQ, &tmQ, b_q, h * D, row0 + q0);
-      tma_load_2d(sDO, &tmDO, b_q, h * D, row0 + q0);
+      tma_load_2d(sQ, &tmQ, b_q, colQ & ~63, row0 + q0);
+      tma_load_2d(sDO, &tmDO, b_q, colQ & ~63, row0 + q0);
     }
     // row statistics: issued before the waits (lse_i, and the ctx row for D_i = dO_i . O_i)
     const float lse2 = P.lse[(size_t)(b * P.heads + h) * T + ic] * AT_LOG2E;
@@ -537,20 +546,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < D; ++c) dof[c] = 0.f;
     } else {
-      at_load_row<D>(sDO, r, dof);
+      at_load_row<D>(sDO, r, dof, cq);
     }
     if (P.cosT) {
       float x[D];
       if (valid && cg == 0) {
-        at_load_row<D>(sQ, r, x);
+        at_load_row<D>(sQ, r, x, cq);
         at_rope<D, false>(x, P.cosT, P.sinT, i);
-        at_store_row<D>(sQ, r, x);
+        at_store_row<D>(sQ, r, x, cq);
       }
       if (qt == 0) {
         for (int rr = tid; rr < KP; rr += AT_TC_THREADS) {
-          at_load_row<D>(sK, rr, x);
+          at_load_row<D>(sK, rr, x, ck);
           at_rope<D, false>(x, P.cosT, P.sinT, rr < Tk ? key0 + rr : 0);
-          at_store_row<D>(sK, rr, x);
+          at_store_row<D>(sK, rr, x, ck);
         }
       }
     }
