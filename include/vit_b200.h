@@ -242,6 +242,51 @@ int vitb200_fused_layer_bwd_lower(const vitb200_layer_bwd_lower_args* args, void
 int vitb200_grad_reduce(const float* gpart, int slots, size_t stride, size_t start, size_t end, float* grad,
                         void* stream);
 
+/* ---- whole-network kernels (bf16, hidden 32, 2 heads of 16, 4H MLP, T = Np + 1 <= 129) --------------------------------
+ * The configured model (configs/exp/att_clp/baseline.yaml, configs/config.yaml) is so small that a training step is a
+ * chain of dependent launches, not bandwidth or math.  Samples are independent until the gradient reduction, so ONE
+ * persistent kernel per direction gives every CTA whole samples and runs the complete network on them:
+ *   forward : spectrum -> patch GEMM, CLS, (+pos), dropout -> [LN1, QKV, attention (S = QK^T, softmax, PV), out-proj,
+ *             dropout, +res, LN2, MLP-up, GELU, MLP-down, dropout, +res] x layers -> final LN of the CLS row -> head ->
+ *             logits, loss     (src/models/embedding.py:79-100, HF:328-346, HF:454-455, src/models/specvit.py:78-89)
+ *   backward: autograd of the above for the same sample: head, final LN, every layer (MLP, LN2, out-proj, attention,
+ *             QKV, LN1), embedding; parameter gradients accumulate per CTA and leave as ONE partial set per CTA
+ *             (gpart[cta][n_opt], summed in CTA order by vitb200_clip_adamw_fused).
+ * 128 token rows of a sample run on tcgen05 (TMEM lane = row, all weights TMA-staged in shared memory, activations
+ * handed from GEMM to GEMM through swizzled shared-memory tiles); the 129th token runs beside them on a 17th warp.
+ * Same math, same dropout masks and the same saved-for-backward tensors as the per-op entry points, so either
+ * direction can be mixed with them.
+ * Parameters are addressed inside the flat arena: `params` (fp32 master) and `shadow` (bf16 GEMM operands) with element
+ * offsets; layer l's block starts at off_layer0 + l * layer_stride and o_* are offsets inside a block (q, k, v weights
+ * and biases adjacent, see vit_b200/arena.py).  Saved activations are layer-major: z [layers+1, B*T, H] f32,
+ * hmid [layers, B*T, H] f32, u / u2 / ctx [layers, B*T, H], qkv [layers, B*T, 3H], a / m [layers, B*T, 4H] (bf16),
+ * stats [4*layers + 2, B*T] f32 (mean1, rstd1, mean2, rstd2 per layer; then mean / rstd of the final LN of the CLS rows,
+ * indexed by sample), lse [layers, B, heads, T] f32. */
+typedef struct {
+  int B, L, P, S, Np, n_valid;       /* spectrum length L, patch P, stride S, Np patches (n_valid real windows) */
+  int layers, C, loss_kind, cluster; /* encoder layers, labels, VITB200_LOSS_*, CTAs per sample (1, or 2 = one head each) */
+  float eps, p_hidden, p_attn;       /* dropout probabilities (0 in eval mode) */
+  const uint64_t* rng;
+  const float* x;                    /* [B, L] f32 */
+  const void* labels;                /* f32 [B*C] (MSE / L1) or int64 [B] (CE); NULL: logits only */
+  const float* params; const void* shadow;
+  int off_cls, off_pos, off_wp, off_bp;          /* off_pos < 0: no learned positions */
+  int off_layer0, layer_stride;
+  int o_ln1g, o_ln1b, o_wqkv, o_bqkv, o_wo, o_bo, o_ln2g, o_ln2b, o_w1, o_b1, o_w2, o_b2;
+  int off_lnfg, off_lnfb, off_wh, off_bh;
+  const float *rope_cos, *rope_sin;  /* [T, 8] f32 or NULL */
+  float *z, *hmid; void *u, *u2, *qkv, *ctx, *a, *m;
+  float *stats, *lse;
+  void* s_cls;                       /* [B, H] bf16: final-LayerNorm'd CLS rows */
+  float *logits, *loss;              /* [B, C], [1] */
+  void* ws;                          /* vitb200_mega_ws_bytes() bytes, zeroed once by the caller */
+} vitb200_mega_fwd_args;
+int vitb200_mega_supported(int H, int heads, int T, int P, int C, int layers, int rope);
+size_t vitb200_mega_ws_bytes(void);
+size_t vitb200_mega_fwd_smem_bytes(int layers);
+int vitb200_mega_grid(int B, int cluster);
+int vitb200_mega_fwd(const vitb200_mega_fwd_args* args, void* stream);
+
 /* ---- multi-head self-attention ----------------------------------------------------------------
  * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and
  * ViTSelfAttentionWithRoPE.forward (src/models/vit_with_rope.py:43-84; RoPE = src/models/rope.py:60-98):

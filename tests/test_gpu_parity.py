@@ -332,7 +332,10 @@ def test_fused_paths_are_the_ones_tested(golden):
     dev = _cuda()
     fix = golden("baseline")
     eng = _build(fix, "bf16-mixed", dev)._engine(fix["batch"])
-    assert eng.fused and eng.fused_bwd
+    assert eng.fused and eng.fused_bwd and eng.mega
+    names = [fn.__name__ for fn, _ in eng._build_forward(True, True)]
+    assert names == ["vitb200_mega_fwd"]          # the whole forward is ONE launch at the configured shape
+    eng.mega = False                              # the per-op fused programs stay available (longer sequences, H = 64)
     names = [fn.__name__ for fn, _ in eng._build_forward(True, True)]
     assert names.count("vitb200_fused_layer_fwd") == 3 and names[0] == "vitb200_fused_embed_fwd"
     names = [fn.__name__ for fn, _ in eng._build_backward(True, None)]

@@ -33,23 +33,29 @@ for _ in range(5):
     st.step(x, y)
 torch.cuda.synchronize()
 lib = _lib.load()
-SLOTS, CTAS = 16, 512
+SLOTS, CTAS = 32, 512
 names = {
     "layer_fwd": ["prologue", "pdl_wait", "tmem+sync", "ctx TMA+MMA1", "epi1 (drop,LN)+sync", "MMA2", "GELU+sync", "MMA3",
                   "epi3 (drop,LN)", "sync+MMA4", "epi4 (qkv)+sync"],
     "bwd_upper": ["prologue", "pdl_wait", "tmem+sync", "dz,drop->sD +sync", "tile TMA+MMA1", "gelu'+sync", "MMA2",
                   "LN bwd+sync", "MMA3", "dctx epi", "grad tail"],
     "tail": ["pdl_wait", "reduce partial slots", "block sum + ticket + wait", "norm, coef, bias corrections", "AdamW"],
+    "mega_fwd": ["prologue+pdl_wait+weights", "embed+QKV(0)", "S MMA wait", "max pass", "exp pass", "PV (+2nd head)", "O epi+exchange",
+                 "hop1", "hop2", "hop3", "layers 1..", "exit"],
     "attn_fwd": ["prologue", "pdl_wait", "tmem+sync", "K/V/Q TMA", "rope+bar+MMA S", "max pass+bar", "exp pass+bar", "MMA PV",
                  "O epi"],
 }
 for key, labels in names.items():
     buf = (ctypes.c_longlong * (SLOTS * CTAS))()
+    if not hasattr(lib, f"vitb200_tl_{key}"):
+        continue
     rc = getattr(lib, f"vitb200_tl_{key}")(buf)
     assert rc == 0
     a = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)
     n = len(labels) + 1
     live = a[:, 0] != 0
+    if not live.any():
+        continue          # kernel not launched by this program (e.g. the per-op kernels when the whole-network kernel runs)
     a = a[live][:, :n]
     d = np.diff(a, axis=1)
     print(f"== {key}: {a.shape[0]} CTAs, total mean {d.sum(1).mean():.0f} cycles (max {d.sum(1).max()}) "

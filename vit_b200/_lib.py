@@ -64,6 +64,17 @@ class EmbedBwdArgs(C.Structure):  # vitb200_embed_bwd_args
                [(n, _p) for n in ("rng", "dz0", "x", "gpart")] + [(n, _i) for n in ("n_opt", "off_wp", "off_bp", "off_cls")]
 
 
+class MegaFwdArgs(C.Structure):  # vitb200_mega_fwd_args
+    _fields_ = [(n, _i) for n in ("B", "L", "P", "S", "Np", "n_valid", "layers", "C", "loss_kind", "cluster")] + \
+               [("eps", _f), ("p_hidden", _f), ("p_attn", _f)] + \
+               [(n, _p) for n in ("rng", "x", "labels", "params", "shadow")] + \
+               [(n, _i) for n in ("off_cls", "off_pos", "off_wp", "off_bp", "off_layer0", "layer_stride", "o_ln1g", "o_ln1b",
+                                  "o_wqkv", "o_bqkv", "o_wo", "o_bo", "o_ln2g", "o_ln2b", "o_w1", "o_b1", "o_w2", "o_b2",
+                                  "off_lnfg", "off_lnfb", "off_wh", "off_bh")] + \
+               [(n, _p) for n in ("rope_cos", "rope_sin", "z", "hmid", "u", "u2", "qkv", "ctx", "a", "m", "stats", "lse",
+                                  "s_cls", "logits", "loss", "ws")]
+
+
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
 SIGNATURES = {
     "vitb200_strerror": (C.c_char_p, [_i]),
@@ -96,6 +107,11 @@ SIGNATURES = {
     "vitb200_fused_layer_bwd_upper": (_i, [_p, _p]),
     "vitb200_fused_layer_bwd_lower": (_i, [_p, _p]),
     "vitb200_grad_reduce": (_i, [_p, _i, _sz, _sz, _sz, _p, _p]),
+    "vitb200_mega_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "vitb200_mega_ws_bytes": (_sz, []),
+    "vitb200_mega_fwd_smem_bytes": (_sz, [_i]),
+    "vitb200_mega_grid": (_i, [_i, _i]),
+    "vitb200_mega_fwd": (_i, [_p, _p]),
     "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_set_attn_mode": (_i, [_i]),

@@ -45,7 +45,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Thread 0 of every CTA stamps clock64() at phase boundaries; tools/timeline.py prints the per-phase cycles.
 // ---------------------------------------------------------------------------------------------
 #ifdef VB_TIMELINE
-#define VB_TL_SLOTS 16
+#define VB_TL_SLOTS 32
 #define VB_TL_CTAS 512
 #define VB_TL_DECL(name) __device__ long long name[VB_TL_CTAS * VB_TL_SLOTS];
 #define VB_TL(name, k)                                                                                        \
@@ -280,6 +280,35 @@ static inline void vb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   static const bool no_pdl = getenv("VITB200_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
   cfg.attrs = at;
   cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// the same with a thread-block cluster of `cluster` CTAs along x (1 = no cluster attribute)
+template <typename... KArgs, typename... Args>
+static inline void vb_launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  static const bool no_pdl = getenv("VITB200_NO_PDL") != nullptr;
+  if (!no_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

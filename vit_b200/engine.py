@@ -63,17 +63,28 @@ class ViTEngine:
             self.labels = torch.zeros(B * c.num_labels, **f32)
         self.logits = torch.zeros(B, c.num_labels, **f32)
         self.loss = torch.zeros(1, **f32)
-        # ---- saved activations ----
-        self.z = [torch.empty(M, H, **f32) for _ in range(Lh + 1)]
-        self.hmid = [torch.empty(M, H, **f32) for _ in range(Lh)]
-        self.u = [torch.empty(M, H, **act) for _ in range(max(Lh, 1))]
-        self.u2 = [torch.empty(M, H, **act) for _ in range(Lh)]
+        # ---- saved activations: one layer-major tensor per kind (the whole-network kernels address them through ONE
+        # 4-D tensor map [cols, T, B, layers]); the per-layer lists are views for the per-op programs ----
+        Ln = max(Lh, 1)
+        self.z_all = torch.empty(Lh + 1, M, H, **f32)
+        self.hmid_all = torch.empty(Ln, M, H, **f32)
+        self.u_all = torch.empty(Ln, M, H, **act)
+        self.u2_all = torch.empty(Ln, M, H, **act)
+        self.qkv_all = torch.empty(Ln, M, 3 * H, **act)
+        self.ctx_all = torch.empty(Ln, M, H, **act)
+        self.lse_all = torch.empty(Ln, B, c.num_attention_heads, T, **f32)
+        self.a_all = torch.empty(Ln, M, I, **act)
+        self.m_all = torch.empty(Ln, M, I, **act)
+        self.z = [self.z_all[l] for l in range(Lh + 1)]
+        self.hmid = [self.hmid_all[l] for l in range(Lh)]
+        self.u = [self.u_all[l] for l in range(Ln)]
+        self.u2 = [self.u2_all[l] for l in range(Lh)]
         self.stats = torch.empty(4 * max(Lh, 1) + 2, M, **f32)  # mean1,rstd1,mean2,rstd2 per layer + final
-        self.qkv = [torch.empty(M, 3 * H, **act) for _ in range(Lh)]
-        self.ctx = [torch.empty(M, H, **act) for _ in range(Lh)]
-        self.lse = [torch.empty(B, c.num_attention_heads, T, **f32) for _ in range(Lh)]
-        self.a = [torch.empty(M, I, **act) for _ in range(Lh)]
-        self.m = [torch.empty(M, I, **act) for _ in range(Lh)]
+        self.qkv = [self.qkv_all[l] for l in range(Lh)]
+        self.ctx = [self.ctx_all[l] for l in range(Lh)]
+        self.lse = [self.lse_all[l] for l in range(Lh)]
+        self.a = [self.a_all[l] for l in range(Lh)]
+        self.m = [self.m_all[l] for l in range(Lh)]
         self.delta = torch.empty(M, H, **act)
         self.s_cls = torch.empty(B, H, **act)
         # ---- backward scratch (allocated lazily) ----
@@ -98,6 +109,12 @@ class ViTEngine:
                           and os.environ.get("VITB200_FUSED", "1") != "0")
         self.fused_bwd = bool(self.fused and self.lib.vitb200_fused_bwd_supported(H)
                               and os.environ.get("VITB200_FUSED_BWD", "1") != "0")
+        # whole-network kernels (one persistent CTA per sample): bf16, hidden 32, 2 heads, T <= 129
+        self.mega = bool(self.fused and Lh >= 1 and self.lib.vitb200_mega_supported(
+            H, c.num_attention_heads, T, c.patch_size, c.num_labels, Lh, 1 if c.pos_encoding_type == "rope" else 0)
+            and os.environ.get("VITB200_MEGA", "1") != "0")
+        # CTA pairs (one attention head per CTA, 2 SMs per sample) while every sample still gets its own pair in one wave
+        self.mega_cluster = int(os.environ.get("VITB200_MEGA_CLUSTER", "2" if 2 * self.B <= 148 else "1"))
         self._keep = []  # ctypes argument structs referenced by the cached programs
         ws_bytes = self._ws_bytes()
         self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
@@ -205,9 +222,56 @@ class ViTEngine:
             P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
             self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), self.dt))
 
+    def _mega_fwd_args(self, train: bool, with_labels: bool):
+        c, lay, P_ = self.cfg, self.arena.layout, self._ptr
+        if not hasattr(self, "mega_ws"):
+            self.mega_ws = torch.zeros(int(self.lib.vitb200_mega_ws_bytes()), dtype=torch.uint8, device=self.device)
+        emb, L0 = "vit.embeddings.", "vit.encoder.layer.0."
+        base0 = lay.off(L0 + "layernorm_before.weight")
+        stride = (lay.off("vit.encoder.layer.1.layernorm_before.weight") - base0) if c.num_hidden_layers > 1 else 0
+        rel = lambda n: lay.off(L0 + n) - base0   # noqa: E731
+        a = _lib.MegaFwdArgs(
+            B=self.B, L=c.image_size, P=c.patch_size, S=c.stride, Np=c.num_patches, n_valid=c.n_valid,
+            layers=c.num_hidden_layers, C=c.num_labels, loss_kind=self.loss_kind, cluster=self.mega_cluster,
+            eps=float(c.layer_norm_eps), p_hidden=float(c.hidden_dropout_prob) if train else 0.0,
+            p_attn=float(c.attention_probs_dropout_prob) if train else 0.0, rng=self.rng.data_ptr(), x=P_(self.x),
+            labels=P_(self.labels) if with_labels else None, params=self.arena.data.data_ptr(),
+            shadow=self.arena.shadow.data_ptr(), off_cls=lay.off(emb + "cls_token"),
+            off_pos=lay.off(emb + "position_embeddings") if c.pos_encoding_type == "learned" else -1,
+            off_wp=lay.off(emb + "patch_embeddings.projection.weight"), off_bp=lay.off(emb + "patch_embeddings.projection.bias"),
+            off_layer0=base0, layer_stride=stride, o_ln1g=0, o_ln1b=rel("layernorm_before.bias"),
+            o_wqkv=rel("attention.attention.query.weight"), o_bqkv=rel("attention.attention.query.bias"),
+            o_wo=rel("attention.output.dense.weight"), o_bo=rel("attention.output.dense.bias"),
+            o_ln2g=rel("layernorm_after.weight"), o_ln2b=rel("layernorm_after.bias"),
+            o_w1=rel("intermediate.dense.weight"), o_b1=rel("intermediate.dense.bias"),
+            o_w2=rel("output.dense.weight"), o_b2=rel("output.dense.bias"),
+            off_lnfg=lay.off("vit.layernorm.weight"), off_lnfb=lay.off("vit.layernorm.bias"),
+            off_wh=lay.off(lay.head_name + ".weight"), off_bh=lay.off(lay.head_name + ".bias"),
+            rope_cos=P_(self.rope_cos), rope_sin=P_(self.rope_sin), z=P_(self.z_all), hmid=P_(self.hmid_all),
+            u=P_(self.u_all), u2=P_(self.u2_all), qkv=P_(self.qkv_all), ctx=P_(self.ctx_all), a=P_(self.a_all),
+            m=P_(self.m_all), stats=P_(self.stats), lse=P_(self.lse_all), s_cls=P_(self.s_cls), logits=P_(self.logits),
+            loss=P_(self.loss), ws=P_(self.mega_ws))
+        self._keep.append(a)
+        return a
+
     def _build_forward_fused(self, train: bool, with_labels: bool, head_bwd: bool = False) -> List[Tuple[Callable, tuple]]:
-        """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L."""
+        """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L;
+        whole-network kernel when the shape allows: ONE launch (+ the head backward for training steps)."""
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        if self.mega:
+            a = self._mega_fwd_args(train, with_labels)
+            prog = [(lib.vitb200_mega_fwd, (ctypes.addressof(a),))]
+            if head_bwd:
+                self._alloc_backward()
+                self._ensure_dz_cls()
+                T, H, Lh, hd = c.tokens, c.hidden_size, c.num_hidden_layers, self.arena.layout.head_name
+                fin = 4 * max(Lh, 1)
+                prog.append((lib.vitb200_head_fused_bwd, (
+                    P_(self.s_cls), self._w(hd + ".weight"), P_(self.logits), P_(self.labels), None, P_(self.z[Lh]), T * H,
+                    self._stat(fin), self._stat(fin + 1), self._p("vit.layernorm.weight"), P_(self.dz_cls),
+                    self._g("vit.layernorm.weight"), self._g("vit.layernorm.bias"), self._g(hd + ".weight"),
+                    self._g(hd + ".bias"), self.B, H, c.num_labels, self.loss_kind, 0, dt)))
+            return prog
         B, T, H, Lh, M = self.B, c.tokens, c.hidden_size, c.num_hidden_layers, self.M
         ph = float(c.hidden_dropout_prob) if train else 0.0
         pa = float(c.attention_probs_dropout_prob) if train else 0.0
