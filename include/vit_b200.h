@@ -286,6 +286,22 @@ size_t vitb200_mega_ws_bytes(void);
 size_t vitb200_mega_fwd_smem_bytes(int layers);
 int vitb200_mega_grid(int B, int cluster);
 int vitb200_mega_fwd(const vitb200_mega_fwd_args* args, void* stream);
+/* Backward of the above for ONE sample per CTA (pair): B * cluster <= 148.  `f` is the forward call's argument block
+ * (same buffers, dropout probabilities and rng: the masks are regenerated).  labels / loss_kind as in forward, or
+ * VITB200_LOSS_GIVEN with labels = d(objective)/d(logits) [B, C] f32; gloss: DEVICE scalar d(objective)/d(loss) or NULL.
+ * gpart [B, n_opt] f32 receives the sample's gradient of EVERY optimised parameter at the parameter's arena offset
+ * (alignment gaps are not written); dz0 [B*T, H] f32 (optional) receives d loss / d(embedding output). */
+typedef struct {
+  vitb200_mega_fwd_args f;
+  const void* labels;
+  const float* gloss;
+  int loss_kind, n_opt;
+  float* gpart;
+  float* dz0;
+} vitb200_mega_bwd_args;
+int vitb200_mega_bwd_supported(int H, int heads, int T, int P, int C, int layers, int B, int cluster);
+size_t vitb200_mega_bwd_smem_bytes(int layers);
+int vitb200_mega_bwd(const vitb200_mega_bwd_args* args, void* stream);
 
 /* ---- multi-head self-attention ----------------------------------------------------------------
  * Replaces ViTSelfAttention.forward's SDPA / eager attention (HF:171-196,232-249) and

@@ -75,6 +75,10 @@ class MegaFwdArgs(C.Structure):  # vitb200_mega_fwd_args
                                   "s_cls", "logits", "loss", "ws")]
 
 
+class MegaBwdArgs(C.Structure):  # vitb200_mega_bwd_args
+    _fields_ = [("f", MegaFwdArgs), ("labels", _p), ("gloss", _p), ("loss_kind", _i), ("n_opt", _i), ("gpart", _p), ("dz0", _p)]
+
+
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
 SIGNATURES = {
     "vitb200_strerror": (C.c_char_p, [_i]),
@@ -112,6 +116,9 @@ SIGNATURES = {
     "vitb200_mega_fwd_smem_bytes": (_sz, [_i]),
     "vitb200_mega_grid": (_i, [_i, _i]),
     "vitb200_mega_fwd": (_i, [_p, _p]),
+    "vitb200_mega_bwd_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "vitb200_mega_bwd_smem_bytes": (_sz, [_i]),
+    "vitb200_mega_bwd": (_i, [_p, _p]),
     "vitb200_attn_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_attn_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _i, _p]),
     "vitb200_set_attn_mode": (_i, [_i]),

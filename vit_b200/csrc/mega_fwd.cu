@@ -404,7 +404,15 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       if (tid == 0) tma_store_wait_read<0>();
       __syncthreads();
       if (l == 0) VB_TL(tl_mega_fwd, 2);
-      if (tid == 0) {
+      auto issue_scores = [&]() {   // thread 0: S[i, j] = q_i . k_j for this CTA's head(s)  (HF:232-249 / vit_with_rope.py:43-84)
+        tc_fence_after();
+        for (int hd = hd_lo; hd < hd_hi; ++hd) {
+          const MgOp Qh{aQ0 + hd * 32, 16, 0, 0}, Kh{aQ0 + 64 + hd * 32, 16, 0, 0};
+          mg_issue(tmem + (hd ? MC_S1 : MC_S0), Qh, Kh, KP, 1, false);
+        }
+        umma_commit(b_mma);
+      };
+      auto store_qkv = [&]() {      // thread 0: the q|k|v rows leave for HBM; the next layer's Wqkv is staged
         if (lead) {
           tma_store_4d(&TM.qkv, sQ0, 0, 0, b, l);
           tma_store_4d(&TM.qkv, sQ1, 64, 0, b, l);
@@ -412,10 +420,12 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         }
         const int ln = l + 1 < L ? l + 1 : 0;   // the next QKV event: layer l + 1, or layer 0 of the next sample
         if (reload && (l + 1 < L || more)) load_wq(ln);
-      }
-      if (P.rope_cos) {
+      };
+      if (!P.rope_cos) {
+        if (tid == 0) { issue_scores(); store_qkv(); }
+      } else {
         // q / k of the tensor-core rows are rotated in place AFTER the un-rotated rows left for HBM (backward rotates again)
-        if (tid == 0) tma_store_wait_read<0>();
+        if (tid == 0) { store_qkv(); tma_store_wait_read<0>(); }
         __syncthreads();
         if (!is_side) {
           // cg 0: q head 0, cg 1: q head 1, cg 2: k head 0, cg 3: k head 1  (16 columns = 2 chunks each)
@@ -435,17 +445,10 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         }
         fence_proxy_async();
         __syncthreads();
+        if (tid == 0) issue_scores();
       }
 
-      // ---- attention (HF:232-249 / vit_with_rope.py:43-84) ----
-      if (tid == 0) {
-        tc_fence_after();
-        for (int hd = hd_lo; hd < hd_hi; ++hd) {
-          const MgOp Qh{aQ0 + hd * 32, 16, 0, 0}, Kh{aQ0 + 64 + hd * 32, 16, 0, 0};
-          mg_issue(tmem + (hd ? MC_S1 : MC_S0), Qh, Kh, KP, 1, false);   // S[i, j] = q_i . k_j
-        }
-        umma_commit(b_mma);
-      }
+      // ---- attention ----
       const DropCtx dca = make_drop(P.p_attn, seed, step, VITB200_SITE_ATTN(l));
       float cs_ = 0.f;   // side: attention output row (column = lane)
       if (is_side) {

@@ -115,6 +115,10 @@ class ViTEngine:
             and os.environ.get("VITB200_MEGA", "1") != "0")
         # CTA pairs (one attention head per CTA, 2 SMs per sample) while every sample still gets its own pair in one wave
         self.mega_cluster = int(os.environ.get("VITB200_MEGA_CLUSTER", "2" if 2 * self.B <= 148 else "1"))
+        # whole-network backward: one sample per CTA (pair), i.e. small batches -- the latency-bound regime it exists for
+        self.mega_bwd = bool(self.mega and self.fused_bwd and os.environ.get("VITB200_MEGA_BWD", "1") != "0"
+                             and self.lib.vitb200_mega_bwd_supported(H, c.num_attention_heads, T, c.patch_size, c.num_labels,
+                                                                     Lh, self.B, self.mega_cluster))
         self._keep = []  # ctypes argument structs referenced by the cached programs
         ws_bytes = self._ws_bytes()
         self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
@@ -261,7 +265,7 @@ class ViTEngine:
         if self.mega:
             a = self._mega_fwd_args(train, with_labels)
             prog = [(lib.vitb200_mega_fwd, (ctypes.addressof(a),))]
-            if head_bwd:
+            if head_bwd and not self.mega_bwd:
                 self._alloc_backward()
                 self._ensure_dz_cls()
                 T, H, Lh, hd = c.tokens, c.hidden_size, c.num_hidden_layers, self.arena.layout.head_name
@@ -431,7 +435,8 @@ class ViTEngine:
         fin = 4 * max(Lh, 1)
         G = int(lib.vitb200_fused_bwd_grid(M))
         if not hasattr(self, "gpart"):
-            self.gpart = torch.zeros(G, lay.n_opt, dtype=torch.float32, device=self.device)  # padding stays zero
+            slots = max(G, B) if self.mega_bwd else G
+            self.gpart = torch.zeros(slots, lay.n_opt, dtype=torch.float32, device=self.device)  # padding stays zero
         gp = self.gpart.data_ptr()
         prog = []
         if given and not hasattr(self, "dlogits"):
@@ -439,6 +444,17 @@ class ViTEngine:
         lab_ptr = P_(self.dlogits) if given else P_(self.labels)
         kind = _lib.LOSS_GIVEN if given else self.loss_kind
         gl = None if given else gloss_ptr
+        if self.mega_bwd:
+            # the whole backward is ONE launch: head, final LN, every layer, embeddings; one gradient set per sample
+            fa = self._mega_fwd_args(train, True)
+            ba = _lib.MegaBwdArgs(f=fa, labels=lab_ptr, gloss=gl, loss_kind=kind, n_opt=lay.n_opt, gpart=gp,
+                                  dz0=P_(self.dzA))
+            self._keep.append(ba)
+            prog.append((lib.vitb200_mega_bwd, (ctypes.addressof(ba),)))
+            self._red = (B, 0, lay.n_opt)
+            if not skip_reduce:
+                prog.append((lib.vitb200_grad_reduce, (gp, B, lay.n_opt, 0, lay.n_opt, self.arena.grad.data_ptr())))
+            return prog
         cur, other = self.dzA, self.dzB
         top_cls = bool(lib.vitb200_head_fused_supported(H, c.num_labels))
         if top_cls and skip_head:
