@@ -308,8 +308,9 @@ def kernel_table(eng, train: bool):
     eng.backward(train=train, skip_reduce=True, skip_head=fh)
     eng.optimizer_step(fused_reduce=True)
     torch.cuda.synchronize()
-    bkey = ("bwd", train, None, True, fh) if eng.fused_bwd else ("bwd", train, None)
-    fkey = ("fwd", train, True, True) if fh else ("fwd", train, True)
+    co = bool(eng.cls_only and eng.mega)
+    bkey = ("bwd", train, None, True, fh, co) if eng.fused_bwd else ("bwd", train, None, co)
+    fkey = ("fwd", train, True, True, co) if fh else ("fwd", train, True, co)
     ar = eng.arena
     slots, start, end = eng._red if eng.fused_bwd else (0, 0, 0)
     tail = (eng.lib.vitb200_clip_adamw_fused, (

@@ -265,6 +265,9 @@ int vitb200_grad_reduce(const float* gpart, int slots, size_t stride, size_t sta
 typedef struct {
   int B, L, P, S, Np, n_valid;       /* spectrum length L, patch P, stride S, Np patches (n_valid real windows) */
   int layers, C, loss_kind, cluster; /* encoder layers, labels, VITB200_LOSS_*, CTAs per sample (1, or 2 = one head each) */
+  int cls_only;                      /* != 0: the caller only needs logits / loss / gradients, not every token's last hidden
+                                      * state: the last layer then runs for the CLS row alone (specvit.py:78 reads nothing
+                                      * else); z[layers] and the last layer's saved rows are valid for the CLS row only */
   float eps, p_hidden, p_attn;       /* dropout probabilities (0 in eval mode) */
   const uint64_t* rng;
   const float* x;                    /* [B, L] f32 */

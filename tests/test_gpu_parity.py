@@ -338,6 +338,11 @@ def test_fused_paths_are_the_ones_tested(golden):
     eng.mega = False                              # the per-op fused programs stay available (longer sequences, H = 64)
     names = [fn.__name__ for fn, _ in eng._build_forward(True, True)]
     assert names.count("vitb200_fused_layer_fwd") == 3 and names[0] == "vitb200_fused_embed_fwd"
+    eng.mega = True
+    assert eng.mega_bwd
+    names = [fn.__name__ for fn, _ in eng._build_backward(True, None)]
+    assert names == ["vitb200_mega_bwd", "vitb200_grad_reduce"]   # ... and so is the whole backward
+    eng.mega_bwd = False
     names = [fn.__name__ for fn, _ in eng._build_backward(True, None)]
     assert names.count("vitb200_fused_layer_bwd_upper") == 3 and names.count("vitb200_fused_layer_bwd_lower") == 3
     assert names[-1] == "vitb200_grad_reduce"

@@ -42,8 +42,9 @@ names = {
     "tail": ["pdl_wait", "reduce partial slots", "block sum + ticket + wait", "norm, coef, bias corrections", "AdamW"],
     "mega_fwd": ["prologue+pdl_wait+weights", "embed+QKV(0)", "S MMA wait", "max pass", "exp pass", "PV (+2nd head)", "O epi+exchange",
                  "hop1", "hop2", "hop3", "layers 1..", "exit"],
-    "mega_bwd": ["prologue", "pdl_wait", "tmem+head", "stage1 (ddelta2, side dm)", "gelu'", "LN2 bwd", "dctx epi", "grad tail (MLP half)",
-                 "attn: S/dP + P,dS", "attn: dQ/dK/dV MMA", "attn epi + exchange", "lower + tail", "layers below", "embedding"],
+    "mega_bwd": ["prologue", "pdl_wait", "head + layers above the stamped one + stage 1 (ddelta2)", "dm MMA + gelu'", "du2 MMA + LN2 bwd",
+                 "dctx MMA + epi", "grad tail (MLP half)", "qkv wait + S/dP MMA + P,dS", "dQ/dK/dV MMA", "attn epi + exchange",
+                 "lower (du MMA, LN1) + staging", "layers below", "embedding"],
     "attn_fwd": ["prologue", "pdl_wait", "tmem+sync", "K/V/Q TMA", "rope+bar+MMA S", "max pass+bar", "exp pass+bar", "MMA PV",
                  "O epi"],
 }

@@ -65,7 +65,7 @@ class EmbedBwdArgs(C.Structure):  # vitb200_embed_bwd_args
 
 
 class MegaFwdArgs(C.Structure):  # vitb200_mega_fwd_args
-    _fields_ = [(n, _i) for n in ("B", "L", "P", "S", "Np", "n_valid", "layers", "C", "loss_kind", "cluster")] + \
+    _fields_ = [(n, _i) for n in ("B", "L", "P", "S", "Np", "n_valid", "layers", "C", "loss_kind", "cluster", "cls_only")] + \
                [("eps", _f), ("p_hidden", _f), ("p_attn", _f)] + \
                [(n, _p) for n in ("rng", "x", "labels", "params", "shadow")] + \
                [(n, _i) for n in ("off_cls", "off_pos", "off_wp", "off_bp", "off_layer0", "layer_stride", "o_ln1g", "o_ln1b",

@@ -34,14 +34,20 @@ constexpr uint32_t MB_WQ = MB_WO + 4096;         // 12 KB
 constexpr uint32_t MB_BAR = MB_WQ + 12288;       // barriers, TMEM slot
 constexpr uint32_t MB_EX = MB_BAR + 256;         // 4 KB  float2 [4][128] LayerNorm-backward sums | float [4][128] D_i partials
 constexpr uint32_t MB_RED = MB_EX + 4096;        // 4 KB  float [2][512] bias-gradient partials
-constexpr uint32_t MB_SIDE = MB_RED + 4096;      // 4 KB  side-row vectors (floats), see SV_*
-constexpr uint32_t MB_PRM = MB_SIDE + 4096 + 1024;   // LayerNorm gammas: [layers][2][32] + final [32]
+constexpr uint32_t MB_SIDE = MB_RED + 4096;      // 8 KB  side-row vectors (floats), see SV_*
+constexpr uint32_t MB_PRM = MB_SIDE + 8192 + 1024;   // LayerNorm gammas: [layers][2][32] + final [32]
+// The side row (token 128) is carried by FOUR warps (128 lanes, sid = lane index in the group): 128-wide vectors have one
+// element per lane, 32-wide vectors are replicated in every warp (lane = column), contractions are split over the warps
+// and their partial sums are combined through shared memory in warp order (deterministic).
+constexpr int MB_SIDE_WARPS = 4;
+constexpr int MB_THREADS = MG_MAIN + 32 * MB_SIDE_WARPS;   // 640
 constexpr uint32_t MB_QKV_BLK = 18432;
 // side-row vectors (float offsets into MB_SIDE)
 constexpr int SV_DD2 = 0, SV_M = 32, SV_DA = 160, SV_U2 = 288, SV_DD1 = 320, SV_CTX = 352, SV_DQKV = 384, SV_U = 480,
-              SV_XDS = 512, SV_XPT = 672, SV_XQ = 832, SV_XDO = 848, SV_DZC = 864, SV_LN = 896, SV_LN1 = 960;
+              SV_XDS = 512, SV_XPT = 672, SV_XQ = 832, SV_XDO = 848, SV_DZC = 864, SV_LN = 896, SV_LN1 = 960,
+              SV_PART = 1024 /* [4][32] */, SV_DQP = 1152 /* [4][16] */, SV_DQC = 1216 /* [32] dq of the CLS row (CLS-only top layer) */;
 // per-row terms of the side KEY (token 128): dS[i, 128] and P~[i, 128] of the 128 tensor-core query rows
-constexpr uint32_t MB_K128 = MB_SIDE + 4096;     // float [2][128]
+constexpr uint32_t MB_K128 = MB_SIDE + 8192;     // float [2][128]
 // TMEM columns (phases re-use them)
 constexpr uint32_t UB_W2 = 0, UB_WO = 128, UB_DM = 160, UB_DU2 = 288, UB_DCTX = 320, UB_W1 = 352;   // upper
 constexpr uint32_t AB_S = 0, AB_DP = 160, AB_DQ = 320, AB_DK = 352, AB_DV = 384;   // attention
@@ -70,6 +76,7 @@ __device__ __forceinline__ void mb_st_peer4(uint32_t addr, float v) {
 }
 __device__ __forceinline__ void mb_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mb_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mb_bar_side() { asm volatile("bar.sync 2, 128;" ::: "memory"); }   // the 4 side-row warps
 
 // sum over rows [rb, rb + 8) of column `col` (< 64) of a swizzled bf16 block (rows in order => deterministic)
 __device__ __forceinline__ float mb_colsum8(const uint8_t* blk, int col, int rb) {
@@ -143,7 +150,7 @@ __device__ __forceinline__ void mb_dlogits(const float* lg, const void* labels, 
   }
 }
 
-__global__ void __launch_bounds__(MG_THREADS, 1)
+__global__ void __launch_bounds__(MB_THREADS, 1)
 mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_args PA) {
   constexpr int H = MG_H, I = MG_I, HC = MG_HC, D = MG_D;
   const vitb200_mega_fwd_args& P = PA.f;
@@ -173,7 +180,11 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   const uint32_t crank = csz == 2 ? mb_cluster_rank() : 0u;
   const bool lead = crank == 0;
   const int hd_lo = csz == 2 ? (int)crank : 0, hd_hi = csz == 2 ? (int)crank + 1 : MG_NH;
-  const bool is_side = warp == 16;
+  const bool is_side = warp >= 16;
+  const int sw = warp - 16, sid = tid - MG_MAIN;   // side group: warp / lane index inside the group
+  const bool s0 = sw == 0;                         // the side warp that publishes replicated vectors
+  float* sp = reinterpret_cast<float*>(base + MB_SIDE) + SV_PART;
+  float* sdqp = reinterpret_cast<float*>(base + MB_SIDE) + SV_DQP;
   const int r = ((warp & 3) << 5) | lane;
   const int cg = warp >> 2, hc0 = cg * HC;
   const int T = P.Np + 1, L = P.layers, B = P.B, C = P.C;
@@ -195,7 +206,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     for (int i = 0; i < 11; ++i) mbar_init(bars + i, 1);
     fence_barrier_init();
   }
-  for (int j = tid; j < L * 64 + 32; j += MG_THREADS) {   // gammas are parameters: the optimizer ran two kernels ago
+  for (int j = tid; j < L * 64 + 32; j += MB_THREADS) {   // gammas are parameters: the optimizer ran two kernels ago
     if (j < L * 64) {
       const int l = j >> 6, e = j & 63;
       const float* lp = P.params + P.off_layer0 + (size_t)l * P.layer_stride;
@@ -228,7 +239,8 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   pdl_wait();     // everything below reads what the forward kernel produced
   pdl_trigger();
   VB_TL(tl_mega_bwd, 2);
-  if (tid == 0) { load_a(L - 1); load_upper(L - 1); load_ctx(L - 1); }
+  const bool cls_only = P.cls_only != 0;
+  if (tid == 0 && !cls_only) { load_a(L - 1); load_upper(L - 1); load_ctx(L - 1); }   // (a CLS-only top layer loads no tiles)
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -273,8 +285,8 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     const float xh = (P.z[((size_t)L * M + (size_t)b * T) * H + lane] - mu) * rs;
     const float gg = ds * s_gam[L * 64 + lane];
     const float c1 = mg_wsum(gg) * (1.f / H), c2 = mg_wsum(gg * xh) * (1.f / H);
-    sv[SV_DZC + lane] = rs * (gg - c1 - xh * c2);
-    if (lead) {
+    if (s0) sv[SV_DZC + lane] = rs * (gg - c1 - xh * c2);
+    if (lead && s0) {
       gp[P.off_lnfg + lane] = ds * xh;
       gp[P.off_lnfb + lane] = ds;
 #pragma unroll
@@ -283,14 +295,25 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     }
   }
   __syncthreads();
-  if (!is_side && r == 0) {
+  if (!is_side && r == 0 && !cls_only) {
 #pragma unroll
     for (int j = 0; j < HC; ++j) dz[j] = sv[SV_DZC + hc0 + j];
   }
 
   // =============================== layers, top down ===============================
+  const int tl_l = L >= 2 ? L - 2 : L - 1;   // (debug build: the layer whose phases are time-stamped -- a steady-state one)
+  (void)tl_l;
   for (int l = L - 1; l >= 0; --l) {
     const uint32_t par = (uint32_t)((L - 1 - l) & 1);   // every per-layer barrier completes once per layer
+    // CLS-only top layer (see mega_fwd.cu): only the CLS row carries a gradient into the last layer (specvit.py:78), so its
+    // MLP / out-proj / attention backward is ONE row: the side group runs it with FMAs (token 0 instead of token 128), the
+    // weight gradients of that half are rank-1, dK / dV are rank-1 in the CLS query, and the tensor-core rows join again
+    // at the QKV projection (lower stage).
+    const bool ct = cls_only && l == L - 1;
+    const bool s_on = has_side || ct;
+    const int stok = ct ? 0 : 128;
+    const size_t sgrow = (size_t)b * T + stok;
+    const uint32_t parU = (uint32_t)((L - 1 - l - (cls_only ? 1 : 0)) & 1);   // b_up / b_a / b_ctx: first used one layer later
     const float* g1 = s_gam + l * 64;
     const float* g2 = s_gam + l * 64 + 32;
     const DropCtx dc_mlp = make_drop(P.p_hidden, seed, step, VITB200_SITE_MLP(l));
@@ -300,62 +323,55 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     float gam2[HC], bet2[HC];   // LN2 gamma / beta gradient terms of this thread's row
     float mu2 = 0.f, rs2 = 0.f;
     if (!is_side) { mu2 = P.stats[(size_t)(4 * l + 2) * M + grow]; rs2 = P.stats[(size_t)(4 * l + 3) * M + grow]; }
+#pragma unroll
+    for (int j = 0; j < HC; ++j) { gam2[j] = 0.f; bet2[j] = 0.f; }
+    const float dzin = ct ? sv[SV_DZC + lane] : dzs;   // side chain: incoming gradient of its row (CLS: from the head)
 
     // ---------------- upper, stage 1: ddelta2 = dropout'(dz) -> sD ; dm = ddelta2 W2 ; dW2 += ddelta2^T m ----------------
-    float dd2s = 0.f, dms[4], das[4], as_[4];   // side row
+    float dd2s = 0.f, dms = 0.f, das = 0.f, as_ = 0.f;   // side row (128-wide vectors: element sid)
     float mu2s = 0.f, rs2s = 0.f, hms = 0.f, u2s = 0.f, ctxs = 0.f;
-    if (!is_side) {
+    if (!is_side && !ct) {
       float kp[8], d2[HC];
       drop8(dc_mlp, (grow * H + hc0) >> 3, kp);
 #pragma unroll
       for (int j = 0; j < HC; ++j) d2[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
       *reinterpret_cast<uint4*>(mg_chunk(sD, r, cg)) = mg_pack8(d2);
       *reinterpret_cast<uint4*>(mg_chunk(sD, r, 4 + cg)) = make_uint4(0u, 0u, 0u, 0u);   // columns 32..63: read by the MN-major view
-    } else if (has_side) {
+    } else if (is_side && s_on) {
       // loads of the side row's saved activations (global, L2-resident): issued first, consumed along the chain
-      const size_t lr = (size_t)l * M + grow;
-      const bf16* arow = reinterpret_cast<const bf16*>(P.a) + lr * I;
-      const bf16* mrow = reinterpret_cast<const bf16*>(P.m) + lr * I;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { as_[i] = __bfloat162float(arow[lane + 32 * i]); sv[SV_M + lane + 32 * i] = __bfloat162float(mrow[lane + 32 * i]); }
-      mu2s = P.stats[(size_t)(4 * l + 2) * M + grow]; rs2s = P.stats[(size_t)(4 * l + 3) * M + grow];
+      const size_t lr = (size_t)l * M + sgrow;
+      as_ = __bfloat162float(reinterpret_cast<const bf16*>(P.a)[lr * I + sid]);
+      sv[SV_M + sid] = __bfloat162float(reinterpret_cast<const bf16*>(P.m)[lr * I + sid]);
+      mu2s = P.stats[(size_t)(4 * l + 2) * M + sgrow]; rs2s = P.stats[(size_t)(4 * l + 3) * M + sgrow];
       hms = P.hmid[lr * H + lane];
       u2s = __bfloat162float(reinterpret_cast<const bf16*>(P.u2)[lr * H + lane]);
       ctxs = __bfloat162float(reinterpret_cast<const bf16*>(P.ctx)[lr * H + lane]);
-      sv[SV_U2 + lane] = u2s; sv[SV_CTX + lane] = ctxs;
-      dd2s = bf16_round(dzs) * drop1(dc_mlp, grow * H + lane);
-      sv[SV_DD2 + lane] = dd2s;
+      dd2s = bf16_round(dzin) * drop1(dc_mlp, sgrow * H + lane);
+      if (s0) { sv[SV_U2 + lane] = u2s; sv[SV_CTX + lane] = ctxs; sv[SV_DD2 + lane] = dd2s; }
       mbar_wait(b_w2, par);
-      // dm[i] = sum_h ddelta2[h] W2[h][i],  i = lane + 32 k
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dms[k] = 0.f;
-#pragma unroll 4
-      for (int hh = 0; hh < H; ++hh) {
-        const float dv = __shfl_sync(0xffffffffu, dd2s, hh);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = lane + 32 * k;
-          dms[k] = fmaf(dv, __bfloat162float(*mg_elem(sW2 + (i >> 6) * 4096, hh, i & 63)), dms[k]);
-        }
-      }
+      // dm[i] = sum_h ddelta2[h] W2[h][i],  i = sid
+      const uint8_t* wcol = sW2 + (sid >> 6) * 4096;
+#pragma unroll 8
+      for (int hh = 0; hh < H; ++hh)
+        dms = fmaf(__shfl_sync(0xffffffffu, dd2s, hh), __bfloat162float(*mg_elem(wcol, hh, sid & 63)), dms);
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (l == L - 1) VB_TL(tl_mega_bwd, 3);
-    if (tid == 0) {
+    if (l == tl_l) VB_TL(tl_mega_bwd, 3);
+    if (tid == 0 && !ct) {
       tc_fence_after();
       mbar_wait(b_w2, par);
       mg_issue(tmem + UB_DM, D_k, W2_mn, I, H / 16, false);      // dm[row, i] = sum_h ddelta2[row,h] W2[h,i]
       umma_commit(b_mma);                                        // the gelu' stage only needs dm
-      mbar_wait(b_up, par);                                      // (m, u2, hmid were requested a whole stage ago)
+      mbar_wait(b_up, parU);                                     // (m, u2, hmid were requested a whole stage ago)
       tc_fence_after();
       mg_issue(tmem + UB_W2, D_mn, M_mn, I, 8, false);           // dW2[h, i] = sum_rows ddelta2[row,h] m[row,i]
     }                                                            // (completion is covered by the next commit)
-    if (!is_side) {
+    if (!is_side && !ct) {
       acc_b2 = mb_colsum8(sD, tid & 31, (tid >> 5) * 8);          // bias gradient partial: column tid & 31, rows 8 (tid >> 5) ..
-      mbar_wait(b_up, par);
-      mbar_wait(b_a, par);
+      mbar_wait(b_up, parU);
+      mbar_wait(b_a, parU);
       // a column of ones next to u2 (columns H..63 are TMA zero fill): the dW1 MMA then also emits db1
       if (cg == 0) *reinterpret_cast<uint32_t*>(mg_chunk(sU2, r, H / 8)) = valid ? 0x00003F80u : 0u;   // bf16 {1, 0}
       mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
@@ -378,28 +394,27 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         }
         *reinterpret_cast<uint4*>(mg_swz(sDA, r, (c0 >> 3) + q)) = mg_pack8(o);
       }
-    } else if (has_side) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        das[k] = bf16_round(bf16_round(dms[k]) * gelu_grad_f(as_[k]));
-        sv[SV_DA + lane + 32 * k] = das[k];
-      }
+    } else if (is_side && s_on) {
+      das = bf16_round(bf16_round(dms) * gelu_grad_f(as_));
+      sv[SV_DA + sid] = das;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (l == L - 1) VB_TL(tl_mega_bwd, 4);
+    if (l == tl_l) VB_TL(tl_mega_bwd, 4);
     // ---------------- stage 2: du2 = da W1 ; dW1 (+ db1) += da^T [u2 | 1] ; LN2 backward -> dh ; ddelta1 -> sD ----------------
     if (tid == 0) {
       tc_fence_after();
       mbar_wait(b_w1, par);
-      mg_issue(tmem + UB_DU2, DA_k, W1_mn, H, I / 16, false);    // du2[row, h] = sum_i da[row,i] W1[i,h]
-      mg_issue(tmem + UB_W1, DA_mn, U2_mn, H + 16, 8, false);    // dW1[i, h] = sum_rows da[row,i] u2[row,h] ; column H: db1[i]
-      umma_commit(b_mma);
+      if (!ct) {
+        mg_issue(tmem + UB_DU2, DA_k, W1_mn, H, I / 16, false);    // du2[row, h] = sum_i da[row,i] W1[i,h]
+        mg_issue(tmem + UB_W1, DA_mn, U2_mn, H + 16, 8, false);    // dW1[i, h] = sum_rows da[row,i] u2[row,h] ; column H: db1[i]
+        umma_commit(b_mma);
+      }
       if (l > 0) load_w2(l - 1);                                 // W2: its GEMM completed a stage ago, the side warp is past it
     }
     float dd1s = 0.f, dhs = 0.f, xh2s = 0.f;
-    if (!is_side) {
+    if (!is_side && !ct) {
       mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
       tc_fence_after();
       float du[HC], xh[HC], g[HC];
@@ -424,45 +439,44 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
 #pragma unroll
       for (int j = 0; j < HC; ++j) d1[j] = valid ? bf16_round(dz[j]) * kp[j] : 0.f;
       *reinterpret_cast<uint4*>(mg_chunk(sD, r, cg)) = mg_pack8(d1);
-    } else if (has_side) {
+    } else if (is_side && s_on) {
       mbar_wait(b_w1, par);
-      // du2[h] = sum_i da[i] W1[i][h],  h = lane
-      float du2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      // du2[h] = sum_i da[i] W1[i][h],  h = lane; warp w contracts i in [32 w, 32 w + 32)
+      float part = 0.f;
 #pragma unroll 8
-        for (int ii = 0; ii < 32; ++ii) {
-          const float dv = __shfl_sync(0xffffffffu, das[k], ii);
-          du2 = fmaf(dv, __bfloat162float(*mg_elem(sW1, 32 * k + ii, lane)), du2);
-        }
-      }
-      du2 = bf16_round(du2);
+      for (int ii = 0; ii < 32; ++ii)
+        part = fmaf(__shfl_sync(0xffffffffu, das, ii), __bfloat162float(*mg_elem(sW1, 32 * sw + ii, lane)), part);
+      sp[sw * 32 + lane] = part;
+      mb_bar_side();
+      const float du2 = bf16_round((sp[lane] + sp[32 + lane]) + (sp[64 + lane] + sp[96 + lane]));
       xh2s = (hms - mu2s) * rs2s;
       const float gg = du2 * g2[lane];
       const float c1 = mg_wsum(gg) * (1.f / H), c2 = mg_wsum(gg * xh2s) * (1.f / H);
-      dhs = dzs + rs2s * (gg - c1 - xh2s * c2);
-      dd1s = bf16_round(dhs) * drop1(dc_proj, grow * H + lane);
-      sv[SV_DD1 + lane] = dd1s;
-      sv[SV_LN + lane] = du2 * xh2s; sv[SV_LN + 32 + lane] = du2;   // side-row terms of dgamma2 / dbeta2
+      dhs = dzin + rs2s * (gg - c1 - xh2s * c2);
+      dd1s = bf16_round(dhs) * drop1(dc_proj, sgrow * H + lane);
+      if (s0) { sv[SV_DD1 + lane] = dd1s; sv[SV_LN + lane] = du2 * xh2s; sv[SV_LN + 32 + lane] = du2; }   // dgamma2 / dbeta2 terms
+      if (ct && s0) sv[SV_DZC + lane] = dhs;   // CLS-only top layer: dh of the CLS row goes back to tile row 0 (lower stage)
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (l == L - 1) VB_TL(tl_mega_bwd, 5);
+    if (l == tl_l) VB_TL(tl_mega_bwd, 5);
     // ---------------- stage 3: dctx = ddelta1 Wo ; dWo += ddelta1^T ctx ----------------
     if (tid == 0) {
       tc_fence_after();
       mbar_wait(b_wo, par);
-      mbar_wait(b_ctx, par);
-      mg_issue(tmem + UB_DCTX, D_k, WO_mn, H, H / 16, false);    // dctx[row, k] = sum_n ddelta1[row,n] Wo[n,k]
-      mg_issue(tmem + UB_WO, D_mn, CTX_mn, H, 8, false);         // dWo[n, k] = sum_rows ddelta1[row,n] ctx[row,k]
-      umma_commit(b_mma);
+      if (!ct) {
+        mbar_wait(b_ctx, parU);
+        mg_issue(tmem + UB_DCTX, D_k, WO_mn, H, H / 16, false);    // dctx[row, k] = sum_n ddelta1[row,n] Wo[n,k]
+        mg_issue(tmem + UB_WO, D_mn, CTX_mn, H, 8, false);         // dWo[n, k] = sum_rows ddelta1[row,n] ctx[row,k]
+        umma_commit(b_mma);
+      }
       if (l > 0) load_w1(l - 1);
     }
     float dctxs = 0.f;   // side: dctx row, column = lane
-    if (!is_side) {
+    if (!is_side && !ct) {
       acc_bo = mb_colsum8(sD, tid & 31, (tid >> 5) * 8);
-      mbar_wait(b_ctx, par);
+      mbar_wait(b_ctx, parU);
       mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
       tc_fence_after();
       // dctx -> bf16 -> the ctx tile (dead: its wgrad MMA is done), which becomes the dO operand of attention backward;
@@ -476,7 +490,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       for (int j = 0; j < HC; ++j) { v[j] = valid ? bf16_round(v[j]) : 0.f; dpart = fmaf(v[j], o8[j], dpart); }
       *reinterpret_cast<uint4*>(cp) = mg_pack8(v);
       s_dp[cg * 128 + r] = dpart;
-    } else if (has_side) {
+    } else if (is_side && s_on) {
       mbar_wait(b_wo, par);
 #pragma unroll 8
       for (int n = 0; n < H; ++n) {
@@ -491,7 +505,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     // CTA pair: from here on this CTA's dqkv tile (R1 @64K, until now u2 / hmid) and side-row dqkv vector may be written
     // by the peer (barrier B: arrive here, the peer waits right before it pushes)
     if (csz == 2) mb_cluster_arrive();
-    if (l == L - 1) VB_TL(tl_mega_bwd, 6);
+    if (l == tl_l) VB_TL(tl_mega_bwd, 6);
     // ---------------- upper: parameter gradients of the layer's MLP / out-proj half -> gpart ----------------
     // The ddelta / da tiles (R3) are dead: the q|k|v rows of the layer are fetched while the gradients drain.
     if (tid == 0) {
@@ -509,8 +523,9 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       float4* t_w2 = reinterpret_cast<float4*>(sM + 16384);    // [32 rows][32 pieces]   dW2 (16 KB)
       float4* t_wo = reinterpret_cast<float4*>(sAct);          // [32 rows][8 pieces]    dWo (4 KB)
       float* t_b1 = reinterpret_cast<float*>(sAct + 4096);     // [128]                  db1
-      float* red = reinterpret_cast<float*>(sAct + 8192);      // [2 * H][128]           LN2 gamma / beta terms (32 KB... uses 32 KB)
-      if (!is_side) {
+      float* red = reinterpret_cast<float*>(sAct + 8192);      // [2 * H][128]           LN2 gamma / beta terms (32 KB)
+      const bool mm = !ct;                                     // tensor-core terms exist (CLS-only top layer: rank-1 terms only)
+      if (!is_side && mm) {
         if ((warp & 3) == 0) {  // dW2 / dWo rows h = lanes 0..31: column group cg of each
           float v[32];
           tmem_ld_32x32(my_tmem + UB_W2 + cg * 32, v);
@@ -539,6 +554,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       tc_fence_before();
       __syncthreads();
       if (!is_side && lead) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         // side-row terms (rank 1): dW[n][k] += dy[n] x[k]; zero vectors when the sample has no side row
         const float* sdd2 = sv + SV_DD2; const float* sm = sv + SV_M; const float* sda = sv + SV_DA;
         const float* su2 = sv + SV_U2; const float* sdd1 = sv + SV_DD1; const float* sctx = sv + SV_CTX;
@@ -547,33 +563,34 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         float4* o_wo = reinterpret_cast<float4*>(gp + lo + P.o_wo);
         for (int e = tid; e < 128 * 8; e += MG_MAIN) {
           const int rr = e >> 3, c = e & 7;
-          float4 t = t_w1[rr * 8 + (c ^ (rr & 7))];
-          if (has_side) { const float d = sda[rr]; t.x = fmaf(d, su2[4 * c], t.x); t.y = fmaf(d, su2[4 * c + 1], t.y); t.z = fmaf(d, su2[4 * c + 2], t.z); t.w = fmaf(d, su2[4 * c + 3], t.w); }
+          float4 t = mm ? t_w1[rr * 8 + (c ^ (rr & 7))] : z4;
+          if (s_on) { const float d = sda[rr]; t.x = fmaf(d, su2[4 * c], t.x); t.y = fmaf(d, su2[4 * c + 1], t.y); t.z = fmaf(d, su2[4 * c + 2], t.z); t.w = fmaf(d, su2[4 * c + 3], t.w); }
           o_w1[e] = t;
         }
         for (int e = tid; e < 32 * 32; e += MG_MAIN) {
           const int rr = e >> 5, c = e & 31;
-          float4 t = t_w2[rr * 32 + (c ^ (rr & 31))];
-          if (has_side) { const float d = sdd2[rr]; t.x = fmaf(d, sm[4 * c], t.x); t.y = fmaf(d, sm[4 * c + 1], t.y); t.z = fmaf(d, sm[4 * c + 2], t.z); t.w = fmaf(d, sm[4 * c + 3], t.w); }
+          float4 t = mm ? t_w2[rr * 32 + (c ^ (rr & 31))] : z4;
+          if (s_on) { const float d = sdd2[rr]; t.x = fmaf(d, sm[4 * c], t.x); t.y = fmaf(d, sm[4 * c + 1], t.y); t.z = fmaf(d, sm[4 * c + 2], t.z); t.w = fmaf(d, sm[4 * c + 3], t.w); }
           o_w2[e] = t;
         }
         for (int e = tid; e < 32 * 8; e += MG_MAIN) {
           const int rr = e >> 3, c = e & 7;
-          float4 t = t_wo[rr * 8 + (c ^ (rr & 7))];
-          if (has_side) { const float d = sdd1[rr]; t.x = fmaf(d, sctx[4 * c], t.x); t.y = fmaf(d, sctx[4 * c + 1], t.y); t.z = fmaf(d, sctx[4 * c + 2], t.z); t.w = fmaf(d, sctx[4 * c + 3], t.w); }
+          float4 t = mm ? t_wo[rr * 8 + (c ^ (rr & 7))] : z4;
+          if (s_on) { const float d = sdd1[rr]; t.x = fmaf(d, sctx[4 * c], t.x); t.y = fmaf(d, sctx[4 * c + 1], t.y); t.z = fmaf(d, sctx[4 * c + 2], t.z); t.w = fmaf(d, sctx[4 * c + 3], t.w); }
           o_wo[e] = t;
         }
-        if (tid < I) gp[lo + P.o_b1 + tid] = t_b1[tid] + (has_side ? sda[tid] : 0.f);
+        if (tid < I) gp[lo + P.o_b1 + tid] = (mm ? t_b1[tid] : 0.f) + (s_on ? sda[tid] : 0.f);
         mb_reduce_rows(red, 2 * H, [&](int e, float s) {
-          if (e < H) gp[lo + P.o_ln2g + e] = s + (has_side ? sv[SV_LN + e] : 0.f);
-          else gp[lo + P.o_ln2b + e - H] = s + (has_side ? sv[SV_LN + 32 + e - H] : 0.f);
+          if (!mm) s = 0.f;
+          if (e < H) gp[lo + P.o_ln2g + e] = s + (s_on ? sv[SV_LN + e] : 0.f);
+          else gp[lo + P.o_ln2b + e - H] = s + (s_on ? sv[SV_LN + 32 + e - H] : 0.f);
         });
         if (tid >= 128 && tid < 128 + H) {
           const int c = tid - 128;
           float s2 = 0.f, so = 0.f;
-          for (int k = 0; k < 16; ++k) { s2 += bsum[k * 32 + c]; so += bsum[512 + k * 32 + c]; }
-          gp[lo + P.o_b2 + c] = s2 + (has_side ? sdd2[c] : 0.f);
-          gp[lo + P.o_bo + c] = so + (has_side ? sdd1[c] : 0.f);
+          if (mm) for (int k = 0; k < 16; ++k) { s2 += bsum[k * 32 + c]; so += bsum[512 + k * 32 + c]; }
+          gp[lo + P.o_b2 + c] = s2 + (s_on ? sdd2[c] : 0.f);
+          gp[lo + P.o_bo + c] = so + (s_on ? sdd1[c] : 0.f);
         }
       }
     }
@@ -592,7 +609,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       }
     }
     __syncthreads();   // the gradient staging in R1 has been read: R1 becomes dS / P~ / dqkv
-    if (l == L - 1) VB_TL(tl_mega_bwd, 7);
+    if (l == tl_l) VB_TL(tl_mega_bwd, 7);
     if (!is_side) {
       mbar_wait(b_qkv, par);
       if (P.rope_cos) {   // rotate q / k rows in place (the saved rows are un-rotated): cg 0/1: q head 0/1, cg 2/3: k head 0/1
@@ -615,7 +632,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         const int blk = tid / 120, rem = tid - blk * 120;
         *reinterpret_cast<uint4*>(base + MB_R3 + blk * MB_QKV_BLK + (129 + (rem >> 3)) * 128 + (rem & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
-    } else if (has_side) {
+    } else if (has_side && s0) {
       *mg_elem(sQ0, 128, 32 + lane) = __float2bfloat16_rn(kss);
       *mg_elem(sQ1, 128, lane) = __float2bfloat16_rn(vss);
     }
@@ -623,13 +640,15 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     tc_fence_before();
     __syncthreads();
     float* xds = sv + SV_XDS; float* xpt = sv + SV_XPT; float* xq = sv + SV_XQ; float* xdo = sv + SV_XDO;
+    // the query row the side group carries: token 128, or the CLS row (tile row 0, already rotated) in a CLS-only top layer
+    const float qc = (is_side && ct) ? __bfloat162float(*mg_elem(sQ0, 0, lane)) : qss;
     for (int hd = hd_lo; hd < hd_hi; ++hd) {
       const MgOp Qk{aQ0 + hd * 32, 16, 16384, 0}, Qmn{aQ0 + hd * 32, 16384, 0, 1};
       const MgOp Kk{aQ0 + 64 + hd * 32, 16, 16384, 0}, Kmn{aQ0 + 64 + hd * 32, 16384, 0, 1};
       const MgOp Vk{aQ1 + hd * 32, 16, 16384, 0};
       const MgOp DOk{aCtx + hd * 32, 16, 16384, 0}, DOmn{aCtx + hd * 32, 16384, 0, 1};
       const MgOp DS_mn{aDS, 16384, 0, 1}, PT_mn{aPT, 16384, 0, 1};
-      if (tid == 0) {
+      if (tid == 0 && !ct) {
         tc_fence_after();
         mg_issue(tmem + AB_S, Qk, Kk, KP, 1, false);     // S  = Q K^T   (all keys, incl. the side row as key 128)
         mg_issue(tmem + AB_DP, DOk, Vk, KP, 1, false);   // dP = dO V^T
@@ -638,26 +657,27 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       float dq_side = 0.f;   // side: dq of token 128 for this head, lane = hd * 16 + c
       float side_dq = 0.f, side_dk = 0.f, side_dv = 0.f;   // side: finished dqkv entries of token 128 (see below)
       if (is_side) {
-        if (has_side) {
-          // token 128 as a QUERY with plain FMAs: dq directly; its rank-1 contributions to dK / dV of every key are handed
+        if (s_on) {
+          // token 128 (or the CLS row) as a QUERY with plain FMAs: dq directly; its rank-1 contributions to dK / dV of every key are handed
           // to the key-row epilogue through shared memory (xds, xpt, xq, xdo)
           float qf[D], dof[D];
           float Di = 0.f;
 #pragma unroll
           for (int c = 0; c < D; ++c) {
-            qf[c] = __shfl_sync(0xffffffffu, qss, hd * D + c);
+            qf[c] = __shfl_sync(0xffffffffu, qc, hd * D + c);
             dof[c] = __shfl_sync(0xffffffffu, dctxs, hd * D + c);
             Di = fmaf(dof[c], __shfl_sync(0xffffffffu, ctxs, hd * D + c), Di);
           }
-          const float lse2 = P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + 128] * MG_LOG2E;
-          const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + 128) * (uint64_t)Tpad;
+          const float lse2 = P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + stok] * MG_LOG2E;
+          const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + stok) * (uint64_t)Tpad;
           float dq[D];
 #pragma unroll
           for (int c = 0; c < D; ++c) dq[c] = 0.f;
+          // key j = sid (one key per lane of the group); key 128 -- the side row itself -- is lane 0's second key
 #pragma unroll
-          for (int jj = 0; jj < MG_SIDE_KEYS; ++jj) {
-            const int j = lane + 32 * jj;
-            if (j < T) {
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = sid + 128 * jj;
+            if (j < T && (jj == 0 || sid == 0)) {
               float kr[D], vr[D];
               mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sQ0, j, 4 + 2 * hd)), &kr[0]);
               mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sQ0, j, 5 + 2 * hd)), &kr[8]);
@@ -675,15 +695,24 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
               for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, kr[c], dq[c]);
             }
           }
+          // dq: warp sums, then the four warps' partials in warp order
 #pragma unroll
           for (int c = 0; c < D; ++c) {
             const float t = mg_wsum(dq[c]);
-            if (lane == hd * D + c) dq_side = t;
+            if (lane == c) sdqp[sw * D + c] = t;
           }
+          mb_bar_side();
+          if ((lane >> 4) == hd) {
+            const int c = lane & 15;
+            dq_side = (sdqp[c] + sdqp[D + c]) + (sdqp[2 * D + c] + sdqp[3 * D + c]);
+            if (ct && s0) sv[SV_DQC + lane] = dq_side;   // CLS-only top layer: dq of the CLS row -> tile row 0 (epilogue below)
+          }
+          if (s0) {
 #pragma unroll
-          for (int c = 0; c < D; ++c) if (lane == c) { xq[c] = qf[c]; xdo[c] = dof[c]; }
+            for (int c = 0; c < D; ++c) if (lane == c) { xq[c] = qf[c]; xdo[c] = dof[c]; }
+          }
         }
-      } else {
+      } else if (!ct) {
         const float lse2 = (valid ? P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + r] : 0.f) * MG_LOG2E;
         const float Di = s_dp[(2 * hd) * 128 + r] + s_dp[(2 * hd + 1) * 128 + r];
         const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + (valid ? r : 0)) * (uint64_t)Tpad;
@@ -739,8 +768,8 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (l == L - 1 && hd == hd_lo) VB_TL(tl_mega_bwd, 8);
-      if (tid == 0) {
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 8);
+      if (tid == 0 && !ct) {
         tc_fence_after();
         mg_issue(tmem + AB_DQ, DS_k, Kmn, D, KM / 16, false);   // dQ[i,:] = sum_{j<128} dS[i,j] k_j
         mg_issue(tmem + AB_DK, DS_mn, Qmn, D, 8, false);        // dK[j,:] = sum_i dS[i,j] q_i
@@ -752,15 +781,24 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       if (is_side && has_side) {
         const int c = lane & 15;
         const bool isv = lane >= 16;
-        const uint8_t* tile = isv ? sCtx : sQ0;
-        const float* wv = isv ? k128 + 128 : k128;
         float acc = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < 128; ++i) acc = fmaf(wv[i], __bfloat162float(*mg_elem(tile, i, hd * D + c)), acc);
-        float dk = acc * scale + xds[128] * __shfl_sync(0xffffffffu, qss, hd * D + c);
+        if (!ct) {   // (CLS-only top layer: the tensor-core query rows carry no gradient)
+          const uint8_t* tile = isv ? sCtx : sQ0;
+          const float* wv = isv ? k128 + 128 : k128;
+          float part = 0.f;
+#pragma unroll 8
+          for (int ii = 0; ii < 32; ++ii) {
+            const int i = 32 * sw + ii;
+            part = fmaf(wv[i], __bfloat162float(*mg_elem(tile, i, hd * D + c)), part);
+          }
+          sp[sw * 32 + lane] = part;
+          mb_bar_side();
+          acc = (sp[lane] + sp[32 + lane]) + (sp[64 + lane] + sp[96 + lane]);
+        }
+        float dk = acc * scale + xds[128] * __shfl_sync(0xffffffffu, qc, hd * D + c);
         float dv = acc + xpt[128] * __shfl_sync(0xffffffffu, dctxs, hd * D + c);
         // gather the row: lane n of this head's 16 columns holds dq; dk / dv come from lanes c / 16 + c
-        float dq = dq_side * 1.f;
+        float dq = ct ? 0.f : dq_side;   // (CLS-only: token 128 is no query of the top layer)
         const float dk_n = __shfl_sync(0xffffffffu, dk, lane & 15), dv_n = __shfl_sync(0xffffffffu, dv, 16 + (lane & 15));
         float dqn = dq, dkn = dk_n, dvn = dv_n;
         if (P.rope_cos) {   // inverse rotation of dq / dk (bf16-rounded first, like the tensor-core rows)
@@ -773,7 +811,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         }
         side_dq = bf16_round(dqn); side_dk = bf16_round(dkn); side_dv = bf16_round(dvn);
       }
-      if (!is_side) { mbar_wait(b_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); }
+      if (!is_side && !ct) { mbar_wait(b_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); }
       if (tid == 0 && hd == hd_hi - 1) {
         // dS / P~ (R1 @0 .. 64K) are dead: the u / z rows of this layer and the pre-GELU rows of the layer below arrive there
         mbar_expect_tx(b_low, 32768);
@@ -781,11 +819,11 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         tma_load_4d(sZ, &TM.z, b_low, 0, 0, b, l);
         if (l > 0) load_a(l - 1);
       }
-      if (l == L - 1 && hd == hd_lo) VB_TL(tl_mega_bwd, 9);
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 9);
       // ---- dQ / dK / dV epilogue -> dqkv tile (R1 @64K).  In a CTA pair the pieces also go into the peer's tile, which
       //      is free once the peer has passed stage 2 of its upper half (its u2 / hmid tiles sat there): barrier B. ----
       if (csz == 2) mb_cluster_wait();
-      if (is_side && has_side) {
+      if (is_side && has_side && s0) {
         // dqkv row of token 128: dq in lanes hd * 16 + c; (dk, dv) of column c = lane & 15 in every lane
         if ((lane >> 4) == hd) {
           sv[SV_DQKV + lane] = side_dq;
@@ -801,19 +839,25 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         }
       }
       if (!is_side) {
-        const float k0 = has_side ? 1.f : 0.f;
         if (P.rope_cos) {
           // the inverse rotation pairs columns c and c + 8: cg 0 takes the dQ row, cg 1 the dK row, cg 2 the dV row
           if (cg < 3) {
             float x[16];
-            tmem_ld_32x16(my_tmem + (cg == 0 ? AB_DQ : cg == 1 ? AB_DK : AB_DV), x);
+            if (!ct) {
+              tmem_ld_32x16(my_tmem + (cg == 0 ? AB_DQ : cg == 1 ? AB_DK : AB_DV), x);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) x[c] = valid ? x[c] * (cg < 2 ? scale : 1.f) : 0.f;
-            if (has_side && valid) {
+              for (int c = 0; c < 16; ++c) x[c] = valid ? x[c] * (cg < 2 ? scale : 1.f) : 0.f;
+            } else {   // CLS-only top layer: no tensor-core terms; dq exists for the CLS row (tile row 0) only
+#pragma unroll
+              for (int c = 0; c < 16; ++c) x[c] = (cg == 0 && r == 0) ? sv[SV_DQC + hd * D + c] : 0.f;
+            }
+            if (s_on && valid) {
               if (cg == 0) {   // key 128 of the tensor-core query rows
+                if (!ct && has_side) {
                 const float a = k128[r] * scale;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) x[c] = fmaf(a, __bfloat162float(*mg_elem(sQ0, 128, 32 + hd * D + c)), x[c]);
+                }
               } else {         // the side QUERY's rank-1 term
                 const float a = cg == 1 ? xds[r] : xpt[r];
                 const float* xr = cg == 1 ? xq : xdo;
@@ -846,14 +890,21 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
           for (int pc = cg; pc < 6; pc += MG_CG) {
             const int kind = pc >> 1, c8 = (pc & 1) * 8;   // 0 = dQ, 1 = dK, 2 = dV
             float o[8];
-            tmem_ld_32x8(my_tmem + (kind == 0 ? AB_DQ : kind == 1 ? AB_DK : AB_DV) + c8, o);
+            if (!ct) {
+              tmem_ld_32x8(my_tmem + (kind == 0 ? AB_DQ : kind == 1 ? AB_DK : AB_DV) + c8, o);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = valid ? o[c] * (kind < 2 ? scale : 1.f) : 0.f;
-            if (has_side && valid) {
+              for (int c = 0; c < 8; ++c) o[c] = valid ? o[c] * (kind < 2 ? scale : 1.f) : 0.f;
+            } else {   // CLS-only top layer: no tensor-core terms; dq exists for the CLS row (tile row 0) only
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = (kind == 0 && r == 0) ? sv[SV_DQC + hd * D + c8 + c] : 0.f;
+            }
+            if (s_on && valid) {
               if (kind == 0) {
-                const float a = k128[r] * scale * k0;
+                if (!ct && has_side) {
+                  const float a = k128[r] * scale;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = fmaf(a, __bfloat162float(*mg_elem(sQ0, 128, 32 + hd * D + c8 + c)), o[c]);
+                  for (int c = 0; c < 8; ++c) o[c] = fmaf(a, __bfloat162float(*mg_elem(sQ0, 128, 32 + hd * D + c8 + c)), o[c]);
+                }
               } else {
                 const float a = kind == 1 ? xds[r] : xpt[r];
                 const float* xr = kind == 1 ? xq : xdo;
@@ -875,7 +926,11 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       if (csz == 2) { mb_cluster_arrive(); mb_cluster_wait(); fence_proxy_async(); } else __syncthreads();
       tc_fence_after();
     }
-    if (l == L - 1) VB_TL(tl_mega_bwd, 10);
+    if (ct && !is_side && r == 0) {
+#pragma unroll
+      for (int j = 0; j < HC; ++j) dz[j] = sv[SV_DZC + hc0 + j];   // dh of the CLS row (side chain) rejoins the tile
+    }
+    if (l == tl_l) VB_TL(tl_mega_bwd, 10);
     // ---------------- lower: du = dqkv Wqkv ; dWqkv (+ dbqkv) += dqkv^T [u | 1] ; LN1 backward (+ dh) -> dz ----------------
     float mu1 = 0.f, rs1 = 0.f;
     float us_ = 0.f, zs_ = 0.f, mu1s = 0.f, rs1s = 0.f;
@@ -888,7 +943,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       us_ = __bfloat162float(reinterpret_cast<const bf16*>(P.u)[lr * H + lane]);
       zs_ = P.z[lr * H + lane];
       mu1s = P.stats[(size_t)(4 * l) * M + grow]; rs1s = P.stats[(size_t)(4 * l + 1) * M + grow];
-      sv[SV_U + lane] = us_;
+      if (s0) sv[SV_U + lane] = us_;
     }
     if (tid == 0 && l > 0) load_ctx(l - 1);   // the dO tile is dead
     fence_proxy_async();
@@ -926,15 +981,20 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     } else if (has_side) {
       mbar_wait(b_wq, par);
       // du[h] = sum_n dqkv[n] Wqkv[n][h]  (h = lane); the dqkv row of token 128 sits in sv[SV_DQKV ..] (both heads)
-      float du = 0.f;
+      // warps 0..2 contract 32 rows of Wqkv each
+      float part = 0.f;
+      if (sw < 3) {
 #pragma unroll 8
-      for (int n = 0; n < MG_Q; ++n) du = fmaf(sv[SV_DQKV + n], __bfloat162float(*mg_elem(sWq, n, lane)), du);
-      du = bf16_round(du);
+        for (int nn = 0; nn < 32; ++nn) part = fmaf(sv[SV_DQKV + 32 * sw + nn], __bfloat162float(*mg_elem(sWq, 32 * sw + nn, lane)), part);
+      }
+      sp[sw * 32 + lane] = part;
+      mb_bar_side();
+      const float du = bf16_round((sp[lane] + sp[32 + lane]) + sp[64 + lane]);
       const float xh = (zs_ - mu1s) * rs1s;
       const float gg = du * g1[lane];
       const float c1 = mg_wsum(gg) * (1.f / H), c2 = mg_wsum(gg * xh) * (1.f / H);
-      dzs = dhs + rs1s * (gg - c1 - xh * c2);
-      sv[SV_LN1 + lane] = du * xh; sv[SV_LN1 + 32 + lane] = du;
+      dzs = (ct ? 0.f : dhs) + rs1s * (gg - c1 - xh * c2);   // (CLS-only top layer: token 128 has no gradient above this point)
+      if (s0) { sv[SV_LN1 + lane] = du * xh; sv[SV_LN1 + 32 + lane] = du; }
     }
     {
       // parameter gradients of the QKV projection and LN1 -> gpart (staging in the dead dS region would collide with u / z:
@@ -961,7 +1021,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       }
       tc_fence_before();
       __syncthreads();
-      if (l == L - 1) VB_TL(tl_mega_bwd, 11);
+      if (l == tl_l) VB_TL(tl_mega_bwd, 11);
       if (tid == 0 && l > 0) { load_upper(l - 1); load_wq(l - 1); }   // u / z / dqkv are consumed: m, u2, hmid of the layer below
       if (!is_side && (csz == 1 || !lead)) {   // (CTA pair: rank 1 writes this half, rank 0 wrote the MLP half)
         const size_t lo = (size_t)P.off_layer0 + (size_t)l * P.layer_stride;
@@ -1037,15 +1097,17 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       }
     } else if (has_side) {
       gs = dzs * drop1(dc, grow * H + lane);
-      if (lead) {
-        if (PA.dz0) PA.dz0[grow * H + lane] = dzs;
-        if (P.off_pos >= 0) gp[P.off_pos + (size_t)128 * H + lane] = gs;
+      if (s0) {
+        if (lead) {
+          if (PA.dz0) PA.dz0[grow * H + lane] = dzs;
+          if (P.off_pos >= 0) gp[P.off_pos + (size_t)128 * H + lane] = gs;
+        }
+        sv[SV_DD2 + lane] = bf16_round(gs);
+        const bool has = 127 < P.n_valid;
+        const float* xp = P.x + (size_t)b * P.L + (size_t)127 * P.S;
+        sv[SV_M + lane] = (has && lane < P.P) ? bf16_round(xp[lane]) : 0.f;
+        sv[SV_M + 32 + lane] = (has && lane + 32 < P.P) ? bf16_round(xp[lane + 32]) : 0.f;
       }
-      sv[SV_DD2 + lane] = bf16_round(gs);
-      const bool has = 127 < P.n_valid;
-      const float* xp = P.x + (size_t)b * P.L + (size_t)127 * P.S;
-      sv[SV_M + lane] = (has && lane < P.P) ? bf16_round(xp[lane]) : 0.f;
-      sv[SV_M + 32 + lane] = (has && lane + 32 < P.P) ? bf16_round(xp[lane + 32]) : 0.f;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -1142,7 +1204,7 @@ extern "C" int vitb200_mega_bwd(const vitb200_mega_bwd_args* pa, void* stream) {
     if (e != cudaSuccess) return vb_cuda_error(e);
     max_set = smem;
   }
-  vb_launch_pdl_cluster(mega_bwd_kernel, dim3(B * a->cluster), dim3(MG_THREADS), smem, (cudaStream_t)stream, a->cluster, tm, *pa);
+  vb_launch_pdl_cluster(mega_bwd_kernel, dim3(B * a->cluster), dim3(MB_THREADS), smem, (cudaStream_t)stream, a->cluster, tm, *pa);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

@@ -118,10 +118,21 @@ __device__ __forceinline__ uint64_t mg_desc(const MgOp& o, int k) {
   if (o.mn) return make_sdesc_sw128(o.addr + k * 2048, o.lbo, 1024);
   return make_sdesc_sw128(o.addr + (k >> 2) * o.kblk + (k & 3) * 32, 16, 1024);
 }
-// D[128, N] (+)= A * B over `ksteps` k-steps of 16 (issued by one thread)
+// D[128, N] (+)= A * B over `ksteps` k-steps of 16 (issued by one thread).  The two descriptors are built once and
+// advanced by adding to their start-address field (16-byte units): a k-step is +32 B inside a K-major 64-column block
+// (the next block after 4 steps) or +2048 B (16 rows) of an MN-major tile.  The issue loop is on the critical path of
+// every phase: rebuilding both descriptors from scratch cost ~12 uniform-datapath instructions per MMA.
 __device__ __forceinline__ void mg_issue(uint32_t tmem_d, const MgOp& A, const MgOp& B, int N, int ksteps, bool acc) {
   const uint32_t idesc = make_idesc_bf16(128, N, A.mn, B.mn);
-  for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, mg_desc(A, k), mg_desc(B, k), idesc, (acc || k > 0) ? 1u : 0u);
+  uint64_t da = mg_desc(A, 0), db = mg_desc(B, 0);
+  const uint32_t a_in = A.mn ? 128u : 2u, b_in = B.mn ? 128u : 2u;
+  const uint32_t a_blk = A.mn ? 128u : ((A.kblk - 96u) >> 4), b_blk = B.mn ? 128u : ((B.kblk - 96u) >> 4);
+  for (int k = 0; k < ksteps; ++k) {
+    umma_bf16(tmem_d, da, db, idesc, (acc || k > 0) ? 1u : 0u);
+    const bool wrap = (k & 3) == 3;
+    da += wrap ? a_blk : a_in;
+    db += wrap ? b_blk : b_in;
+  }
 }
 
 __device__ __forceinline__ void mg_bar_main() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 MMA-path warps

@@ -34,8 +34,9 @@ constexpr uint32_t MF_BAR = MF_WP + 4096;           // barriers, TMEM slot
 constexpr uint32_t MF_EX = MF_BAR + 256;            // float2 [4][128] LayerNorm statistics exchange
 constexpr uint32_t MF_MX = MF_EX + 4096;            // float [4][128] row-max exchange
 constexpr uint32_t MF_SM = MF_MX + 2048;            // float [2][4][128] row-sum exchange (both heads)
-constexpr uint32_t MF_SC = MF_SM + 4096;            // float [32] final-LayerNorm'd CLS row, float [32] side-row attention output
-constexpr uint32_t MF_PRM = MF_SC + 256;            // staged fp32 vectors
+constexpr uint32_t MF_SC = MF_SM + 4096;            // float [32] final-LayerNorm'd CLS row, [32] side-row attention output,
+                                                    // [32] CLS row of the residual stream
+constexpr uint32_t MF_PRM = MF_SC + 512;            // staged fp32 vectors
 // TMEM columns
 constexpr uint32_t MC_S0 = 0, MC_S1 = 160, MC_O = 320, MC_LIN = 352, MC_COLS = 512;
 
@@ -302,6 +303,10 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         *mg_f32(sH, r, hc0 + 4) = make_float4(h[4], h[5], h[6], h[7]);
         if (lead && valid && cg == 0) { P.stats[grow] = mu; P.stats[M + grow] = rs; }
         *reinterpret_cast<uint4*>(mg_chunk(sA, r, cg)) = mg_pack8(u);
+        if (r == 0) {   // CLS row of the residual stream: the side warp takes it over in a CLS-only last layer
+#pragma unroll
+          for (int j = 0; j < HC; ++j) s_sc[64 + hc0 + j] = h[j];
+        }
       } else if (has_side) {
         float e = bf16_round(es + s_fin[64 + lane]);
         if (P.off_pos >= 0) e += P.params[P.off_pos + (size_t)128 * H + lane];
@@ -329,7 +334,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       const bool last = l == L;
       if (last) {
         // residual stream after the last layer; the final LayerNorm of the CLS row was written to s_sc in hop 3
-        if (tid == 0 && lead) {
+        if (tid == 0 && lead && !P.cls_only) {
           tma_store_4d(&TM.z, sH, 0, 0, b, L);
           tma_store_commit();
         }
@@ -353,6 +358,14 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       }
       const float* lp = s_prm + l * MG_PRM_LAYER;
       const uint32_t wpar = reload ? (uint32_t)(it & 1) : 0u;
+      // CLS-only last layer (training steps, logits-only evaluation): the head reads nothing but last_hidden_state[:, 0]
+      // (specvit.py:78), so in the last layer only the CLS row needs attention output, MLP and final LayerNorm.  Its
+      // keys / values are still every token's (the QKV projection above runs for all rows); the row itself (tile row 0)
+      // is carried by the side warp with FMAs while the tensor-core rows idle.
+      const bool ct = P.cls_only != 0 && l == L - 1;
+      const bool s_on = has_side || ct;                 // the side warp carries a row in this layer
+      const int stok = ct ? 0 : 128;                    // ... this token
+      const size_t sgrow = (size_t)b * T + stok;
       if (tid == 0) {
         tc_fence_after();
         mbar_wait(b_wq, wpar);
@@ -422,7 +435,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         if (reload && (l + 1 < L || more)) load_wq(ln);
       };
       if (!P.rope_cos) {
-        if (tid == 0) { issue_scores(); store_qkv(); }
+        if (tid == 0) { if (!ct) issue_scores(); store_qkv(); }
       } else {
         // q / k of the tensor-core rows are rotated in place AFTER the un-rotated rows left for HBM (backward rotates again)
         if (tid == 0) { store_qkv(); tma_store_wait_read<0>(); }
@@ -445,7 +458,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) issue_scores();
+        if (tid == 0 && !ct) issue_scores();
       }
 
       // ---- attention ----
@@ -453,7 +466,11 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       float cs_ = 0.f;   // side: attention output row (column = lane)
       if (is_side) {
         if (csz == 2) mf_cluster_wait();   // the peer has finished reading last layer's exchange buffers
-        if (has_side) {
+        if (ct) {   // take over the CLS row: its residual row and its (rotated) query row, tile row 0
+          zs = s_sc[64 + lane];
+          qs = __bfloat162float(*mg_elem(sQ0, 0, lane));
+        }
+        if (s_on) {
           for (int hd = hd_lo; hd < hd_hi; ++hd) {
             float qf[MG_D];
 #pragma unroll
@@ -476,7 +493,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
               mx = fmaxf(mx, acc);
             }
             mx = mg_wmax(mx);
-            const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + 128) * (uint64_t)Tpad;
+            const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + stok) * (uint64_t)Tpad;
             float sum = 0.f, o[MG_D];
 #pragma unroll
             for (int c = 0; c < MG_D; ++c) o[c] = 0.f;
@@ -501,14 +518,16 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
               const float oc = mg_wsum(o[c]) * inv;
               if (lane == hd * MG_D + c) cs_ = bf16_round(oc);
             }
-            if (lane == 0) P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + 128] = mx * scale + logf(sum);
+            if (lane == 0) P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + stok] = mx * scale + logf(sum);
           }
           if ((lane >> 4) >= hd_lo && (lane >> 4) < hd_hi) {   // this CTA's head(s)
-            reinterpret_cast<bf16*>(P.ctx)[((size_t)l * M + grow) * H + lane] = __float2bfloat16_rn(cs_);
+            reinterpret_cast<bf16*>(P.ctx)[((size_t)l * M + sgrow) * H + lane] = __float2bfloat16_rn(cs_);
             s_sc[32 + lane] = cs_;
             if (csz == 2) mf_st_peer4(mf_peer_addr(&s_sc[32 + lane], crank ^ 1u), cs_);
           }
         }
+      } else if (ct) {
+        if (csz == 2) mf_cluster_wait();
       } else {
         float mxh[MG_NH];
         for (int hd = hd_lo; hd < hd_hi; ++hd) {
@@ -609,23 +628,25 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       tc_fence_before();
       if (tid == 0) tma_store_wait_read<0>();
       if (csz == 2) { mf_cluster_sync(); fence_proxy_async(); } else __syncthreads();
-      if (is_side && has_side) cs_ = s_sc[32 + lane];   // the full attention output row (both heads)
+      if (is_side && s_on) cs_ = s_sc[32 + lane];   // the full attention output row (both heads)
       if (l == 0) VB_TL(tl_mega_fwd, 7);
 
       // ---- hop 1: attention output projection + dropout + residual, LayerNorm-after (HF:262-268,337-340) ----
       if (tid == 0) {
         tc_fence_after();
         mbar_wait(b_wo, wpar);
-        mg_issue(tmem + MC_LIN, CTX_k, WO_k, H, H / 16, false);
-        umma_commit(b_mma);
-        if (lead) {
-          tma_store_4d(&TM.ctx, sCtx, 0, 0, b, l);
-          tma_store_commit();
+        if (!ct) {
+          mg_issue(tmem + MC_LIN, CTX_k, WO_k, H, H / 16, false);
+          umma_commit(b_mma);
+          if (lead) {
+            tma_store_4d(&TM.ctx, sCtx, 0, 0, b, l);
+            tma_store_commit();
+          }
         }
       }
       {
         const DropCtx dc = make_drop(P.p_hidden, seed, step, VITB200_SITE_PROJ(l));
-        if (!is_side) {
+        if (!is_side && !ct) {
           mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
           tc_fence_after();
           float v[HC], kp[8];
@@ -642,18 +663,18 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           *mg_f32(sH, r, hc0 + 4) = make_float4(h[4], h[5], h[6], h[7]);
           if (lead && valid && cg == 0) { P.stats[(size_t)(4 * l + 2) * M + grow] = mu; P.stats[(size_t)(4 * l + 3) * M + grow] = rs; }
           *reinterpret_cast<uint4*>(mg_chunk(sA, r, cg)) = mg_pack8(u2);
-        } else if (has_side) {
+        } else if (is_side && s_on) {
           mbar_wait(b_wo, wpar);
           float y[1];
           mg_side_gemv32<1>(sWo, lane, cs_, y);
-          zs += bf16_round(bf16_round(y[0] + lp[MP_BO + lane]) * drop1(dc, grow * H + lane));
+          zs += bf16_round(bf16_round(y[0] + lp[MP_BO + lane]) * drop1(dc, sgrow * H + lane));
           float mu, rs;
           mg_side_ln(zs, P.eps, mu, rs);
           us = bf16_round((zs - mu) * rs * lp[MP_G2 + lane] + lp[MP_B2LN + lane]);
           if (lead) {
-            P.hmid[((size_t)l * M + grow) * H + lane] = zs;
-            reinterpret_cast<bf16*>(P.u2)[((size_t)l * M + grow) * H + lane] = __float2bfloat16_rn(us);
-            if (lane == 0) { P.stats[(size_t)(4 * l + 2) * M + grow] = mu; P.stats[(size_t)(4 * l + 3) * M + grow] = rs; }
+            P.hmid[((size_t)l * M + sgrow) * H + lane] = zs;
+            reinterpret_cast<bf16*>(P.u2)[((size_t)l * M + sgrow) * H + lane] = __float2bfloat16_rn(us);
+            if (lane == 0) { P.stats[(size_t)(4 * l + 2) * M + sgrow] = mu; P.stats[(size_t)(4 * l + 3) * M + sgrow] = rs; }
           }
         }
       }
@@ -669,16 +690,18 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         tc_fence_after();
         if (reload && (l + 1 < L || more)) load_wo(l + 1 < L ? l + 1 : 0);
         mbar_wait(b_w1, wpar);
-        mg_issue(tmem + MC_LIN, A_k, W1_k, I, H / 16, false);
-        umma_commit(b_mma);
-        if (lead) {
-          tma_store_4d(&TM.hmid, sH, 0, 0, b, l);
-          tma_store_4d(&TM.u2, sA, 0, 0, b, l);
-          tma_store_commit();
+        if (!ct) {
+          mg_issue(tmem + MC_LIN, A_k, W1_k, I, H / 16, false);
+          umma_commit(b_mma);
+          if (lead) {
+            tma_store_4d(&TM.hmid, sH, 0, 0, b, l);
+            tma_store_4d(&TM.u2, sA, 0, 0, b, l);
+            tma_store_commit();
+          }
         }
       }
       float ms[4] = {0.f, 0.f, 0.f, 0.f};   // side: gelu output, columns lane + 32 i
-      if (!is_side) {
+      if (!is_side && !ct) {
         mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
         tc_fence_after();
         const int c0 = cg * 32;
@@ -699,12 +722,12 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           *reinterpret_cast<uint4*>(mg_swz(sAct, r, (c0 + j) >> 3)) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
           *reinterpret_cast<uint4*>(mg_swz(sM, r, (c0 + j) >> 3)) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
         }
-      } else if (has_side) {
+      } else if (is_side && s_on) {
         mbar_wait(b_w1, wpar);
         float y[4];
         mg_side_gemv32<4>(sW1, lane, us, y);
-        bf16* arow = reinterpret_cast<bf16*>(P.a) + ((size_t)l * M + grow) * I;
-        bf16* mrow = reinterpret_cast<bf16*>(P.m) + ((size_t)l * M + grow) * I;
+        bf16* arow = reinterpret_cast<bf16*>(P.a) + ((size_t)l * M + sgrow) * I;
+        bf16* mrow = reinterpret_cast<bf16*>(P.m) + ((size_t)l * M + sgrow) * I;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float a = bf16_round(y[i] + lp[MP_B1 + lane + 32 * i]);
@@ -726,14 +749,16 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         tc_fence_after();
         if (reload && (l + 1 < L || more)) load_w1(l + 1 < L ? l + 1 : 0);
         mbar_wait(b_w2, wpar);
-        mg_issue(tmem + MC_LIN, M_k, W2_k, H, I / 16, false);
-        umma_commit(b_mma);
-        if (lead) {
-          tma_store_4d(&TM.a, sAct, 0, 0, b, l);
-          tma_store_4d(&TM.a, sAct + 16384, 64, 0, b, l);
-          tma_store_4d(&TM.m, sM, 0, 0, b, l);
-          tma_store_4d(&TM.m, sM + 16384, 64, 0, b, l);
-          tma_store_commit();
+        if (!ct) {
+          mg_issue(tmem + MC_LIN, M_k, W2_k, H, I / 16, false);
+          umma_commit(b_mma);
+          if (lead) {
+            tma_store_4d(&TM.a, sAct, 0, 0, b, l);
+            tma_store_4d(&TM.a, sAct + 16384, 64, 0, b, l);
+            tma_store_4d(&TM.m, sM, 0, 0, b, l);
+            tma_store_4d(&TM.m, sM + 16384, 64, 0, b, l);
+            tma_store_commit();
+          }
         }
       }
       {
@@ -741,7 +766,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         const bool top = l + 1 == L;
         const float* gn = top ? s_fin : s_prm + (l + 1) * MG_PRM_LAYER + MP_LN1G;
         const float* bn = top ? s_fin + 32 : s_prm + (l + 1) * MG_PRM_LAYER + MP_LN1B;
-        if (!is_side) {
+        if (!is_side && !ct) {
           mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
           tc_fence_after();
           float v[HC], kp[8];
@@ -751,6 +776,10 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           for (int e = 0; e < HC; ++e) h[e] += bf16_round(bf16_round(v[e] + lp[MP_B2 + hc0 + e]) * kp[e]);
           *mg_f32(sH, r, hc0) = make_float4(h[0], h[1], h[2], h[3]);
           *mg_f32(sH, r, hc0 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+          if (r == 0) {
+#pragma unroll
+            for (int j = 0; j < HC; ++j) s_sc[64 + hc0 + j] = h[j];
+          }
           float mu, rs;
           mf_row_stats(h, s_ln, r, cg, P.eps, mu, rs);
           float un[HC];
@@ -765,7 +794,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
 #pragma unroll
             for (int j = 0; j < HC; ++j) s_sc[hc0 + j] = un[j];
           }
-        } else if (has_side) {
+        } else if (is_side && s_on) {
           mbar_wait(b_w2, wpar);
           float y = 0.f;
 #pragma unroll
@@ -776,9 +805,18 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
 #pragma unroll
             for (int k = 0; k < 32; ++k) y = fmaf(__shfl_sync(0xffffffffu, ms[i], k), w[k], y);
           }
-          zs += bf16_round(bf16_round(y + lp[MP_B2 + lane]) * drop1(dc, grow * H + lane));
-          if (lead) P.z[((size_t)(l + 1) * M + grow) * H + lane] = zs;
-          if (!top) {
+          zs += bf16_round(bf16_round(y + lp[MP_B2 + lane]) * drop1(dc, sgrow * H + lane));
+          if (lead) P.z[((size_t)(l + 1) * M + sgrow) * H + lane] = zs;
+          if (ct) {   // final LayerNorm of the CLS row (HF:455), handed to the head
+            float mu, rs;
+            mg_side_ln(zs, P.eps, mu, rs);
+            const float un = bf16_round((zs - mu) * rs * gn[lane] + bn[lane]);
+            s_sc[lane] = un;
+            if (lead) {
+              reinterpret_cast<bf16*>(P.s_cls)[(size_t)b * H + lane] = __float2bfloat16_rn(un);
+              if (lane == 0) { P.stats[(size_t)(4 * L) * M + b] = mu; P.stats[(size_t)(4 * L + 1) * M + b] = rs; }
+            }
+          } else if (!top) {
             float mu, rs;
             mg_side_ln(zs, P.eps, mu, rs);
             us = bf16_round((zs - mu) * rs * gn[lane] + bn[lane]);

@@ -119,6 +119,10 @@ class ViTEngine:
         self.mega_bwd = bool(self.mega and self.fused_bwd and os.environ.get("VITB200_MEGA_BWD", "1") != "0"
                              and self.lib.vitb200_mega_bwd_supported(H, c.num_attention_heads, T, c.patch_size, c.num_labels,
                                                                      Lh, self.B, self.mega_cluster))
+        # cls_only: the caller needs logits / loss / gradients only (TrainStep, EvalStep, MyViT.forward without
+        # output_hidden_states): the whole-network kernels then run the LAST layer for the CLS row alone -- the head reads
+        # nothing else (specvit.py:78).  Callers that read every token's last hidden state leave it False.
+        self.cls_only = False
         self._keep = []  # ctypes argument structs referenced by the cached programs
         ws_bytes = self._ws_bytes()
         self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
@@ -237,6 +241,7 @@ class ViTEngine:
         a = _lib.MegaFwdArgs(
             B=self.B, L=c.image_size, P=c.patch_size, S=c.stride, Np=c.num_patches, n_valid=c.n_valid,
             layers=c.num_hidden_layers, C=c.num_labels, loss_kind=self.loss_kind, cluster=self.mega_cluster,
+            cls_only=1 if self.cls_only else 0,
             eps=float(c.layer_norm_eps), p_hidden=float(c.hidden_dropout_prob) if train else 0.0,
             p_attn=float(c.attention_probs_dropout_prob) if train else 0.0, rng=self.rng.data_ptr(), x=P_(self.x),
             labels=P_(self.labels) if with_labels else None, params=self.arena.data.data_ptr(),
@@ -650,11 +655,12 @@ class ViTEngine:
         """head_bwd (training steps, needs can_fuse_head): the last launch also runs the head / final-LayerNorm backward
         with dloss = 1; the caller must then use backward(skip_head=True)."""
         self.refresh_shadow()
+        co = bool(self.cls_only and self.mega)
         if head_bwd:
             assert with_labels and self.can_fuse_head
-            self._run(("fwd", train, True, True), lambda: self._build_forward_fused(train, True, head_bwd=True))
+            self._run(("fwd", train, True, True, co), lambda: self._build_forward_fused(train, True, head_bwd=True))
         else:
-            self._run(("fwd", train, with_labels), lambda: self._build_forward(train, with_labels))
+            self._run(("fwd", train, with_labels, co), lambda: self._build_forward(train, with_labels))
 
     def backward(self, train: bool, gloss: Optional[torch.Tensor] = None, skip_reduce: bool = False,
                  skip_head: bool = False) -> None:
@@ -663,12 +669,13 @@ class ViTEngine:
         gp = None if gloss is None else gloss.data_ptr()
         skip = bool(skip_reduce and self.fused_bwd)
         sh = bool(skip_head and self.fused_bwd)
-        self._run(("bwd", train, gp, skip, sh) if (skip or sh) else ("bwd", train, gp),
+        co = bool(self.cls_only and self.mega)
+        self._run(("bwd", train, gp, skip, sh, co) if (skip or sh) else ("bwd", train, gp, co),
                   lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh))
 
     def backward_from_dlogits(self, train: bool, dlogits: torch.Tensor) -> None:
         """Backward when the caller computed its own loss from `logits` (labels=None forward)."""
-        key = ("bwd_given", train)
+        key = ("bwd_given", train, bool(self.cls_only and self.mega))
         if key not in self._progs:
             self._progs[key] = self._build_backward(train, None, given=True)
             self.launches[key] = len(self._progs[key])
@@ -789,10 +796,11 @@ class ViTEngine:
         fused_tail: the TrainStep single-GPU sequence (gradient-partial reduction folded into the optimizer kernel)."""
         skip = bool(fused_tail and self.fused_bwd)
         sh = bool(skip and self.can_fuse_head)
-        fkey = ("fwd", train, True, True) if sh else ("fwd", train, True)
+        co = bool(self.cls_only and self.mega)
+        fkey = ("fwd", train, True, True, co) if sh else ("fwd", train, True, co)
         if fkey not in self._progs:
             self._progs[fkey] = self._build_forward_fused(train, True, head_bwd=True) if sh else self._build_forward(train, True)
-        bkey = ("bwd", train, None, skip, sh) if (skip or sh) else ("bwd", train, None)
+        bkey = ("bwd", train, None, skip, sh, co) if (skip or sh) else ("bwd", train, None, co)
         if bkey not in self._progs:
             self._progs[bkey] = self._build_backward(train, None, skip_reduce=skip, skip_head=sh)
         per_call = {"vitb200_head_loss_fwd": 2, "vitb200_head_loss_bwd": 2, "vitb200_patch_embed_bwd": 2}

@@ -257,6 +257,7 @@ class ViTModel(nn.Module):
                                hidden_states=enc.hidden_states if output_hidden_states else None, attentions=None)
         eng = owner._engine(pixel_values.shape[0])
         owner._stage_inputs(eng, pixel_values, None)
+        eng.cls_only = False   # last_hidden_state of every token is the result here
         eng.forward(train=False, with_labels=False)
         hs = None
         if output_hidden_states:
@@ -547,6 +548,7 @@ class MyViT(nn.Module):
             attentions = out["attentions"] if output_attentions else None
         else:
             eng = self._engine(B)
+            eng.cls_only = not output_hidden_states   # every token's last hidden state is only computed when asked for
             if grad_needed:
                 loss, logits = _FusedViTFunction.apply(self, eng, pixel_values, labels, self.training,
                                                        self._param_names, *self._param_list)

@@ -50,6 +50,7 @@ class TrainStep:
     # ---- one step's kernel sequence (also what gets captured) ---------------------------------
     def _launch(self) -> None:
         eng = self.eng
+        eng.cls_only = True   # a training step reads the loss only: the last layer runs for the CLS row alone
         if self.world > 1 and getattr(eng, "peer", None) is None:
             eng.forward(train=self.train, with_labels=True)
             self._backward_overlapped()   # NCCL: gradients are summed across ranks before the optimizer kernel reads them
@@ -70,7 +71,7 @@ class TrainStep:
         on the critical path either way, so the whole optimised range goes out as ONE all-reduce (161 KB at the
         configured shape: latency-bound, ~one NCCL launch)."""
         eng = self.eng
-        key = ("bwd", self.train, None)
+        key = ("bwd", self.train, None, bool(eng.cls_only and eng.mega))
         if key not in eng._progs:
             eng._progs[key] = eng._build_backward(self.train, None)
             eng.launches[key] = len(eng._progs[key])
@@ -339,6 +340,7 @@ class EvalStep:
 
     def _run(self, with_labels: bool) -> None:
         eng = self.eng
+        eng.cls_only = True   # logits / loss only
         if not self.use_graph:
             eng.forward(train=False, with_labels=with_labels)
             return
