@@ -36,7 +36,13 @@ constexpr uint32_t MF_MX = MF_EX + 4096;            // float [4][128] row-max ex
 constexpr uint32_t MF_SM = MF_MX + 2048;            // float [2][4][128] row-sum exchange (both heads)
 constexpr uint32_t MF_SC = MF_SM + 4096;            // float [32] final-LayerNorm'd CLS row, [32] side-row attention output,
                                                     // [32] CLS row of the residual stream
-constexpr uint32_t MF_PRM = MF_SC + 512;            // staged fp32 vectors
+constexpr uint32_t MF_SP = MF_SC + 512;             // 1 KB  side group: partial sums [4][32], attention partials [4][20]
+constexpr uint32_t MF_PRM = MF_SP + 1024;           // staged fp32 vectors
+// The side row is carried by FOUR warps (see mega_bwd.cu): 32-wide vectors are replicated per warp (lane = column),
+// keys / MLP columns are spread over the 128 lanes, contractions over 128 are split by warp and combined in warp order.
+constexpr int MF_SIDE_WARPS = 4;
+constexpr int MF_THREADS = MG_MAIN + 32 * MF_SIDE_WARPS;   // 640
+__device__ __forceinline__ void mf_bar_side() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 // TMEM columns
 constexpr uint32_t MC_S0 = 0, MC_S1 = 160, MC_O = 320, MC_LIN = 352, MC_COLS = 512;
 
@@ -112,7 +118,7 @@ __device__ __forceinline__ float mf_loss_term(const float (&lg)[4], const void* 
   return t;
 }
 
-__global__ void __launch_bounds__(MG_THREADS, 1)
+__global__ void __launch_bounds__(MF_THREADS, 1)
 mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_args P) {
   constexpr int H = MG_H, I = MG_I, HC = MG_HC;
   extern __shared__ uint8_t smem_raw[];
@@ -137,7 +143,11 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   const uint32_t crank = csz == 2 ? mf_cluster_rank() : 0u;
   const bool lead = crank == 0;
   const int hd_lo = csz == 2 ? (int)crank : 0, hd_hi = csz == 2 ? (int)crank + 1 : MG_NH;
-  const bool is_side = warp == 16;
+  const bool is_side = warp >= 16;
+  const int sw = warp - 16, sid = tid - MG_MAIN;   // side group: warp / lane index inside the group
+  const bool s0 = sw == 0;                         // the side warp that publishes replicated vectors
+  float* sp = reinterpret_cast<float*>(base + MF_SP);        // [4][32]
+  float* spa = reinterpret_cast<float*>(base + MF_SP) + 128; // [4][20]: max, sum, o[16] partials of the side query
   const int r = ((warp & 3) << 5) | lane;    // main path: token row of the sample = TMEM lane
   const int cg = warp >> 2;                  // main path: column group
   const int hc0 = cg * HC;
@@ -180,7 +190,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
     load_wq(0); load_wo(0); load_w1(0); load_w2(0);
   }
   if (warp == 0) tmem_alloc(tmem_slot, MC_COLS);
-  for (int j = tid; j < L * MG_PRM_LAYER; j += MG_THREADS) {
+  for (int j = tid; j < L * MG_PRM_LAYER; j += MF_THREADS) {
     const int l = j / MG_PRM_LAYER, e = j - l * MG_PRM_LAYER;
     const float* lp = P.params + P.off_layer0 + (size_t)l * P.layer_stride;
     const float* src = e < MP_LN1B ? lp + P.o_ln1g + e : e < MP_BQ ? lp + P.o_ln1b + (e - MP_LN1B)
@@ -193,7 +203,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
     s_fin[tid] = P.params[P.off_lnfg + tid]; s_fin[32 + tid] = P.params[P.off_lnfb + tid];
     s_fin[64 + tid] = P.params[P.off_bp + tid]; s_fin[96 + tid] = P.params[P.off_cls + tid];
   }
-  for (int j = tid; j < C * H + C; j += MG_THREADS)
+  for (int j = tid; j < C * H + C; j += MF_THREADS)
     s_fin[128 + j] = j < C * H ? __bfloat162float(reinterpret_cast<const bf16*>(P.shadow)[P.off_wh + j]) : P.params[P.off_bh + (j - C * H)];
   tc_fence_before();
   __syncthreads();
@@ -314,7 +324,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         float mu, rs;
         mg_side_ln(zs, P.eps, mu, rs);
         us = bf16_round((zs - mu) * rs * lp0[MP_LN1G + lane] + lp0[MP_LN1B + lane]);
-        if (lead) {
+        if (lead && s0) {
           P.z[grow * H + lane] = zs;
           reinterpret_cast<bf16*>(P.u)[grow * H + lane] = __float2bfloat16_rn(us);
           if (lane == 0) { P.stats[grow] = mu; P.stats[M + grow] = rs; }
@@ -338,7 +348,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           tma_store_4d(&TM.z, sH, 0, 0, b, L);
           tma_store_commit();
         }
-        if (is_side && lead) {
+        if (is_side && s0 && lead) {
           // head (specvit.py:81-89): logits = s . Wh^T + bh; loss term of the sample
           float mine[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -398,7 +408,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         qs = bf16_round(y[0] + lp[MP_BQ + lane]);
         ks = bf16_round(y[1] + lp[MP_BQ + 32 + lane]);
         vs = bf16_round(y[2] + lp[MP_BQ + 64 + lane]);
-        if (lead) {
+        if (lead && s0) {
           bf16* qrow = reinterpret_cast<bf16*>(P.qkv) + ((size_t)l * M + grow) * MG_Q;
           qrow[lane] = __float2bfloat16_rn(qs); qrow[32 + lane] = __float2bfloat16_rn(ks); qrow[64 + lane] = __float2bfloat16_rn(vs);
         }
@@ -409,8 +419,10 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           qs = bf16_round((lane & 8) ? qs * cs + qo * sn : qs * cs - qo * sn);
           ks = bf16_round((lane & 8) ? ks * cs + ko * sn : ks * cs - ko * sn);
         }
-        *mg_elem(sQ0, 128, 32 + lane) = __float2bfloat16_rn(ks);
-        *mg_elem(sQ1, 128, lane) = __float2bfloat16_rn(vs);
+        if (s0) {
+          *mg_elem(sQ0, 128, 32 + lane) = __float2bfloat16_rn(ks);
+          *mg_elem(sQ1, 128, lane) = __float2bfloat16_rn(vs);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -475,13 +487,14 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
             float qf[MG_D];
 #pragma unroll
             for (int c = 0; c < MG_D; ++c) qf[c] = __shfl_sync(0xffffffffu, qs, hd * MG_D + c);
-            float sc[MG_SIDE_KEYS];
+            // key j = sid (one key per lane of the group); key 128 -- the side row -- is lane 0's second key
+            float sc[2];
             float mx = -INFINITY;
 #pragma unroll
-            for (int jj = 0; jj < MG_SIDE_KEYS; ++jj) {
-              const int j = lane + 32 * jj;
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = sid + 128 * jj;
               float acc = -INFINITY;
-              if (j < T) {
+              if (j < T && (jj == 0 || sid == 0)) {
                 float kr[MG_D];
                 mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sQ0, j, 4 + 2 * hd)), &kr[0]);
                 mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sQ0, j, 5 + 2 * hd)), &kr[8]);
@@ -493,14 +506,17 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
               mx = fmaxf(mx, acc);
             }
             mx = mg_wmax(mx);
+            if (lane == 0) spa[sw * 20] = mx;
+            mf_bar_side();
+            mx = fmaxf(fmaxf(spa[0], spa[20]), fmaxf(spa[40], spa[60]));
             const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + stok) * (uint64_t)Tpad;
             float sum = 0.f, o[MG_D];
 #pragma unroll
             for (int c = 0; c < MG_D; ++c) o[c] = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < MG_SIDE_KEYS; ++jj) {
-              const int j = lane + 32 * jj;
-              if (j < T) {
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = sid + 128 * jj;
+              if (j < T && (jj == 0 || sid == 0)) {
                 float p = exp2f((sc[jj] - mx) * sl2);
                 sum += p;
                 p = bf16_round(p * drop1(dca, drow + (uint64_t)j));
@@ -511,16 +527,25 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
                 for (int c = 0; c < MG_D; ++c) o[c] = fmaf(p, vr[c], o[c]);
               }
             }
+            // warp sums, then the four warps' partials in warp order
             sum = mg_wsum(sum);
-            const float inv = 1.f / sum;
+            if (lane == 0) spa[sw * 20 + 1] = sum;
 #pragma unroll
             for (int c = 0; c < MG_D; ++c) {
-              const float oc = mg_wsum(o[c]) * inv;
-              if (lane == hd * MG_D + c) cs_ = bf16_round(oc);
+              const float t = mg_wsum(o[c]);
+              if (lane == c) spa[sw * 20 + 2 + c] = t;
             }
-            if (lane == 0) P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + stok] = mx * scale + logf(sum);
+            mf_bar_side();
+            sum = (spa[1] + spa[21]) + (spa[41] + spa[61]);
+            const float inv = 1.f / sum;
+            if ((lane >> 4) == hd) {
+              const int c = lane & 15;
+              cs_ = bf16_round(((spa[2 + c] + spa[22 + c]) + (spa[42 + c] + spa[62 + c])) * inv);
+            }
+            if (lane == 0 && s0) P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + stok] = mx * scale + logf(sum);
+            mf_bar_side();   // spa is rewritten by the next head
           }
-          if ((lane >> 4) >= hd_lo && (lane >> 4) < hd_hi) {   // this CTA's head(s)
+          if (s0 && (lane >> 4) >= hd_lo && (lane >> 4) < hd_hi) {   // this CTA's head(s)
             reinterpret_cast<bf16*>(P.ctx)[((size_t)l * M + sgrow) * H + lane] = __float2bfloat16_rn(cs_);
             s_sc[32 + lane] = cs_;
             if (csz == 2) mf_st_peer4(mf_peer_addr(&s_sc[32 + lane], crank ^ 1u), cs_);
@@ -671,7 +696,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           float mu, rs;
           mg_side_ln(zs, P.eps, mu, rs);
           us = bf16_round((zs - mu) * rs * lp[MP_G2 + lane] + lp[MP_B2LN + lane]);
-          if (lead) {
+          if (lead && s0) {
             P.hmid[((size_t)l * M + sgrow) * H + lane] = zs;
             reinterpret_cast<bf16*>(P.u2)[((size_t)l * M + sgrow) * H + lane] = __float2bfloat16_rn(us);
             if (lane == 0) { P.stats[(size_t)(4 * l + 2) * M + sgrow] = mu; P.stats[(size_t)(4 * l + 3) * M + sgrow] = rs; }
@@ -700,7 +725,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           }
         }
       }
-      float ms[4] = {0.f, 0.f, 0.f, 0.f};   // side: gelu output, columns lane + 32 i
+      float ms = 0.f;   // side: gelu output, column sid
       if (!is_side && !ct) {
         mbar_wait(b_mma, ph_mma); ph_mma ^= 1;
         tc_fence_after();
@@ -724,18 +749,13 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         }
       } else if (is_side && s_on) {
         mbar_wait(b_w1, wpar);
-        float y[4];
-        mg_side_gemv32<4>(sW1, lane, us, y);
-        bf16* arow = reinterpret_cast<bf16*>(P.a) + ((size_t)l * M + sgrow) * I;
-        bf16* mrow = reinterpret_cast<bf16*>(P.m) + ((size_t)l * M + sgrow) * I;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = bf16_round(y[i] + lp[MP_B1 + lane + 32 * i]);
-          ms[i] = bf16_round(gelu_f(a));
-          if (lead) {
-            arow[lane + 32 * i] = __float2bfloat16_rn(a);
-            mrow[lane + 32 * i] = __float2bfloat16_rn(ms[i]);
-          }
+        float y[1];
+        mg_side_gemv32<1>(sW1, sid, us, y);   // MLP column sid (us is replicated in every warp)
+        const float a = bf16_round(y[0] + lp[MP_B1 + sid]);
+        ms = bf16_round(gelu_f(a));
+        if (lead) {
+          reinterpret_cast<bf16*>(P.a)[((size_t)l * M + sgrow) * I + sid] = __float2bfloat16_rn(a);
+          reinterpret_cast<bf16*>(P.m)[((size_t)l * M + sgrow) * I + sid] = __float2bfloat16_rn(ms);
         }
       }
       fence_proxy_async();
@@ -796,23 +816,26 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           }
         } else if (is_side && s_on) {
           mbar_wait(b_w2, wpar);
-          float y = 0.f;
+          // warp w contracts columns 32 w .. 32 w + 31 (k-block w >> 1, chunks 4 (w & 1) ..) of output row n = lane
+          float part = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {   // contraction columns 32 i .. 32 i + 31 sit in k-block i >> 1, chunks 4 (i & 1) ..
-            float w[32];
+          for (int c = 0; c < 4; ++c) {
+            float w[8];
+            mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sW2 + (sw >> 1) * 4096, lane, 4 * (sw & 1) + c)), w);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) mg_unpack8(*reinterpret_cast<const uint4*>(mg_chunk(sW2 + (i >> 1) * 4096, lane, 4 * (i & 1) + c)), &w[8 * c]);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) y = fmaf(__shfl_sync(0xffffffffu, ms[i], k), w[k], y);
+            for (int q = 0; q < 8; ++q) part = fmaf(__shfl_sync(0xffffffffu, ms, 8 * c + q), w[q], part);
           }
+          sp[sw * 32 + lane] = part;
+          mf_bar_side();
+          const float y = (sp[lane] + sp[32 + lane]) + (sp[64 + lane] + sp[96 + lane]);
           zs += bf16_round(bf16_round(y + lp[MP_B2 + lane]) * drop1(dc, sgrow * H + lane));
-          if (lead) P.z[((size_t)(l + 1) * M + sgrow) * H + lane] = zs;
+          if (lead && s0) P.z[((size_t)(l + 1) * M + sgrow) * H + lane] = zs;
           if (ct) {   // final LayerNorm of the CLS row (HF:455), handed to the head
             float mu, rs;
             mg_side_ln(zs, P.eps, mu, rs);
             const float un = bf16_round((zs - mu) * rs * gn[lane] + bn[lane]);
-            s_sc[lane] = un;
-            if (lead) {
+            if (s0) s_sc[lane] = un;
+            if (lead && s0) {
               reinterpret_cast<bf16*>(P.s_cls)[(size_t)b * H + lane] = __float2bfloat16_rn(un);
               if (lane == 0) { P.stats[(size_t)(4 * L) * M + b] = mu; P.stats[(size_t)(4 * L + 1) * M + b] = rs; }
             }
@@ -820,7 +843,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
             float mu, rs;
             mg_side_ln(zs, P.eps, mu, rs);
             us = bf16_round((zs - mu) * rs * gn[lane] + bn[lane]);
-            if (lead) {
+            if (lead && s0) {
               reinterpret_cast<bf16*>(P.u)[((size_t)(l + 1) * M + grow) * H + lane] = __float2bfloat16_rn(us);
               if (lane == 0) { P.stats[(size_t)(4 * l + 4) * M + grow] = mu; P.stats[(size_t)(4 * l + 5) * M + grow] = rs; }
             }
@@ -837,7 +860,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   if (csz == 2) { mf_cluster_wait(); mf_cluster_sync(); }   // no CTA of a pair exits while its peer may still touch its shared memory
   float* loss_part = reinterpret_cast<float*>(reinterpret_cast<char*>(P.ws) + 256);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(P.ws);
-  if (tid == MG_MAIN) loss_part[blockIdx.x] = loss_acc;
+  if (tid == MG_MAIN) loss_part[blockIdx.x] = loss_acc;   // lane 0 of side warp 0
   if (tid == 0) tma_store_wait_all();
   tc_fence_before();
   if (last_block_ticket(ticket, gridDim.x) && P.labels && tid == 0) {
@@ -908,7 +931,7 @@ extern "C" int vitb200_mega_fwd(const vitb200_mega_fwd_args* a, void* stream) {
     if (e != cudaSuccess) return vb_cuda_error(e);
     max_set = smem;
   }
-  vb_launch_pdl_cluster(mega_fwd_kernel, dim3(vitb200_mega_grid(B, a->cluster)), dim3(MG_THREADS), smem, (cudaStream_t)stream,
+  vb_launch_pdl_cluster(mega_fwd_kernel, dim3(vitb200_mega_grid(B, a->cluster)), dim3(MF_THREADS), smem, (cudaStream_t)stream,
                         a->cluster, tm, *a);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
