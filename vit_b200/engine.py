@@ -230,8 +230,19 @@ class ViTEngine:
             P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
             self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), self.dt))
 
-    def _mega_fwd_args(self, train: bool, with_labels: bool):
+    def input_slot(self, slot: int):
+        """(pixels, labels) input buffers of `slot`.  Slot 0 is `self.x` / `self.labels`; slot 1 is a second pair the
+        whole-network programs can be built on, so that a host pipeline uploads batch i + 1 while step i still reads
+        batch i (TrainStep.fit_host) -- no device-to-device staging copy on the step's critical path."""
+        if slot == 0:
+            return self.x, self.labels
+        if not hasattr(self, "_slot1"):
+            self._slot1 = (torch.zeros_like(self.x), torch.zeros_like(self.labels))
+        return self._slot1
+
+    def _mega_fwd_args(self, train: bool, with_labels: bool, slot: int = 0):
         c, lay, P_ = self.cfg, self.arena.layout, self._ptr
+        x_in, lab_in = self.input_slot(slot)
         if not hasattr(self, "mega_ws"):
             self.mega_ws = torch.zeros(int(self.lib.vitb200_mega_ws_bytes()), dtype=torch.uint8, device=self.device)
         emb, L0 = "vit.embeddings.", "vit.encoder.layer.0."
@@ -243,8 +254,8 @@ class ViTEngine:
             layers=c.num_hidden_layers, C=c.num_labels, loss_kind=self.loss_kind, cluster=self.mega_cluster,
             cls_only=1 if self.cls_only else 0,
             eps=float(c.layer_norm_eps), p_hidden=float(c.hidden_dropout_prob) if train else 0.0,
-            p_attn=float(c.attention_probs_dropout_prob) if train else 0.0, rng=self.rng.data_ptr(), x=P_(self.x),
-            labels=P_(self.labels) if with_labels else None, params=self.arena.data.data_ptr(),
+            p_attn=float(c.attention_probs_dropout_prob) if train else 0.0, rng=self.rng.data_ptr(), x=P_(x_in),
+            labels=P_(lab_in) if with_labels else None, params=self.arena.data.data_ptr(),
             shadow=self.arena.shadow.data_ptr(), off_cls=lay.off(emb + "cls_token"),
             off_pos=lay.off(emb + "position_embeddings") if c.pos_encoding_type == "learned" else -1,
             off_wp=lay.off(emb + "patch_embeddings.projection.weight"), off_bp=lay.off(emb + "patch_embeddings.projection.bias"),
@@ -263,12 +274,14 @@ class ViTEngine:
         self._keep.append(a)
         return a
 
-    def _build_forward_fused(self, train: bool, with_labels: bool, head_bwd: bool = False) -> List[Tuple[Callable, tuple]]:
+    def _build_forward_fused(self, train: bool, with_labels: bool, head_bwd: bool = False, slot: int = 0) -> List[Tuple[Callable, tuple]]:
         """embed -> [attention, fused layer] x L -> head: 2 + 2L (+1 loss) launches instead of 4 + 7L;
         whole-network kernel when the shape allows: ONE launch (+ the head backward for training steps)."""
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
+        if slot != 0 and not (self.mega and self.mega_bwd):
+            raise RuntimeError("vit_b200: input slot 1 exists for the whole-network programs only")
         if self.mega:
-            a = self._mega_fwd_args(train, with_labels)
+            a = self._mega_fwd_args(train, with_labels, slot)
             prog = [(lib.vitb200_mega_fwd, (ctypes.addressof(a),))]
             if head_bwd and not self.mega_bwd:
                 self._alloc_backward()
@@ -425,7 +438,7 @@ class ViTEngine:
         return prog
 
     def _build_backward_fused(self, train: bool, gloss_ptr: Optional[int], given: bool, skip_reduce: bool = False,
-                              skip_head: bool = False):
+                              skip_head: bool = False, slot: int = 0):
         """head -> final LN -> [upper, attention bwd, lower] x L -> embed -> reduce of the per-CTA partials."""
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
@@ -446,12 +459,12 @@ class ViTEngine:
         prog = []
         if given and not hasattr(self, "dlogits"):
             self.dlogits = torch.zeros(B, c.num_labels, dtype=torch.float32, device=self.device)
-        lab_ptr = P_(self.dlogits) if given else P_(self.labels)
+        lab_ptr = P_(self.dlogits) if given else P_(self.input_slot(slot)[1])
         kind = _lib.LOSS_GIVEN if given else self.loss_kind
         gl = None if given else gloss_ptr
         if self.mega_bwd:
             # the whole backward is ONE launch: head, final LN, every layer, embeddings; one gradient set per sample
-            fa = self._mega_fwd_args(train, True)
+            fa = self._mega_fwd_args(train, True, slot)
             ba = _lib.MegaBwdArgs(f=fa, labels=lab_ptr, gloss=gl, loss_kind=kind, n_opt=lay.n_opt, gpart=gp,
                                   dz0=P_(self.dzA))
             self._keep.append(ba)
@@ -533,9 +546,9 @@ class ViTEngine:
         return prog
 
     def _build_backward(self, train: bool, gloss_ptr: Optional[int] = None,
-                        given: bool = False, skip_reduce: bool = False, skip_head: bool = False) -> List[Tuple[Callable, tuple]]:
+                        given: bool = False, skip_reduce: bool = False, skip_head: bool = False, slot: int = 0) -> List[Tuple[Callable, tuple]]:
         if self.fused_bwd:
-            return self._build_backward_fused(train, gloss_ptr, given, skip_reduce, skip_head)
+            return self._build_backward_fused(train, gloss_ptr, given, skip_reduce, skip_head, slot)
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
@@ -651,27 +664,32 @@ class ViTEngine:
         _lib.check(self.lib.vitb200_cast_bf16(ar.data.data_ptr(), ar.shadow.data_ptr(), ar.layout.n_total, st), "cast")
         ar.mark_shadow_fresh()
 
-    def forward(self, train: bool, with_labels: bool = True, head_bwd: bool = False) -> None:
+    def forward(self, train: bool, with_labels: bool = True, head_bwd: bool = False, slot: int = 0) -> None:
         """head_bwd (training steps, needs can_fuse_head): the last launch also runs the head / final-LayerNorm backward
         with dloss = 1; the caller must then use backward(skip_head=True)."""
         self.refresh_shadow()
         co = bool(self.cls_only and self.mega)
         if head_bwd:
             assert with_labels and self.can_fuse_head
-            self._run(("fwd", train, True, True, co), lambda: self._build_forward_fused(train, True, head_bwd=True))
+            key = ("fwd", train, True, True, co) if slot == 0 else ("fwd", train, True, True, co, slot)
+            self._run(key, lambda: self._build_forward_fused(train, True, head_bwd=True, slot=slot))
+        elif slot != 0:
+            self._run(("fwd", train, with_labels, co, slot), lambda: self._build_forward_fused(train, with_labels, slot=slot))
         else:
             self._run(("fwd", train, with_labels, co), lambda: self._build_forward(train, with_labels))
 
     def backward(self, train: bool, gloss: Optional[torch.Tensor] = None, skip_reduce: bool = False,
-                 skip_head: bool = False) -> None:
+                 skip_head: bool = False, slot: int = 0) -> None:
         """skip_reduce (fused programs only): leave the layer / embedding gradients as per-CTA partials; the caller
         must follow with optimizer_step(fused_reduce=True), which sums them inside the optimizer kernel."""
         gp = None if gloss is None else gloss.data_ptr()
         skip = bool(skip_reduce and self.fused_bwd)
         sh = bool(skip_head and self.fused_bwd)
         co = bool(self.cls_only and self.mega)
-        self._run(("bwd", train, gp, skip, sh, co) if (skip or sh) else ("bwd", train, gp, co),
-                  lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh))
+        key = ("bwd", train, gp, skip, sh, co) if (skip or sh) else ("bwd", train, gp, co)
+        if slot != 0:
+            key = key + (slot,)
+        self._run(key, lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh, slot=slot))
 
     def backward_from_dlogits(self, train: bool, dlogits: torch.Tensor) -> None:
         """Backward when the caller computed its own loss from `logits` (labels=None forward)."""

@@ -41,6 +41,7 @@ class TrainStep:
         self.noise_level = float(noise_level)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph1: Optional[torch.cuda.CUDAGraph] = None   # the same step on input slot 1 (fit_host pipeline)
         c = model.config
         self.h_x = torch.empty(batch_size, model.input_dim, dtype=torch.float32, pin_memory=True)
         self.h_y = torch.empty(self.eng.labels.shape, dtype=self.eng.labels.dtype, pin_memory=True)
@@ -48,10 +49,14 @@ class TrainStep:
         self._segments = None
 
     # ---- one step's kernel sequence (also what gets captured) ---------------------------------
-    def _launch(self) -> None:
+    def _launch(self, slot: int = 0) -> None:
         eng = self.eng
         eng.cls_only = True   # a training step reads the loss only: the last layer runs for the CLS row alone
-        if self.world > 1 and getattr(eng, "peer", None) is None:
+        if slot != 0:
+            eng.forward(train=self.train, with_labels=True, head_bwd=True, slot=slot)
+            eng.backward(train=self.train, skip_reduce=True, skip_head=True, slot=slot)
+            eng.optimizer_step(fused_reduce=True)
+        elif self.world > 1 and getattr(eng, "peer", None) is None:
             eng.forward(train=self.train, with_labels=True)
             self._backward_overlapped()   # NCCL: gradients are summed across ranks before the optimizer kernel reads them
             eng.optimizer_step()
@@ -118,22 +123,41 @@ class TrainStep:
             d.copy_(s)
         e.arena.mark_shadow_fresh()
 
-    def _capture(self) -> None:
+    def _capture(self, slot: int = 0) -> None:
         eng = self.eng
         eng.refresh_shadow()
         snap = self._snapshot()
         side = torch.cuda.Stream(device=eng.device)
         side.wait_stream(torch.cuda.current_stream(eng.device))
         with torch.cuda.stream(side):
-            self._launch()  # loads every kernel before capture; state is restored below
+            self._launch(slot)  # loads every kernel before capture; state is restored below
         torch.cuda.current_stream(eng.device).wait_stream(side)
         self._restore(snap)
         torch.cuda.synchronize(eng.device)
         g = torch.cuda.CUDAGraph()
         # thread_local: other threads (NCCL watchdog, data loaders) may touch CUDA while this thread captures
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self._launch()
-        self.graph = g
+            self._launch(slot)
+        if slot == 0:
+            self.graph = g
+        else:
+            self._graph1 = g
+
+    @property
+    def two_slots(self) -> bool:
+        """fit_host can upload straight into the engine's two input slots (whole-network programs, one graph per slot):
+        no device-to-device staging copy between the upload and the step."""
+        e = self.eng
+        return bool(self.use_graph and e.mega and e.mega_bwd and self.model.preprocessor is None
+                    and (self.world == 1 or getattr(e, "peer", None) is not None))
+
+    def _run_slot(self, slot: int) -> None:
+        """One step on the inputs sitting in the engine's input slot `slot`."""
+        if slot == 0:
+            return self._run_staged()
+        if self._graph1 is None:
+            self._capture(1)
+        self._graph1.replay()
 
     # ---- public -----------------------------------------------------------------------------
     def step(self, flux: torch.Tensor, labels: torch.Tensor, error: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -248,6 +272,14 @@ class TrainStep:
         P = self._pipe
         copy = P["copy"]
         losses = []
+        direct = self.two_slots   # uploads land in the engine's own input slots: the step reads them in place
+        if direct:
+            P["d_x"] = [eng.input_slot(0)[0], eng.input_slot(1)[0]]
+            P["d_y"] = [eng.input_slot(0)[1], eng.input_slot(1)[1]]
+            if self.graph is None:
+                self._capture(0)
+            if self._graph1 is None:
+                self._capture(1)
 
         def upload(i, batch):
             s = i & 1
@@ -255,8 +287,10 @@ class TrainStep:
                 P["ev_free"][s].synchronize()   # the host slot / device slot of step i-2 are reusable
             hx, hy = self._pinned(batch[0], batch[1], P["h_x"][s], P["h_y"][s])
             with torch.cuda.stream(copy):
+                if direct and i < 2:
+                    copy.wait_stream(main)      # (the slots may still be read by steps enqueued before this loop)
                 P["d_x"][s].copy_(hx, non_blocking=True)
-                P["d_y"][s].copy_(hy, non_blocking=True)
+                P["d_y"][s].copy_(hy.reshape(P["d_y"][s].shape), non_blocking=True)
                 P["ev_in"][s].record(copy)
 
         def collect(i):
@@ -275,7 +309,11 @@ class TrainStep:
         while nxt is not None:
             s = i & 1
             main.wait_event(P["ev_in"][s])
-            loss = self.step(P["d_x"][s], P["d_y"][s])
+            if direct:
+                self._run_slot(s)
+                loss = eng.loss[0]
+            else:
+                loss = self.step(P["d_x"][s], P["d_y"][s])
             P["ev_free"][s].record(main)
             P["h_loss"][s].copy_(loss.reshape(1), non_blocking=True)
             P["ev_loss"][s].record(main)
@@ -308,6 +346,7 @@ class TrainStep:
         import gc
 
         self.graph = None
+        self._graph1 = None
         self._pipe = None
         gc.collect()
         torch.cuda.synchronize(self.eng.device)
