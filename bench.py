@@ -177,7 +177,7 @@ def call_work(name: str, args: tuple, es: int):
     if name == "vitb200_patch_embed_bwd":
         B, L, P, S, Np, nv, H = args[6:13]
         return 2.0 * B * Np * P * H, 4 * B * L + 4 * B * (Np + 1) * H + 4 * H * P
-    if name.startswith("vitb200_fused_") or name.startswith("vitb200_head_fused"):
+    if name.startswith("vitb200_fused_") or name.startswith("vitb200_head_fused") or name.startswith("vitb200_mega_"):
         return fused_call_work(name, args)
     if name == "vitb200_clip_adamw_fused":
         n, slots, start, end = args[5], args[10], args[12], args[13]
@@ -202,6 +202,24 @@ def fused_call_work(name: str, args: tuple):
     def st(tp):
         return ctypes.cast(args[0], ctypes.POINTER(tp)).contents
 
+    if name in ("vitb200_mega_fwd", "vitb200_mega_bwd"):
+        # whole-network kernels: algorithmic work of ONE launch = all samples.  Bytes = compulsory HBM traffic: the input
+        # spectra, the parameters once, the tensors saved for backward written once (forward) / read once (backward), and
+        # the per-sample gradient partials (backward).  With cls_only the last layer saves / reads only what its CLS row
+        # and the keys / values of every token need.
+        a = st(_lib.MegaBwdArgs).f if name.endswith("bwd") else st(_lib.MegaFwdArgs)
+        B, T, H, L, P, Np, C = a.B, a.Np + 1, 32, a.layers, a.P, a.Np, a.C
+        I = 4 * H
+        row_full = 2 * I + 2 * I + 2 * H + 4 * H + 2 * H + 6 * H + 2 * H + 4 * H      # m a u2 hmid ctx qkv u z   (bytes / token / layer)
+        row_top = 6 * H + 2 * H + 4 * H                                               # qkv u z                   (CLS-only last layer)
+        n_full = L - 1 if a.cls_only else L
+        saved = B * T * (n_full * row_full + (row_top if a.cls_only else 0)) + B * T * 4 * H * (0 if a.cls_only else 1)
+        n_par = 3 * H + H * P + L * (12 * H * H + 13 * H) + 2 * H + C * H + C
+        gemm = 2.0 * Np * P * H + (n_full * 24.0 * T * H * H) + (24.0 * H * H + 6.0 * T * H * H if a.cls_only else 0.0) + 2.0 * H * C
+        attn = n_full * 4.0 * T * T * H + (4.0 * T * H if a.cls_only else 0.0)
+        if name.endswith("fwd"):
+            return B * (gemm + attn), float(4 * B * a.L + saved + 6 * n_par + 4 * B * C)
+        return B * (2.0 * gemm + 2.5 * attn), float(4 * B * a.L + saved + 2 * n_par + 4 * B * n_par)
     if name == "vitb200_fused_layer_fwd":
         a = st(_lib.LayerFwdArgs)
         M, H = a.B * a.T, a.H
