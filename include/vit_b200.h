@@ -347,6 +347,14 @@ int vitb200_attn_tc_blocked_fwd(const void* qkv, void* ctx, float* lse, const fl
 int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d,
                                 float scale, float p_drop, const uint64_t* rng, uint32_t site, void* ws, void* stream);
+/* Flash attention forward for ANY sequence length in ONE launch (bf16, d in {16, 32, 64}, fused [B*T, 3H] QKV buffer): the
+ * key/value loop runs inside the kernel (TMA double-buffered K/V blocks of 128 keys, S = QK^T and P~V on tcgen05, online
+ * softmax with the running max / sum and the output row in registers).  No workspace, no partial outputs, no merge
+ * kernel.  Same dropout masks, RoPE and lse output as vitb200_attn_tc_fwd.  (HF:232-249, vit_with_rope.py:43-84) */
+int vitb200_attn_flash_supported(int T, int d, int ld, int H);
+int vitb200_attn_flash_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin, int B,
+                           int T, int heads, int d, float scale, float p_drop, const uint64_t* rng, uint32_t site,
+                           void* stream);
 /* probs[B,heads,T,T] f32 = softmax probabilities before dropout (what the eager / RoPE attention returns
  * as `attention_probs`, src/models/vit_with_rope.py:84); for hooks / output_attentions only. */
 int vitb200_attn_probs(const void* q, const void* k, int ld, const float* lse, float* probs, const float* rope_cos,

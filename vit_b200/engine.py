@@ -205,6 +205,13 @@ class ViTEngine:
         qkv = self.qkv[l].data_ptr()
         scale = 1.0 / math.sqrt(c.head_dim)
         rng = self.rng.data_ptr()
+        if (self.dt == BF16 and os.environ.get("VITB200_FLASH", "1") != "0"
+                and not self.lib.vitb200_attn_tc_supported(T, c.head_dim, 3 * H, H)
+                and self.lib.vitb200_attn_flash_supported(T, c.head_dim, 3 * H, H)):
+            # longer sequences / head_dim 64: the in-kernel key/value loop (one launch, online softmax)
+            return (self.lib.vitb200_attn_flash_fwd, (
+                qkv, P_(self.ctx[l]), P_(self.lse[l]), P_(self.rope_cos), P_(self.rope_sin), self.B, T,
+                c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l)))
         if self._attn_blocked():
             return (self.lib.vitb200_attn_tc_blocked_fwd, (
                 qkv, P_(self.ctx[l]), P_(self.lse[l]), P_(self.rope_cos), P_(self.rope_sin), self.B, T,
