@@ -465,8 +465,24 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----
-    for i in range(args.warmup):
-        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    # The pool is a device-resident dataset (vit_b200.data.DeviceDataset): TrainStep.fit_device walks a
+    # shuffled permutation of its rows, batch after batch.  With the whole-network kernels the step graph reads the rows
+    # itself (no gather launch, no staging copy); otherwise a gather kernel fills the engine's input buffers first.
+    from vit_b200.data import DeviceDataset
+
+    pool_ds = DeviceDataset(pool_x.view(-1, 4096), pool_y.view(-1), device=dev)
+    epoch_no = [0]
+
+    def run_steps(n):
+        """Exactly n training steps over the device-resident pool (a new shuffled epoch whenever one is used up)."""
+        done = 0
+        while done < n:
+            got = step.fit_device(pool_ds, epochs=1, shuffle=True, seed=1234 + rank, start_epoch=epoch_no[0],
+                                  max_steps=n - done)
+            epoch_no[0] += 1
+            done += int(got[0].numel())
+
+    run_steps(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     stream = torch.cuda.current_stream(dev)
@@ -476,11 +492,9 @@ def main():
     # untimed steps first let the in-kernel exchange align the GPUs (and fill the launch queue); the events then bracket
     # exactly K steps of steady state on the launching stream.  Same code path at N = 1.
     lead = 8
-    for i in range(lead):
-        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    run_steps(lead)
     e0.record(stream)
-    for i in range(lead, lead + args.steps):
-        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    run_steps(args.steps)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -490,6 +504,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t[0]) / args.steps
     value = world * B * 1e3 / ms_step
+    # the same through TrainStep.step(x, y) on device tensors (one staging copy of the inputs per step)
+    for i in range(lead):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    e0.record(stream)
+    for i in range(lead, lead + args.steps):
+        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_api_value = world * B * 1e3 / (float(t[0]) / args.steps)
 
     # ---- end to end through the public API: host batches -> H2D -> step -> D2H loss, every step ----
     # TrainStep.fit_host is the training loop a user calls with an iterable of host batches; it pipelines the copies
@@ -531,8 +557,7 @@ def main():
     # more second so that the clock / throttle-reason samples describe this load.  The count derives from the all-reduced
     # step time, so every rank runs the same number of steps (the in-kernel gradient exchange needs that).
     extra = max(0, min(8000, int(1.0 / max(ms_step * 1e-3, 1e-6))))
-    for i in range(extra):
-        step.step(pool_x[i % pool_n], pool_y[i % pool_n])
+    run_steps(extra)
     barrier()
     clocks = sampler.stop() if sampler is not None else None
     if clocks is not None:
@@ -782,7 +807,9 @@ def main():
                    "cuda_graph": not args.no_graph,
                    "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                       "in-kernel over NVLink peer memory (vitb200_clip_adamw_fused_dp), no NCCL call per step"),
-                   "l2": f"inputs rotate through a pool of {pool_n} device batches ({pool_n * B * 4096 * 4 / 1e6:.0f} MB > 126 MB L2)"},
+                   "l2": f"inputs = shuffled rows of a device-resident dataset of {pool_n * B} spectra "
+                         f"({pool_n * B * 4096 * 4 / 1e6:.0f} MB > 126 MB L2), TrainStep.fit_device"},
+        "step_api_samples_per_s": step_api_value,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_b,
                 "d2h_bytes_per_step": d2h_b, "ms_per_step": 1e3 * float(te[0]) / args.steps,
                 "api": "TrainStep.fit_host(iterable of host batches): per step H2D of the inputs from pinned memory "

@@ -283,6 +283,13 @@ typedef struct {
   void* s_cls;                       /* [B, H] bf16: final-LayerNorm'd CLS rows */
   float *logits, *loss;              /* [B, C], [1] */
   void* ws;                          /* vitb200_mega_ws_bytes() bytes, zeroed once by the caller */
+  /* Device-resident dataset mode (src/dataloader/base.py:219-245 hands the model rows of an in-RAM tensor; here the
+   * tensor lives in HBM and the kernels pick the rows themselves).  rows == NULL: sample b reads x[b], labels[b].
+   * Otherwise x / labels are the WHOLE dataset and sample b of this step reads row rows[pos * B + b], where
+   * pos = rng[1] - rows_base[0] is the number of steps taken since the host stored rows_base (the optimizer kernel
+   * advances rng[1]), so one captured launch walks through an epoch's permutation.  loss_log (optional): the step's
+   * loss is also stored at loss_log[pos]. */
+  const int64_t* rows; const uint64_t* rows_base; float* loss_log;
 } vitb200_mega_fwd_args;
 int vitb200_mega_supported(int H, int heads, int T, int P, int C, int layers, int rope);
 size_t vitb200_mega_ws_bytes(void);

@@ -306,6 +306,42 @@ def test_fit_device_matches_stepping_by_hand(precision):
 
 
 @pytest.mark.parametrize("task", ["reg", "cls"])
+def test_fit_device_rows_mode_equals_gather_mode(task, monkeypatch):
+    """Device-resident dataset mode of the whole-network kernels (they pick the rows of the epoch permutation themselves,
+    steps replayed 4 per graph) == the gather-kernel path, bit for bit: per-step losses and final weights; dropout ON,
+    a remainder of single steps, max_steps, two epochs (fresh permutation uploaded between them)."""
+    from vit_b200 import get_model
+    from vit_b200.data import DeviceDataset
+    from vit_b200.step import TrainStep
+
+    dev = _cuda()
+    cfg = copy.deepcopy(BASE)
+    cfg["model"].update(image_size=4096, patch_size=32, stride_size=32)
+    B, N = 8, 83
+    x, y = vo.synthetic_batch(N, 4096, seed=5, kind="rand")
+    if task == "cls":
+        cfg["model"].update(task_type="cls", num_labels=4)
+        y = torch.randint(0, 4, (N,), generator=torch.Generator().manual_seed(2))
+    ds = DeviceDataset(x, y, device=dev)
+    res = []
+    for rows in ("1", "0"):
+        monkeypatch.setenv("VITB200_ROWS", rows)
+        torch.manual_seed(3)
+        m = get_model(copy.deepcopy(cfg), precision="bf16-mixed", device=dev).train()
+        st = TrainStep(m, B, use_graph=True, train=True)
+        assert st.two_slots
+        got = st.fit_device(ds, epochs=2, shuffle=True, seed=9)          # 83 -> 11 steps per epoch = 2 x 4 + 3
+        got += st.fit_device(ds, epochs=1, seed=9, start_epoch=2, max_steps=6)
+        assert [g.numel() for g in got] == [11, 11, 6]
+        assert (len(st._graph_rows) > 0) == (rows == "1")
+        res.append((torch.cat(got).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+        st.close()
+    assert torch.equal(res[0][0], res[1][0])
+    for k, v in res[0][1].items():
+        assert torch.equal(v, res[1][1][k]), k
+
+
+@pytest.mark.parametrize("task", ["reg", "cls"])
 def test_evaluate_metrics_on_device(task):
     """EvalStep.evaluate: one forward per batch, metrics accumulated by vitb200_eval_metrics_accum, exact tail batch."""
     from vit_b200 import get_model

@@ -261,6 +261,8 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
 
   const uint64_t seed = P.rng ? P.rng[0] : 0ull;
   const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
+  // dataset row of this sample (device-resident dataset mode, see vitb200_mega_fwd_args.rows)
+  const size_t bsrc = P.rows ? (size_t)P.rows[(size_t)(P.rng[1] - P.rows_base[0]) * (size_t)B + b] : (size_t)b;
   const float scale = rsqrtf((float)D), sl2 = scale * MG_LOG2E;
   const int Tpad = attn_drop_tpad(T);
   uint32_t ph_mma = 0;
@@ -275,7 +277,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
 #pragma unroll
     for (int c = 0; c < 4; ++c) lg[c] = c < C ? P.logits[(size_t)b * C + c] : 0.f;
     const float gl = PA.gloss ? PA.gloss[0] : 1.f;
-    mb_dlogits(lg, PA.labels, b, B, C, PA.loss_kind, gl, dl);
+    mb_dlogits(lg, PA.labels, (int)bsrc, B, C, PA.loss_kind, gl, dl);
     const float s = __bfloat162float(reinterpret_cast<const bf16*>(P.s_cls)[(size_t)b * H + lane]);
     float ds = 0.f;
 #pragma unroll
@@ -1078,7 +1080,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       const int nchunk = P.P / 8;
       const bool vec = (P.S % 4 == 0) && (P.L % 4 == 0);
       const bool has = valid && r >= 1 && (r - 1) < P.n_valid;
-      const float* xp = P.x + (size_t)b * P.L + (size_t)(r >= 1 ? r - 1 : 0) * P.S;
+      const float* xp = P.x + bsrc * P.L + (size_t)(r >= 1 ? r - 1 : 0) * P.S;
       for (int c = cg; c < 8; c += MG_CG) {
         float v[8];
         if (c < nchunk && has) {
@@ -1104,7 +1106,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         }
         sv[SV_DD2 + lane] = bf16_round(gs);
         const bool has = 127 < P.n_valid;
-        const float* xp = P.x + (size_t)b * P.L + (size_t)127 * P.S;
+        const float* xp = P.x + bsrc * P.L + (size_t)127 * P.S;
         sv[SV_M + lane] = (has && lane < P.P) ? bf16_round(xp[lane]) : 0.f;
         sv[SV_M + 32 + lane] = (has && lane + 32 < P.P) ? bf16_round(xp[lane + 32]) : 0.f;
       }
@@ -1174,7 +1176,8 @@ extern "C" int vitb200_mega_bwd(const vitb200_mega_bwd_args* pa, void* stream) {
   if (!pa) return VITB200_ERR_ARG;
   const vitb200_mega_fwd_args* a = &pa->f;
   if (!a->x || !a->params || !a->shadow || !a->z || !a->hmid || !a->u || !a->u2 || !a->qkv || !a->ctx || !a->a || !a->m ||
-      !a->stats || !a->lse || !a->s_cls || !a->logits || !pa->labels || !pa->gpart)
+      !a->stats || !a->lse || !a->s_cls || !a->logits || !pa->labels || !pa->gpart ||
+      (a->rows && (!a->rng || !a->rows_base || pa->loss_kind == VITB200_LOSS_GIVEN)))
     return VITB200_ERR_ARG;
   const int T = a->Np + 1;
   if (!vitb200_mega_bwd_supported(MG_H, MG_NH, T, a->P, a->C, a->layers, a->B, a->cluster)) return VITB200_ERR_SHAPE;

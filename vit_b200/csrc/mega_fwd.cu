@@ -221,6 +221,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
 
   const uint64_t seed = P.rng ? P.rng[0] : 0ull;
   const uint32_t step = P.rng ? (uint32_t)P.rng[1] : 0u;
+  const size_t pos = P.rows ? (size_t)(P.rng[1] - P.rows_base[0]) : 0;   // steps into the epoch's permutation
   const float scale = rsqrtf((float)MG_D), sl2 = scale * MG_LOG2E;
   const int Tpad = attn_drop_tpad(T);
   uint32_t ph_mma = 0;
@@ -240,6 +241,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
     float zs = 0.f;         // side: residual row, column = lane
     float us = 0.f;         // side: LayerNorm output feeding the next GEMV (bf16-rounded)
     float qs = 0.f;         // side: q row (column = lane) of the current layer
+    const size_t bsrc = P.rows ? (size_t)P.rows[pos * (size_t)B + b] : (size_t)b;   // dataset row of this sample
 
     // =============================== embedding ===============================
     if (!is_side) {
@@ -249,7 +251,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       for (int itx = tid; itx < 128 * nchunk; itx += MG_MAIN) {
         const int rr = itx / nchunk, c = itx - rr * nchunk;
         const bool has = rr >= 1 && rr < Tm && (rr - 1) < P.n_valid;
-        const float* xp = P.x + (size_t)b * P.L + (size_t)(rr >= 1 ? rr - 1 : 0) * P.S;
+        const float* xp = P.x + bsrc * P.L + (size_t)(rr >= 1 ? rr - 1 : 0) * P.S;
         float v[8];
         if (vec && has && c * 8 + 8 <= P.P) {
           const float4 a0 = *reinterpret_cast<const float4*>(xp + c * 8), a1 = *reinterpret_cast<const float4*>(xp + c * 8 + 4);
@@ -264,7 +266,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
     float es = 0.f;   // side: patch projection of token 128 (before bias)
     if (is_side && has_side) {
       const bool has = 127 < P.n_valid;
-      const float* xp = P.x + (size_t)b * P.L + (size_t)127 * P.S;
+      const float* xp = P.x + bsrc * P.L + (size_t)127 * P.S;
       const float x0 = (has && lane < P.P) ? bf16_round(xp[lane]) : 0.f;
       const float x1 = (has && lane + 32 < P.P) ? bf16_round(xp[lane + 32]) : 0.f;
       mbar_wait(b_wp, 0);
@@ -361,7 +363,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (c < C) P.logits[(size_t)b * C + c] = mine[c];
-            if (P.labels) loss_acc += mf_loss_term(mine, P.labels, b, C, P.loss_kind);
+            if (P.labels) loss_acc += mf_loss_term(mine, P.labels, (int)bsrc, C, P.loss_kind);
           }
         }
         break;
@@ -866,7 +868,9 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   if (last_block_ticket(ticket, gridDim.x) && P.labels && tid == 0) {
     float t = 0.f;
     for (unsigned int k = 0; k < gridDim.x; ++k) t += __ldcg(&loss_part[k]);
-    P.loss[0] = t / (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+    t /= (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+    P.loss[0] = t;
+    if (P.loss_log) P.loss_log[pos] = t;
   }
   if (warp == 0) tmem_dealloc(tmem, MC_COLS);
   VB_TL(tl_mega_fwd, 12);
@@ -900,7 +904,8 @@ extern "C" int vitb200_mega_grid(int B, int cluster) {
 
 extern "C" int vitb200_mega_fwd(const vitb200_mega_fwd_args* a, void* stream) {
   if (!a || !a->x || !a->params || !a->shadow || !a->z || !a->hmid || !a->u || !a->u2 || !a->qkv || !a->ctx || !a->a ||
-      !a->m || !a->stats || !a->lse || !a->s_cls || !a->logits || !a->ws || (a->labels && !a->loss))
+      !a->m || !a->stats || !a->lse || !a->s_cls || !a->logits || !a->ws || (a->labels && !a->loss) ||
+      (a->rows && (!a->rng || !a->rows_base)))
     return VITB200_ERR_ARG;
   const int T = a->Np + 1;
   if (a->B <= 0 || !vitb200_mega_supported(MG_H, MG_NH, T, a->P, a->C, a->layers, a->rope_cos != nullptr)) return VITB200_ERR_SHAPE;

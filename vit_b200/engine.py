@@ -20,6 +20,8 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, BF16, F32, SITE_EMB, site_attn, site_mlp, site_proj
 from .arena import ParamArena
 
+ROWS_SLOT = 2   # input slot of the device-resident dataset mode (ViTEngine.bind_rows)
+
 
 def _normalize_precision(precision) -> str:
     p = str(precision).lower()
@@ -243,9 +245,31 @@ class ViTEngine:
         batch i (TrainStep.fit_host) -- no device-to-device staging copy on the step's critical path."""
         if slot == 0:
             return self.x, self.labels
+        if slot == ROWS_SLOT:
+            return self._rows["x"], self._rows["labels"]
         if not hasattr(self, "_slot1"):
             self._slot1 = (torch.zeros_like(self.x), torch.zeros_like(self.labels))
         return self._slot1
+
+    def bind_rows(self, x_all: torch.Tensor, labels_all: torch.Tensor, rows: torch.Tensor, loss_log: torch.Tensor) -> None:
+        """Device-resident dataset mode of the whole-network kernels (input slot ROWS_SLOT): x_all [N, L] f32 and labels_all
+        are the whole dataset, rows (int64) the epoch's permutation, loss_log [>= steps per epoch] f32.  The kernels read
+        row rows[pos * B + b] with pos = rng[1] - rows_base (vitb200_mega_fwd_args.rows), so a captured step needs no
+        gather launch and no staging copy.  `start_rows()` restarts pos at 0."""
+        if x_all.dtype != torch.float32 or not x_all.is_contiguous() or x_all.shape[1] != self.cfg.image_size:
+            raise ValueError("bind_rows: x_all must be a contiguous [N, image_size] float32 tensor")
+        if labels_all.dtype != self.labels.dtype or not labels_all.is_contiguous() or rows.dtype != torch.int64:
+            raise ValueError("bind_rows: labels / rows dtype mismatch")
+        if labels_all.numel() != x_all.shape[0] * (self.labels.numel() // self.B):
+            raise ValueError("bind_rows: labels do not match the dataset rows")
+        self._rows = dict(x=x_all, labels=labels_all, rows=rows, loss_log=loss_log,
+                          base=torch.zeros(1, dtype=torch.int64, device=self.device))
+        for k in [k for k in self._progs if k[-1] == ROWS_SLOT and k[0] in ("fwd", "bwd")]:
+            del self._progs[k]
+
+    def start_rows(self) -> None:
+        """The next step reads rows[0 : B] (stream-ordered: rows_base <- the device step counter)."""
+        self._rows["base"].copy_(self.rng[1:2])
 
     def _mega_fwd_args(self, train: bool, with_labels: bool, slot: int = 0):
         c, lay, P_ = self.cfg, self.arena.layout, self._ptr
@@ -278,6 +302,9 @@ class ViTEngine:
             u=P_(self.u_all), u2=P_(self.u2_all), qkv=P_(self.qkv_all), ctx=P_(self.ctx_all), a=P_(self.a_all),
             m=P_(self.m_all), stats=P_(self.stats), lse=P_(self.lse_all), s_cls=P_(self.s_cls), logits=P_(self.logits),
             loss=P_(self.loss), ws=P_(self.mega_ws))
+        if slot == ROWS_SLOT:
+            a.rows, a.rows_base = P_(self._rows["rows"]), P_(self._rows["base"])
+            a.loss_log = P_(self._rows["loss_log"])
         self._keep.append(a)
         return a
 

@@ -10,11 +10,13 @@ end-to-end call: pinned-host inputs -> H2D -> step -> D2H of the loss.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
 from . import dp as _dp
+from .engine import ROWS_SLOT
 from .model import MyViT
 
 
@@ -42,6 +44,9 @@ class TrainStep:
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph1: Optional[torch.cuda.CUDAGraph] = None   # the same step on input slot 1 (fit_host pipeline)
+        self._graph_rows: dict = {}   # unroll -> graph of `unroll` steps in device-resident dataset mode (fit_device)
+        self._rows_key = None
+        self._rows_buf = None
         c = model.config
         self.h_x = torch.empty(batch_size, model.input_dim, dtype=torch.float32, pin_memory=True)
         self.h_y = torch.empty(self.eng.labels.shape, dtype=self.eng.labels.dtype, pin_memory=True)
@@ -123,7 +128,7 @@ class TrainStep:
             d.copy_(s)
         e.arena.mark_shadow_fresh()
 
-    def _capture(self, slot: int = 0) -> None:
+    def _capture(self, slot: int = 0, unroll: int = 1) -> None:
         eng = self.eng
         eng.refresh_shadow()
         snap = self._snapshot()
@@ -137,9 +142,12 @@ class TrainStep:
         g = torch.cuda.CUDAGraph()
         # thread_local: other threads (NCCL watchdog, data loaders) may touch CUDA while this thread captures
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self._launch(slot)
+            for _ in range(unroll):
+                self._launch(slot)
         if slot == 0:
             self.graph = g
+        elif slot == ROWS_SLOT:
+            self._graph_rows[unroll] = g
         else:
             self._graph1 = g
 
@@ -181,8 +189,55 @@ class TrainStep:
             self.eng.refresh_shadow()
             self._launch()
 
+    def _fit_device_rows(self, dataset, epochs, shuffle, seed, tail, start_epoch, max_steps) -> list:
+        """fit_device for the whole-network kernels: they read the dataset rows of the epoch's permutation themselves
+        (ViTEngine.bind_rows), so a step is the bare 3-launch graph -- no gather launch, no staging copy, no per-step loss
+        copy (the forward kernel logs the loss of step i at loss_log[i]).  Steps are replayed `unroll` at a time (one graph
+        of `unroll` consecutive steps, chained by programmatic dependent launch) plus single steps for the remainder."""
+        from .data import epoch_indices
+
+        eng = self.eng
+        B = self.B
+        rank = 0
+        if self.world > 1:
+            import torch.distributed as dist
+
+            rank = dist.get_rank(self.group)
+        unroll = max(1, int(os.environ.get("VITB200_UNROLL", "4")))
+        lab = dataset.labels if dataset.labels.dtype == eng.labels.dtype else dataset.labels.to(eng.labels.dtype)
+        out, left = [], max_steps
+        for ep in range(start_epoch, start_epoch + epochs):
+            order = epoch_indices(len(dataset), ep, seed=seed, shuffle=shuffle, rank=rank, world=self.world, batch=B,
+                                  tail=tail)
+            nb = order.numel() // B
+            key = (dataset.flux.data_ptr(), lab.data_ptr(), len(dataset))
+            if self._rows_key != key or self._rows_buf.numel() < order.numel():
+                self._rows_buf = torch.zeros(order.numel(), dtype=torch.int64, device=eng.device)
+                self._rows_log = torch.zeros(max(nb, 1), dtype=torch.float32, device=eng.device)
+                self._rows_lab = lab
+                eng.bind_rows(dataset.flux, lab, self._rows_buf, self._rows_log)
+                self._rows_key, self._graph_rows = key, {}
+            self._rows_buf[:order.numel()].copy_(order.to(eng.device, non_blocking=True))
+            eng.start_rows()
+            if left is not None:
+                nb = min(nb, left)
+                left -= nb
+            for u in ((unroll, 1) if unroll > 1 and nb >= unroll else (1,)):
+                if u not in self._graph_rows:
+                    self._capture(ROWS_SLOT, u)
+            q, r = (nb // unroll, nb % unroll) if unroll > 1 and nb >= unroll else (0, nb)
+            gq, g1 = self._graph_rows.get(unroll), self._graph_rows.get(1)
+            for _ in range(q):
+                gq.replay()
+            for _ in range(r):
+                g1.replay()
+            out.append(self._rows_log[:nb].clone())
+            if left is not None and left <= 0:
+                break
+        return out
+
     def fit_device(self, dataset, epochs: int = 1, shuffle: bool = True, seed: int = 0, tail: str = "wrap",
-                   start_epoch: int = 0) -> list:
+                   start_epoch: int = 0, max_steps: Optional[int] = None) -> list:
         """The training loop over a DEVICE-resident dataset (`vit_b200.data.DeviceDataset`): per step
         one gather kernel assembles the batch (row gather by the epoch's permutation, noise injection when
         noise_level > 0, labels) directly in the engine's input buffers, then the step graph runs; the loss of every
@@ -197,6 +252,9 @@ class TrainStep:
         if dataset.labels is None:
             raise ValueError("fit_device needs a dataset with labels")
         pre = model.preprocessor
+        noisy = self.noise_level > 0 and getattr(dataset, "error", None) is not None
+        if self.two_slots and not noisy and os.environ.get("VITB200_ROWS", "1") != "0":
+            return self._fit_device_rows(dataset, epochs, shuffle, seed, tail, start_epoch, max_steps)
         x_dst = model._raw_buffer(eng)    # eng.x, or the staging buffer in front of a frozen preprocessor
         rank = 0
         if self.world > 1:
@@ -209,6 +267,9 @@ class TrainStep:
             order = epoch_indices(len(dataset), ep, seed=seed, shuffle=shuffle, rank=rank, world=self.world, batch=B,
                                   tail=tail).to(eng.device, non_blocking=True)
             nb = order.numel() // B
+            if max_steps is not None:
+                nb = min(nb, max_steps)
+                max_steps -= nb
             losses = torch.empty(nb, dtype=torch.float32, device=eng.device)
             for i in range(nb):
                 dataset.gather(order[i * B:(i + 1) * B], x_dst, eng.labels, noise_level=self.noise_level, rng=eng.rng)
@@ -217,6 +278,8 @@ class TrainStep:
                 self._run_staged()
                 losses[i:i + 1].copy_(eng.loss, non_blocking=True)
             out.append(losses)
+            if max_steps is not None and max_steps <= 0:
+                break
         return out
 
     def _pinned(self, flux_host: torch.Tensor, labels_host: torch.Tensor, slot_x: torch.Tensor, slot_y: torch.Tensor):
@@ -347,6 +410,7 @@ class TrainStep:
 
         self.graph = None
         self._graph1 = None
+        self._graph_rows, self._rows_key = {}, None
         self._pipe = None
         gc.collect()
         torch.cuda.synchronize(self.eng.device)
