@@ -308,6 +308,11 @@ typedef struct {
   int loss_kind, n_opt;
   float* gpart;
   float* dz0;
+  /* Streamed gradient groups (optional, NULL = off): DEVICE counters [layers + 2], zeroed once by the caller.  Every CTA
+   * adds 1 to counter g when its partial gradients of group g are in gpart: g = 1 + layers (final LayerNorm + head) and
+   * g = 1 + l (encoder layer l) as the layers finish, top first; g = 0 (everything in front of layer 0: cls token,
+   * positions, patch projection) at the end.  vitb200_clip_adamw_fused_streamed consumes and resets them. */
+  unsigned int* done;
 } vitb200_mega_bwd_args;
 int vitb200_mega_bwd_supported(int H, int heads, int T, int P, int C, int layers, int B, int cluster);
 size_t vitb200_mega_bwd_smem_bytes(int layers);
@@ -417,6 +422,25 @@ size_t vitb200_clip_adamw_fused_ws_bytes(void);
 int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
                              float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
                              size_t red_start, size_t red_end, void* ws, void* stream);
+
+/* Streamed variant of the tail (single GPU: peer_bufs == NULL, world == 1; data parallel otherwise, as _dp below): instead
+ * of waiting for the backward kernel to finish, every block waits only for the gradient groups its slice of the arena
+ * belongs to (counters raised by vitb200_mega_bwd, see vitb200_mega_bwd_args.done), so the partial-sum reduction -- and
+ * in a data-parallel run the NVLink exchange -- of the upper layers' gradients runs WHILE the backward kernel is still
+ * working on the lower layers (the bucketed overlap of DDP, without a collective launch).  Must directly follow the
+ * vitb200_mega_bwd launch that raises the counters, on the same stream; it resets the counters to zero.
+ * gs->lo / hi: arena element range [lo, hi) of each group (multiples of 4; together they cover [0, n)). */
+#define VITB200_MAX_GROUPS 20
+typedef struct {
+  unsigned int* done;     /* DEVICE counters [n_groups] */
+  unsigned int expect;    /* arrivals per group = CTAs of the backward launch */
+  int n_groups;
+  unsigned int lo[VITB200_MAX_GROUPS], hi[VITB200_MAX_GROUPS];
+} vitb200_grad_stream;
+int vitb200_clip_adamw_fused_streamed(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                                      float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
+                                      size_t red_start, size_t red_end, void* ws, const vitb200_grad_stream* gs,
+                                      void* const* peer_bufs, int rank, int world, void* stream);
 
 /* Data-parallel optimizer tail: the DDP gradient all-reduce (implicit in the reference: strategy='ddp',
  * src/hardware_utils.py:86-95) is fused INTO the kernel.  Each rank owns one exchange buffer

@@ -76,7 +76,15 @@ class MegaFwdArgs(C.Structure):  # vitb200_mega_fwd_args
 
 
 class MegaBwdArgs(C.Structure):  # vitb200_mega_bwd_args
-    _fields_ = [("f", MegaFwdArgs), ("labels", _p), ("gloss", _p), ("loss_kind", _i), ("n_opt", _i), ("gpart", _p), ("dz0", _p)]
+    _fields_ = [("f", MegaFwdArgs), ("labels", _p), ("gloss", _p), ("loss_kind", _i), ("n_opt", _i), ("gpart", _p), ("dz0", _p),
+                ("done", _p)]
+
+
+MAX_GROUPS = 20
+
+
+class GradStream(C.Structure):  # vitb200_grad_stream
+    _fields_ = [("done", _p), ("expect", C.c_uint), ("n_groups", _i), ("lo", C.c_uint * MAX_GROUPS), ("hi", C.c_uint * MAX_GROUPS)]
 
 
 # name -> (restype, argtypes); order and meaning follow include/vit_b200.h exactly
@@ -149,6 +157,7 @@ SIGNATURES = {
     "vitb200_peer_close": (_i, [_p]),
     "vitb200_peer_free": (_i, [_p]),
     "vitb200_clip_adamw_fused_dp": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p, _i, _i, _p]),
+    "vitb200_clip_adamw_fused_streamed": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p, _p, _i, _i, _p]),
     "vitb200_cast_bf16": (_i, [_p, _p, _sz, _p]),
     "vitb200_gelu_fwd": (_i, [_p, _p, _sz, _i, _p]),
     "vitb200_residual_add": (_i, [_p, _p, _p, _sz, _i, _p]),

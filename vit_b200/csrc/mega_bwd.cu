@@ -150,6 +150,13 @@ __device__ __forceinline__ void mb_dlogits(const float* lg, const void* labels, 
   }
 }
 
+// "this CTA's partial gradients of group g are written": one thread, after a CTA barrier that follows the stores (the
+// release is cumulative over what the thread observed through the barrier).  The optimizer kernel of the step acquires
+// the counter and starts summing that group's partials while the layers below are still running.
+__device__ __forceinline__ void mb_signal(unsigned int* done, int g) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + g) : "memory");
+}
+
 __global__ void __launch_bounds__(MB_THREADS, 1)
 mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_args PA) {
   constexpr int H = MG_H, I = MG_I, HC = MG_HC, D = MG_D;
@@ -1042,6 +1049,10 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         });
       }
       __syncthreads();   // staging (R3) is read: the next layer's ddelta / da tiles go there
+      if (tid == 0 && PA.done) {   // group 1 + l = layer l; group 1 + L = final LayerNorm + head (written first of all)
+        if (l == L - 1) mb_signal(PA.done, 1 + L);
+        mb_signal(PA.done, 1 + l);
+      }
     }
   }
 
@@ -1154,6 +1165,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   VB_TL(tl_mega_bwd, 13);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0 && PA.done) mb_signal(PA.done, 0);   // group 0 = embeddings (cls, positions, patch projection)
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

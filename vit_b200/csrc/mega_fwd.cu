@@ -865,12 +865,20 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   if (tid == MG_MAIN) loss_part[blockIdx.x] = loss_acc;   // lane 0 of side warp 0
   if (tid == 0) tma_store_wait_all();
   tc_fence_before();
-  if (last_block_ticket(ticket, gridDim.x) && P.labels && tid == 0) {
-    float t = 0.f;
-    for (unsigned int k = 0; k < gridDim.x; ++k) t += __ldcg(&loss_part[k]);
-    t /= (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
-    P.loss[0] = t;
-    if (P.loss_log) P.loss_log[pos] = t;
+  if (last_block_ticket(ticket, gridDim.x) && P.labels && warp == 0) {
+    // fixed-order sum of the CTA partials: lane l adds partials l, l + 32, ... (all loads in flight at once), then a
+    // shuffle tree -- the serial loop over 128 dependent L2 reads used to hold the next kernel back by ~4 us
+    float v[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v[q] = (unsigned)(lane + 32 * q) < gridDim.x ? __ldcg(&loss_part[lane + 32 * q]) : 0.f;
+    float t = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      t /= (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+      P.loss[0] = t;
+      if (P.loss_log) P.loss_log[pos] = t;
+    }
   }
   if (warp == 0) tmem_dealloc(tmem, MC_COLS);
   VB_TL(tl_mega_fwd, 12);

@@ -102,6 +102,19 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // ---- peer (NVLink) exchange buffer of the data-parallel optimizer tail ------------------------------------------
 // layout: [16 KB header: uint32 flags[world][148 blocks]] [parity 0: xfloats fp32] [parity 1: xfloats fp32]
 constexpr size_t PEER_HEADER = 16384;   // >= 4 * world * 148 for world <= 27
+// streamed gradient groups (vitb200_grad_stream): counters raised by the backward kernel, arena ranges in float4 units
+struct GradStream {
+  unsigned int* done;
+  unsigned int expect;
+  int n;
+  unsigned int lo4[VITB200_MAX_GROUPS], hi4[VITB200_MAX_GROUPS];
+};
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct PeerX {
   void* const* bufs;   // DEVICE array [world]: every rank's exchange buffer (own entry = local memory)
   int rank, world;     // world <= 1: no exchange
@@ -140,10 +153,14 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS)
 clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, float* __restrict__ state,
                         uint64_t* rng, const float* __restrict__ gpart, int slots, size_t stride4, size_t red_lo4,
-                        size_t red_hi4, float* __restrict__ partial, unsigned int* sync, const PeerX X) {
+                        size_t red_hi4, float* __restrict__ partial, unsigned int* sync, const PeerX X, const GradStream GS) {
   __shared__ float red[TAIL_MAX_THREADS / 32];
   VB_TL(tl_tail, 0);
-  pdl_wait();
+  // Streamed mode: the backward kernel is still running.  Nothing it reads is written before the pdl_wait() further down
+  // (behind the grid barrier, which no block passes before every gradient group has been signalled), and the next
+  // kernel of the stream (the forward of the next step) touches no memory before its own dependency wait, so it may be
+  // made resident early.
+  if (GS.n == 0) pdl_wait();
   pdl_trigger();
   VB_TL(tl_tail, 1);
   unsigned int* ticket = sync;
@@ -157,6 +174,24 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   float keep[TAIL_KEEP];
   float acc = 0.f;
   float* mine = X.world > 1 ? peer_data(X.bufs[X.rank], seq & 1u, X.xfloats) : nullptr;
+  if (GS.n > 0) {
+    // wait for the gradient groups this block's elements belong to (one pass: a contiguous slice; several passes: all)
+    if (threadIdx.x == 0) {
+      const bool one_pass = estride >= n4;
+      const size_t blo = one_pass ? (size_t)blockIdx.x * epb : 0;
+      const size_t bhi = one_pass ? min(n4, blo + epb) : n4;
+      for (int gi = 0; gi < GS.n; ++gi) {
+        if (GS.lo4[gi] >= bhi || GS.hi4[gi] <= blo) continue;
+        unsigned int spins = 0;
+        while (ld_acquire_gpu(GS.done + gi) < GS.expect) {
+          __nanosleep(64);
+          if (++spins > (1u << 26)) { state[7] = 2.f; break; }   // a backward launch that never signals must not hang the device
+        }
+      }
+    }
+    __syncthreads();
+    VB_TL(tl_tail, 9);
+  }
   int k = 0;
   for (size_t e = e0; e < n4; e += estride, ++k) {
     float gj;
@@ -254,6 +289,12 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   // the block partials itself (same fixed order => same bits) and derives coef / bias corrections: there is no serial
   // "last block computes, everybody polls a second flag" hop.  Block 0 alone records the results.
   if (threadIdx.x < 32) {
+    // everything the norm step needs besides the block partials is fetched BEFORE the barrier (hyper-parameters and the
+    // running beta powers were written by earlier launches), so only one L2 round trip follows it
+    const float h_scale = hyper[6], max_norm = hyper[5];
+    const double* cur = reinterpret_cast<const double*>(sync + 16) + ((seq - 1u) & 1u) * 8;
+    const double b1d = (double)hyper[1], b2d = (double)hyper[2];
+    const double c0 = cur[0], c1 = cur[1], c2 = cur[2], c3 = cur[3], c4 = cur[4];
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
@@ -269,24 +310,26 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     }
     __syncwarp();
     VB_TL(tl_tail, 3);
-    double tot = 0.0;   // lane l sums partial[l], partial[l + 32], ... then a fixed shuffle tree (deterministic)
-    for (unsigned int bb = threadIdx.x; bb < gridDim.x; bb += 32) tot += (double)__ldcg(&partial[bb]);
+    // lane l sums partial[l], partial[l + 32], ... (loads issued together) then a fixed shuffle tree (deterministic)
+    float pv[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) pv[q] = threadIdx.x + 32 * q < gridDim.x ? __ldcg(&partial[threadIdx.x + 32 * q]) : 0.f;
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) tot += (double)pv[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (threadIdx.x == 0) {
-      const float norm = (float)sqrt(tot) * fabsf(hyper[6]);
-      const float max_norm = hyper[5];
+      const float norm = (float)sqrt(tot) * fabsf(h_scale);
       float coef = 1.f;
       if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
       const float step = step_prev + 1.f;
       // beta^step: a double pow() is ~2 us of dependent FP64; the running products {beta1^t, beta2^t, t, beta1, beta2} are
       // kept next to the barrier words (two copies, by launch parity, so block 0 can write while the others read) and
       // only recomputed when the step counter was changed behind our back (restore / load_state)
-      const double* cur = reinterpret_cast<const double*>(sync + 16) + ((seq - 1u) & 1u) * 8;
-      const double b1d = (double)hyper[1], b2d = (double)hyper[2];
       double p1, p2;
-      if (cur[2] == (double)step_prev && cur[3] == b1d && cur[4] == b2d && step_prev > 0.f) {
-        p1 = cur[0] * b1d; p2 = cur[1] * b2d;
+      if (c2 == (double)step_prev && c3 == b1d && c4 == b2d && step_prev > 0.f) {
+        p1 = c0 * b1d; p2 = c1 * b2d;
       } else {
         p1 = pow(b1d, (double)step); p2 = pow(b2d, (double)step);
       }
@@ -303,10 +346,13 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
         state[4] = red[2];
         if (rng) rng[1] += 1ull;
         sync[2] = seq;
+        for (int gi = 0; gi < GS.n; ++gi) GS.done[gi] = 0u;   // every block is past its waits (grid barrier above)
       }
     }
   }
   __syncthreads();
+  if (GS.n > 0) pdl_wait();   // the backward kernel has signalled everything; this makes its completion formal before the
+                              // parameters it was reading are rewritten
   VB_TL(tl_tail, 4);
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float gmul = hyper[6] * red[0];
@@ -410,7 +456,40 @@ extern "C" int vitb200_clip_adamw_fused(float* p, float* g, float* m, float* v, 
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
   vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3((unsigned)threads), 0, (cudaStream_t)stream, p, g, m, v,
                 (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
-                PeerX{nullptr, 0, 1, 0});
+                PeerX{nullptr, 0, 1, 0}, GradStream{nullptr, 0u, 0, {}, {}});
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_clip_adamw_fused_streamed(float* p, float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
+                                                 float* state, uint64_t* rng, const float* gpart, int slots, size_t stride,
+                                                 size_t red_start, size_t red_end, void* ws, const vitb200_grad_stream* gs,
+                                                 void* const* peer_bufs, int rank, int world, void* stream) {
+  if (!p || !g || !m || !v || !hyper || !state || !ws || !gs || !gs->done) return VITB200_ERR_ARG;
+  if (gs->n_groups < 1 || gs->n_groups > VITB200_MAX_GROUPS || gs->expect == 0 || slots <= 0) return VITB200_ERR_ARG;
+  if (peer_bufs ? (world < 2 || world > 27 || rank < 0 || rank >= world) : (world != 1)) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if (!gpart || (stride | red_start | red_end) % 4 != 0 || red_end < red_start || red_end > n) return VITB200_ERR_ARG;
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(gpart)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(shadow) & 7) != 0)
+    return VITB200_ERR_ALIGN;
+  GradStream GS{gs->done, gs->expect, gs->n_groups, {}, {}};
+  size_t covered = 0;
+  for (int i = 0; i < gs->n_groups; ++i) {   // ascending, contiguous, float4-aligned, covering [0, n)
+    if (gs->lo[i] != covered || gs->hi[i] < gs->lo[i] || (gs->lo[i] | gs->hi[i]) % 4 != 0) return VITB200_ERR_ARG;
+    covered = gs->hi[i];
+    GS.lo4[i] = gs->lo[i] / 4; GS.hi4[i] = gs->hi[i] / 4;
+  }
+  if (covered != n) return VITB200_ERR_ARG;
+  const size_t n4 = n / 4;
+  int threads, grid;
+  tail_launch_shape(n4, &threads, &grid);
+  unsigned int* sync = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3((unsigned)threads), 0, (cudaStream_t)stream, p, g, m, v,
+                (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
+                peer_bufs ? PeerX{peer_bufs, rank, world, n} : PeerX{nullptr, 0, 1, 0}, GS);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }
@@ -466,7 +545,7 @@ extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* 
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
   vb_launch_pdl(clip_adamw_fused_kernel, dim3((unsigned)grid), dim3((unsigned)threads), 0, (cudaStream_t)stream, p, g, m, v,
                 (bf16*)shadow, n4, hyper, state, rng, gpart, slots, stride / 4, red_start / 4, red_end / 4, partial, sync,
-                PeerX{peer_bufs, rank, world, n});
+                PeerX{peer_bufs, rank, world, n}, GradStream{nullptr, 0u, 0, {}, {}});
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

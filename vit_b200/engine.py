@@ -305,6 +305,12 @@ class ViTEngine:
         if slot == ROWS_SLOT:
             a.rows, a.rows_base = P_(self._rows["rows"]), P_(self._rows["base"])
             a.loss_log = P_(self._rows["loss_log"])
+        elif with_labels:
+            # the loss also lands in page-locked HOST memory (unified addressing: the kernel stores through the host
+            # pointer), so a host loop reads it after the step's event without a device-to-host copy launch
+            if not hasattr(self, "loss_pinned"):
+                self.loss_pinned = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+            a.loss_log = self.loss_pinned.data_ptr() + 4 * slot
         self._keep.append(a)
         return a
 
@@ -472,7 +478,7 @@ class ViTEngine:
         return prog
 
     def _build_backward_fused(self, train: bool, gloss_ptr: Optional[int], given: bool, skip_reduce: bool = False,
-                              skip_head: bool = False, slot: int = 0):
+                              skip_head: bool = False, slot: int = 0, streamed: bool = False):
         """head -> final LN -> [upper, attention bwd, lower] x L -> embed -> reduce of the per-CTA partials."""
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
@@ -501,6 +507,8 @@ class ViTEngine:
             fa = self._mega_fwd_args(train, True, slot)
             ba = _lib.MegaBwdArgs(f=fa, labels=lab_ptr, gloss=gl, loss_kind=kind, n_opt=lay.n_opt, gpart=gp,
                                   dz0=P_(self.dzA))
+            if streamed:
+                ba.done = self.grad_stream().done
             self._keep.append(ba)
             prog.append((lib.vitb200_mega_bwd, (ctypes.addressof(ba),)))
             self._red = (B, 0, lay.n_opt)
@@ -580,9 +588,10 @@ class ViTEngine:
         return prog
 
     def _build_backward(self, train: bool, gloss_ptr: Optional[int] = None,
-                        given: bool = False, skip_reduce: bool = False, skip_head: bool = False, slot: int = 0) -> List[Tuple[Callable, tuple]]:
+                        given: bool = False, skip_reduce: bool = False, skip_head: bool = False, slot: int = 0,
+                        streamed: bool = False) -> List[Tuple[Callable, tuple]]:
         if self.fused_bwd:
-            return self._build_backward_fused(train, gloss_ptr, given, skip_reduce, skip_head, slot)
+            return self._build_backward_fused(train, gloss_ptr, given, skip_reduce, skip_head, slot, streamed)
         self._alloc_backward()
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         B, T, H, I, Lh, M = self.B, c.tokens, c.hidden_size, c.intermediate_size, c.num_hidden_layers, self.M
@@ -713,17 +722,22 @@ class ViTEngine:
             self._run(("fwd", train, with_labels, co), lambda: self._build_forward(train, with_labels))
 
     def backward(self, train: bool, gloss: Optional[torch.Tensor] = None, skip_reduce: bool = False,
-                 skip_head: bool = False, slot: int = 0) -> None:
+                 skip_head: bool = False, slot: int = 0, streamed: bool = False) -> None:
         """skip_reduce (fused programs only): leave the layer / embedding gradients as per-CTA partials; the caller
-        must follow with optimizer_step(fused_reduce=True), which sums them inside the optimizer kernel."""
+        must follow with optimizer_step(fused_reduce=True), which sums them inside the optimizer kernel.
+        streamed (whole-network backward only): the kernel also signals every finished gradient group; the NEXT launch on
+        the stream must then be optimizer_step(fused_reduce=True, streamed=True), which consumes the signals."""
         gp = None if gloss is None else gloss.data_ptr()
         skip = bool(skip_reduce and self.fused_bwd)
         sh = bool(skip_head and self.fused_bwd)
         co = bool(self.cls_only and self.mega)
         key = ("bwd", train, gp, skip, sh, co) if (skip or sh) else ("bwd", train, gp, co)
-        if slot != 0:
+        streamed = bool(streamed and skip and self.mega_bwd)
+        if slot != 0 or streamed:
             key = key + (slot,)
-        self._run(key, lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh, slot=slot))
+        if streamed:
+            key = key + ("streamed",)
+        self._run(key, lambda: self._build_backward(train, gp, skip_reduce=skip, skip_head=sh, slot=slot, streamed=streamed))
 
     def backward_from_dlogits(self, train: bool, dlogits: torch.Tensor) -> None:
         """Backward when the caller computed its own loss from `logits` (labels=None forward)."""
@@ -772,15 +786,47 @@ class ViTEngine:
         if ar.shadow is not None:
             ar.mark_shadow_fresh()
 
-    def optimizer_step(self, fused_reduce: bool = False) -> None:
+    def grad_stream(self):
+        """vitb200_grad_stream of this engine: one counter per gradient group (everything in front of layer 0, each
+        encoder layer, final LayerNorm + head), raised by the whole-network backward kernel and consumed by the streamed
+        optimizer kernel."""
+        if not hasattr(self, "_gs"):
+            c, lay = self.cfg, self.arena.layout
+            Lh = c.num_hidden_layers
+            base0 = lay.off("vit.encoder.layer.0.layernorm_before.weight")
+            stride = (lay.off("vit.encoder.layer.1.layernorm_before.weight") - base0) if Lh > 1 else (lay.off("vit.layernorm.weight") - base0)
+            cuts = [0] + [base0 + l * stride for l in range(Lh + 1)] + [lay.n_opt]
+            assert cuts == sorted(cuts) and cuts[Lh + 1] <= lay.off("vit.layernorm.weight") and all(v % 4 == 0 for v in cuts)
+            self.grad_done = torch.zeros(Lh + 2, dtype=torch.int32, device=self.device)
+            gs = _lib.GradStream(done=self.grad_done.data_ptr(), expect=self.B * self.mega_cluster, n_groups=Lh + 2)
+            for i in range(Lh + 2):
+                gs.lo[i], gs.hi[i] = cuts[i], cuts[i + 1]
+            self._gs = gs
+        return self._gs
+
+    def optimizer_step(self, fused_reduce: bool = False, streamed: bool = False) -> None:
         """clip_grad_norm_ + AdamW.step in ONE launch (vitb200_clip_adamw_fused).  fused_reduce: the backward ran with
-        skip_reduce=True, so the kernel first sums the per-CTA gradient partials."""
+        skip_reduce=True, so the kernel first sums the per-CTA gradient partials.  streamed: the backward ran with
+        streamed=True and is the previous launch on the stream: the kernel starts on each gradient group as soon as the
+        backward kernel has signalled it (and, data parallel, exchanges it over NVLink) instead of waiting for its end."""
         self._ensure_opt_state()
         ar = self.arena
         if not hasattr(self, "tail_ws"):
             self.tail_ws = torch.zeros(int(self.lib.vitb200_clip_adamw_fused_ws_bytes()), dtype=torch.uint8, device=self.device)
         slots, start, end = (self._red if (fused_reduce and self.fused_bwd) else (0, 0, 0))
         st = torch.cuda.current_stream(self.device).cuda_stream
+        if streamed and fused_reduce and self.mega_bwd:
+            pr = getattr(self, "peer", None)
+            _lib.check(self.lib.vitb200_clip_adamw_fused_streamed(
+                ar.data.data_ptr(), ar.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                None if ar.shadow is None else ar.shadow.data_ptr(), ar.layout.n_opt, self.hyper.data_ptr(),
+                self.state.data_ptr(), self.rng.data_ptr(), self.gpart.data_ptr(), slots, ar.layout.n_opt, start, end,
+                (pr.tail_ws if pr is not None else self.tail_ws).data_ptr(), ctypes.addressof(self.grad_stream()),
+                None if pr is None else pr.table.data_ptr(), 0 if pr is None else pr.rank, 1 if pr is None else pr.world,
+                st), "clip_adamw_fused_streamed")
+            if ar.shadow is not None:
+                ar.mark_shadow_fresh()
+            return
         if getattr(self, "peer", None) is not None:   # data parallel: gradient all-reduce over peer memory, in-kernel
             pr = self.peer
             tail_ws = pr.tail_ws

@@ -57,10 +57,12 @@ class TrainStep:
     def _launch(self, slot: int = 0) -> None:
         eng = self.eng
         eng.cls_only = True   # a training step reads the loss only: the last layer runs for the CLS row alone
+        # the optimizer kernel consumes each layer's gradient partials as soon as the backward kernel signals them
+        sg = bool(eng.mega_bwd and os.environ.get("VITB200_STREAM", "1") != "0")
         if slot != 0:
             eng.forward(train=self.train, with_labels=True, head_bwd=True, slot=slot)
-            eng.backward(train=self.train, skip_reduce=True, skip_head=True, slot=slot)
-            eng.optimizer_step(fused_reduce=True)
+            eng.backward(train=self.train, skip_reduce=True, skip_head=True, slot=slot, streamed=sg)
+            eng.optimizer_step(fused_reduce=True, streamed=sg)
         elif self.world > 1 and getattr(eng, "peer", None) is None:
             eng.forward(train=self.train, with_labels=True)
             self._backward_overlapped()   # NCCL: gradients are summed across ranks before the optimizer kernel reads them
@@ -69,8 +71,8 @@ class TrainStep:
             # single GPU: head backward rides on forward's last launch, the gradient-partial reduction on the optimizer's
             fh = eng.can_fuse_head
             eng.forward(train=self.train, with_labels=True, head_bwd=fh)
-            eng.backward(train=self.train, skip_reduce=True, skip_head=fh)
-            eng.optimizer_step(fused_reduce=True)
+            eng.backward(train=self.train, skip_reduce=True, skip_head=fh, streamed=sg)
+            eng.optimizer_step(fused_reduce=True, streamed=sg)
 
     def _backward_overlapped(self) -> None:
         """Backward + gradient all-reduce (SUM; the 1/world mean is folded into the optimizer's grad_scale).
@@ -378,7 +380,10 @@ class TrainStep:
             else:
                 loss = self.step(P["d_x"][s], P["d_y"][s])
             P["ev_free"][s].record(main)
-            P["h_loss"][s].copy_(loss.reshape(1), non_blocking=True)
+            if direct:
+                P["h_loss"][s] = eng.loss_pinned[s:s + 1]   # written by the forward kernel itself (4 bytes over PCIe)
+            else:
+                P["h_loss"][s].copy_(loss.reshape(1), non_blocking=True)
             P["ev_loss"][s].record(main)
             nxt = next(it, None)
             if nxt is not None:
