@@ -346,16 +346,12 @@ int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void* dctx, cons
                         const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d, float scale,
                         float p_drop, const uint64_t* rng, uint32_t site, void* stream);
 
-/* Key-blocked tcgen05 attention for ANY sequence length (bf16, d in {16, 32}, fused [B*T, 3H] QKV buffer): the
- * single-tile kernels run once per block of 128 keys.  Forward writes block-normalised partial outputs and block
- * log-sum-exps into `ws` and merges them (split-KV flash attention); backward recomputes P from the merged lse, so the
- * dK / dV rows of a block are complete and dQ is accumulated over the launches in fp32 (in `ws`).  Same dropout masks
- * and tolerances as vitb200_attn_tc_fwd/bwd.  ws: vitb200_attn_tc_blocked_ws_bytes(...) bytes, 16-byte aligned. */
+/* Per-key-block tcgen05 attention BACKWARD for any sequence length (bf16, d in {16, 32}, fused [B*T, 3H] QKV buffer): the
+ * single-tile backward kernel launched once per block of 128 keys, dQ accumulated over the launches in fp32.  Kept as the
+ * independent cross-check of vitb200_attn_flash_bwd (bit-identical results); the engine uses the flash kernels.
+ * ws: vitb200_attn_tc_blocked_ws_bytes(...) bytes, 16-byte aligned. */
 int vitb200_attn_tc_blocked_supported(int T, int d, int ld, int H);
 size_t vitb200_attn_tc_blocked_ws_bytes(int B, int T, int heads, int d);
-int vitb200_attn_tc_blocked_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin,
-                                int B, int T, int heads, int d, float scale, float p_drop, const uint64_t* rng,
-                                uint32_t site, void* ws, void* stream);
 int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d,
                                 float scale, float p_drop, const uint64_t* rng, uint32_t site, void* ws, void* stream);
@@ -367,6 +363,13 @@ int vitb200_attn_flash_supported(int T, int d, int ld, int H);
 int vitb200_attn_flash_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin, int B,
                            int T, int heads, int d, float scale, float p_drop, const uint64_t* rng, uint32_t site,
                            void* stream);
+/* Backward of the above in ONE launch for any T (+ one small reduction launch): one CTA per (block of 128 keys, head,
+ * sample) keeps dK / dV in tensor memory while it walks over the query tiles; dQ leaves as fp32 partials per key block
+ * (ws) and is summed in block order.  dqkv [B*T, 3H] bf16 receives dq | dk | dv.  Same dropout masks as forward. */
+size_t vitb200_attn_flash_bwd_ws_bytes(int B, int T, int heads, int d);
+int vitb200_attn_flash_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                           const float* rope_cos, const float* rope_sin, int B, int T, int heads, int d, float scale,
+                           float p_drop, const uint64_t* rng, uint32_t site, void* ws, void* stream);
 /* probs[B,heads,T,T] f32 = softmax probabilities before dropout (what the eager / RoPE attention returns
  * as `attention_probs`, src/models/vit_with_rope.py:84); for hooks / output_attentions only. */
 int vitb200_attn_probs(const void* q, const void* k, int ld, const float* lse, float* probs, const float* rope_cos,

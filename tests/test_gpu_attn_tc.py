@@ -95,8 +95,9 @@ def test_attn_tc_matches_simt_and_torch(B, T, heads, d, p, rope):
 @pytest.mark.parametrize("B,T,heads,d,p", [(2, 510, 2, 16, 0.1), (1, 513, 2, 16, 0.1), (2, 200, 2, 32, 0.1),
                                             (1, 257, 1, 16, 0.0), (1, 129, 2, 16, 0.1), (1, 1030, 2, 16, 0.0)])
 def test_attn_tc_key_blocked_matches_torch(B, T, heads, d, p, rope):
-    """Key-blocked tcgen05 attention (any T: the long-sequence sweep) vs. a plain fp32 torch attention built from the
-    same bf16 inputs and the kernels' own dropout mask; run twice for bitwise reproducibility."""
+    """Flash forward + the per-key-block tcgen05 backward (the cross-check of the flash backward) for any T vs. a plain
+    fp32 torch attention built from the same bf16 inputs and the kernels' own dropout mask; run twice for bitwise
+    reproducibility."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from vit_b200 import _lib
@@ -123,8 +124,8 @@ def test_attn_tc_key_blocked_matches_torch(B, T, heads, d, p, rope):
         ctx = torch.full((B * T, H), float("nan"), device=dev, dtype=torch.bfloat16)
         lse = torch.zeros(B, heads, T, device=dev)
         dq = torch.full((B * T, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.vitb200_attn_tc_blocked_fwd(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), P(cos), P(sin), B, T,
-                                                   heads, d, scale, p, rng.data_ptr(), 4, ws.data_ptr(), st), "fwd")
+        _lib.check(lib.vitb200_attn_flash_fwd(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), P(cos), P(sin), B, T,
+                                              heads, d, scale, p, rng.data_ptr(), 4, st), "fwd")
         _lib.check(lib.vitb200_attn_tc_blocked_bwd(qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(),
                                                    dq.data_ptr(), P(cos), P(sin), B, T, heads, d, scale, p,
                                                    rng.data_ptr(), 4, ws.data_ptr(), st), "bwd")
@@ -241,3 +242,22 @@ def test_attn_flash_fwd_matches_torch_and_blocked_backward(B, T, heads, d, p, ro
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         e = rel_err(dq.float()[:, sl], ref_dqkv[:, sl])
         assert e < 3e-2, (name, e)
+    # the one-launch flash backward (dK / dV resident in TMEM over the query loop, dQ partials summed in key-block
+    # order): vs torch autograd, bitwise reproducible, and -- same products, same accumulation order -- bit-identical
+    # to the per-key-block launches where those run the tcgen05 tiles for every row (T not of the form 128 n + 1)
+    fws = torch.zeros(int(lib.vitb200_attn_flash_bwd_ws_bytes(B, T, heads, d)), dtype=torch.uint8, device=dev)
+    outs = []
+    for _ in range(2):
+        df = torch.full((B * T, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.vitb200_attn_flash_bwd(qkv.data_ptr(), ctx_a.data_ptr(), dctx.data_ptr(), lse_a.data_ptr(),
+                                              df.data_ptr(), P(cos), P(sin), B, T, heads, d, scale, p, rng.data_ptr(), 4,
+                                              fws.data_ptr(), st), "flash bwd")
+        torch.cuda.synchronize()
+        outs.append(df)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.isfinite(outs[0].float()).all()
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        e = rel_err(outs[0].float()[:, sl], ref_dqkv[:, sl])
+        assert e < 3e-2, ("flash " + name, e)
+    if d in (16, 32) and (T % 128 != 1 or rope):
+        assert torch.equal(outs[0], dq)

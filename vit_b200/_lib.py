@@ -135,10 +135,11 @@ SIGNATURES = {
     "vitb200_attn_tc_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _p]),
     "vitb200_attn_tc_blocked_supported": (_i, [_i, _i, _i, _i]),
     "vitb200_attn_tc_blocked_ws_bytes": (_sz, [_i, _i, _i, _i]),
-    "vitb200_attn_tc_blocked_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _p, _p]),
     "vitb200_attn_tc_blocked_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _p, _p]),
     "vitb200_attn_flash_supported": (_i, [_i, _i, _i, _i]),
     "vitb200_attn_flash_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _p]),
+    "vitb200_attn_flash_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "vitb200_attn_flash_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _u32, _p, _p]),
     "vitb200_attn_probs": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "vitb200_head_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vitb200_head_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

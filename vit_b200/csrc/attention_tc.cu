@@ -101,11 +101,11 @@ struct AttnTcParams {
   int B, T, heads, H, ld, KP;   // KP = keys (of this launch) padded to a multiple of 16
   float scale, p_drop; const uint64_t* rng; uint32_t site;
   // key-blocked mode (long sequences): this launch handles keys [key0, key0 + Tk) of every sample only.
-  //   forward : writes the block-normalised output (fp32) and the block log-sum-exp; attn_tc_combine_kernel merges blocks
+  //   forward : not available (long sequences run attention_flash.cu)
   //   backward: dK / dV of the block's keys are complete; dQ is accumulated over the launches in an fp32 buffer
   //             (first: store, otherwise add; last: the bf16 dq rows are written)
   int kb, key0, Tk, first, last;
-  float* o_part; float* lse_part; float* dq_acc;
+  float* dq_acc;
 };
 
 // ================================================================================================
@@ -229,17 +229,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float inv = 1.f / sum;
 #pragma unroll
         for (int c = 0; c < D; ++c) o[c] *= inv;
-        if (P.kb) {
-          float* dst = P.o_part + (size_t)(row0 + i) * P.H + h * D;
+        bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
 #pragma unroll
-          for (int c = 0; c < D; ++c) dst[c] = o[c];
-          P.lse_part[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
-        } else {
-          bf16* dst = P.ctx + (size_t)(row0 + i) * P.H + h * D;
-#pragma unroll
-          for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&o[c]);
-          P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
-        }
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = at_pack8(&o[c]);
+        P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
       }
     }
   } else {
@@ -357,14 +350,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float inv = 1.f / sum;
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] *= inv;
-        if (P.kb) {
-          float4* dst = reinterpret_cast<float4*>(P.o_part + (size_t)(row0 + i) * P.H + h * D + cg * 8);
-          dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          if (cg == 0) P.lse_part[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
-        } else {
-          *reinterpret_cast<uint4*>(P.ctx + (size_t)(row0 + i) * P.H + h * D + cg * 8) = at_pack8(o);
-          if (cg == 0) P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
-        }
+        *reinterpret_cast<uint4*>(P.ctx + (size_t)(row0 + i) * P.H + h * D + cg * 8) = at_pack8(o);
+        if (cg == 0) P.lse[(size_t)(b * P.heads + h) * T + i] = mx * P.scale + logf(sum);
       }
     }
     tc_fence_before();
@@ -734,41 +721,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// merge of the key-blocked forward: ctx = sum_blk exp(lse_blk - lse) O_blk,  lse = log sum_blk exp(lse_blk).
-// One thread per (row, head, 8 columns).
-__global__ void __launch_bounds__(256)
-attn_tc_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ lse_part, bf16* __restrict__ ctx,
-                       float* __restrict__ lse, int B, int T, int heads, int D, int nblk) {
-  pdl_wait();
-  pdl_trigger();
-  const int H = heads * D, cpr = H / 8;
-  const size_t M = (size_t)B * T, BHT = (size_t)B * heads * T;
-  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= M * cpr) return;
-  const size_t row = idx / cpr;
-  const int c8 = (int)(idx - row * cpr) * 8, h = c8 / D;
-  const size_t b = row / T, t = row - b * T;
-  const size_t li = (b * heads + h) * T + t;
-  float mx = -INFINITY;
-  for (int k = 0; k < nblk; ++k) mx = fmaxf(mx, lse_part[(size_t)k * BHT + li]);
-  float se = 0.f, o[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) o[c] = 0.f;
-  for (int k = 0; k < nblk; ++k) {
-    const float w = __expf(lse_part[(size_t)k * BHT + li] - mx);
-    se += w;
-    const float4* src = reinterpret_cast<const float4*>(o_part + ((size_t)k * M + row) * H + c8);
-    const float4 a0 = src[0], a1 = src[1];
-    o[0] = fmaf(w, a0.x, o[0]); o[1] = fmaf(w, a0.y, o[1]); o[2] = fmaf(w, a0.z, o[2]); o[3] = fmaf(w, a0.w, o[3]);
-    o[4] = fmaf(w, a1.x, o[4]); o[5] = fmaf(w, a1.y, o[5]); o[6] = fmaf(w, a1.z, o[6]); o[7] = fmaf(w, a1.w, o[7]);
-  }
-  const float inv = 1.f / se;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) o[c] *= inv;
-  *reinterpret_cast<uint4*>(ctx + row * H + c8) = at_pack8(o);
-  if ((c8 % D) == 0) lse[li] = mx + logf(se);
-}
-
 constexpr int AT_KB = 128;   // keys per launch in key-blocked mode
 
 constexpr int AT_FWD_SMEM = 16384 + 32768 + 32768 + 4 * 16384 + 1024 + 64 + 2 * AT_CG * 128 * 4 + 1024;
@@ -803,7 +755,7 @@ extern "C" int vitb200_attn_tc_fwd(const void* qkv, void* ctx, float* lse, const
   if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
   if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
   AttnTcParams P{(const bf16*)qkv, (bf16*)ctx, lse, nullptr, nullptr, 0, rope_cos, rope_sin, B, T, heads, H, ld, KP,
-                 scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr};
+                 scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr};
   dim3 grid(heads, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_F(DD)                                                                                             \
@@ -835,8 +787,7 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
   if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
   if ((rc = get_tmap(dctx, H, M, 64, 128, &tDO))) return rc;
   AttnTcParams P{(const bf16*)qkv, (bf16*)const_cast<void*>(ctx), const_cast<float*>(lse), (const bf16*)dctx, (bf16*)dqkv,
-                 ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr, nullptr,
-                 nullptr};
+                 ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site, 0, 0, 0, 0, 0, nullptr};
   dim3 grid(heads, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_B(DD)                                                                                             \
@@ -856,66 +807,18 @@ extern "C" int vitb200_attn_tc_bwd(const void* qkv, const void* ctx, const void*
 }
 
 // ---- key-blocked mode: any sequence length (the long-sequence sweep: T = 510 / 513 / 2034 / 2049) -------------------
-// The single-tile kernels above keep a whole key range in one TMEM tile.  Longer sequences are handled by launching
-// them once per block of 128 keys: forward writes block-normalised partial outputs + block log-sum-exps and one merge
-// kernel combines them (split-KV flash attention); backward recomputes P from the merged lse, so dK / dV of a block are
-// complete and dQ is accumulated over the launches in fp32.  Same math, same dropout masks, same tolerances.
+// The single-tile kernels above keep a whole key range in one TMEM tile.  Longer sequences run the one-launch flash
+// kernels of attention_flash.cu (forward and backward).  What remains here is the per-key-block BACKWARD: the single-tile
+// backward kernel launched once per block of 128 keys (P recomputed from the lse, dK / dV of a block complete, dQ
+// accumulated over the launches in fp32).  It is the independent cross-check of the flash backward in the tests (same
+// products, same accumulation order => bit-identical results) and is not used by the engine.
 extern "C" int vitb200_attn_tc_blocked_supported(int T, int d, int ld, int H) {
   if (!(d == 16 || d == 32)) return 0;
   if (ld != 3 * H || (ld % 8) != 0 || (H % 8) != 0) return 0;
   return T > 0 ? 1 : 0;
 }
 extern "C" size_t vitb200_attn_tc_blocked_ws_bytes(int B, int T, int heads, int d) {
-  const size_t nblk = (size_t)(T + AT_KB - 1) / AT_KB, M = (size_t)B * T, H = (size_t)heads * d;
-  const size_t nl = (nblk * (size_t)B * heads * T + 3) / 4 * 4;   // keeps the fp32 dq accumulator 16-byte aligned
-  return sizeof(float) * (nblk * M * H + nl + M * H) + 256;
-}
-static inline void at_blocked_ws(void* ws, int B, int T, int heads, int d, float** o_part, float** lse_part, float** dq_acc) {
-  const size_t nblk = (size_t)(T + AT_KB - 1) / AT_KB, M = (size_t)B * T, H = (size_t)heads * d;
-  float* p = reinterpret_cast<float*>(ws);
-  *o_part = p;
-  *lse_part = p + nblk * M * H;
-  *dq_acc = *lse_part + (nblk * (size_t)B * heads * T + 3) / 4 * 4;
-}
-
-extern "C" int vitb200_attn_tc_blocked_fwd(const void* qkv, void* ctx, float* lse, const float* rope_cos, const float* rope_sin,
-                                           int B, int T, int heads, int d, float scale, float p_drop, const uint64_t* rng,
-                                           uint32_t site, void* ws, void* stream) {
-  if (!qkv || !ctx || !lse || !ws || B <= 0 || T <= 0 || heads <= 0) return VITB200_ERR_ARG;
-  const int H = heads * d, ld = 3 * H;
-  if (!vitb200_attn_tc_blocked_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
-  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return VITB200_ERR_ALIGN;
-  const int M = B * T, nblk = (T + AT_KB - 1) / AT_KB;
-  float *o_part, *lse_part, *dq_acc;
-  at_blocked_ws(ws, B, T, heads, d, &o_part, &lse_part, &dq_acc);
-  CUtensorMap tQ, tKV;
-  int rc;
-  if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
-  dim3 grid(heads, B);
-  cudaStream_t st = (cudaStream_t)stream;
-  static bool done16 = false, done32 = false;
-  bool& done = d == 16 ? done16 : done32;
-  if (!done) {
-    cudaError_t e = d == 16 ? cudaFuncSetAttribute(attn_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM)
-                            : cudaFuncSetAttribute(attn_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-    if (e != cudaSuccess) return vb_cuda_error(e);
-    done = true;
-  }
-  for (int kb = 0; kb < nblk; ++kb) {
-    const int key0 = kb * AT_KB, Tk = T - key0 < AT_KB ? T - key0 : AT_KB, KP = at_kp(Tk);
-    if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
-    AttnTcParams P{(const bf16*)qkv, (bf16*)ctx, lse, nullptr, nullptr, 0, rope_cos, rope_sin, B, T, heads, H, ld, KP,
-                   scale, p_drop, rng, site, 1, key0, Tk, kb == 0, kb == nblk - 1,
-                   o_part + (size_t)kb * M * H, lse_part + (size_t)kb * B * heads * T, dq_acc};
-    if (d == 16) vb_launch_pdl(attn_tc_fwd_kernel<16>, grid, dim3(AT_ALL_THREADS), AT_FWD_SMEM, st, tQ, tKV, P);
-    else vb_launch_pdl(attn_tc_fwd_kernel<32>, grid, dim3(AT_ALL_THREADS), AT_FWD_SMEM, st, tQ, tKV, P);
-    VB_CHECK_LAUNCH();
-  }
-  const size_t items = (size_t)M * (H / 8);
-  vb_launch_pdl(attn_tc_combine_kernel, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st, (const float*)o_part,
-                (const float*)lse_part, (bf16*)ctx, lse, B, T, heads, d, nblk);
-  VB_CHECK_LAUNCH();
-  return VITB200_OK;
+  return sizeof(float) * (size_t)B * T * heads * d + 256;   // the fp32 dQ accumulator
 }
 
 extern "C" int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
@@ -927,8 +830,7 @@ extern "C" int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, con
   if (!vitb200_attn_tc_blocked_supported(T, d, ld, H)) return VITB200_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return VITB200_ERR_ALIGN;
   const int M = B * T, nblk = (T + AT_KB - 1) / AT_KB;
-  float *o_part, *lse_part, *dq_acc;
-  at_blocked_ws(ws, B, T, heads, d, &o_part, &lse_part, &dq_acc);
+  float* dq_acc = reinterpret_cast<float*>(ws);
   CUtensorMap tQ, tKV, tDO;
   int rc;
   if ((rc = get_tmap(qkv, ld, M, 64, 128, &tQ))) return rc;
@@ -948,7 +850,7 @@ extern "C" int vitb200_attn_tc_blocked_bwd(const void* qkv, const void* ctx, con
     if ((rc = get_tmap(qkv, ld, M, 64, KP, &tKV))) return rc;
     AttnTcParams P{(const bf16*)qkv, (bf16*)const_cast<void*>(ctx), const_cast<float*>(lse), (const bf16*)dctx, (bf16*)dqkv,
                    ld, rope_cos, rope_sin, B, T, heads, H, ld, KP, scale, p_drop, rng, site, 1, key0, Tk, kb == 0,
-                   kb == nblk - 1, nullptr, nullptr, dq_acc};
+                   kb == nblk - 1, dq_acc};
     if (d == 16) vb_launch_pdl(attn_tc_bwd_kernel<16>, grid, dim3(AT_ALL_THREADS), AT_BWD_SMEM, st, tQ, tKV, tDO, P);
     else vb_launch_pdl(attn_tc_bwd_kernel<32>, grid, dim3(AT_ALL_THREADS), AT_BWD_SMEM, st, tQ, tKV, tDO, P);
     VB_CHECK_LAUNCH();

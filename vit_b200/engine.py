@@ -186,21 +186,6 @@ class ViTEngine:
 
     # ---- programs -----------------------------------------------------------------------------
     # ---- attention call selection ----------------------------------------------------------------
-    def _attn_blocked(self) -> bool:
-        """bf16 sequences too long for the single-tile tcgen05 kernels run them once per block of 128 keys
-        (vitb200_attn_tc_blocked_*) instead of falling back to the SIMT kernels."""
-        c = self.cfg
-        if self.dt != BF16:
-            return False
-        if self.lib.vitb200_attn_tc_supported(c.tokens, c.head_dim, 3 * c.hidden_size, c.hidden_size):
-            return False
-        if not self.lib.vitb200_attn_tc_blocked_supported(c.tokens, c.head_dim, 3 * c.hidden_size, c.hidden_size):
-            return False
-        if not hasattr(self, "attn_ws"):
-            nbytes = int(self.lib.vitb200_attn_tc_blocked_ws_bytes(self.B, c.tokens, c.num_attention_heads, c.head_dim))
-            self.attn_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        return True
-
     def _attn_fwd_call(self, l: int, pa: float, es: int):
         c, P_ = self.cfg, self._ptr
         H, T = c.hidden_size, c.tokens
@@ -214,10 +199,6 @@ class ViTEngine:
             return (self.lib.vitb200_attn_flash_fwd, (
                 qkv, P_(self.ctx[l]), P_(self.lse[l]), P_(self.rope_cos), P_(self.rope_sin), self.B, T,
                 c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l)))
-        if self._attn_blocked():
-            return (self.lib.vitb200_attn_tc_blocked_fwd, (
-                qkv, P_(self.ctx[l]), P_(self.lse[l]), P_(self.rope_cos), P_(self.rope_sin), self.B, T,
-                c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), P_(self.attn_ws)))
         return (self.lib.vitb200_attn_fwd, (
             qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.lse[l]),
             P_(self.rope_cos), P_(self.rope_sin), self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng,
@@ -230,10 +211,16 @@ class ViTEngine:
         dqkv = self.dqkv.data_ptr()
         scale = 1.0 / math.sqrt(c.head_dim)
         rng = self.rng.data_ptr()
-        if self._attn_blocked():
-            return (self.lib.vitb200_attn_tc_blocked_bwd, (
+        if (self.dt == BF16 and os.environ.get("VITB200_FLASH", "1") != "0"
+                and not self.lib.vitb200_attn_tc_supported(T, c.head_dim, 3 * H, H)
+                and self.lib.vitb200_attn_flash_supported(T, c.head_dim, 3 * H, H)):
+            # longer sequences / head_dim 64: one launch over (key block, head, sample), dK / dV resident in TMEM
+            if not hasattr(self, "flash_ws"):
+                nbytes = int(self.lib.vitb200_attn_flash_bwd_ws_bytes(self.B, T, c.num_attention_heads, c.head_dim))
+                self.flash_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            return (self.lib.vitb200_attn_flash_bwd, (
                 qkv, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]), dqkv, P_(self.rope_cos), P_(self.rope_sin),
-                self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), P_(self.attn_ws)))
+                self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), P_(self.flash_ws)))
         return (self.lib.vitb200_attn_bwd, (
             qkv, qkv + H * es, qkv + 2 * H * es, 3 * H, P_(self.ctx[l]), P_(self.dctx), P_(self.lse[l]),
             P_(self.dsum), dqkv, dqkv + H * es, dqkv + 2 * H * es, 3 * H, P_(self.rope_cos), P_(self.rope_sin),
