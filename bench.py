@@ -793,6 +793,37 @@ def main():
             torch.cuda.empty_cache()
         except Exception as ex:  # noqa: BLE001
             other["zca4096_frozen_train_b64"] = {"error": str(ex)[:200]}
+        try:   # the same stage for a frozen LOW-RANK ZCA (warmup.r = 32): factored kernel, 2 r D values instead of D^2
+            from vit_b200.preprocessor import compute_zca_matrix, zca_lowrank_factors
+
+            gd = torch.Generator(device="cpu").manual_seed(9)
+            ev = torch.linalg.qr(torch.randn(4096, 4096, generator=gd).to(dev))[0]
+            lam = torch.sort(torch.rand(4096, generator=gd) + 0.01, descending=True)[0].to(dev)
+            Pz = compute_zca_matrix(ev, lam, eps=1e-5, r=32, shrinkage=0.0)
+            pre6 = LinearPreprocessor(Pz, bias=torch.zeros(4096), freeze=True)
+            pre6.set_lowrank_factors(*zca_lowrank_factors(ev, lam, 1e-5, 32, 0.0))
+            cz = json.loads(json.dumps(BASELINE_CFG))
+            m6 = MyViT(get_vit_config(cz), loss_name="mae", model_name="ZCA32_fzperm_ViT", preprocessor=pre6, full_config=cz,
+                       precision=args.precision, device=dev).train()
+            s6 = TrainStep(m6, B, use_graph=not args.no_graph, train=True)
+            x6 = torch.rand(B, 4096, device=dev); y6 = torch.rand(B, device=dev)
+            ms7 = timed(lambda: s6.step(x6, y6), 50)
+            from vit_b200 import preprocessor as _vp
+            active = _vp._lowrank_state(m6.preprocessor.linear, m6.preprocessor.linear.weight) is not None
+            raw6 = m6._raw_buffer(s6.eng)
+            g6 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g6):
+                for _ in range(20):
+                    m6.preprocessor.forward_into(raw6, s6.eng.x)
+            ms8 = timed(g6.replay, 10) / 20
+            es6 = 2 if "bf16" in args.precision else 4
+            other["zca4096_r32_lowrank_frozen_train_b64"] = {
+                "samples_per_s": B * 1e3 / ms7, "ms": ms7, "preprocessor_ms": ms8, "factored_kernel": bool(active),
+                "preprocessor_gbs": (2 * B * 4096 * 4 + 4096 * 32 * es6) / (ms8 * 1e-3) / 1e9}
+            del m6, s6, Pz, ev, pre6
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            other["zca4096_r32_lowrank_frozen_train_b64"] = {"error": str(ex)[:200]}
 
     if world == 1 and not args.no_cpu_baseline:   # reported at N=1 only
         r = cpu_reference_run(steps=60, warmup=3)

@@ -486,6 +486,15 @@ int vitb200_cast_f32(const void* src, float* dst, size_t n, void* stream);
 size_t vitb200_tc_prelinear_ws_bytes(int M, int N, int K);
 int vitb200_tc_prelinear_fwd(const void* x, const void* w, const float* bias, float* y, int M, int N, int K, void* ws,
                              void* stream);
+/* Low-rank ZCA (src/models/preprocessor.py:40-72: P = Vr diag(1/sqrt(lam_r + eps)) Vr^T + s_perp (I - Vr Vr^T), applied as
+ * a dense Linear by src/models/layers.py:62-63) in factored form while the matrix is frozen:
+ *     y = s_perp x + ((x Vr) o g) Vr^T + bias,   g = 1/sqrt(lam_r + eps) - s_perp
+ * two skinny products in ONE launch (one thread-block cluster per spectrum), 2 r D values of Vr instead of D^2 of P.
+ * x [B, D] f32; vr [D, R] bf16 (dtype BF16: bf16 operands, fp32 accumulation, bf16-rounded fp32 output) or f32; R in
+ * {32, 64}, columns beyond the true rank zero; g [R] f32; bias [D] f32 or NULL; y [B, D] f32. */
+int vitb200_zca_lowrank_supported(int D, int R);
+int vitb200_zca_lowrank_fwd(const float* x, const void* vr, const float* g, float s_perp, const float* bias, float* y,
+                            int B, int D, int R, int dtype, void* stream);
 /* Gradient of the patch embedding w.r.t. its input pixels -- what autograd hands to a TRAINABLE preprocessor
  * (PrefilledLinear.freeze(False), src/models/layers.py:51-60):
  *   dx[b, l] = sum_{n : n*S <= l < n*S+P, n < n_valid} sum_h drop'(dz[b, 1+n, h]) * w[h, l - n*S]

@@ -9,7 +9,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_VARIANTS = ["baseline", "config2", "rope", "learned", "cnn", "stride8", "pad48", "cls", "l1",
-                   "h64multi", "h128d64rope", "long510", "long2034"]
+                   "h64multi", "h128d64rope", "heads8d4rope", "long510", "long2034"]
 # input-preprocessor variants (src/models/builder.py:43-133): the fixture also carries the covariance statistics
 PRE_VARIANTS = ["pre_zca_full", "pre_zca_r32", "pre_pca_r128", "pre_attn_r64"]
 

@@ -62,6 +62,8 @@ def variants():
     c = base_cfg(image_size=2048, hidden_size=128, num_attention_heads=2, num_hidden_layers=1,
                  pos_encoding_type="rope", stride_size=16)
     v["h128d64rope"] = (c, 2, "rand")
+    # head_dim 4 (hidden 32 over 8 heads, the small end of the head-count sweep), with RoPE on 2 rotation pairs
+    v["heads8d4rope"] = (base_cfg(image_size=1024, num_attention_heads=8, pos_encoding_type="rope"), 3, "rand")
     # BASELINE config 4, the long-sequence sweep at its full spectrum length: x4 tokens (T = 510) and x16 (T = 2034)
     v["long510"] = (base_cfg(stride_size=8), 2, "rand")
     v["long2034"] = (base_cfg(stride_size=2, num_hidden_layers=2), 1, "rand")

@@ -174,6 +174,47 @@ def test_preprocessor_forward_backward_vs_reference_golden(golden, name, precisi
 
 
 @pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
+def test_lowrank_zca_factored_kernel_vs_reference_golden(golden, precision, tmp_path, monkeypatch):
+    """A FROZEN low-rank ZCA matrix runs as y = s_perp x + ((x Vr) o g) Vr^T + b (vitb200_zca_lowrank_fwd, one launch)
+    instead of the dense [D, D] Linear: preprocessed pixels vs the reference's, vs the dense kernel, bitwise reproducible,
+    through TrainStep's staging path; a matrix that no longer equals its factors (trained / overwritten) silently takes
+    the dense path again."""
+    from vit_b200 import preprocessor as vp
+    from vit_b200.step import TrainStep
+
+    dev = _cuda()
+    fix = golden("pre_zca_r32")
+    m = _build_pre(fix, precision, dev, tmp_path).eval()
+    m.preprocessor.freeze(True)
+    lin = m.preprocessor.linear
+    assert vp._lowrank_state(lin, lin.weight) is not None          # factors attached by the builder and still valid
+    x, y = _inputs(fix, dev)
+    tol = TOL[precision]
+    with torch.no_grad():
+        a = m.preprocessor(x)
+        b = m.preprocessor(x)
+        monkeypatch.setenv("VITB200_ZCA_LOWRANK", "0")
+        dense = m.preprocessor(x)
+        monkeypatch.delenv("VITB200_ZCA_LOWRANK")
+    assert torch.equal(a, b) and a.dtype == torch.float32
+    assert rel_err(a, fix["eval"]["preprocessed"]) < tol
+    assert rel_err(a, dense) < tol
+    if precision == "bf16-mixed":
+        assert torch.equal(a, a.bfloat16().float())                   # bf16-representable values, like autocast's output
+    # the step path: raw spectra -> factored kernel -> pixel buffer -> training step
+    step = TrainStep(m, fix["batch"], use_graph=True, train=False)
+    l0 = float(step.step(x, y))
+    assert abs(l0 - float(fix["eval"]["loss"])) < 5 * tol * max(1.0, abs(float(fix["eval"]["loss"])))
+    assert rel_err(step.eng.x.view(fix["batch"], -1), fix["eval"]["preprocessed"]) < tol
+    step.close()
+    # overwritten matrix: the factors no longer describe it
+    with torch.no_grad():
+        lin.weight.mul_(1.5)
+        assert vp._lowrank_state(lin, lin.weight) is None
+        assert rel_err(m.preprocessor(x), 1.5 * (dense - lin.bias) + lin.bias if lin.bias is not None else 1.5 * dense) < 5 * tol
+
+
+@pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
 @pytest.mark.parametrize("name", ["pre_zca_full", "pre_pca_r128"])
 def test_train_steps_with_frozen_preprocessor(golden, name, precision, tmp_path):
     """TrainStep (one CUDA graph per step) behind a FROZEN preprocessor: raw spectra in, 3 steps vs the reference."""

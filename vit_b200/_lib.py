@@ -165,6 +165,8 @@ SIGNATURES = {
     "vitb200_cast_f32": (_i, [_p, _p, _sz, _p]),
     "vitb200_tc_prelinear_ws_bytes": (_sz, [_i, _i, _i]),
     "vitb200_tc_prelinear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "vitb200_zca_lowrank_supported": (_i, [_i, _i]),
+    "vitb200_zca_lowrank_fwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _p]),
     "vitb200_patch_embed_dgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _u32, _i, _p]),
     "vitb200_gather_batch": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, C.c_longlong, _f, _p, _p]),
     "vitb200_eval_metrics_accum": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),

@@ -73,8 +73,8 @@ class VitConfig:
         H, d = self.hidden_size, self.head_dim
         if H % 4 != 0 or H > 1024:
             raise ValueError(f"vit_b200: hidden_size must be a multiple of 4 and <= 1024 (got {H})")
-        if d not in (8, 16, 32, 64, 128):
-            raise ValueError(f"vit_b200: head_dim must be one of 8,16,32,64,128 (got {d})")
+        if d not in (4, 8, 16, 32, 64, 128):
+            raise ValueError(f"vit_b200: head_dim must be one of 4,8,16,32,64,128 (got {d})")
 
     @property
     def tokens(self) -> int:
@@ -206,7 +206,12 @@ def build_preprocessor(preproc_type: str, warmup_cfg: dict, stats: dict, input_d
             prefix = f"{'PCA' + str(r) if r is not None else 'PCA'}_fz{fz}{'' if use_bias else '_nobias'}"
             desc = f"PCA with r={r}, bias={use_bias}" if r else f"full-rank PCA, bias={use_bias}"
         bias = -mean @ P.t() if (use_bias and mean is not None) else None   # y = (x - mean) P^T
-        return LinearPreprocessor(P, bias=bias, freeze=initial_freeze), P.shape[0], prefix, desc
+        pre = LinearPreprocessor(P, bias=bias, freeze=initial_freeze)
+        if kind == "zca" and r is not None:
+            from .preprocessor import zca_lowrank_factors
+
+            pre.set_lowrank_factors(*zca_lowrank_factors(eigvecs, stats["eigvals"], eps, int(r), shrinkage))
+        return pre, P.shape[0], prefix, desc
     if kind == "attention":
         eigvals = stats.get("eigvals", None)
         scale = warmup_cfg.get("scale_by_eigvals", True)

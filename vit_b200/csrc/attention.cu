@@ -43,7 +43,24 @@ __device__ __forceinline__ void rope_frag(float (&x)[DPT], const float* __restri
 template <typename T, int D, int KT, bool ROUND>
 __device__ __forceinline__ void load_tile(float (*S)[D], const T* __restrict__ base, int ld, int r0, int Tlen,
                                           const float* __restrict__ cosT, const float* __restrict__ sinT, int tid) {
-  constexpr int HALF = D / 2, CH = HALF / 4;
+  if constexpr (D == 4) {   // head_dim 4 (hidden 32 / 8 heads of the sweep grid): one 4-vector per row, rotation pairs (0,2), (1,3)
+    for (int j = tid; j < KT; j += AT_THREADS) {
+      const int t = r0 + j;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < Tlen) {
+        x = Vec4<T>::ld(base + (size_t)t * ld);
+        if (cosT) {
+          const float c0 = cosT[(size_t)t * 2], c1 = cosT[(size_t)t * 2 + 1], s0 = sinT[(size_t)t * 2], s1 = sinT[(size_t)t * 2 + 1];
+          float4 y = make_float4(x.x * c0 - x.z * s0, x.y * c1 - x.w * s1, x.z * c0 + x.x * s0, x.w * c1 + x.y * s1);
+          if (ROUND) { y.x = round_to<T>(y.x); y.y = round_to<T>(y.y); y.z = round_to<T>(y.z); y.w = round_to<T>(y.w); }
+          x = y;
+        }
+      }
+      *reinterpret_cast<float4*>(&S[j][0]) = x;
+    }
+    return;
+  }
+  constexpr int HALF = D / 2, CH = HALF / 4 > 0 ? HALF / 4 : 1;
   for (int idx = tid; idx < KT * CH; idx += AT_THREADS) {
     const int j = idx / CH, c = (idx % CH) * 4;
     const int t = r0 + j;
@@ -394,6 +411,7 @@ static int attn_dispatch(int which, const void* q, const void* k, const void* v,
                                                                   sinT, Tlen, heads, scale);                          \
   }
   switch (d) {
+    case 4: ATTN_CASE(4, 1) break;
     case 8: ATTN_CASE(8, 1) break;
     case 16: ATTN_CASE(16, 1) break;
     case 32: ATTN_CASE(16, 2) break;
@@ -430,7 +448,7 @@ static inline bool fused_qkv(const void* q, const void* k, const void* v, int ld
 
 static int attn_check(int ld, int B, int Tlen, int heads, int d) {
   if (B < 0 || Tlen <= 0 || heads <= 0 || d <= 0) return VITB200_ERR_ARG;
-  if (!(d == 8 || d == 16 || d == 32 || d == 64 || d == 128)) return VITB200_ERR_SHAPE;
+  if (!(d == 4 || d == 8 || d == 16 || d == 32 || d == 64 || d == 128)) return VITB200_ERR_SHAPE;
   if (ld % 4 != 0 || ld < heads * d) return VITB200_ERR_SHAPE;
   if (heads > 65535 || B > 65535) return VITB200_ERR_SHAPE;
   return VITB200_OK;

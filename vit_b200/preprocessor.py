@@ -17,6 +17,7 @@ bf16-rounded values, as autocast's bf16 Linear output does.  A trainable preproc
 from __future__ import annotations
 
 import math
+import os
 from pathlib import Path
 from typing import Dict, Optional
 
@@ -52,6 +53,21 @@ def compute_zca_matrix(eigvecs: torch.Tensor, eigvals: torch.Tensor, eps: float 
     D = eigvecs.shape[0]
     eye = torch.eye(D, dtype=eigvecs.dtype, device=eigvecs.device)
     return (Vr * inv_sqrt_r) @ Vr.t() + s_perp * (eye - Vr @ Vr.t())
+
+
+def zca_lowrank_factors(eigvecs: torch.Tensor, eigvals: torch.Tensor, eps: float, r: int, shrinkage: float):
+    """(Vr [D, r], g [r], s_perp) with compute_zca_matrix(..., r) == s_perp I + (Vr * g) Vr^T: the factored form of the
+    low-rank ZCA matrix (preprocessor.py:40-72), g = 1/sqrt(lam_r + eps) - s_perp."""
+    lam = eigvals
+    if shrinkage > 0.0:
+        lam = (1.0 - shrinkage) * eigvals + shrinkage * eigvals.mean()
+    Vr = eigvecs[:, :r]
+    inv_sqrt_r = torch.rsqrt(lam[:r] + eps)
+    tail = lam[r:]
+    lam0 = tail.median() if tail.numel() > 0 else lam[r - 1]
+    lam0 = torch.clamp(lam0, min=1e-3 * lam[:r].mean())
+    s_perp = 1.0 / torch.sqrt(lam0 + eps)
+    return Vr.contiguous(), (inv_sqrt_r - s_perp).contiguous(), float(s_perp)
 
 
 def compute_pca_matrix(eigvecs: torch.Tensor, r: int | None = None) -> torch.Tensor:
@@ -223,11 +239,62 @@ class _PreLinearFunction(torch.autograd.Function):
         return None, dx, dw, db
 
 
+def _lowrank_state(mod: nn.Module, weight: torch.Tensor):
+    """The factored form of a FROZEN low-rank ZCA matrix, or None.  The factors come from the builder (they are not part
+    of the state_dict, which stays the reference's); they are trusted only while the dense matrix still equals
+    s_perp I + (Vr g) Vr^T -- re-checked (one D x D product) whenever the matrix tensor was replaced or written, e.g. by
+    load_state_dict of a trained matrix, which silently falls back to the dense kernel."""
+    lr = mod.__dict__.get("_lowrank")
+    if lr is None or not getattr(mod, "_is_frozen", False) or weight.requires_grad:
+        return None
+    if os.environ.get("VITB200_ZCA_LOWRANK", "1") == "0":
+        return None
+    key = (weight.data_ptr(), weight._version, weight.device)
+    if lr.get("key") != key:
+        lr["key"] = key
+        lr["ok"] = False
+        D, r = lr["Vr"].shape
+        R = 32 if r <= 32 else 64
+        if r <= 64 and weight.shape == (D, D) and _lib.load().vitb200_zca_lowrank_supported(D, R):
+            dev = weight.device
+            Vr = torch.zeros(D, R, dtype=torch.float32, device=dev)
+            Vr[:, :r] = lr["Vr"].to(dev, torch.float32)
+            g = torch.zeros(R, dtype=torch.float32, device=dev)
+            g[:r] = lr["g"].to(dev, torch.float32)
+            dense = (Vr * g) @ Vr.t()
+            dense.diagonal().add_(lr["s_perp"])
+            w = weight.detach().to(torch.float32)
+            if float((dense - w).abs().max()) <= 1e-5 * max(float(w.abs().max()), 1e-30):
+                lr.update(ok=True, R=R, Vr32=Vr.contiguous(), Vr16=Vr.to(torch.bfloat16).contiguous(), g32=g)
+            del dense
+    return lr if lr["ok"] else None
+
+
+def lowrank_forward(mod: nn.Module, lr: dict, x: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """y = s_perp x + ((x Vr) o g) Vr^T + bias in one launch (vitb200_zca_lowrank_fwd)."""
+    if not x.is_cuda:
+        raise RuntimeError("vit_b200 has no CPU path: the preprocessor and its input must live on a CUDA (sm_100a) device")
+    B, D = x.shape
+    if D != lr["Vr32"].shape[0]:
+        raise ValueError(f"expected input of shape [B, {lr['Vr32'].shape[0]}], got {tuple(x.shape)}")
+    xin = _aligned(x.detach().to(torch.float32))
+    y = out if out is not None else torch.empty(B, D, dtype=torch.float32, device=x.device)
+    bf = _precision_of(mod) == "bf16"
+    bptr = None if bias is None else _aligned(bias.detach().to(torch.float32)).data_ptr()
+    _lib.check(_lib.load().vitb200_zca_lowrank_fwd(
+        xin.data_ptr(), (lr["Vr16"] if bf else lr["Vr32"]).data_ptr(), lr["g32"].data_ptr(), lr["s_perp"], bptr,
+        y.data_ptr(), B, D, lr["R"], BF16 if bf else F32, _stream(x)), "zca_lowrank_fwd")
+    return y
+
+
 def _apply_linear(mod: nn.Module, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     needs = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
                                          (bias is not None and bias.requires_grad))
     if needs:
         return _PreLinearFunction.apply(mod, x, weight, bias)
+    lr = _lowrank_state(mod, weight)
+    if lr is not None:
+        return lowrank_forward(mod, lr, x, bias)
     return linear_forward(mod, x, weight, bias)[0]
 
 
@@ -302,7 +369,16 @@ class LinearPreprocessor(nn.Module):
 
     def forward_into(self, x: torch.Tensor, out: torch.Tensor) -> None:
         """No-grad forward straight into the engine's pixel buffer (TrainStep / EvalStep with a frozen preprocessor)."""
+        lr = _lowrank_state(self.linear, self.linear.weight)
+        if lr is not None:
+            lowrank_forward(self.linear, lr, x, self.linear.bias, out=out)
+            return
         linear_forward(self.linear, x, self.linear.weight, self.linear.bias, out=out)
+
+    def set_lowrank_factors(self, Vr: torch.Tensor, g: torch.Tensor, s_perp: float) -> None:
+        """Builder hook: the matrix is s_perp I + (Vr g) Vr^T (zca_lowrank_factors).  While it stays frozen and unchanged
+        the forward runs the factored kernel instead of streaming the dense matrix."""
+        self.linear.__dict__["_lowrank"] = dict(Vr=Vr.detach().clone(), g=g.detach().clone(), s_perp=float(s_perp))
 
     def freeze(self, freeze: bool = True) -> None:
         self.linear.freeze(freeze)
