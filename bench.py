@@ -843,8 +843,9 @@ def main():
         "step_api_samples_per_s": step_api_value,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_b,
                 "d2h_bytes_per_step": d2h_b, "ms_per_step": 1e3 * float(te[0]) / args.steps,
-                "api": "TrainStep.fit_host(iterable of host batches): per step H2D of the inputs from pinned memory "
-                       "(copy stream, prefetch depth 1), step, D2H of the loss (read one step late)",
+                "api": "TrainStep.fit_host(iterable of host batches): per step H2D of the inputs from pinned memory into one of "
+                       "the engine's four input slots (copy stream, two steps ahead), steps run two per CUDA graph, the "
+                       "forward kernel stores each step's loss into pinned host memory (read one group late)",
                 "blocking_step_host_samples_per_s": e2e_blocking},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,

@@ -24,7 +24,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math" if False else "-DVITB200_NO_FAST_MATH",  # fast-math stays off: fp32 mode has a 1e-4 parity bar
     "-Xcompiler", "-fPIC", "-I", INCLUDE,
-] + (["-DVB_TIMELINE"] if os.environ.get("VITB200_TIMELINE") == "1" else [])
+] + (["-DVB_TIMELINE"] if os.environ.get("VITB200_TIMELINE") == "1" else []) \
+  + (["-DVB_TL_TOP"] if os.environ.get("VITB200_TL_TOP") == "1" else [])
 
 
 def _nvcc() -> str:

@@ -310,7 +310,11 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   }
 
   // =============================== layers, top down ===============================
+#ifdef VB_TL_TOP
+  const int tl_l = L - 1;                    // (debug build, -DVB_TL_TOP: stamp the top layer -- CLS-only in a training step)
+#else
   const int tl_l = L >= 2 ? L - 2 : L - 1;   // (debug build: the layer whose phases are time-stamped -- a steady-state one)
+#endif
   (void)tl_l;
   for (int l = L - 1; l >= 0; --l) {
     const uint32_t par = (uint32_t)((L - 1 - l) & 1);   // every per-layer barrier completes once per layer

@@ -20,7 +20,8 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, BF16, F32, SITE_EMB, site_attn, site_mlp, site_proj
 from .arena import ParamArena
 
-ROWS_SLOT = 2   # input slot of the device-resident dataset mode (ViTEngine.bind_rows)
+ROWS_SLOT = 99   # input slot of the device-resident dataset mode (ViTEngine.bind_rows)
+HOST_SLOTS = 4   # regular input slots 0 .. 3 (TrainStep.fit_host: two groups of two steps)
 
 
 def _normalize_precision(precision) -> str:
@@ -227,16 +228,21 @@ class ViTEngine:
             self.B, T, c.num_attention_heads, c.head_dim, scale, pa, rng, site_attn(l), self.dt))
 
     def input_slot(self, slot: int):
-        """(pixels, labels) input buffers of `slot`.  Slot 0 is `self.x` / `self.labels`; slot 1 is a second pair the
-        whole-network programs can be built on, so that a host pipeline uploads batch i + 1 while step i still reads
-        batch i (TrainStep.fit_host) -- no device-to-device staging copy on the step's critical path."""
+        """(pixels, labels) input buffers of `slot`.  Slot 0 is `self.x` / `self.labels`; slots 1 .. HOST_SLOTS - 1 are
+        further pairs the whole-network programs can be built on, so that a host pipeline uploads the next batches while
+        the running steps still read theirs (TrainStep.fit_host) -- no device-to-device staging copy on the step's
+        critical path."""
         if slot == 0:
             return self.x, self.labels
         if slot == ROWS_SLOT:
             return self._rows["x"], self._rows["labels"]
-        if not hasattr(self, "_slot1"):
-            self._slot1 = (torch.zeros_like(self.x), torch.zeros_like(self.labels))
-        return self._slot1
+        if not 0 < slot < HOST_SLOTS:
+            raise ValueError(f"input slot {slot} does not exist")
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        if slot not in self._slots:
+            self._slots[slot] = (torch.zeros_like(self.x), torch.zeros_like(self.labels))
+        return self._slots[slot]
 
     def bind_rows(self, x_all: torch.Tensor, labels_all: torch.Tensor, rows: torch.Tensor, loss_log: torch.Tensor) -> None:
         """Device-resident dataset mode of the whole-network kernels (input slot ROWS_SLOT): x_all [N, L] f32 and labels_all
@@ -296,7 +302,7 @@ class ViTEngine:
             # the loss also lands in page-locked HOST memory (unified addressing: the kernel stores through the host
             # pointer), so a host loop reads it after the step's event without a device-to-host copy launch
             if not hasattr(self, "loss_pinned"):
-                self.loss_pinned = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+                self.loss_pinned = torch.zeros(HOST_SLOTS, dtype=torch.float32, pin_memory=True)
             a.loss_log = self.loss_pinned.data_ptr() + 4 * slot
         self._keep.append(a)
         return a
@@ -306,7 +312,7 @@ class ViTEngine:
         whole-network kernel when the shape allows: ONE launch (+ the head backward for training steps)."""
         c, lib, dt, P_ = self.cfg, self.lib, self.dt, self._ptr
         if slot != 0 and not (self.mega and self.mega_bwd):
-            raise RuntimeError("vit_b200: input slot 1 exists for the whole-network programs only")
+            raise RuntimeError("vit_b200: input slots other than 0 exist for the whole-network programs only")
         if self.mega:
             a = self._mega_fwd_args(train, with_labels, slot)
             prog = [(lib.vitb200_mega_fwd, (ctypes.addressof(a),))]

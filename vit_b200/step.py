@@ -43,7 +43,8 @@ class TrainStep:
         self.noise_level = float(noise_level)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._graph1: Optional[torch.cuda.CUDAGraph] = None   # the same step on input slot 1 (fit_host pipeline)
+        self._graph_slot: dict = {}    # slot -> the same step on input slot 1 .. 3 (fit_host pipeline)
+        self._graph_group: dict = {}   # (slots) -> one graph of consecutive steps on those slots (fit_host pipeline)
         self._graph_rows: dict = {}   # unroll -> graph of `unroll` steps in device-resident dataset mode (fit_device)
         self._rows_key = None
         self._rows_buf = None
@@ -130,28 +131,34 @@ class TrainStep:
             d.copy_(s)
         e.arena.mark_shadow_fresh()
 
-    def _capture(self, slot: int = 0, unroll: int = 1) -> None:
+    def _capture(self, slot: int = 0, unroll: int = 1, slots=None) -> None:
+        """Capture one step on `slot` (x `unroll` in device-resident dataset mode), or -- `slots` given -- one step per
+        listed input slot, in order, as ONE graph (fit_host: consecutive steps chained by programmatic dependent launch)."""
         eng = self.eng
         eng.refresh_shadow()
         snap = self._snapshot()
+        seq = list(slots) if slots is not None else [slot] * unroll
         side = torch.cuda.Stream(device=eng.device)
         side.wait_stream(torch.cuda.current_stream(eng.device))
         with torch.cuda.stream(side):
-            self._launch(slot)  # loads every kernel before capture; state is restored below
+            for sl in dict.fromkeys(seq):
+                self._launch(sl)  # loads every kernel before capture; state is restored below
         torch.cuda.current_stream(eng.device).wait_stream(side)
         self._restore(snap)
         torch.cuda.synchronize(eng.device)
         g = torch.cuda.CUDAGraph()
         # thread_local: other threads (NCCL watchdog, data loaders) may touch CUDA while this thread captures
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            for _ in range(unroll):
-                self._launch(slot)
-        if slot == 0:
+            for sl in seq:
+                self._launch(sl)
+        if slots is not None:
+            self._graph_group[tuple(seq)] = g
+        elif slot == 0:
             self.graph = g
         elif slot == ROWS_SLOT:
             self._graph_rows[unroll] = g
         else:
-            self._graph1 = g
+            self._graph_slot[slot] = g
 
     @property
     def two_slots(self) -> bool:
@@ -165,9 +172,9 @@ class TrainStep:
         """One step on the inputs sitting in the engine's input slot `slot`."""
         if slot == 0:
             return self._run_staged()
-        if self._graph1 is None:
-            self._capture(1)
-        self._graph1.replay()
+        if slot not in self._graph_slot:
+            self._capture(slot)
+        self._graph_slot[slot].replay()
 
     # ---- public -----------------------------------------------------------------------------
     def step(self, flux: torch.Tensor, labels: torch.Tensor, error: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -321,6 +328,8 @@ class TrainStep:
         eng = self.eng
         dev = eng.device
         main = torch.cuda.current_stream(dev)
+        if self.two_slots and os.environ.get("VITB200_HOST_GROUP", "2") not in ("0", "1"):
+            return self._fit_host_grouped(batches, on_loss)
         if getattr(self, "_pipe", None) is None:
             c = self.model.config
             self._pipe = dict(
@@ -343,7 +352,7 @@ class TrainStep:
             P["d_y"] = [eng.input_slot(0)[1], eng.input_slot(1)[1]]
             if self.graph is None:
                 self._capture(0)
-            if self._graph1 is None:
+            if 1 not in self._graph_slot:
                 self._capture(1)
 
         def upload(i, batch):
@@ -395,6 +404,98 @@ class TrainStep:
             collect(i - 1)
         return losses
 
+    def _fit_host_grouped(self, batches, on_loss=None) -> list:
+        """fit_host for the whole-network programs: the engine has four input slots = two groups of G = 2.  The G batches of
+        group k + 1 are uploaded (copy stream, straight into the engine's slots) while the G steps of group k run as ONE
+        graph (6 kernels chained by programmatic dependent launch -- no graph boundary, no event wait between the two
+        steps); every step's loss is stored by the forward kernel itself into pinned host memory and read by the host
+        after the next group has been enqueued.  A tail of fewer than G batches runs per-slot graphs."""
+        from .engine import HOST_SLOTS
+
+        eng = self.eng
+        dev = eng.device
+        main = torch.cuda.current_stream(dev)
+        G = HOST_SLOTS // 2
+        if getattr(self, "_gpipe", None) is None:
+            self._gpipe = dict(
+                copy=torch.cuda.Stream(device=dev),
+                h_x=[torch.empty(self.B, self.model.input_dim, dtype=torch.float32, pin_memory=True) for _ in range(HOST_SLOTS)],
+                h_y=[torch.empty(eng.labels.shape, dtype=eng.labels.dtype, pin_memory=True) for _ in range(HOST_SLOTS)],
+                ev_in=[torch.cuda.Event() for _ in range(2)],      # the group's slots are filled (copy stream)
+                ev_done=[torch.cuda.Event() for _ in range(2)],    # the group's steps are finished (main stream)
+            )
+        Q = self._gpipe
+        copy = Q["copy"]
+        d = [eng.input_slot(sl) for sl in range(HOST_SLOTS)]
+        for p in range(2):
+            key = tuple(range(p * G, p * G + G))
+            if key not in self._graph_group:
+                self._capture(slots=key)
+        losses = []
+        it = iter(batches)
+
+        def take():
+            out = []
+            for _ in range(G):
+                b = next(it, None)
+                if b is None:
+                    break
+                out.append(b)
+            return out
+
+        def upload(k, group):
+            p = k & 1
+            if k >= 2:
+                Q["ev_done"][p].synchronize()   # host staging + device slots of group k - 2 are reusable
+            with torch.cuda.stream(copy):
+                if k < 2:
+                    copy.wait_stream(main)      # (the slots may still be read by steps enqueued before this loop)
+                for j, batch in enumerate(group):
+                    sl = p * G + j
+                    hx, hy = self._pinned(batch[0], batch[1], Q["h_x"][sl], Q["h_y"][sl])
+                    d[sl][0].copy_(hx, non_blocking=True)
+                    d[sl][1].copy_(hy.reshape(d[sl][1].shape), non_blocking=True)
+                Q["ev_in"][p].record(copy)
+
+        def launch(k, n):
+            p = k & 1
+            main.wait_event(Q["ev_in"][p])
+            if n == G:
+                self._graph_group[tuple(range(p * G, p * G + G))].replay()
+            else:
+                for j in range(n):
+                    self._run_slot(p * G + j)
+            Q["ev_done"][p].record(main)
+
+        def collect(k, n, first):
+            p = k & 1
+            Q["ev_done"][p].synchronize()
+            for j in range(n):
+                v = float(eng.loss_pinned[p * G + j])   # written by the forward kernel itself (4 bytes over PCIe)
+                losses.append(v)
+                if on_loss is not None:
+                    on_loss(first + j, v)
+
+        group = take()
+        k, done, prev = 0, 0, None
+        if group:
+            upload(0, group)
+        while group:
+            n = len(group)
+            launch(k, n)
+            nxt = take()
+            if nxt:
+                upload(k + 1, nxt)          # overlaps the steps of group k
+            if prev is not None:
+                collect(*prev)              # one group late: never stalls the GPU
+            prev = (k, n, done)
+            done += n
+            group = nxt
+            k += 1
+        if prev is not None:
+            collect(*prev)
+        return losses
+
     @property
     def h2d_bytes_per_step(self) -> int:
         return self.h_x.numel() * 4 + self.h_y.numel() * self.h_y.element_size()
@@ -414,7 +515,7 @@ class TrainStep:
         import gc
 
         self.graph = None
-        self._graph1 = None
+        self._graph_slot, self._graph_group, self._gpipe = {}, {}, None
         self._graph_rows, self._rows_key = {}, None
         self._pipe = None
         gc.collect()
