@@ -290,6 +290,10 @@ typedef struct {
    * advances rng[1]), so one captured launch walks through an epoch's permutation.  loss_log (optional): the step's
    * loss is also stored at loss_log[pos]. */
   const int64_t* rows; const uint64_t* rows_base; float* loss_log;
+  /* defer_loss != 0 (training step: vitb200_mega_bwd with the same argument block is the next launch): forward only
+   * stores its per-CTA loss terms in ws; the backward kernel sums them and writes loss / loss_log.  Saves the fence +
+   * ticket at the end of the forward kernel, which the backward kernel's start is waiting for. */
+  int defer_loss;
 } vitb200_mega_fwd_args;
 int vitb200_mega_supported(int H, int heads, int T, int P, int C, int layers, int rope);
 size_t vitb200_mega_ws_bytes(void);

@@ -65,3 +65,9 @@ for key, labels in names.items():
           f"= {d.sum(1).mean() / 1.965e3:.2f} us @1.965 GHz")
     for i, lab in enumerate(labels):
         print(f"   {lab:<24} mean {d[:, i].mean():8.0f}   max {d[:, i].max():8d}")
+    if key == "mega_bwd" and os.environ.get("VITB200_TL_EXTRA") == "1":   # finer stamps (debug): slot -> offset from stamp 5 / 8 / 9
+        full = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)[live]
+        for a_, b_, what in ((5, 16, "dctx: tid0 waits done"), (5, 17, "dctx: CTA barrier"), (5, 6, "dctx: cluster arrive"),
+                             (8, 14, "attn: after MMA issue"), (8, 15, "attn: after mma wait"), (8, 9, "attn: TMA issued"),
+                             (9, 18, "epi: cluster wait"), (9, 19, "epi: pieces written"), (9, 10, "epi: cluster sync")):
+            print(f"      stamp {a_} -> {b_}  {what:<26} mean {(full[:, b_] - full[:, a_]).mean():8.0f}")

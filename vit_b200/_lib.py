@@ -72,7 +72,7 @@ class MegaFwdArgs(C.Structure):  # vitb200_mega_fwd_args
                                   "o_wqkv", "o_bqkv", "o_wo", "o_bo", "o_ln2g", "o_ln2b", "o_w1", "o_b1", "o_w2", "o_b2",
                                   "off_lnfg", "off_lnfb", "off_wh", "off_bh")] + \
                [(n, _p) for n in ("rope_cos", "rope_sin", "z", "hmid", "u", "u2", "qkv", "ctx", "a", "m", "stats", "lse",
-                                  "s_cls", "logits", "loss", "ws", "rows", "rows_base", "loss_log")]
+                                  "s_cls", "logits", "loss", "ws", "rows", "rows_base", "loss_log")] + [("defer_loss", _i)]
 
 
 class MegaBwdArgs(C.Structure):  # vitb200_mega_bwd_args

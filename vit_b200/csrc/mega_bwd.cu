@@ -74,7 +74,20 @@ __device__ __forceinline__ void mb_st_peer16(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void mb_st_peer4(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// DSMEM pushes that signal the receiver's own mbarrier (see mega_fwd.cu)
+__device__ __forceinline__ void mb_st_async16(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mb_st_async4(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)),
+               "r"(mbar)
+               : "memory");
+}
 __device__ __forceinline__ void mb_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// write-after-read hand-off ("my tile may be overwritten"): nothing is published, so no release fence (MEMBAR.ALL.GPU)
+__device__ __forceinline__ void mb_cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mb_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mb_bar_side() { asm volatile("bar.sync 2, 128;" ::: "memory"); }   // the 4 side-row warps
 
@@ -172,7 +185,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   uint8_t *sW2 = base + MB_W2, *sW1 = base + MB_W1, *sWo = base + MB_WO, *sWq = base + MB_WQ;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + MB_BAR);
   uint64_t *b_w2 = bars, *b_w1 = bars + 1, *b_wo = bars + 2, *b_wq = bars + 3, *b_up = bars + 4, *b_ctx = bars + 5,
-           *b_qkv = bars + 6, *b_low = bars + 7, *b_mma = bars + 8, *b_wg = bars + 9, *b_a = bars + 10;
+           *b_qkv = bars + 6, *b_low = bars + 7, *b_mma = bars + 8, *b_wg = bars + 9, *b_a = bars + 10, *b_x = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float2* s_ex = reinterpret_cast<float2*>(base + MB_EX);
   float* s_dp = reinterpret_cast<float*>(base + MB_EX);      // [4][128] D_i partials (attention phase)
@@ -210,7 +223,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     tma_prefetch_desc(&TM.wq); tma_prefetch_desc(&TM.wo); tma_prefetch_desc(&TM.w1); tma_prefetch_desc(&TM.w2);
     tma_prefetch_desc(&TM.z); tma_prefetch_desc(&TM.hmid); tma_prefetch_desc(&TM.u); tma_prefetch_desc(&TM.u2);
     tma_prefetch_desc(&TM.qkv); tma_prefetch_desc(&TM.ctx); tma_prefetch_desc(&TM.a); tma_prefetch_desc(&TM.m);
-    for (int i = 0; i < 11; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < 12; ++i) mbar_init(bars + i, 1);
     fence_barrier_init();
   }
   for (int j = tid; j < L * 64 + 32; j += MB_THREADS) {   // gammas are parameters: the optimizer ran two kernels ago
@@ -247,6 +260,14 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   pdl_trigger();
   VB_TL(tl_mega_bwd, 2);
   const bool cls_only = P.cls_only != 0;
+  if (P.defer_loss && blockIdx.x == 0 && warp == 1 && P.labels) {   // the forward kernel left the loss as per-CTA terms
+    const float t = mg_loss_sum(reinterpret_cast<const float*>(reinterpret_cast<const char*>(P.ws) + 256), gridDim.x, lane);
+    if (lane == 0) {
+      const float v = t / (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+      P.loss[0] = v;
+      if (P.loss_log) P.loss_log[P.rows ? (size_t)(P.rng[1] - P.rows_base[0]) : 0] = v;
+    }
+  }
   if (tid == 0 && !cls_only) { load_a(L - 1); load_upper(L - 1); load_ctx(L - 1); }   // (a CLS-only top layer loads no tiles)
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -272,7 +293,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   const size_t bsrc = P.rows ? (size_t)P.rows[(size_t)(P.rng[1] - P.rows_base[0]) * (size_t)B + b] : (size_t)b;
   const float scale = rsqrtf((float)D), sl2 = scale * MG_LOG2E;
   const int Tpad = attn_drop_tpad(T);
-  uint32_t ph_mma = 0;
+  uint32_t ph_mma = 0, ph_x = 0;
 
   // =============================== head + final LayerNorm of the CLS row (HF:455, specvit.py:78-89) ===============================
   float dz[HC];      // main: gradient of the residual row, columns hc0 .. hc0 + 7
@@ -332,6 +353,10 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     const DropCtx dc_mlp = make_drop(P.p_hidden, seed, step, VITB200_SITE_MLP(l));
     const DropCtx dc_proj = make_drop(P.p_hidden, seed, step, VITB200_SITE_PROJ(l));
     const DropCtx dc_att = make_drop(P.p_attn, seed, step, VITB200_SITE_ATTN(l));
+    // bytes the peer pushes into this CTA per layer: its head's dQ | dK | dV pieces (6 x 16 B x 128 rows) and, with a side
+    // row, that row's 48 values
+    if (csz == 2 && tid == 0) mbar_expect_tx(b_x, 12288u + (has_side ? 192u : 0u));
+    const uint32_t x_peer = csz == 2 ? mb_peer_addr(b_x, crank ^ 1u) : 0u;
     float acc_b2 = 0.f, acc_bo = 0.f;
     float gam2[HC], bet2[HC];   // LN2 gamma / beta gradient terms of this thread's row
     float mu2 = 0.f, rs2 = 0.f;
@@ -486,6 +511,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       }
       if (l > 0) load_w1(l - 1);
     }
+    if (l == tl_l) VB_TL(tl_mega_bwd, 16);
     float dctxs = 0.f;   // side: dctx row, column = lane
     if (!is_side && !ct) {
       acc_bo = mb_colsum8(sD, tid & 31, (tid >> 5) * 8);
@@ -515,9 +541,10 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (l == tl_l) VB_TL(tl_mega_bwd, 17);
     // CTA pair: from here on this CTA's dqkv tile (R1 @64K, until now u2 / hmid) and side-row dqkv vector may be written
     // by the peer (barrier B: arrive here, the peer waits right before it pushes)
-    if (csz == 2) mb_cluster_arrive();
+    if (csz == 2) mb_cluster_arrive_relaxed();
     if (l == tl_l) VB_TL(tl_mega_bwd, 6);
     // ---------------- upper: parameter gradients of the layer's MLP / out-proj half -> gpart ----------------
     // The ddelta / da tiles (R3) are dead: the q|k|v rows of the layer are fetched while the gradients drain.
@@ -789,6 +816,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         mg_issue(tmem + AB_DV, PT_mn, DOmn, D, 8, false);       // dV[j,:] = sum_i P~[i,j] dO_i
         umma_commit(b_mma);
       }
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 14);
       // side warp meanwhile: the side row as a KEY.  dk_128 = scale * sum_i dS[i,128] q_i + (own query term),
       // dv_128 = sum_i P~[i,128] dO_i + (own query term); lanes 0..15: dk column c, lanes 16..31: dv column c
       if (is_side && has_side) {
@@ -825,6 +853,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         side_dq = bf16_round(dqn); side_dk = bf16_round(dkn); side_dv = bf16_round(dvn);
       }
       if (!is_side && !ct) { mbar_wait(b_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); }
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 15);
       if (tid == 0 && hd == hd_hi - 1) {
         // dS / P~ (R1 @0 .. 64K) are dead: the u / z rows of this layer and the pre-GELU rows of the layer below arrive there
         mbar_expect_tx(b_low, 32768);
@@ -836,18 +865,19 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
       // ---- dQ / dK / dV epilogue -> dqkv tile (R1 @64K).  In a CTA pair the pieces also go into the peer's tile, which
       //      is free once the peer has passed stage 2 of its upper half (its u2 / hmid tiles sat there): barrier B. ----
       if (csz == 2) mb_cluster_wait();
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 18);
       if (is_side && has_side && s0) {
         // dqkv row of token 128: dq in lanes hd * 16 + c; (dk, dv) of column c = lane & 15 in every lane
         if ((lane >> 4) == hd) {
           sv[SV_DQKV + lane] = side_dq;
-          if (csz == 2) mb_st_peer4(mb_peer_addr(&sv[SV_DQKV + lane], crank ^ 1u), side_dq);
+          if (csz == 2) mb_st_async4(mb_peer_addr(&sv[SV_DQKV + lane], crank ^ 1u), side_dq, x_peer);
         }
         if (lane < 16) {
           sv[SV_DQKV + 32 + hd * D + lane] = side_dk;
           sv[SV_DQKV + 64 + hd * D + lane] = side_dv;
           if (csz == 2) {
-            mb_st_peer4(mb_peer_addr(&sv[SV_DQKV + 32 + hd * D + lane], crank ^ 1u), side_dk);
-            mb_st_peer4(mb_peer_addr(&sv[SV_DQKV + 64 + hd * D + lane], crank ^ 1u), side_dv);
+            mb_st_async4(mb_peer_addr(&sv[SV_DQKV + 32 + hd * D + lane], crank ^ 1u), side_dk, x_peer);
+            mb_st_async4(mb_peer_addr(&sv[SV_DQKV + 64 + hd * D + lane], crank ^ 1u), side_dv, x_peer);
           }
         }
       }
@@ -895,7 +925,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
             const uint4 p0 = mg_pack8(&x[0]), p1 = mg_pack8(&x[8]);
             uint8_t* d0 = mg_chunk(blk, r, ch0); uint8_t* d1 = mg_chunk(blk, r, ch0 + 1);
             *reinterpret_cast<uint4*>(d0) = p0; *reinterpret_cast<uint4*>(d1) = p1;
-            if (csz == 2) { mb_st_peer16(mb_peer_addr(d0, crank ^ 1u), p0); mb_st_peer16(mb_peer_addr(d1, crank ^ 1u), p1); }
+            if (csz == 2) { mb_st_async16(mb_peer_addr(d0, crank ^ 1u), p0, x_peer); mb_st_async16(mb_peer_addr(d1, crank ^ 1u), p1, x_peer); }
           }
         } else {
           // 6 pieces of 8 columns per row: dQ0 dQ1 | dK0 dK1 | dV0 dV1 ; group cg takes pieces cg and cg + 4
@@ -930,13 +960,16 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
             const uint4 pk = mg_pack8(o);
             uint8_t* dst = mg_chunk(blk, r, ch);
             *reinterpret_cast<uint4*>(dst) = pk;
-            if (csz == 2) mb_st_peer16(mb_peer_addr(dst, crank ^ 1u), pk);
+            if (csz == 2) mb_st_async16(mb_peer_addr(dst, crank ^ 1u), pk, x_peer);
           }
         }
       }
       fence_proxy_async();
       tc_fence_before();
-      if (csz == 2) { mb_cluster_arrive(); mb_cluster_wait(); fence_proxy_async(); } else __syncthreads();
+      if (l == tl_l && hd == hd_lo) VB_TL(tl_mega_bwd, 19);
+      if (csz == 2) { mbar_wait(b_x, ph_x); ph_x ^= 1; }   // the peer's pieces have landed
+      __syncthreads();                                     // (and this CTA's own)
+      if (csz == 2) fence_proxy_async();
       tc_fence_after();
     }
     if (ct && !is_side && r == 0) {
@@ -1193,7 +1226,8 @@ extern "C" int vitb200_mega_bwd(const vitb200_mega_bwd_args* pa, void* stream) {
   const vitb200_mega_fwd_args* a = &pa->f;
   if (!a->x || !a->params || !a->shadow || !a->z || !a->hmid || !a->u || !a->u2 || !a->qkv || !a->ctx || !a->a || !a->m ||
       !a->stats || !a->lse || !a->s_cls || !a->logits || !pa->labels || !pa->gpart ||
-      (a->rows && (!a->rng || !a->rows_base || pa->loss_kind == VITB200_LOSS_GIVEN)))
+      (a->rows && (!a->rng || !a->rows_base || pa->loss_kind == VITB200_LOSS_GIVEN)) ||
+      (a->defer_loss && (!a->ws || !a->loss || !a->labels)))
     return VITB200_ERR_ARG;
   const int T = a->Np + 1;
   if (!vitb200_mega_bwd_supported(MG_H, MG_NH, T, a->P, a->C, a->layers, a->B, a->cluster)) return VITB200_ERR_SHAPE;

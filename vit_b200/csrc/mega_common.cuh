@@ -138,6 +138,17 @@ __device__ __forceinline__ void mg_issue(uint32_t tmem_d, const MgOp& A, const M
 __device__ __forceinline__ void mg_bar_main() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 MMA-path warps
 
 // ---- side row (one warp, lane = column) -----------------------------------------------------------------------------
+// fixed-order sum of the per-CTA loss partials by one warp: lane l adds partials l, l + 32, ... (<= 160, all loads in
+// flight at once), then a shuffle tree; every lane returns the total
+__device__ __forceinline__ float mg_loss_sum(const float* __restrict__ part, unsigned int n, int lane) {
+  float v[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) v[q] = (unsigned)(lane + 32 * q) < n ? __ldcg(&part[lane + 32 * q]) : 0.f;
+  float t = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
 __device__ __forceinline__ float mg_wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -65,7 +65,23 @@ __device__ __forceinline__ void mf_st_peer16(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void mf_st_peer4(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// DSMEM push that signals the RECEIVER's mbarrier itself (st.async ... mbarrier::complete_tx::bytes): the receiver posts the
+// byte count it expects per layer and waits on its own barrier -- no cluster-wide release / acquire barrier (whose
+// arrive.release is a MEMBAR.ALL.GPU) between the push and the consumer.
+__device__ __forceinline__ void mf_st_async16(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mf_st_async4(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)),
+               "r"(mbar)
+               : "memory");
+}
 __device__ __forceinline__ void mf_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// "my exchange buffers may be overwritten" (write-after-read hand-off, nothing is published): no memory ordering needed.
+// The .release form costs a MEMBAR.ALL.GPU + ERRBAR (~2 k cycles) in front of the arrive.
+__device__ __forceinline__ void mf_cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mf_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mf_cluster_sync() { mf_cluster_arrive(); mf_cluster_wait(); }
 
@@ -128,7 +144,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   uint8_t *sU = base + MF_U, *sM = base + MF_U, *sAct = base + MF_U + 32768, *sCtx = base + MF_CTX;
   uint8_t *sWo = base + MF_WO, *sW1 = base + MF_W1, *sW2 = base + MF_W2, *sWq = base + MF_WQ, *sWp = base + MF_WP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + MF_BAR);
-  uint64_t *b_wp = bars, *b_wo = bars + 1, *b_w1 = bars + 2, *b_w2 = bars + 3, *b_wq = bars + 4, *b_mma = bars + 5;
+  uint64_t *b_wp = bars, *b_wo = bars + 1, *b_w1 = bars + 2, *b_w2 = bars + 3, *b_wq = bars + 4, *b_mma = bars + 5, *b_x = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float2* s_ln = reinterpret_cast<float2*>(base + MF_EX);
   float* s_mx = reinterpret_cast<float*>(base + MF_MX);
@@ -164,7 +180,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
     tma_prefetch_desc(&TM.w2); tma_prefetch_desc(&TM.z); tma_prefetch_desc(&TM.hmid); tma_prefetch_desc(&TM.u);
     tma_prefetch_desc(&TM.u2); tma_prefetch_desc(&TM.qkv); tma_prefetch_desc(&TM.ctx); tma_prefetch_desc(&TM.a);
     tma_prefetch_desc(&TM.m);
-    mbar_init(b_wp, 1); mbar_init(b_wo, 1); mbar_init(b_w1, 1); mbar_init(b_w2, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1);
+    mbar_init(b_wp, 1); mbar_init(b_wo, 1); mbar_init(b_w1, 1); mbar_init(b_w2, 1); mbar_init(b_wq, 1); mbar_init(b_mma, 1); mbar_init(b_x, 1);
     fence_barrier_init();
   }
   // key rows 128 .. 143 of the q|k and v blocks: zero once (row 128 is rewritten per layer when the sample has 129 tokens;
@@ -224,7 +240,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   const size_t pos = P.rows ? (size_t)(P.rng[1] - P.rows_base[0]) : 0;   // steps into the epoch's permutation
   const float scale = rsqrtf((float)MG_D), sl2 = scale * MG_LOG2E;
   const int Tpad = attn_drop_tpad(T);
-  uint32_t ph_mma = 0;
+  uint32_t ph_mma = 0, ph_x = 0;
   int it = 0;                 // layer iterations done (over samples): parity of the weight barriers
   float loss_acc = 0.f;       // lane 0 of warp 16: loss terms of this CTA's samples, in sample order
 
@@ -232,7 +248,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
   // CTA pair protocol, per layer: [wait B] push my head's attention output into both ctx tiles [sync A] ... hop 1 reads
   // the tile ... [arrive B] = "my tile may be overwritten".  B is split (arrive here, wait a whole layer later), so it
   // costs nothing; the first wait is matched by this arrive.
-  if (csz == 2) mf_cluster_arrive();
+  if (csz == 2) mf_cluster_arrive();   // (release: also publishes the mbarrier initialisation to the peer)
   const int nsamp_par = (int)gridDim.x / csz;   // samples in flight
   for (int b = (int)blockIdx.x / csz; b < B; b += nsamp_par) {
     const bool more = b + nsamp_par < B;
@@ -477,6 +493,10 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
 
       // ---- attention ----
       const DropCtx dca = make_drop(P.p_attn, seed, step, VITB200_SITE_ATTN(l));
+      // bytes the peer pushes into this CTA per layer: its head's ctx columns of 128 rows (16 B each, two column groups)
+      // and the 16 ctx values of its head for the side row
+      if (csz == 2 && tid == 0) mbar_expect_tx(b_x, (ct ? 0u : 4096u) + (s_on ? 64u : 0u));
+      const uint32_t x_peer = csz == 2 ? mf_peer_addr(b_x, crank ^ 1u) : 0u;
       float cs_ = 0.f;   // side: attention output row (column = lane)
       if (is_side) {
         if (csz == 2) mf_cluster_wait();   // the peer has finished reading last layer's exchange buffers
@@ -550,7 +570,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           if (s0 && (lane >> 4) >= hd_lo && (lane >> 4) < hd_hi) {   // this CTA's head(s)
             reinterpret_cast<bf16*>(P.ctx)[((size_t)l * M + sgrow) * H + lane] = __float2bfloat16_rn(cs_);
             s_sc[32 + lane] = cs_;
-            if (csz == 2) mf_st_peer4(mf_peer_addr(&s_sc[32 + lane], crank ^ 1u), cs_);
+            if (csz == 2) mf_st_async4(mf_peer_addr(&s_sc[32 + lane], crank ^ 1u), cs_, x_peer);
           }
         }
       } else if (ct) {
@@ -647,14 +667,16 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           const uint4 pk = mg_pack8(o);
           uint8_t* dst = mg_chunk(sCtx, r, chunk);
           *reinterpret_cast<uint4*>(dst) = pk;
-          if (csz == 2) mf_st_peer16(mf_peer_addr(dst, crank ^ 1u), pk);
+          if (csz == 2) mf_st_async16(mf_peer_addr(dst, crank ^ 1u), pk, x_peer);
           if (valid && (chunk & 1) == 0) P.lse[(((size_t)l * B + b) * MG_NH + hd) * T + r] = mxh[hd] * scale + logf(sum);
         }
       }
       fence_proxy_async();
       tc_fence_before();
       if (tid == 0) tma_store_wait_read<0>();
-      if (csz == 2) { mf_cluster_sync(); fence_proxy_async(); } else __syncthreads();
+      if (csz == 2) { mbar_wait(b_x, ph_x); ph_x ^= 1; }   // the peer's pushes have landed
+      __syncthreads();                                     // (and this CTA's own writes)
+      if (csz == 2) fence_proxy_async();
       if (is_side && s_on) cs_ = s_sc[32 + lane];   // the full attention output row (both heads)
       if (l == 0) VB_TL(tl_mega_fwd, 7);
 
@@ -709,7 +731,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       tc_fence_before();
       if (tid == 0) tma_store_wait_read<0>();
       __syncthreads();
-      if (csz == 2) mf_cluster_arrive();   // hop 1 (and the ctx store) have consumed the exchange buffers
+      if (csz == 2) mf_cluster_arrive_relaxed();   // hop 1 (and the ctx store) have consumed the exchange buffers
       if (l == 0) VB_TL(tl_mega_fwd, 8);
 
       // ---- hop 2: MLP up + GELU (HF:296-299) ----
@@ -859,27 +881,25 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
 
   // ---- loss: CTA partials summed by the last CTA, in CTA order ----
   VB_TL(tl_mega_fwd, 11);
-  if (csz == 2) { mf_cluster_wait(); mf_cluster_sync(); }   // no CTA of a pair exits while its peer may still touch its shared memory
+  // no CTA of a pair exits while its peer may still touch its shared memory (nothing is published: relaxed arrive)
+  if (csz == 2) { mf_cluster_wait(); mf_cluster_arrive_relaxed(); mf_cluster_wait(); }
   float* loss_part = reinterpret_cast<float*>(reinterpret_cast<char*>(P.ws) + 256);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(P.ws);
   if (tid == MG_MAIN) loss_part[blockIdx.x] = loss_acc;   // lane 0 of side warp 0
-  if (tid == 0) tma_store_wait_all();
+  if (tid == 0) tma_store_wait_read<0>();                 // (shared memory may be released; the stores complete with the grid)
   tc_fence_before();
-  if (last_block_ticket(ticket, gridDim.x) && P.labels && warp == 0) {
+  // defer_loss: the backward kernel of the same step (vitb200_mega_bwd) sums the partials -- no fence / ticket here
+  if (!P.defer_loss && last_block_ticket(ticket, gridDim.x) && P.labels && warp == 0) {
     // fixed-order sum of the CTA partials: lane l adds partials l, l + 32, ... (all loads in flight at once), then a
     // shuffle tree -- the serial loop over 128 dependent L2 reads used to hold the next kernel back by ~4 us
-    float v[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) v[q] = (unsigned)(lane + 32 * q) < gridDim.x ? __ldcg(&loss_part[lane + 32 * q]) : 0.f;
-    float t = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const float t = mg_loss_sum(loss_part, gridDim.x, lane);
     if (lane == 0) {
-      t /= (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
-      P.loss[0] = t;
-      if (P.loss_log) P.loss_log[pos] = t;
+      const float v = t / (P.loss_kind == VITB200_LOSS_CE ? (float)B : (float)B * (float)C);
+      P.loss[0] = v;
+      if (P.loss_log) P.loss_log[pos] = v;
     }
   }
+  if (P.defer_loss) __syncthreads();   // (the ticket's barrier otherwise: TMEM is released after every warp is done with it)
   if (warp == 0) tmem_dealloc(tmem, MC_COLS);
   VB_TL(tl_mega_fwd, 12);
 }

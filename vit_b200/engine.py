@@ -264,7 +264,7 @@ class ViTEngine:
         """The next step reads rows[0 : B] (stream-ordered: rows_base <- the device step counter)."""
         self._rows["base"].copy_(self.rng[1:2])
 
-    def _mega_fwd_args(self, train: bool, with_labels: bool, slot: int = 0):
+    def _mega_fwd_args(self, train: bool, with_labels: bool, slot: int = 0, defer_loss: bool = False):
         c, lay, P_ = self.cfg, self.arena.layout, self._ptr
         x_in, lab_in = self.input_slot(slot)
         if not hasattr(self, "mega_ws"):
@@ -295,6 +295,7 @@ class ViTEngine:
             u=P_(self.u_all), u2=P_(self.u2_all), qkv=P_(self.qkv_all), ctx=P_(self.ctx_all), a=P_(self.a_all),
             m=P_(self.m_all), stats=P_(self.stats), lse=P_(self.lse_all), s_cls=P_(self.s_cls), logits=P_(self.logits),
             loss=P_(self.loss), ws=P_(self.mega_ws))
+        a.defer_loss = 1 if (defer_loss and with_labels) else 0   # the backward kernel of the step finishes the loss
         if slot == ROWS_SLOT:
             a.rows, a.rows_base = P_(self._rows["rows"]), P_(self._rows["base"])
             a.loss_log = P_(self._rows["loss_log"])
@@ -314,7 +315,7 @@ class ViTEngine:
         if slot != 0 and not (self.mega and self.mega_bwd):
             raise RuntimeError("vit_b200: input slots other than 0 exist for the whole-network programs only")
         if self.mega:
-            a = self._mega_fwd_args(train, with_labels, slot)
+            a = self._mega_fwd_args(train, with_labels, slot, defer_loss=bool(head_bwd and self.mega_bwd))
             prog = [(lib.vitb200_mega_fwd, (ctypes.addressof(a),))]
             if head_bwd and not self.mega_bwd:
                 self._alloc_backward()
@@ -497,7 +498,7 @@ class ViTEngine:
         gl = None if given else gloss_ptr
         if self.mega_bwd:
             # the whole backward is ONE launch: head, final LN, every layer, embeddings; one gradient set per sample
-            fa = self._mega_fwd_args(train, True, slot)
+            fa = self._mega_fwd_args(train, True, slot, defer_loss=bool(skip_head and not given))
             ba = _lib.MegaBwdArgs(f=fa, labels=lab_ptr, gloss=gl, loss_kind=kind, n_opt=lay.n_opt, gpart=gp,
                                   dz0=P_(self.dzA))
             if streamed:
