@@ -68,6 +68,32 @@ def test_forward_backward_vs_reference_golden(golden, name, precision):
         assert rel_err(out.logits, fix["bf16"]["logits"]) < tol
 
 
+def test_streamed_gradient_groups_equal_plain_tail(golden, monkeypatch):
+    """VITB200_STREAM=1 (the backward kernel signals every finished gradient group, the optimizer kernel's blocks start on
+    a group as soon as it is signalled) == the default tail that waits for the backward kernel: bit-identical losses,
+    weights and AdamW moments over 6 graph-replayed steps with dropout ON; the group counters are back at zero."""
+    from vit_b200.step import TrainStep
+
+    dev = _cuda()
+    fix = golden("baseline")
+    x, y = _inputs(fix, dev)
+    res = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VITB200_STREAM", mode)
+        m = _build(fix, "bf16-mixed", dev).train()
+        step = TrainStep(m, fix["batch"], use_graph=True, train=True)
+        losses = [float(step.step(x, y)) for _ in range(6)]
+        if mode == "1":
+            assert hasattr(step.eng, "grad_done") and int(step.eng.grad_done.abs().sum()) == 0
+        else:
+            assert not hasattr(step.eng, "grad_done")
+        res.append((losses, m._arena.data.clone(), step.eng.exp_avg.clone(), step.eng.exp_avg_sq.clone()))
+        step.close()
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
 @pytest.mark.parametrize("name", ["baseline", "learned", "cls"])
 def test_train_steps_vs_reference_golden(golden, name, precision):

@@ -70,4 +70,6 @@ for key, labels in names.items():
         for a_, b_, what in ((5, 16, "dctx: tid0 waits done"), (5, 17, "dctx: CTA barrier"), (5, 6, "dctx: cluster arrive"),
                              (8, 14, "attn: after MMA issue"), (8, 15, "attn: after mma wait"), (8, 9, "attn: TMA issued"),
                              (9, 18, "epi: cluster wait"), (9, 19, "epi: pieces written"), (9, 10, "epi: cluster sync")):
-            print(f"      stamp {a_} -> {b_}  {what:<26} mean {(full[:, b_] - full[:, a_]).mean():8.0f}")
+            dd = full[:, b_] - full[:, a_]
+            print(f"      stamp {a_} -> {b_}  {what:<26} mean {dd.mean():8.0f}  even CTAs {dd[0::2].mean():8.0f}  odd CTAs {dd[1::2].mean():8.0f}"
+                  f"  min {dd.min()} max {dd.max()}")

@@ -1086,7 +1086,9 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
         });
       }
       __syncthreads();   // staging (R3) is read: the next layer's ddelta / da tiles go there
-      if (tid == 0 && PA.done) {   // group 1 + l = layer l; group 1 + L = final LayerNorm + head (written first of all)
+      // (signalled by a side thread: the release is a MEMBAR.ALL.GPU, ~2 k cycles that thread 0 -- the TMA / MMA issuer --
+      //  must not spend here)
+      if (tid == MG_MAIN + 96 && PA.done) {   // group 1 + l = layer l; group 1 + L = final LayerNorm + head (written first of all)
         if (l == L - 1) mb_signal(PA.done, 1 + L);
         mb_signal(PA.done, 1 + l);
       }
@@ -1202,7 +1204,7 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
   VB_TL(tl_mega_bwd, 13);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0 && PA.done) mb_signal(PA.done, 0);   // group 0 = embeddings (cls, positions, patch projection)
+  if (tid == MG_MAIN + 96 && PA.done) mb_signal(PA.done, 0);   // group 0 = embeddings (cls, positions, patch projection)
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

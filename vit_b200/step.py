@@ -58,8 +58,11 @@ class TrainStep:
     def _launch(self, slot: int = 0) -> None:
         eng = self.eng
         eng.cls_only = True   # a training step reads the loss only: the last layer runs for the CLS row alone
-        # the optimizer kernel consumes each layer's gradient partials as soon as the backward kernel signals them
-        sg = bool(eng.mega_bwd and os.environ.get("VITB200_STREAM", "1") != "0")
+        # VITB200_STREAM=1: the optimizer kernel consumes each layer's gradient partials as soon as the backward kernel
+        # signals them (bucketed overlap).  Off by default: measured neutral at 1 and 2 GPUs (the blocks that own the last
+        # groups still pay the full reduce -> exchange -> barrier chain after the backward kernel, and every signal is a
+        # MEMBAR.ALL.GPU inside the backward kernel), see DESIGN.md section 5.
+        sg = bool(eng.mega_bwd and os.environ.get("VITB200_STREAM", "0") == "1")
         if slot != 0:
             eng.forward(train=self.train, with_labels=True, head_bwd=True, slot=slot)
             eng.backward(train=self.train, skip_reduce=True, skip_head=True, slot=slot, streamed=sg)
