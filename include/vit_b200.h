@@ -451,13 +451,15 @@ int vitb200_clip_adamw_fused_streamed(float* p, float* g, float* m, float* v, vo
 
 /* Data-parallel optimizer tail: the DDP gradient all-reduce (implicit in the reference: strategy='ddp',
  * src/hardware_utils.py:86-95) is fused INTO the kernel.  Each rank owns one exchange buffer
- * (vitb200_peer_buffer_bytes(n) bytes: flags + two gradient copies, double-buffered by launch parity) allocated with
- * vitb200_peer_alloc, which also returns a 64-byte CUDA IPC handle; the ranks of one node exchange handles (host side)
+ * (vitb200_peer_buffer_bytes(n) bytes: two launch parities x 8 source ranks x n slots of {value, launch tag}) allocated
+ * with vitb200_peer_alloc, which also returns a 64-byte CUDA IPC handle; the ranks of one node exchange handles (host side)
  * and map each other's buffers with vitb200_peer_open (NVLink / NVSwitch peer access).  peer_bufs is a DEVICE array of
- * `world` pointers in rank order (entry `rank` = the local buffer).  Per launch: publish the locally reduced gradient,
- * raise this rank's flag in every rank's buffer, wait for all flags, sum the ranks' gradients in rank order (bit-identical
- * on every rank), then norm -> clip -> AdamW as vitb200_clip_adamw_fused.  Every rank must launch it the same number of
- * times.  grad_scale (hyper[6]) carries the 1/world mean. */
+ * `world` (2 .. 8) pointers in rank order (entry `rank` = the local buffer).  Per launch: every locally reduced gradient
+ * element is PUSHED, tagged with the launch number, into every rank's buffer with one 8-byte store (value and tag travel
+ * together: no flag, no fence, no acknowledgement); each rank polls its own buffer until all ranks' tags of an element
+ * match and sums the values in rank order (bit-identical on every rank), then norm -> clip -> AdamW as
+ * vitb200_clip_adamw_fused.  Every rank must launch it the same number of times.  grad_scale (hyper[6]) carries the
+ * 1/world mean. */
 size_t vitb200_peer_buffer_bytes(size_t n);
 int vitb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int vitb200_peer_open(const unsigned char* handle64, void** ptr);

@@ -27,12 +27,12 @@ for _ in range(50):
     step.step(x, y)
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (ctypes.c_longlong * (16 * 512))()
+buf = (ctypes.c_longlong * (32 * 512))()
 assert lib.vitb200_tl_tail(buf) == 0
-a = np.frombuffer(buf, dtype=np.int64).reshape(512, 16)
+a = np.frombuffer(buf, dtype=np.int64).reshape(512, 32)
 a = a[a[:, 0] != 0]
-order = [0, 1, 6, 7, 8, 2, 3, 4, 5]
-labels = ["pdl_wait", "slot reduce + publish", "fence.sys + sync", "flag store + wait for all ranks", "peer loads + sum",
+order = [0, 1, 6, 8, 2, 3, 4, 5]
+labels = ["pdl_wait", "slot reduce + push to every rank", "poll own buffer + sum in rank order",
           "block sum + ticket + wait", "norm/coef", "AdamW"]
 t = a[:, order]
 d = np.diff(t, axis=1)

@@ -100,8 +100,13 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // Each thread keeps its (<= TAIL_KEEP) reduced gradient vectors in registers across the barrier.
 // ------------------------------------------------------------------------------------------------
 // ---- peer (NVLink) exchange buffer of the data-parallel optimizer tail ------------------------------------------
-// layout: [16 KB header: uint32 flags[world][148 blocks]] [parity 0: xfloats fp32] [parity 1: xfloats fp32]
-constexpr size_t PEER_HEADER = 16384;   // >= 4 * world * 148 for world <= 27
+// layout: [16 KB header (unused words kept for alignment)] [parity 0: world_max x n slots] [parity 1: ...]; a slot is
+// 8 bytes {gradient value bits, launch tag}.  Rank r PUSHES every reduced gradient element, tagged with the launch number,
+// into slot [parity][r][i] of EVERY rank's buffer with ONE 8-byte store (value and tag travel together, so no flag, no
+// release fence, no acknowledgement round trip -- the "LL" idea of NCCL); a rank polls its OWN buffer until the tags of
+// all ranks' slots of an element equal the launch number and sums the values in rank order.
+constexpr size_t PEER_HEADER = 16384;
+constexpr int PEER_MAX_WORLD = 8;   // one NVLink / NVSwitch node
 // streamed gradient groups (vitb200_grad_stream): counters raised by the backward kernel, arena ranges in float4 units
 struct GradStream {
   unsigned int* done;
@@ -120,21 +125,15 @@ struct PeerX {
   int rank, world;     // world <= 1: no exchange
   size_t xfloats;
 };
-__device__ __forceinline__ unsigned int* peer_flags(void* buf) { return reinterpret_cast<unsigned int*>(buf); }
-__device__ __forceinline__ float* peer_data(void* buf, unsigned int parity, size_t xfloats) {
-  return reinterpret_cast<float*>(reinterpret_cast<char*>(buf) + PEER_HEADER) + (size_t)parity * xfloats;
+__device__ __forceinline__ uint2* peer_slots(void* buf, unsigned int parity, int src, size_t xfloats) {
+  return reinterpret_cast<uint2*>(reinterpret_cast<char*>(buf) + PEER_HEADER) + ((size_t)parity * PEER_MAX_WORLD + src) * xfloats;
 }
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_v2(uint2* p, uint32_t a, uint32_t b) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_relaxed_sys_v2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 VB_TL_DECL(tl_tail)
@@ -173,7 +172,6 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   const size_t e0 = (size_t)blockIdx.x * epb + (threadIdx.x >> 2);
   float keep[TAIL_KEEP];
   float acc = 0.f;
-  float* mine = X.world > 1 ? peer_data(X.bufs[X.rank], seq & 1u, X.xfloats) : nullptr;
   if (GS.n > 0) {
     // wait for the gradient groups this block's elements belong to (one pass: a contiguous slice; several passes: all)
     if (threadIdx.x == 0) {
@@ -227,8 +225,10 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     } else {
       gj = g[4 * e + lane4];
     }
-    if (X.world > 1) {   // data parallel: publish the local gradient, the sum over ranks is formed below
-      mine[4 * e + lane4] = gj;
+    if (X.world > 1) {   // data parallel: push the local gradient element to every rank (own buffer included)
+      const size_t i = 4 * e + lane4;
+      for (int q = 0; q < X.world; ++q)
+        st_relaxed_sys_v2(peer_slots(X.bufs[q], seq & 1u, X.rank, X.xfloats) + i, __float_as_uint(gj), seq);
       continue;
     }
     g[4 * e + lane4] = gj;   // the flat gradient arena stays the public result (p.grad views, tests)
@@ -237,48 +237,42 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   }
   if (X.world > 1) {
     // ---- gradient all-reduce over NVLink peer memory, fused into this kernel (no NCCL launch on the step's critical
-    // path).  Block b handles the same elements on every rank, so the exchange is block-to-block: 1. block b fences its
-    // slice of the published gradient and raises flag [rank][b] (= seq) in EVERY rank's buffer; 2. it waits until the
-    // flags [q][b] of all ranks q in the local buffer reached seq; 3. each element is summed over the ranks' buffers in
-    // rank order -- every rank computes bit-identical sums, so the replicas cannot drift.  Buffers are double-buffered
-    // by launch parity: a rank can only overwrite parity p two launches later, after a full flag round in between
-    // proved that every peer finished reading it.
-    // Memory ordering: the block's gradient stores are ordered before the flag by bar.sync + st.release.sys (release is
-    // cumulative over what the releasing thread observed through the barrier); the consumer's ld.acquire.sys + bar.sync
-    // orders its peer loads after the flag.  No thread executes a stand-alone fence.sys: 40 k of them cost ~6 us each way.
+    // path).  Every element was pushed above as {value, launch tag} into slot [parity][rank][i] of every rank's buffer;
+    // here each thread polls the `world` slots of ITS element in the local buffer until all tags equal this launch and
+    // adds the values in rank order -- every rank computes bit-identical sums, so the replicas cannot drift.  No flag,
+    // no fence, no block barrier: an 8-byte store is a single transaction.  Buffers are double-buffered by launch
+    // parity: a rank overwrites parity p two launches later, after it received the peers' data of the launch in between,
+    // which they only sent after they had finished reading this one.
     VB_TL(tl_tail, 6);
-    __syncthreads();
-    VB_TL(tl_tail, 7);
-    if (threadIdx.x < X.world)
-      st_release_sys(peer_flags(X.bufs[threadIdx.x]) + (size_t)X.rank * TAIL_MAX_BLOCKS + blockIdx.x, seq);
-    if (threadIdx.x < X.world) {
-      const unsigned int* f = peer_flags(X.bufs[X.rank]) + (size_t)threadIdx.x * TAIL_MAX_BLOCKS + blockIdx.x;
+    k = 0;
+    for (size_t e = e0; e < n4; e += estride, ++k) {
+      const size_t i = 4 * e + lane4;
+      const uint2* slot = peer_slots(X.bufs[X.rank], seq & 1u, 0, X.xfloats) + i;
+      uint2 t[PEER_MAX_WORLD];
       unsigned int spins = 0;
-      while ((int)(ld_acquire_sys(f) - seq) < 0) {
+      bool all = false;
+      while (!all) {
+        all = true;
+#pragma unroll
+        for (int q = 0; q < PEER_MAX_WORLD; ++q)
+          if (q < X.world) t[q] = ld_relaxed_sys_v2(slot + (size_t)q * X.xfloats);
+#pragma unroll
+        for (int q = 0; q < PEER_MAX_WORLD; ++q)
+          if (q < X.world && t[q].y != seq) all = false;
         // a peer that never arrives (crashed rank) must not hang the device, and must not poison the context of the
         // surviving ranks either: give up after ~minutes, record the failure in state[7] (the host checks it,
         // PeerExchange.check()) and carry on with whatever the buffer holds
-        if (++spins > (1u << 30)) { state[7] = 1.f; break; }
+        if (!all && ++spins > (1u << 28)) { state[7] = 1.f; break; }
       }
-    }
-    __syncthreads();
-    VB_TL(tl_tail, 8);
-    k = 0;
-    for (size_t e = e0; e < n4; e += estride, ++k) {
-      // all peer loads of an element are issued before the first add: one NVLink round trip per 8 ranks, not one per rank
       float s = 0.f;
-      for (int q0 = 0; q0 < X.world; q0 += 8) {
-        float t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          t[u] = q0 + u < X.world ? ld_relaxed_sys_f32(peer_data(X.bufs[q0 + u], seq & 1u, X.xfloats) + 4 * e + lane4) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += t[u];   // rank order (absent ranks add +0)
-      }
-      g[4 * e + lane4] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
+      for (int q = 0; q < PEER_MAX_WORLD; ++q)
+        if (q < X.world) s += __uint_as_float(t[q].x);   // rank order
+      g[i] = s;   // summed gradient (the 1/world mean is hyper[6] = grad_scale)
       if (k < TAIL_KEEP) keep[k] = s;
       acc = fmaf(s, s, acc);
     }
+    VB_TL(tl_tail, 8);
   }
   VB_TL(tl_tail, 2);
   acc = warp_sum(acc);
@@ -467,7 +461,7 @@ extern "C" int vitb200_clip_adamw_fused_streamed(float* p, float* g, float* m, f
                                                  void* const* peer_bufs, int rank, int world, void* stream) {
   if (!p || !g || !m || !v || !hyper || !state || !ws || !gs || !gs->done) return VITB200_ERR_ARG;
   if (gs->n_groups < 1 || gs->n_groups > VITB200_MAX_GROUPS || gs->expect == 0 || slots <= 0) return VITB200_ERR_ARG;
-  if (peer_bufs ? (world < 2 || world > 27 || rank < 0 || rank >= world) : (world != 1)) return VITB200_ERR_ARG;
+  if (peer_bufs ? (world < 2 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) : (world != 1)) return VITB200_ERR_ARG;
   if (n % 4 != 0) return VITB200_ERR_SHAPE;
   if (!gpart || (stride | red_start | red_end) % 4 != 0 || red_end < red_start || red_end > n) return VITB200_ERR_ARG;
   if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -495,7 +489,7 @@ extern "C" int vitb200_clip_adamw_fused_streamed(float* p, float* g, float* m, f
 }
 
 // ---- data-parallel variant: the gradient all-reduce runs inside the kernel over peer memory ---------------------
-extern "C" size_t vitb200_peer_buffer_bytes(size_t n) { return PEER_HEADER + 2 * n * sizeof(float); }
+extern "C" size_t vitb200_peer_buffer_bytes(size_t n) { return PEER_HEADER + 2 * (size_t)PEER_MAX_WORLD * n * sizeof(uint2); }
 
 extern "C" int vitb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
   if (!ptr || !handle64 || bytes == 0) return VITB200_ERR_ARG;
@@ -531,7 +525,7 @@ extern "C" int vitb200_clip_adamw_fused_dp(float* p, float* g, float* m, float* 
                                            size_t red_start, size_t red_end, void* ws, void* const* peer_bufs, int rank,
                                            int world, void* stream) {
   if (!p || !g || !m || !v || !hyper || !state || !ws || !peer_bufs) return VITB200_ERR_ARG;
-  if (world < 2 || world > 27 || rank < 0 || rank >= world) return VITB200_ERR_ARG;
+  if (world < 2 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return VITB200_ERR_ARG;
   if (n % 4 != 0) return VITB200_ERR_SHAPE;
   if (slots > 0 && (!gpart || (stride | red_start | red_end) % 4 != 0 || red_end < red_start || red_end > n)) return VITB200_ERR_ARG;
   if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |

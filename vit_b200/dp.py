@@ -89,6 +89,8 @@ class PeerExchange:
         self.lib = _lib.load()
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        if self.world > 8:    # the exchange buffers hold 8 source ranks (one NVLink / NVSwitch node)
+            raise PeerUnavailable("the in-kernel exchange covers up to 8 ranks of one node")
         nbytes = int(self.lib.vitb200_peer_buffer_bytes(n_floats))
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
