@@ -94,9 +94,9 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 // ------------------------------------------------------------------------------------------------
 // One-launch optimizer tail:  [sum of the per-CTA gradient partials] -> global L2 norm -> clip -> AdamW.
-// The norm is a grid-wide dependency; the grid is at most one CTA per SM (all co-resident), so a ticket counter in
-// global memory is a safe grid barrier: block b publishes its partial sum and takes a ticket; once all tickets of this
-// launch are in, every block reduces the partials in the same fixed order (deterministic, identical in all blocks).
+// The norm is a grid-wide dependency; the grid is at most one CTA per SM (all co-resident), so spinning on global memory
+// is a safe grid barrier: block b publishes {partial sum, launch number} in one 8-byte store, block 0 collects the slots
+// in a fixed order (deterministic) and publishes {norm, launch number} the same way, everybody else polls that slot.
 // Each thread keeps its (<= TAIL_KEEP) reduced gradient vectors in registers across the barrier.
 // ------------------------------------------------------------------------------------------------
 // ---- peer (NVLink) exchange buffer of the data-parallel optimizer tail ------------------------------------------
@@ -162,7 +162,6 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   if (GS.n == 0) pdl_wait();
   pdl_trigger();
   VB_TL(tl_tail, 1);
-  unsigned int* ticket = sync;
   // read BEFORE this block's ticket: block 0 rewrites them only after every block of this launch took its ticket
   const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): barrier / exchange tag
   const float step_prev = *(volatile float*)state;
@@ -289,32 +288,60 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
     const double* cur = reinterpret_cast<const double*>(sync + 16) + ((seq - 1u) & 1u) * 8;
     const double b1d = (double)hyper[1], b2d = (double)hyper[2];
     const double c0 = cur[0], c1 = cur[1], c2 = cur[2], c3 = cur[3], c4 = cur[4];
+    // Grid barrier without fences or atomics, two hops: block b publishes {partial sum, launch number} as ONE 8-byte
+    // store (the value arrives with its tag); block 0's first warp polls the slots of all blocks, sums them in a fixed
+    // order and publishes {sum of squares, launch number} the same way; every other block polls that single slot.  (All
+    // blocks polling all slots would put 20 k loads on ten cache lines; the fence + ticket form costs two MEMBAR.ALL.GPU
+    // and an atomic round trip on the critical path of every step.)
+    uint2* slots = reinterpret_cast<uint2*>(sync + 256);   // slots of the blocks at byte 1024 of the workspace; [148] = the total
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-      partial[blockIdx.x] = t;
-      __threadfence();
-      atomicAdd(ticket, 1u);
-      const unsigned int target = seq * gridDim.x;
-      unsigned int spins = 0;
-      while ((int)(*(volatile unsigned int*)ticket - target) < 0) {
-        if (++spins > (1u << 28)) __trap();   // a mis-sized grid traps instead of hanging the device
-      }
-      __threadfence();
+      partial[blockIdx.x] = t;   // (kept for inspection)
+      asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slots + blockIdx.x), "r"(__float_as_uint(t)), "r"(seq) : "memory");
     }
-    __syncwarp();
     VB_TL(tl_tail, 3);
-    // lane l sums partial[l], partial[l + 32], ... (loads issued together) then a fixed shuffle tree (deterministic)
-    float pv[5];
+    float totf;
+    if (blockIdx.x == 0) {
+      // lane l takes slots l, l + 32, ... (loads issued together), then a fixed shuffle tree (deterministic)
+      float pv[5];
+      unsigned int spins = 0;
+      bool all = false;
+      while (!all) {
+        all = true;
+        uint2 sv2[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) pv[q] = threadIdx.x + 32 * q < gridDim.x ? __ldcg(&partial[threadIdx.x + 32 * q]) : 0.f;
-    double tot = 0.0;
+        for (int q = 0; q < 5; ++q) {
+          sv2[q] = make_uint2(0u, seq);
+          if (threadIdx.x + 32 * q < gridDim.x)
+            asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(sv2[q].x), "=r"(sv2[q].y) : "l"(slots + threadIdx.x + 32 * q) : "memory");
+        }
 #pragma unroll
-    for (int q = 0; q < 5; ++q) tot += (double)pv[q];
+        for (int q = 0; q < 5; ++q) { pv[q] = __uint_as_float(sv2[q].x); if (sv2[q].y != seq) all = false; }
+        if (!all && ++spins > (1u << 28)) __trap();   // a mis-sized grid traps instead of hanging the device
+      }
+      double tot = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      for (int q = 0; q < 5; ++q) tot += (double)pv[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      totf = (float)sqrt(tot);
+      if (threadIdx.x == 0)
+        asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slots + TAIL_MAX_BLOCKS), "r"(__float_as_uint(totf)), "r"(seq) : "memory");
+    } else {
+      uint2 v = make_uint2(0u, 0u);
+      if (threadIdx.x == 0) {
+        unsigned int spins = 0;
+        for (;;) {
+          asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(slots + TAIL_MAX_BLOCKS) : "memory");
+          if (v.y == seq) break;
+          if (++spins > (1u << 28)) __trap();
+        }
+      }
+      totf = __uint_as_float(__shfl_sync(0xffffffffu, v.x, 0));
+    }
     if (threadIdx.x == 0) {
-      const float norm = (float)sqrt(tot) * fabsf(h_scale);
+      const float norm = totf * fabsf(h_scale);
       float coef = 1.f;
       if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
       const float step = step_prev + 1.f;
