@@ -349,7 +349,7 @@ def test_fit_device_matches_stepping_by_hand(precision):
 @pytest.mark.parametrize("task", ["reg", "cls"])
 def test_fit_device_rows_mode_equals_gather_mode(task, monkeypatch):
     """Device-resident dataset mode of the whole-network kernels (they pick the rows of the epoch permutation themselves,
-    steps replayed 4 per graph) == the gather-kernel path, bit for bit: per-step losses and final weights; dropout ON,
+    steps replayed 8 per graph) == the gather-kernel path, bit for bit: per-step losses and final weights; dropout ON,
     a remainder of single steps, max_steps, two epochs (fresh permutation uploaded between them)."""
     from vit_b200 import get_model
     from vit_b200.data import DeviceDataset
@@ -371,7 +371,7 @@ def test_fit_device_rows_mode_equals_gather_mode(task, monkeypatch):
         m = get_model(copy.deepcopy(cfg), precision="bf16-mixed", device=dev).train()
         st = TrainStep(m, B, use_graph=True, train=True)
         assert st.two_slots
-        got = st.fit_device(ds, epochs=2, shuffle=True, seed=9)          # 83 -> 11 steps per epoch = 2 x 4 + 3
+        got = st.fit_device(ds, epochs=2, shuffle=True, seed=9)          # 83 -> 11 steps per epoch = 8 + 3
         got += st.fit_device(ds, epochs=1, seed=9, start_epoch=2, max_steps=6)
         assert [g.numel() for g in got] == [11, 11, 6]
         assert (len(st._graph_rows) > 0) == (rows == "1")

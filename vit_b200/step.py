@@ -215,7 +215,7 @@ class TrainStep:
             import torch.distributed as dist
 
             rank = dist.get_rank(self.group)
-        unroll = max(1, int(os.environ.get("VITB200_UNROLL", "4")))
+        unroll = max(1, int(os.environ.get("VITB200_UNROLL", "8")))
         lab = dataset.labels if dataset.labels.dtype == eng.labels.dtype else dataset.labels.to(eng.labels.dtype)
         out, left = [], max_steps
         for ep in range(start_epoch, start_epoch + epochs):
