@@ -412,7 +412,8 @@ int vitb200_head_fused_fwd_bwd(const void* s, const void* w, const float* bias, 
  * Replaces Lightning's gradient_clip_val -> torch.nn.utils.clip_grad_norm_ (src/basemodule.py:244) and
  * torch.optim.AdamW.step (src/opt/optimizer.py:108) over ONE flat parameter arena.
  * hyper (DEVICE, 8 floats): {lr, beta1, beta2, eps, weight_decay, max_norm (<=0: no clipping), grad_scale, 0}
- * state (DEVICE, 8 floats): {step, grad_norm, clip_coef, bias_corr1, bias_corr2, 0, 0, 0}
+ * state (DEVICE, 8 floats): {step, grad_norm, clip_coef, bias_corr1, bias_corr2, extra squared norm (see
+ * vitb200_sumsq_accum), 0, peer time-out flag}
  * vitb200_grad_norm: grad_norm = ||grad_scale * g||_2, clip_coef = min(1, max_norm/(norm+1e-6)), step += 1.
  * vitb200_adamw: p, m, v updated in place with g * grad_scale * clip_coef; if shadow != NULL it receives
  * the bf16 copy of the new parameters (the GEMM operands of BF16 mode).  rng != NULL: rng[1] += 1. */
@@ -420,6 +421,12 @@ size_t vitb200_grad_norm_ws_bytes(size_t n);
 int vitb200_grad_norm(const float* g, size_t n, const float* hyper, float* state, void* ws, void* stream);
 int vitb200_adamw(float* p, const float* g, float* m, float* v, void* shadow, size_t n, const float* hyper,
                   const float* state, uint64_t* rng, void* stream);
+/* acc[0] += sum_i g[i]^2 (deterministic).  For parameters that live outside the flat arena (a trainable preprocessor
+ * matrix, src/models/layers.py:51-60): accumulate into state[5] before vitb200_clip_adamw_fused*, which adds it to the
+ * arena's squared norm -- torch's clip_grad_norm_ runs over ALL parameters (src/basemodule.py:244) -- and clears it;
+ * afterwards vitb200_adamw updates those parameters with the same clip coefficient and bias corrections (state[2..4]).
+ * ws: vitb200_grad_norm_ws_bytes(n) bytes, first 4096 zeroed once. */
+int vitb200_sumsq_accum(const float* g, size_t n, float* acc, void* ws, void* stream);
 /* vitb200_clip_adamw_fused: the whole optimizer tail in ONE launch (the configured model has 40 353 parameters: the
  * tail is three launch latencies, not bandwidth).  If slots > 0, the gradient of elements [red_start, red_end) is first
  * formed as a fixed-order sum of `slots` partial arenas (gpart + s*stride; the per-CTA partials of the fused backward

@@ -271,6 +271,64 @@ def test_trainable_preprocessor_with_torch_optimizer(golden, name, tmp_path):
         assert rel_err(m.state_dict()[k], v, 3e-3) < 2e-3, k
 
 
+@pytest.mark.parametrize("precision", ["32", "bf16-mixed"])
+def test_trainable_preprocessor_inside_the_graph_step(golden, precision, tmp_path):
+    """TrainStep with an UNFROZEN ZCA matrix (builder.py:168, the default freeze_epochs = 0): the captured step runs the
+    preprocessor GEMM, its pixel / weight / bias gradients, one clip over ALL parameters and AdamW on the matrix next to the
+    encoder's three launches.  3 steps vs the reference's: losses, total gradient norm, and in fp32 every post-step
+    tensor incl. the preprocessor matrix; bit-identical to running the same kernels eagerly; the AdamW moments of the
+    matrix travel through the .ckpt wire format."""
+    from vit_b200.checkpoint import load_lightning_checkpoint, save_lightning_checkpoint
+    from vit_b200.step import TrainStep
+
+    dev = _cuda()
+    fix = golden("pre_zca_r32")
+    x, y = _inputs(fix, dev)
+    tol = TOL[precision]
+    runs = []
+    for use_graph in (True, False):
+        m = _build_pre(fix, precision, dev, tmp_path)
+        assert not m.preprocessor.is_frozen
+        step = TrainStep(m, fix["batch"], use_graph=use_graph, train=False)
+        assert step._pre_tr is not None
+        losses = []
+        for i in range(3):
+            losses.append(float(step.step(x, y)))
+            if use_graph:
+                ref = float(fix["train3"]["losses"][i])
+                assert abs(losses[-1] - ref) < 5 * tol * max(1.0, abs(ref)), (i, losses[-1], ref)
+                assert rel_err(step.eng.state[1], fix["train3"]["grad_norms"][i]) < 20 * tol
+        runs.append((losses, {k: v.detach().clone() for k, v in m.state_dict().items()}))
+        if use_graph:
+            assert float(step.eng.state[5]) == 0.0                       # the extra squared norm was consumed
+            if precision == "32":
+                for k, v in fix["train3"]["state_dict"].items():
+                    assert rel_err(m.state_dict()[k], v, 3e-3) < 2e-3, k
+            moved = rel_err(m.state_dict()["preprocessor.linear.weight"], fix["state_dict"]["preprocessor.linear.weight"])
+            assert moved > 1e-5                                           # the matrix really was trained
+            # eval through the module's own forward sees the trained matrix (no stale bf16 operand copy)
+            with torch.no_grad():
+                a = m.eval()(x, labels=y).loss
+            assert torch.isfinite(a)
+            # the matrix's AdamW moments in the checkpoint, and back
+            ck = save_lightning_checkpoint(m, train_step=step)
+            names = [n for n, _ in m.named_parameters()]
+            iw = names.index("preprocessor.linear.weight")
+            assert rel_err(ck["optimizer_states"][0]["state"][iw]["exp_avg"], step._pre_tr.m_w) == 0.0
+            m2 = _build_pre(fix, precision, dev, tmp_path)
+            s2 = TrainStep(m2, fix["batch"], use_graph=True, train=False)
+            load_lightning_checkpoint(m2, ck, train_step=s2)
+            assert torch.equal(s2._pre_tr.m_w, step._pre_tr.m_w) and torch.equal(s2._pre_tr.v_w, step._pre_tr.v_w)
+            l4a, l4b = float(step.step(x, y)), float(s2.step(x, y))
+            assert abs(l4a - l4b) < 1e-6 * max(1.0, abs(l4a))
+            s2.close()
+            runs[-1] = (losses, runs[-1][1])
+        step.close()
+    assert runs[0][0] == runs[1][0]
+    for k, v in runs[0][1].items():
+        assert torch.equal(v, runs[1][1][k]), k
+
+
 # ------------------------------------------------------------------------------------------------
 # device-resident dataset hand-off
 # ------------------------------------------------------------------------------------------------

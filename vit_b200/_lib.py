@@ -157,6 +157,7 @@ SIGNATURES = {
     "vitb200_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "vitb200_peer_close": (_i, [_p]),
     "vitb200_peer_free": (_i, [_p]),
+    "vitb200_sumsq_accum": (_i, [_p, _sz, _p, _p, _p]),
     "vitb200_clip_adamw_fused_dp": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p, _i, _i, _p]),
     "vitb200_clip_adamw_fused_streamed": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _i, _sz, _sz, _sz, _p, _p, _p, _i, _i, _p]),
     "vitb200_cast_bf16": (_i, [_p, _p, _sz, _p]),

@@ -124,6 +124,9 @@ def load_lightning_checkpoint(model, ckpt, train_step=None, strict: bool = True)
             h["weight_decay"] = float(hyper["weight_decay"])
             eng.hyper[4] = h["weight_decay"]
         eng.refresh_shadow(force=True)
+        pre_tr = getattr(train_step, "_pre_tr", None)
+        if pre_tr is not None:      # a trainable preprocessor trained inside the step: its moments live next to the step
+            pre_tr.load_optimizer_state(extra)
         info.update(step=step, extra_optimizer_state=extra)
     return info
 
@@ -145,9 +148,11 @@ def save_lightning_checkpoint(model, path=None, train_step=None, epoch: int = 0,
         h = model._opt_hyper   # the python-side copies of the device scalars (exact, not fp32-rounded)
         step = int(float(eng.state[0]))
         names = [n for n, _ in model.named_parameters()]
+        pre_tr = getattr(train_step, "_pre_tr", None)
         ckpt["optimizer_states"] = [adam_state_to_torch(names, eng.arena.layout, eng.exp_avg, eng.exp_avg_sq, step,
                                                         lr=h["lr"], betas=tuple(h["betas"]), eps=h["eps"],
-                                                        weight_decay=h["weight_decay"])]
+                                                        weight_decay=h["weight_decay"],
+                                                        extra=None if pre_tr is None else pre_tr.optimizer_state(step))]
         if global_step is None:
             ckpt["global_step"] = step
     if path is not None:

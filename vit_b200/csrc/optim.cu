@@ -55,6 +55,36 @@ grad_norm_kernel(const float* __restrict__ g, size_t n4, const float* __restrict
   }
 }
 
+// acc[0] += sum g^2 (fixed-order, deterministic): the squared gradient norm of parameters that live OUTSIDE the arena
+// (a trainable preprocessor matrix), handed to the one-launch optimizer tail through state[5]
+__global__ void __launch_bounds__(OP_THREADS)
+sumsq_accum_kernel(const float* __restrict__ g, size_t n4, float* __restrict__ acc_out, float* __restrict__ partial,
+                   unsigned int* counter) {
+  __shared__ float red[OP_THREADS / 32];
+  pdl_wait();
+  pdl_trigger();
+  float acc = 0.f;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = (size_t)blockIdx.x * OP_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * OP_THREADS) {
+    float4 v = g4[i];
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < OP_THREADS / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+  if (!last_block_ticket(counter, gridDim.x)) return;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) tot += (double)__ldcg(&partial[b]);
+    acc_out[0] += (float)tot;
+  }
+}
+
 __global__ void __launch_bounds__(OP_THREADS)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ shadow, size_t n4, const float* __restrict__ hyper, const float* __restrict__ state,
@@ -165,6 +195,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   // read BEFORE this block's ticket: block 0 rewrites them only after every block of this launch took its ticket
   const unsigned int seq = *(volatile unsigned int*)(sync + 2) + 1u;   // launch number (same on every rank): barrier / exchange tag
   const float step_prev = *(volatile float*)state;
+  const float extra_sq = *(volatile float*)(state + 5);   // squared gradient norm of parameters outside the arena (vitb200_sumsq_accum)
   const int lane4 = threadIdx.x & 3;
   const size_t epb = blockDim.x >> 2;   // float4 elements per block pass
   const size_t estride = (size_t)gridDim.x * epb;
@@ -325,6 +356,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
       for (int q = 0; q < 5; ++q) tot += (double)pv[q];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      tot += (double)extra_sq;
       totf = (float)sqrt(tot);
       if (threadIdx.x == 0)
         asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slots + TAIL_MAX_BLOCKS), "r"(__float_as_uint(totf)), "r"(seq) : "memory");
@@ -365,6 +397,7 @@ clip_adamw_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
         state[2] = coef;
         state[3] = red[1];
         state[4] = red[2];
+        state[5] = 0.f;   // consumed
         if (rng) rng[1] += 1ull;
         sync[2] = seq;
         for (int gi = 0; gi < GS.n; ++gi) GS.done[gi] = 0u;   // every block is past its waits (grid barrier above)
@@ -426,6 +459,17 @@ extern "C" int vitb200_grad_norm(const float* g, size_t n, const float* hyper, f
   unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
   vb_launch_pdl(grad_norm_kernel, dim3(op_grid(n)), dim3(OP_THREADS), 0, (cudaStream_t)stream, g, n / 4, hyper, state, partial, counter);
+  VB_CHECK_LAUNCH();
+  return VITB200_OK;
+}
+
+extern "C" int vitb200_sumsq_accum(const float* g, size_t n, float* acc, void* ws, void* stream) {
+  if (!g || !acc || !ws) return VITB200_ERR_ARG;
+  if (n % 4 != 0) return VITB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return VITB200_ERR_ALIGN;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+  vb_launch_pdl(sumsq_accum_kernel, dim3(op_grid(n)), dim3(OP_THREADS), 0, (cudaStream_t)stream, g, n / 4, acc, partial, counter);
   VB_CHECK_LAUNCH();
   return VITB200_OK;
 }

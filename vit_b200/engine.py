@@ -742,13 +742,13 @@ class ViTEngine:
         self.dlogits.copy_(dlogits.reshape(self.dlogits.shape))
         self._run(key, lambda: None)
 
-    def pixel_grad(self, train: bool) -> torch.Tensor:
+    def pixel_grad(self, train: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """d loss / d pixel_values [B, L] (fp32) of the backward that just ran: the embedding kernels' input gradient,
         needed only when a trainable preprocessor (src/models/layers.py:51-60) produced the pixels.  Both backward
         programs leave d loss / d z0 in `dzA`; the dropout mask of the embedding site is regenerated from the same
         (seed, step)."""
         c = self.cfg
-        dx = torch.empty(self.B, c.image_size, dtype=torch.float32, device=self.device)
+        dx = out if out is not None else torch.empty(self.B, c.image_size, dtype=torch.float32, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
         ph = float(c.hidden_dropout_prob) if train else 0.0
         _lib.check(self.lib.vitb200_patch_embed_dgrad(

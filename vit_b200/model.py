@@ -493,33 +493,30 @@ class MyViT(nn.Module):
                 eng.labels.copy_(lab, non_blocking=True)  # copy_ casts to float like labels.view(-1).float()
 
     def _raw_buffer(self, eng: ViTEngine) -> torch.Tensor:
-        """Where RAW spectra go for `eng`: the pixel buffer itself, or -- with a (frozen) preprocessor in front -- a
-        [B, input_dim] staging buffer that `preprocessor.forward_into(raw, eng.x)` turns into pixels."""
+        """Where RAW spectra go for `eng`: the pixel buffer itself, or -- with a preprocessor in front -- a
+        [B, input_dim] staging buffer that the preprocessor kernels turn into pixels."""
         pre = self.preprocessor
         if pre is None:
             return eng.x
         if not hasattr(pre, "forward_into"):
             raise NotImplementedError(f"vit_b200: no kernel path for preprocessor {type(pre).__name__}")
-        if not pre.is_frozen:
-            raise NotImplementedError(
-                "vit_b200: TrainStep/EvalStep run a FROZEN preprocessor (warmup.freeze_epochs != 0 or "
-                "model.set_preprocessor_trainable(False)); train an unfrozen one through MyViT.forward / ViTLModule "
-                "with a torch optimizer (its matrix lives outside the fused parameter arena)")
         raw = eng.__dict__.get("x_raw")
         if raw is None:
             raw = eng.x_raw = torch.empty(eng.B, self.input_dim, dtype=torch.float32, device=eng.device)
         return raw
 
-    def _stage_raw(self, eng: ViTEngine, x: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
-        """RAW spectra -> [frozen preprocessor GEMM ->] the engine's pixel buffer (TrainStep / EvalStep, which drive the
-        engine without autograd).  A trainable preprocessor needs autograd through MyViT.forward instead."""
+    def _stage_raw(self, eng: ViTEngine, x: torch.Tensor, labels: Optional[torch.Tensor], run_pre: bool = True) -> None:
+        """RAW spectra -> [preprocessor kernel ->] the engine's pixel buffer (TrainStep / EvalStep, which drive the engine
+        without autograd).  run_pre=False: only stage the raw spectra (TrainStep with a TRAINABLE matrix runs the
+        preprocessor inside its captured step, next to its weight gradient and optimizer update)."""
         if self.preprocessor is None:
             return self._stage_inputs(eng, x, labels)
         raw = self._raw_buffer(eng)
         if x.dim() != 2 or x.shape[1] != self.input_dim:
             raise ValueError(f"expected spectra of shape [B, {self.input_dim}], got {tuple(x.shape)}")
         raw.copy_(x, non_blocking=True)
-        self.preprocessor.forward_into(raw, eng.x)
+        if run_pre:
+            self.preprocessor.forward_into(raw, eng.x)
         self._stage_labels(eng, labels)
 
     def _has_inner_hooks(self) -> bool:

@@ -20,6 +20,130 @@ from .engine import ROWS_SLOT
 from .model import MyViT
 
 
+class _PreTrainer:
+    """A TRAINABLE LinearPreprocessor (ZCA / PCA matrix as Parameters, src/models/layers.py:51-60, builder.py:168: the
+    default `freeze_epochs: 0`) inside the captured step.  Its matrix lives outside the flat arena, so the step gets four
+    more launches around the encoder's three: forward GEMM in front; pixel gradient (vitb200_patch_embed_dgrad) -> weight /
+    bias gradient (vitb200_linear_wgrad) -> their squared norm into state[5] (vitb200_sumsq_accum) behind the backward
+    kernel, so that the optimizer tail clips by the norm over ALL parameters like torch's clip_grad_norm_; and
+    vitb200_adamw on the matrix (+ its bf16 operand copy) and bias with the tail's clip coefficient and bias corrections."""
+
+    def __init__(self, model: MyViT, eng) -> None:
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.eng, self.lin = eng, model.preprocessor.linear
+        w, b = self.lin.weight, self.lin.bias
+        if w.dtype != torch.float32 or not w.is_contiguous() or w.data_ptr() % 16 or (b is not None and b.data_ptr() % 16):
+            raise ValueError("vit_b200: the trainable preprocessor matrix must be a contiguous, 16-byte aligned fp32 tensor")
+        N, K = w.shape
+        if N % 4 or K % 4 or N != eng.cfg.image_size:
+            raise ValueError("vit_b200: preprocessor dimensions must be multiples of 4 and match the model's image_size")
+        B, dev = eng.B, eng.device
+        self.N, self.K, self.bf = N, K, eng.dt == _lib.BF16
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.raw = model._raw_buffer(eng)
+        self.dx = torch.zeros(B, N, **f32)
+        self.gw, self.m_w, self.v_w = (torch.zeros(N, K, **f32) for _ in range(3))
+        self.gb = self.m_b = self.v_b = None
+        if b is not None:
+            self.gb, self.m_b, self.v_b = (torch.zeros(N, **f32) for _ in range(3))
+        self.x_op, self.dy_op, self.w16, self.y16 = self.raw, self.dx, None, None
+        if self.bf:
+            self.x_op = torch.zeros(B, K, dtype=torch.bfloat16, device=dev)
+            self.dy_op = torch.zeros(B, N, dtype=torch.bfloat16, device=dev)
+            self.w16 = torch.zeros(N, K, dtype=torch.bfloat16, device=dev)
+            self.y16 = torch.zeros(B, N, dtype=torch.bfloat16, device=dev)
+            self.refresh_operand()
+        need = max(int(self.lib.vitb200_linear_wgrad_ws_bytes(B, N, K)) + 4096, int(self.lib.vitb200_grad_norm_ws_bytes(N * K)))
+        self.ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        self.ws_sq = torch.zeros(int(self.lib.vitb200_grad_norm_ws_bytes(N * K)), dtype=torch.uint8, device=dev)
+        self.ws_fwd = None
+        if self.bf and N % 8 == 0 and K % 8 == 0:
+            self.ws_fwd = torch.zeros(int(self.lib.vitb200_tc_prelinear_ws_bytes(B, N, K)), dtype=torch.uint8, device=dev)
+
+    def _st(self) -> int:
+        return torch.cuda.current_stream(self.eng.device).cuda_stream
+
+    def refresh_operand(self) -> None:
+        """bf16 GEMM operand <- the fp32 matrix (after load_state_dict / a restore)."""
+        if self.bf:
+            from . import _lib
+            _lib.check(self.lib.vitb200_cast_bf16(self.lin.weight.data_ptr(), self.w16.data_ptr(), self.N * self.K, self._st()), "cast_bf16")
+
+    def forward(self) -> None:
+        from . import _lib
+        from ._lib import ACT_NONE, BF16, F32
+
+        lib, e, st = self.lib, self.eng, self._st()
+        B, N, K = e.B, self.N, self.K
+        bptr = None if self.lin.bias is None else self.lin.bias.data_ptr()
+        if not self.bf:
+            _lib.check(lib.vitb200_linear_fwd(self.raw.data_ptr(), self.lin.weight.data_ptr(), bptr, e.x.data_ptr(), None, B, N, K,
+                                              ACT_NONE, F32, st), "preprocessor linear_fwd")
+            return
+        _lib.check(lib.vitb200_cast_bf16(self.raw.data_ptr(), self.x_op.data_ptr(), B * K, st), "cast_bf16")
+        if self.ws_fwd is not None:
+            _lib.check(lib.vitb200_tc_prelinear_fwd(self.x_op.data_ptr(), self.w16.data_ptr(), bptr, e.x.data_ptr(), B, N, K,
+                                                    self.ws_fwd.data_ptr(), st), "preprocessor prelinear_fwd")
+        else:
+            _lib.check(lib.vitb200_linear_fwd(self.x_op.data_ptr(), self.w16.data_ptr(), bptr, self.y16.data_ptr(), None, B, N, K,
+                                              ACT_NONE, BF16, st), "preprocessor linear_fwd")
+            _lib.check(lib.vitb200_cast_f32(self.y16.data_ptr(), e.x.data_ptr(), B * N, st), "cast_f32")
+
+    def backward(self, train: bool) -> None:
+        """Behind the encoder's backward: pixel gradient -> dW, db -> state[5] += |dW|^2 + |db|^2."""
+        from . import _lib
+        from ._lib import BF16, F32
+
+        lib, e, st = self.lib, self.eng, self._st()
+        B, N, K = e.B, self.N, self.K
+        e.pixel_grad(train, out=self.dx)
+        if self.bf:
+            _lib.check(lib.vitb200_cast_bf16(self.dx.data_ptr(), self.dy_op.data_ptr(), B * N, st), "cast_bf16")
+        _lib.check(lib.vitb200_linear_wgrad(self.dy_op.data_ptr(), self.x_op.data_ptr(), self.gw.data_ptr(),
+                                            None if self.gb is None else self.gb.data_ptr(), B, N, K, 0, BF16 if self.bf else F32,
+                                            self.ws.data_ptr(), st), "preprocessor linear_wgrad")
+        acc = e.state.data_ptr() + 5 * 4
+        _lib.check(lib.vitb200_sumsq_accum(self.gw.data_ptr(), N * K, acc, self.ws_sq.data_ptr(), st), "sumsq")
+        if self.gb is not None:
+            _lib.check(lib.vitb200_sumsq_accum(self.gb.data_ptr(), N, acc, self.ws_sq.data_ptr(), st), "sumsq")
+
+    def update(self) -> None:
+        """Behind the optimizer tail (which left clip coefficient and bias corrections in `state`)."""
+        from . import _lib
+
+        lib, e, st = self.lib, self.eng, self._st()
+        _lib.check(lib.vitb200_adamw(self.lin.weight.data_ptr(), self.gw.data_ptr(), self.m_w.data_ptr(), self.v_w.data_ptr(),
+                                     None if self.w16 is None else self.w16.data_ptr(), self.N * self.K, e.hyper.data_ptr(),
+                                     e.state.data_ptr(), None, st), "preprocessor adamw")
+        if self.gb is not None:
+            _lib.check(lib.vitb200_adamw(self.lin.bias.data_ptr(), self.gb.data_ptr(), self.m_b.data_ptr(), self.v_b.data_ptr(),
+                                         None, self.N, e.hyper.data_ptr(), e.state.data_ptr(), None, st), "preprocessor adamw")
+
+    def tensors(self):
+        return [t for t in (self.lin.weight.data, None if self.lin.bias is None else self.lin.bias.data, self.m_w, self.v_w,
+                            self.m_b, self.v_b, self.w16) if t is not None]
+
+    def optimizer_state(self, step: int, prefix: str = "preprocessor.linear.") -> dict:
+        """torch.optim.AdamW per-parameter state of the matrix / bias, keyed by parameter name (checkpoint.py `extra`)."""
+        out = {}
+        if step > 0:
+            for name, m, v in (("weight", self.m_w, self.v_w), ("bias", self.m_b, self.v_b)):
+                if m is not None:
+                    out[prefix + name] = {"step": torch.tensor(float(step)), "exp_avg": m.detach().cpu().clone(),
+                                          "exp_avg_sq": v.detach().cpu().clone()}
+        return out
+
+    def load_optimizer_state(self, extra: dict, prefix: str = "preprocessor.linear.") -> None:
+        for name, m, v in (("weight", self.m_w, self.v_w), ("bias", self.m_b, self.v_b)):
+            st = extra.get(prefix + name)
+            if m is not None and st:
+                m.copy_(st["exp_avg"].reshape(m.shape))
+                v.copy_(st["exp_avg_sq"].reshape(v.shape))
+        self.refresh_operand()
+
+
 class TrainStep:
     def __init__(self, model: MyViT, batch_size: int, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, grad_clip: float = 0.5, use_graph: bool = True, process_group=None,
@@ -42,6 +166,19 @@ class TrainStep:
                     self.eng.peer = None    # collective decision (all ranks): NCCL all-reduce of the gradient arena
         self.noise_level = float(noise_level)
         self.use_graph = use_graph
+        # a trainable (unfrozen) ZCA / PCA matrix in front of the encoder: trained inside the captured step (_PreTrainer)
+        self._pre_tr: Optional[_PreTrainer] = None
+        pre = model.preprocessor
+        if pre is not None and not getattr(pre, "is_frozen", True):
+            from .preprocessor import LinearPreprocessor
+            if not isinstance(pre, LinearPreprocessor):
+                raise NotImplementedError(
+                    f"vit_b200: TrainStep trains a LinearPreprocessor (ZCA / PCA) in its graph; train a {type(pre).__name__} "
+                    "through MyViT.forward / ViTLModule with a torch optimizer, or freeze it")
+            if self.world > 1:
+                raise NotImplementedError("vit_b200: a trainable preprocessor inside TrainStep is single-GPU (its gradient is "
+                                          "not part of the in-kernel exchange); freeze it or use ViTLModule under DDP")
+            self._pre_tr = _PreTrainer(model, self.eng)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_slot: dict = {}    # slot -> the same step on input slot 1 .. 3 (fit_host pipeline)
         self._graph_group: dict = {}   # (slots) -> one graph of consecutive steps on those slots (fit_host pipeline)
@@ -54,10 +191,34 @@ class TrainStep:
         self.h_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
         self._segments = None
 
+    def _check_pre(self) -> None:
+        """The captured step either trains the preprocessor matrix or treats it as constant -- decided at construction."""
+        pre = self.model.preprocessor
+        if pre is None:
+            return
+        frozen = bool(getattr(pre, "is_frozen", True))
+        if self._pre_tr is None and not frozen:
+            raise NotImplementedError(
+                "vit_b200: this TrainStep was built around a FROZEN preprocessor and its captured step does not train the "
+                "matrix; build a new TrainStep after model.set_preprocessor_trainable(True)")
+        if self._pre_tr is not None and frozen:
+            raise NotImplementedError(
+                "vit_b200: this TrainStep was built to train the preprocessor matrix, which has been frozen since; build a "
+                "new TrainStep")
+
     # ---- one step's kernel sequence (also what gets captured) ---------------------------------
     def _launch(self, slot: int = 0) -> None:
         eng = self.eng
         eng.cls_only = True   # a training step reads the loss only: the last layer runs for the CLS row alone
+        if self._pre_tr is not None:   # trainable preprocessor: 4 more launches around the encoder's (see _PreTrainer)
+            fh = eng.can_fuse_head
+            self._pre_tr.forward()
+            eng.forward(train=self.train, with_labels=True, head_bwd=fh)
+            eng.backward(train=self.train, skip_reduce=True, skip_head=fh)
+            self._pre_tr.backward(self.train)
+            eng.optimizer_step(fused_reduce=True)
+            self._pre_tr.update()
+            return
         # VITB200_STREAM=1: the optimizer kernel consumes each layer's gradient partials as soon as the backward kernel
         # signals them (bucketed overlap).  Off by default: measured neutral at 1 and 2 GPUs (the blocks that own the last
         # groups still pay the full reduce -> exchange -> barrier chain after the backward kernel, and every signal is a
@@ -124,12 +285,14 @@ class TrainStep:
         e = self.eng
         e._ensure_opt_state()
         return [t.clone() for t in (e.arena.data, e.exp_avg, e.exp_avg_sq, e.state, e.rng)] + \
-               ([e.arena.shadow.clone()] if e.arena.shadow is not None else [])
+               ([e.arena.shadow.clone()] if e.arena.shadow is not None else []) + \
+               ([t.clone() for t in self._pre_tr.tensors()] if self._pre_tr is not None else [])
 
     def _restore(self, snap) -> None:
         e = self.eng
         dst = [e.arena.data, e.exp_avg, e.exp_avg_sq, e.state, e.rng] + \
-              ([e.arena.shadow] if e.arena.shadow is not None else [])
+              ([e.arena.shadow] if e.arena.shadow is not None else []) + \
+              (self._pre_tr.tensors() if self._pre_tr is not None else [])
         for d, s in zip(dst, snap):
             d.copy_(s)
         e.arena.mark_shadow_fresh()
@@ -184,11 +347,14 @@ class TrainStep:
         """flux [B, L] and labels on the device (or pinned host): runs one full training step and returns the
         loss as a 0-dim device tensor (no host sync)."""
         eng = self.eng
+        self._check_pre()
         if self.noise_level > 0 and error is not None:  # src/vit.py:86-88
             flux = flux.to(eng.device, non_blocking=True)
             flux = flux + torch.randn_like(flux) * error.to(eng.device, non_blocking=True) * self.noise_level
-        self.model._stage_raw(eng, flux, labels)
+        self.model._stage_raw(eng, flux, labels, run_pre=self._pre_tr is None)
         self._run_staged()
+        if self._pre_tr is not None:   # the matrix was rewritten through its raw pointer: drop cached operand copies
+            self._pre_tr.lin.__dict__.pop("_w16", None)
         return eng.loss[0]
 
     def _run_staged(self) -> None:
@@ -259,6 +425,7 @@ class TrainStep:
         from .data import epoch_indices
 
         eng, model = self.eng, self.model
+        self._check_pre()
         if dataset.length != model.input_dim:
             raise ValueError(f"dataset spectra have {dataset.length} pixels, the model expects {model.input_dim}")
         if dataset.labels is None:
@@ -285,7 +452,7 @@ class TrainStep:
             losses = torch.empty(nb, dtype=torch.float32, device=eng.device)
             for i in range(nb):
                 dataset.gather(order[i * B:(i + 1) * B], x_dst, eng.labels, noise_level=self.noise_level, rng=eng.rng)
-                if pre is not None:
+                if pre is not None and self._pre_tr is None:
                     pre.forward_into(x_dst, eng.x)
                 self._run_staged()
                 losses[i:i + 1].copy_(eng.loss, non_blocking=True)
