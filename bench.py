@@ -844,7 +844,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_b,
                 "d2h_bytes_per_step": d2h_b, "ms_per_step": 1e3 * float(te[0]) / args.steps,
                 "api": "TrainStep.fit_host(iterable of host batches): per step H2D of the inputs from pinned memory into one of "
-                       "the engine's four input slots (copy stream, two steps ahead), steps run two per CUDA graph, the "
+                       "the engine's eight input slots (copy stream, one group of four steps ahead), steps run four per CUDA graph, the "
                        "forward kernel stores each step's loss into pinned host memory (read one group late)",
                 "blocking_step_host_samples_per_s": e2e_blocking},
         "gpu_launches": launches_per_step * args.steps,

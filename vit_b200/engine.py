@@ -21,7 +21,7 @@ from ._lib import ACT_GELU, ACT_NONE, BF16, F32, SITE_EMB, site_attn, site_mlp, 
 from .arena import ParamArena
 
 ROWS_SLOT = 99   # input slot of the device-resident dataset mode (ViTEngine.bind_rows)
-HOST_SLOTS = 4   # regular input slots 0 .. 3 (TrainStep.fit_host: two groups of two steps)
+HOST_SLOTS = 8   # regular input slots 0 .. 7 (TrainStep.fit_host: two groups of four steps)
 
 
 def _normalize_precision(precision) -> str:

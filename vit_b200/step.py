@@ -575,10 +575,10 @@ class TrainStep:
         return losses
 
     def _fit_host_grouped(self, batches, on_loss=None) -> list:
-        """fit_host for the whole-network programs: the engine has four input slots = two groups of G = 2.  The G batches of
+        """fit_host for the whole-network programs: the engine has eight input slots = two groups of G = 4.  The G batches of
         group k + 1 are uploaded (copy stream, straight into the engine's slots) while the G steps of group k run as ONE
-        graph (6 kernels chained by programmatic dependent launch -- no graph boundary, no event wait between the two
-        steps); every step's loss is stored by the forward kernel itself into pinned host memory and read by the host
+        graph (3 G kernels chained by programmatic dependent launch -- no graph boundary, no event wait between the
+        steps of a group); every step's loss is stored by the forward kernel itself into pinned host memory and read by the host
         after the next group has been enqueued.  A tail of fewer than G batches runs per-slot graphs."""
         from .engine import HOST_SLOTS
 
