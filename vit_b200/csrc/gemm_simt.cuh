@@ -91,23 +91,43 @@ struct AccUnfoldMN {
   }
 };
 
+// A tile moves global -> registers -> shared memory in two steps, so that the loads of tile k + 1 fly while tile k is
+// multiplied (the GEMMs of FP32 mode are small and latency-bound: without this every k-step paid a full L2 round trip).
 template <class Acc, int ROWS>
-__device__ __forceinline__ void fill_tile(float (*S)[ROWS + GPAD], const Acc& acc, int r0, int k0, int tid) {
-  if (Acc::kContigK) {
-    constexpr int N4 = ROWS * GBK / 4;
+struct TileRegs { float4 v[(ROWS * GBK / 4 + GNT - 1) / GNT]; };
+
+template <class Acc, int ROWS>
+__device__ __forceinline__ void load_tile(TileRegs<Acc, ROWS>& t, const Acc& acc, int r0, int k0, int tid) {
+  constexpr int N4 = ROWS * GBK / 4;
 #pragma unroll
-    for (int i = tid; i < N4; i += GNT) {
-      int r = i / (GBK / 4), kq = (i % (GBK / 4)) * 4;
-      float4 v = acc.ld4(r0 + r, k0 + kq);
-      S[kq + 0][r] = v.x; S[kq + 1][r] = v.y; S[kq + 2][r] = v.z; S[kq + 3][r] = v.w;
+  for (int j = 0; j < (N4 + GNT - 1) / GNT; ++j) {
+    const int i = tid + j * GNT;
+    if (i < N4) {
+      if (Acc::kContigK) {
+        const int r = i / (GBK / 4), kq = (i % (GBK / 4)) * 4;
+        t.v[j] = acc.ld4(r0 + r, k0 + kq);
+      } else {
+        const int kk = i / (ROWS / 4), rq = (i % (ROWS / 4)) * 4;
+        t.v[j] = acc.ld4(r0 + rq, k0 + kk);
+      }
     }
-  } else {
-    constexpr int N4 = ROWS * GBK / 4;
+  }
+}
+template <class Acc, int ROWS>
+__device__ __forceinline__ void store_tile(float (*S)[ROWS + GPAD], const TileRegs<Acc, ROWS>& t, int tid) {
+  constexpr int N4 = ROWS * GBK / 4;
 #pragma unroll
-    for (int i = tid; i < N4; i += GNT) {
-      int kk = i / (ROWS / 4), rq = (i % (ROWS / 4)) * 4;
-      float4 v = acc.ld4(r0 + rq, k0 + kk);
-      *reinterpret_cast<float4*>(&S[kk][rq]) = v;
+  for (int j = 0; j < (N4 + GNT - 1) / GNT; ++j) {
+    const int i = tid + j * GNT;
+    if (i < N4) {
+      const float4 v = t.v[j];
+      if (Acc::kContigK) {
+        const int r = i / (GBK / 4), kq = (i % (GBK / 4)) * 4;
+        S[kq + 0][r] = v.x; S[kq + 1][r] = v.y; S[kq + 2][r] = v.z; S[kq + 3][r] = v.w;
+      } else {
+        const int kk = i / (ROWS / 4), rq = (i % (ROWS / 4)) * 4;
+        *reinterpret_cast<float4*>(&S[kk][rq]) = v;
+      }
     }
   }
 }
@@ -129,11 +149,15 @@ __global__ void __launch_bounds__(GNT) gemm_simt_kernel(AAcc A, BAcc B, Epi epi,
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  // accessors zero-fill beyond K; a split's tail beyond ke is excluded because k_chunk % GBK == 0
+  TileRegs<AAcc, GBM> ta;
+  TileRegs<BAcc, BN> tb;
+  if (kb < ke) { load_tile<AAcc, GBM>(ta, A, m0, kb, tid); load_tile<BAcc, BN>(tb, B, n0, kb, tid); }
   for (int k0 = kb; k0 < ke; k0 += GBK) {
-    // accessors zero-fill beyond K; a split's tail beyond ke is excluded because k_chunk % GBK == 0
-    fill_tile<AAcc, GBM>(As, A, m0, k0, tid);
-    fill_tile<BAcc, BN>(Bs, B, n0, k0, tid);
+    store_tile<AAcc, GBM>(As, ta, tid);
+    store_tile<BAcc, BN>(Bs, tb, tid);
     __syncthreads();
+    if (k0 + GBK < ke) { load_tile<AAcc, GBM>(ta, A, m0, k0 + GBK, tid); load_tile<BAcc, BN>(tb, B, n0, k0 + GBK, tid); }
 #pragma unroll
     for (int kk = 0; kk < GBK; ++kk) {
       float a[TM], b[TN];
@@ -178,6 +202,13 @@ __global__ void __launch_bounds__(GNT) gemm_simt_kernel(AAcc A, BAcc B, Epi epi,
         const float* src = partial + (size_t)m * N + n;
         float sum = 0.f;
         unsigned int z = 0;
+        for (; z + 32 <= Z; z += 32) {   // 32 loads in flight, added in split order
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __ldcg(src + (size_t)(z + q) * MN);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) sum += v[q];
+        }
         for (; z + 8 <= Z; z += 8) {
           float v[8];
 #pragma unroll
