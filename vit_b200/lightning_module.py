@@ -81,8 +81,11 @@ class ViTLModule(_Base):
             err = preds - lab
             self.log(f"{prefix}_mae", err.abs().mean(), on_step=False, on_epoch=True)
             self.log(f"{prefix}_mse", (err * err).mean(), on_step=False, on_epoch=True)
-            ss_tot = ((lab - lab.mean()) ** 2).sum().clamp_min(1e-12)
-            self.log(f"{prefix}_r2", 1.0 - (err * err).sum() / ss_tot, on_step=False, on_epoch=True)
+            # torchmetrics.R2Score() (src/vit.py:72,120): R^2 per output column, uniformly averaged
+            e2, l2 = (err.reshape(len(err), -1), lab.reshape(len(lab), -1)) if err.dim() > 0 else (err.reshape(1, 1), lab.reshape(1, 1))
+            ss_res = (e2 * e2).sum(0)
+            ss_tot = ((l2 - l2.mean(0, keepdim=True)) ** 2).sum(0).clamp_min(1e-12)
+            self.log(f"{prefix}_r2", (1.0 - ss_res / ss_tot).mean(), on_step=False, on_epoch=True)
         self._last_outputs = outputs
         return loss
 
@@ -176,12 +179,17 @@ class ViTLModule(_Base):
             optimizer = FusedClipAdamW(self.model, lr=lr, weight_decay=wd, max_norm=0.0)
         else:
             fns = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD,
-                   "rmsprop": torch.optim.RMSprop, "adagrad": torch.optim.Adagrad}
+                   "rmsprop": torch.optim.RMSprop, "adadelta": torch.optim.Adadelta, "adagrad": torch.optim.Adagrad,
+                   "adamax": torch.optim.Adamax, "asgd": torch.optim.ASGD, "lbfgs": torch.optim.LBFGS,
+                   "rprop": torch.optim.Rprop, "sparseadam": torch.optim.SparseAdam}   # src/opt/optimizer.py:14-26
+            # (like the reference, every optimizer is built with lr + weight_decay: the ones whose constructor has no
+            #  weight_decay -- lbfgs, rprop, sparseadam -- raise TypeError there too)
             optimizer = fns[kind](self.model.parameters(), lr=lr, weight_decay=wd)
         if not sch:
             return optimizer
         S = torch.optim.lr_scheduler
-        table = {"cosine": S.CosineAnnealingLR, "cosineannealinglr": S.CosineAnnealingLR, "onecycle": S.OneCycleLR,
+        table = {"cosine": S.CosineAnnealingLR, "cosineannealing": S.CosineAnnealingLR, "cosineannealinglr": S.CosineAnnealingLR,
+                 "onecycle": S.OneCycleLR,
                  "constant": S.ConstantLR, "constantlr": S.ConstantLR, "plateau": S.ReduceLROnPlateau}
         if sch not in table:
             raise ValueError(f"Unknown scheduler: {sch}")
