@@ -69,6 +69,12 @@ for key, labels in names.items():
           f"= {d.sum(1).mean() / 1.965e3:.2f} us @1.965 GHz")
     for i, lab in enumerate(labels):
         print(f"   {lab:<24} mean {d[:, i].mean():8.0f}   max {d[:, i].max():8d}")
+    if key == "mega_fwd" and os.environ.get("VITB200_TL_EXTRA") == "1":   # main thread 0 vs side thread 0, relative to stamp 2
+        full = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)[live]
+        t0 = full[:, 2]
+        for nm, a_, b_ in (("layer top", 2, 18), ("attention work done", 27, 28), ("after exchange barrier", 7, 23),
+                           ("after hop 1", 8, 24), ("after hop 2", 9, 25), ("after hop 3", 10, 26)):
+            print(f"      {nm:<24} main +{(full[:, a_] - t0).mean():8.0f}   side +{(full[:, b_] - t0).mean():8.0f}")
     if key == "mega_bwd" and os.environ.get("VITB200_TL_EXTRA") == "1":   # finer stamps (debug): slot -> offset from stamp 5 / 8 / 9
         full = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)[live]
         for a_, b_, what in ((5, 16, "dctx: tid0 waits done"), (5, 17, "dctx: CTA barrier"), (5, 6, "dctx: cluster arrive"),

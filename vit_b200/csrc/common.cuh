@@ -53,6 +53,12 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
     const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                     \
     if (threadIdx.x == 0 && cta_ < VB_TL_CTAS) name[cta_ * VB_TL_SLOTS + (k)] = clock64();                    \
   } while (0)
+// the same stamp taken by thread `t` (e.g. the first thread of a side warp group)
+#define VB_TL_T(name, k, t)                                                                                   \
+  do {                                                                                                        \
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                     \
+    if (threadIdx.x == (t) && cta_ < VB_TL_CTAS) name[cta_ * VB_TL_SLOTS + (k)] = clock64();                  \
+  } while (0)
 #define VB_TL_EXPORT(fn, name)                                                                                \
   extern "C" int fn(long long* host) {                                                                        \
     return cudaMemcpyFromSymbol(host, name, sizeof(long long) * VB_TL_CTAS * VB_TL_SLOTS) == cudaSuccess ? 0 : -1; \
@@ -60,6 +66,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #else
 #define VB_TL_DECL(name)
 #define VB_TL(name, k) do { } while (0)
+#define VB_TL_T(name, k, t) do { } while (0)
 #define VB_TL_EXPORT(fn, name)
 #endif
 

@@ -761,6 +761,17 @@ mega_bwd_kernel(const __grid_constant__ MegaBwdMaps TM, const vitb200_mega_bwd_a
 #pragma unroll 1
         for (int ch = cg; ch < nch; ch += MG_CG) {
           const int c0 = ch * 16;
+          if (c0 == 128 && T - c0 == 1) {   // key 128 is the only live key of the last chunk: one element (its dS / P~ go to k128)
+            float s8[8], dp8[8], kpa[8];
+            tmem_ld_32x8(my_tmem + AB_S + c0, s8);
+            tmem_ld_32x8(my_tmem + AB_DP + c0, dp8);
+            drop8(dc_att, (drow + (uint64_t)c0) >> 3, kpa);
+            const float p = valid ? ex2_approx(fmaf(s8[0], sl2, -lse2)) : 0.f;
+            const float pk = p * kpa[0];
+            k128[r] = bf16_round(valid ? fmaf(dp8[0], pk, -p * Di) : 0.f);
+            k128[128 + r] = bf16_round(pk);
+            continue;
+          }
           float s[16], dp[16];
           tmem_ld_32x16(my_tmem + AB_S + c0, s);
           tmem_ld_32x16(my_tmem + AB_DP + c0, dp);

@@ -447,6 +447,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       if (tid == 0) tma_store_wait_read<0>();
       __syncthreads();
       if (l == 0) VB_TL(tl_mega_fwd, 2);
+      if (l == 0) VB_TL_T(tl_mega_fwd, 18, MG_MAIN);
       auto issue_scores = [&]() {   // thread 0: S[i, j] = q_i . k_j for this CTA's head(s)  (HF:232-249 / vit_with_rope.py:43-84)
         tc_fence_after();
         for (int hd = hd_lo; hd < hd_hi; ++hd) {
@@ -583,9 +584,15 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           // -- row maximum: this thread reads the 16-key chunks cg, cg + 4, cg + 8 of its query row --
           float mx = -INFINITY;
           for (int ch = cg; ch < nch; ch += MG_CG) {
-            float v[16];
-            tmem_ld_32x16(my_tmem + cS + ch * 16, v);
             const int c0 = ch * 16;
+            if (T - c0 == 1) {   // one live key in the last chunk (T = 16 n + 1: the patches + CLS): one element, not a masked chunk
+              float v8[8];
+              tmem_ld_32x8(my_tmem + cS + c0, v8);
+              mx = fmaxf(mx, v8[0]);
+              continue;
+            }
+            float v[16];
+            tmem_ld_32x16(my_tmem + cS + c0, v);
             if (c0 + 16 <= T) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
@@ -605,9 +612,22 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
           float sum = 0.f;
           const uint64_t drow = ((uint64_t)(b * MG_NH + hd) * T + (valid ? r : 0)) * (uint64_t)Tpad;
           for (int ch = cg; ch < nch; ch += MG_CG) {
-            float v[16];
-            tmem_ld_32x16(my_tmem + cS + ch * 16, v);
             const int c0 = ch * 16;
+            if (T - c0 == 1) {   // one live key in the last chunk: a single exponential and mask, zeros for the padding keys
+              float v8[8], kp[8];
+              tmem_ld_32x8(my_tmem + cS + c0, v8);
+              drop8(dca, (drow + (uint64_t)c0) >> 3, kp);
+              const float p = ex2_approx(fmaf(v8[0], sl2, nmxs));
+              sum += p;
+              v8[0] = p * kp[0];
+#pragma unroll
+              for (int q = 1; q < 8; ++q) v8[q] = 0.f;
+              *reinterpret_cast<uint4*>(mg_swz(sU, r, c0 >> 3)) = mg_pack8(v8);
+              *reinterpret_cast<uint4*>(mg_swz(sU, r, (c0 >> 3) + 1)) = make_uint4(0u, 0u, 0u, 0u);
+              continue;
+            }
+            float v[16];
+            tmem_ld_32x16(my_tmem + cS + c0, v);
             if (c0 + 16 <= T) {
 #pragma unroll
               for (int j = 0; j < 16; j += 8) {
@@ -674,11 +694,13 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       fence_proxy_async();
       tc_fence_before();
       if (tid == 0) tma_store_wait_read<0>();
+      if (l == 0) { VB_TL(tl_mega_fwd, 27); VB_TL_T(tl_mega_fwd, 28, MG_MAIN); }   // (debug: own work of the attention phase done)
       if (csz == 2) { mbar_wait(b_x, ph_x); ph_x ^= 1; }   // the peer's pushes have landed
       __syncthreads();                                     // (and this CTA's own writes)
       if (csz == 2) fence_proxy_async();
       if (is_side && s_on) cs_ = s_sc[32 + lane];   // the full attention output row (both heads)
       if (l == 0) VB_TL(tl_mega_fwd, 7);
+      if (l == 0) VB_TL_T(tl_mega_fwd, 23, MG_MAIN);
 
       // ---- hop 1: attention output projection + dropout + residual, LayerNorm-after (HF:262-268,337-340) ----
       if (tid == 0) {
@@ -733,6 +755,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       __syncthreads();
       if (csz == 2) mf_cluster_arrive_relaxed();   // hop 1 (and the ctx store) have consumed the exchange buffers
       if (l == 0) VB_TL(tl_mega_fwd, 8);
+      if (l == 0) VB_TL_T(tl_mega_fwd, 24, MG_MAIN);
 
       // ---- hop 2: MLP up + GELU (HF:296-299) ----
       if (tid == 0) {
@@ -787,6 +810,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
       if (tid == 0) tma_store_wait_read<0>();
       __syncthreads();
       if (l == 0) VB_TL(tl_mega_fwd, 9);
+      if (l == 0) VB_TL_T(tl_mega_fwd, 25, MG_MAIN);
 
       // ---- hop 3: MLP down + dropout + residual, then LN1 of the next layer / the final LN of the CLS row ----
       if (tid == 0) {
@@ -875,6 +899,7 @@ mega_fwd_kernel(const __grid_constant__ MegaFwdMaps TM, const vitb200_mega_fwd_a
         }
       }
       if (l == 0) VB_TL(tl_mega_fwd, 10);
+      if (l == 0) VB_TL_T(tl_mega_fwd, 26, MG_MAIN);
       ++it;   // (the barrier that closes hop 3 is the one at the top of the loop)
     }
   }
