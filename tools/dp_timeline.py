@@ -32,8 +32,8 @@ assert lib.vitb200_tl_tail(buf) == 0
 a = np.frombuffer(buf, dtype=np.int64).reshape(512, 32)
 a = a[a[:, 0] != 0]
 order = [0, 1, 6, 8, 2, 3, 4, 5]
-labels = ["pdl_wait", "slot reduce + push to every rank", "poll own buffer + sum in rank order",
-          "block sum + ticket + wait", "norm/coef", "AdamW"]
+labels = ["pdl_wait", "slot reduce + push to every rank", "poll own buffer + sum in rank order", "warp sums",
+          "publish block partial", "grid barrier (two hops) + norm / coef", "AdamW"]
 t = a[:, order]
 d = np.diff(t, axis=1)
 if rank == 0:
