@@ -432,6 +432,10 @@ def test_fit_device_rows_mode_equals_gather_mode(task, monkeypatch):
         got = st.fit_device(ds, epochs=2, shuffle=True, seed=9)          # 83 -> 11 steps per epoch = 8 + 3
         got += st.fit_device(ds, epochs=1, seed=9, start_epoch=2, max_steps=6)
         assert [g.numel() for g in got] == [11, 11, 6]
+        # a second dataset (other tensors, other length): the kernels are re-bound, the graphs re-captured
+        ds2 = DeviceDataset(x[:40].flip(0).contiguous(), y[:40].flip(0).contiguous(), device=dev)
+        got += st.fit_device(ds2, epochs=1, shuffle=True, seed=3)
+        assert got[-1].numel() == 5
         assert (len(st._graph_rows) > 0) == (rows == "1")
         res.append((torch.cat(got).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
         st.close()

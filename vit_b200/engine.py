@@ -257,7 +257,7 @@ class ViTEngine:
             raise ValueError("bind_rows: labels do not match the dataset rows")
         self._rows = dict(x=x_all, labels=labels_all, rows=rows, loss_log=loss_log,
                           base=torch.zeros(1, dtype=torch.int64, device=self.device))
-        for k in [k for k in self._progs if k[-1] == ROWS_SLOT and k[0] in ("fwd", "bwd")]:
+        for k in [k for k in self._progs if ROWS_SLOT in k[1:] and k[0] in ("fwd", "bwd")]:
             del self._progs[k]
 
     def start_rows(self) -> None:
