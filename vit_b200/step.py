@@ -395,7 +395,20 @@ class TrainStep:
                 self._rows_lab = lab
                 eng.bind_rows(dataset.flux, lab, self._rows_buf, self._rows_log)
                 self._rows_key, self._graph_rows = key, {}
-            self._rows_buf[:order.numel()].copy_(order.to(eng.device, non_blocking=True))
+            # the permutation goes through one of two page-locked staging buffers, so that the upload is a stream-ordered
+            # DMA behind the previous epoch's graphs instead of a pageable copy that blocks the host until they finish
+            pin = self.__dict__.setdefault("_rows_pin", [None, None, 0, None, None])
+            i = pin[2]
+            pin[2] ^= 1
+            if pin[i] is None or pin[i].numel() < order.numel():
+                pin[i] = torch.empty(order.numel(), dtype=torch.int64, pin_memory=True)
+            if pin[3 + i] is not None:
+                pin[3 + i].synchronize()        # the upload that last used this staging buffer is done
+            pin[i][:order.numel()].copy_(order)
+            self._rows_buf[:order.numel()].copy_(pin[i][:order.numel()], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(eng.device))
+            pin[3 + i] = ev
             eng.start_rows()
             if left is not None:
                 nb = min(nb, left)
